@@ -1,0 +1,112 @@
+"""Build + ctypes binding of libgridaphybrid_b200.so (the C ABI declared in include/ghb.h).
+
+The library is the product; this module only loads it.  There is no CPU fallback: if the shared
+library is missing it is compiled with nvcc for sm_100a, and if no CUDA device is present
+`Context()` raises (ghb_create -> GHB_ENODEVICE).
+"""
+from __future__ import annotations
+
+import ctypes
+import glob
+import os
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+_CSRC = os.path.join(_PKG, "csrc")
+SO_PATH = os.path.join(_PKG, "libgridaphybrid_b200.so")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+# every symbol include/ghb.h declares (tests check the library exports each one)
+SYMBOLS = [
+    "ghb_create", "ghb_destroy", "ghb_last_error", "ghb_set_stream", "ghb_synchronize", "ghb_launch_count",
+    "ghb_plan_kernel_name", "ghb_plan_blocks", "ghb_plan_query", "ghb_condense_f64",
+    "ghb_restrict_facet_dofs_i64", "ghb_assemble_symbolic", "ghb_assemble_pattern", "ghb_assemble_numeric_f64",
+    "ghb_assemble_symbolic_slab", "ghb_pack_cut_plane_f64", "ghb_assemble_numeric_slab_f64",
+    "ghb_condense_assemble_f64", "ghb_backsub_f64", "ghb_scatter_free_dof_values", "ghb_synth_fill_f64",
+    "ghb_cartesian_cell_wise_facets",
+]
+
+GHB_OK, GHB_EINVAL, GHB_ECUDA, GHB_ENODEVICE, GHB_ENOMEM, GHB_EUNSUPPORTED, GHB_ESTATE = 0, -1, -2, -3, -4, -5, -6
+_CODES = {-1: "GHB_EINVAL", -2: "GHB_ECUDA", -3: "GHB_ENODEVICE", -4: "GHB_ENOMEM", -5: "GHB_EUNSUPPORTED",
+          -6: "GHB_ESTATE"}
+
+
+class GhbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{_CODES.get(code, code)}: {msg}")
+        self.code = code
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(_CSRC, "*.cu")))
+
+
+def needs_build() -> bool:
+    if not os.path.exists(SO_PATH):
+        return True
+    t = os.path.getmtime(SO_PATH)
+    deps = sources() + glob.glob(os.path.join(_CSRC, "*.cuh")) + [os.path.join(_ROOT, "include", "ghb.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every .cu under csrc/ for sm_100a into one in-tree shared library."""
+    if force or needs_build():
+        nvcc = os.environ.get("NVCC", "nvcc")
+        cmd = [nvcc] + NVCC_FLAGS + ["-o", SO_PATH] + sources()
+        if verbose:
+            cmd += ["-Xptxas", "-v"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        if verbose:
+            print(res.stderr)
+    return SO_PATH
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(SO_PATH):
+        build()
+    L = ctypes.CDLL(SO_PATH)
+    vp, i32, i64, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint64
+    L.ghb_create.argtypes = [i32, ctypes.POINTER(vp)]
+    L.ghb_destroy.argtypes = [vp]
+    L.ghb_destroy.restype = None
+    L.ghb_last_error.argtypes = [vp]
+    L.ghb_last_error.restype = ctypes.c_char_p
+    L.ghb_set_stream.argtypes = [vp, vp]
+    L.ghb_synchronize.argtypes = [vp]
+    L.ghb_launch_count.argtypes = [vp]
+    L.ghb_launch_count.restype = i64
+    L.ghb_plan_kernel_name.argtypes = [vp, i32]
+    L.ghb_plan_kernel_name.restype = ctypes.c_char_p
+    L.ghb_plan_blocks.argtypes = [vp, i32, vp, vp, i32, vp, i32, vp, ctypes.POINTER(i32)]
+    L.ghb_plan_query.argtypes = [vp, i32, ctypes.POINTER(i64)]
+    L.ghb_condense_f64.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, i32]
+    L.ghb_restrict_facet_dofs_i64.argtypes = [vp, i64, i32, i32, vp, vp, vp]
+    L.ghb_assemble_symbolic.argtypes = [vp, i64, i32, vp, i64, ctypes.POINTER(i64)]
+    L.ghb_assemble_pattern.argtypes = [vp, vp, vp]
+    L.ghb_assemble_numeric_f64.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.ghb_assemble_symbolic_slab.argtypes = [vp, i64, i64, i32, i32, vp, i64, i64, i64, ctypes.POINTER(i64)]
+    L.ghb_pack_cut_plane_f64.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp, vp]
+    L.ghb_assemble_numeric_slab_f64.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.ghb_condense_assemble_f64.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, vp]
+    L.ghb_backsub_f64.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, vp, vp]
+    L.ghb_scatter_free_dof_values.argtypes = [vp, i32, i64, vp, vp, i64, vp]
+    L.ghb_synth_fill_f64.argtypes = [vp, i32, i64, i64, u64, vp, vp]
+    L.ghb_cartesian_cell_wise_facets.argtypes = [vp, i32, vp, i64, i64, vp]
+    for name in SYMBOLS:
+        fn = getattr(L, name)
+        if fn.restype is ctypes.c_int and name not in ("ghb_destroy",):
+            fn.restype = ctypes.c_int
+    _LIB = L
+    return L

@@ -1,0 +1,464 @@
+// api.cu -- C ABI entry points (include/ghb.h): context, block plans, argument staging, dispatch.
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+
+namespace ghb {
+
+int fail(ghb_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+static Plan* get_plan(ghb_ctx* ctx, int id) {
+  if (!ctx || id < 0 || id >= (int)ctx->plans.size()) return nullptr;
+  return ctx->plans[id];
+}
+
+}  // namespace ghb
+
+using namespace ghb;
+
+extern "C" {
+
+int ghb_create(int device_id, ghb_ctx** out) {
+  if (!out) return GHB_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) { cudaGetLastError(); return GHB_ENODEVICE; }
+  if (device_id < 0 || device_id >= ndev) return GHB_EINVAL;
+  ghb_ctx* ctx = new (std::nothrow) ghb_ctx();
+  if (!ctx) return GHB_ENOMEM;
+  ctx->device = device_id;
+  if (cudaSetDevice(device_id) != cudaSuccess) { delete ctx; return GHB_ECUDA; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) { delete ctx; return GHB_ECUDA; }
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return GHB_ECUDA; }
+  if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return GHB_ECUDA; }
+  // keep freed async allocations cached in the pool (avoid re-mapping per call)
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  *out = ctx;
+  return GHB_OK;
+}
+
+void ghb_destroy(ghb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (Plan* p : ctx->plans) {
+    if (p && p->d_emap) cudaFree(p->d_emap);
+    delete p;
+  }
+  asm_free(ctx);
+  if (ctx->fac.d_X) cudaFree(ctx->fac.d_X);
+  for (int i = 0; i < 2; ++i)
+    if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+}
+
+const char* ghb_last_error(const ghb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+int ghb_set_stream(ghb_ctx* ctx, void* s) {
+  if (!ctx) return GHB_EINVAL;
+  cudaSetDevice(ctx->device);
+  if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+  if (s == nullptr) {
+    GHB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+  } else {
+    ctx->stream = (cudaStream_t)s;
+    ctx->own_stream = false;
+  }
+  return GHB_OK;
+}
+
+int ghb_synchronize(ghb_ctx* ctx) {
+  if (!ctx) return GHB_EINVAL;
+  GHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return GHB_OK;
+}
+
+int64_t ghb_launch_count(const ghb_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+const char* ghb_plan_kernel_name(ghb_ctx* ctx, int plan_id) {
+  Plan* p = get_plan(ctx, plan_id);
+  return p ? p->kernel_name : "";
+}
+
+int ghb_plan_blocks(ghb_ctx* ctx, int nfields, const int32_t* ndofs, const uint8_t* touched, int n_int,
+                    const int32_t* interior, int n_bnd, const int32_t* boundary, int* plan_id) {
+  if (!ctx) return GHB_EINVAL;
+  if (!ndofs || !touched || !plan_id || (n_int > 0 && !interior) || (n_bnd > 0 && !boundary))
+    return fail(ctx, GHB_EINVAL, "ghb_plan_blocks: null argument");
+  if (nfields <= 0 || n_int < 0 || n_bnd <= 0 || n_int + n_bnd != nfields)
+    return fail(ctx, GHB_EINVAL, "ghb_plan_blocks: interior+boundary must cover 1:nfields (need >=1 boundary field)");
+  // _check_preconditions (StaticCondensationMap.jl:16-34): disjoint cover of 1:nfields
+  std::vector<int> seen(nfields, 0);
+  for (int k = 0; k < n_int + n_bnd; ++k) {
+    int f = k < n_int ? interior[k] : boundary[k - n_int];
+    if (f < 1 || f > nfields || seen[f - 1]) return fail(ctx, GHB_EINVAL, "ghb_plan_blocks: fields are not a disjoint cover of 1:nfields");
+    seen[f - 1] = 1;
+  }
+  for (int f = 0; f < nfields; ++f)
+    if (ndofs[f] <= 0) return fail(ctx, GHB_EINVAL, "ghb_plan_blocks: ndofs must be positive");
+  // a block row (or column) without any touched block has no defined size in the reference
+  for (int f = 0; f < nfields; ++f) {
+    bool r = false, c = false;
+    for (int q = 0; q < nfields; ++q) { r |= touched[f + nfields * q] != 0; c |= touched[q + nfields * f] != 0; }
+    if (!r || !c) return fail(ctx, GHB_EINVAL, "ghb_plan_blocks: a field has no touched block in its block row/column");
+  }
+  Plan* p = new (std::nothrow) Plan();
+  if (!p) return fail(ctx, GHB_ENOMEM, "plan alloc");
+  p->nfields = nfields;
+  p->ndofs.assign(ndofs, ndofs + nfields);
+  p->touched.assign(touched, touched + nfields * nfields);
+  p->interior.assign(interior, interior + n_int);
+  p->boundary.assign(boundary, boundary + n_bnd);
+  p->block_offset.assign((size_t)nfields * nfields, -1);
+  int64_t off = 0;
+  p->all_touched = true;
+  for (int j = 0; j < nfields; ++j)
+    for (int i = 0; i < nfields; ++i) {
+      if (touched[i + nfields * j]) {
+        p->block_offset[i + nfields * j] = off;
+        off += (int64_t)ndofs[i] * ndofs[j];
+      } else {
+        p->all_touched = false;
+      }
+    }
+  p->lenA = (int)off;
+  p->field_offset_b.resize(nfields);
+  int bo = 0;
+  for (int f = 0; f < nfields; ++f) { p->field_offset_b[f] = bo; bo += ndofs[f]; }
+  p->lenb = bo;
+  for (int k = 0; k < n_int + n_bnd; ++k) {
+    int f = (k < n_int ? interior[k] : boundary[k - n_int]) - 1;
+    for (int l = 0; l < ndofs[f]; ++l) { p->row_field.push_back(f); p->row_local.push_back(l); }
+    (k < n_int ? p->n_i : p->n_b) += ndofs[f];
+  }
+  p->n = p->n_i + p->n_b;
+  if (p->n_b > 255) { delete p; return fail(ctx, GHB_EUNSUPPORTED, "ghb_plan_blocks: n_b > 255 not supported"); }
+  // element map in condensed order
+  const int n = p->n;
+  std::vector<int32_t> emap((size_t)n * (n + 1));
+  for (int j = 0; j < n; ++j)
+    for (int i = 0; i < n; ++i) {
+      int fi = p->row_field[i], fj = p->row_field[j];
+      int64_t bofs = p->block_offset[fi + nfields * fj];
+      emap[i + (size_t)n * j] = bofs < 0 ? -1 : (int32_t)(bofs + p->row_local[i] + (int64_t)p->row_local[j] * ndofs[fi]);
+    }
+  for (int i = 0; i < n; ++i) emap[i + (size_t)n * n] = p->field_offset_b[p->row_field[i]] + p->row_local[i];
+  cudaSetDevice(ctx->device);
+  if (cudaMalloc((void**)&p->d_emap, emap.size() * sizeof(int32_t)) != cudaSuccess) { delete p; return fail(ctx, GHB_ENOMEM, "emap alloc"); }
+  cudaMemcpy(p->d_emap, emap.data(), emap.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+  ctx->plans.push_back(p);
+  *plan_id = (int)ctx->plans.size() - 1;
+  return GHB_OK;
+}
+
+int ghb_plan_query(ghb_ctx* ctx, int plan_id, int64_t out[4]) {
+  Plan* p = get_plan(ctx, plan_id);
+  if (!p || !out) return fail(ctx, GHB_EINVAL, "ghb_plan_query: bad plan id");
+  out[0] = p->n_i; out[1] = p->n_b; out[2] = p->lenA; out[3] = p->lenb;
+  return GHB_OK;
+}
+
+int ghb_condense_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A, const double* b, double* S,
+                     double* g, int32_t* info, int keep_factors) {
+  Plan* p = get_plan(ctx, plan_id);
+  if (!p) return fail(ctx, GHB_EINVAL, "ghb_condense_f64: bad plan id");
+  if (ncells < 0) return fail(ctx, GHB_EINVAL, "ghb_condense_f64: ncells < 0");
+  if (ncells == 0) return GHB_OK;
+  if (!A || !b || !S || !g) return fail(ctx, GHB_EINVAL, "ghb_condense_f64: null array");
+  cudaSetDevice(ctx->device);
+  double* X = nullptr;
+  if (keep_factors) {
+    size_t need = (size_t)ncells * p->n_i * (p->n_b + 1) * sizeof(double);
+    if (ctx->fac.bytes < need) {
+      if (ctx->fac.d_X) cudaFree(ctx->fac.d_X);
+      ctx->fac.d_X = nullptr; ctx->fac.bytes = 0;
+      if (cudaMalloc((void**)&ctx->fac.d_X, need) != cudaSuccess) { cudaGetLastError(); return fail(ctx, GHB_ENOMEM, "factor storage"); }
+      ctx->fac.bytes = need;
+    }
+    ctx->fac.plan_id = plan_id; ctx->fac.ncells = ncells;
+    X = ctx->fac.d_X;
+  } else {
+    ctx->fac.plan_id = -1;
+  }
+  Arg<double> dA(ctx, A, (size_t)ncells * p->lenA, true, false); GHB_TRY(dA.rc);
+  Arg<double> db(ctx, b, (size_t)ncells * p->lenb, true, false); GHB_TRY(db.rc);
+  Arg<double> dS(ctx, S, (size_t)ncells * p->n_b * p->n_b, false, true); GHB_TRY(dS.rc);
+  Arg<double> dg(ctx, g, (size_t)ncells * p->n_b, false, true); GHB_TRY(dg.rc);
+  Arg<int32_t> di(ctx, info, info ? (size_t)ncells : 0, false, true); GHB_TRY(di.rc);
+  GHB_TRY(launch_condense_generic(ctx, *p, ncells, dA.dev, db.dev, dS.dev, dg.dev, di.dev, X));
+  GHB_TRY(dS.finish()); GHB_TRY(dg.finish()); GHB_TRY(di.finish());
+  return GHB_OK;
+}
+
+int ghb_restrict_facet_dofs_i64(ghb_ctx* ctx, int64_t ncells, int nlfacets, int ndofs_f,
+                                const int64_t* cell_wise_facets, const int64_t* facet_data, int64_t* out) {
+  if (!ctx) return GHB_EINVAL;
+  if (ncells < 0 || nlfacets <= 0 || ndofs_f <= 0 || !cell_wise_facets || !facet_data || !out)
+    return fail(ctx, GHB_EINVAL, "ghb_restrict_facet_dofs_i64: bad argument");
+  if (ncells == 0) return GHB_OK;
+  cudaSetDevice(ctx->device);
+  if (!is_device_ptr(facet_data) || !is_device_ptr(cell_wise_facets) || !is_device_ptr(out))
+    return fail(ctx, GHB_EUNSUPPORTED, "ghb_restrict_facet_dofs_i64: device pointers required (facet table size is not passed)");
+  return launch_restrict_facet_dofs(ctx, ncells, nlfacets, ndofs_f, cell_wise_facets, facet_data, out);
+}
+
+int ghb_assemble_symbolic(ghb_ctx* ctx, int64_t ncells, int n_b, const int64_t* cell_ids, int64_t nrows,
+                          int64_t* nnz_out) {
+  if (!ctx) return GHB_EINVAL;
+  if (ncells <= 0 || n_b <= 0 || n_b > 255 || !cell_ids || nrows <= 0)
+    return fail(ctx, GHB_EINVAL, "ghb_assemble_symbolic: bad argument (need ncells>0, 0<n_b<=255, nrows>0)");
+  cudaSetDevice(ctx->device);
+  asm_free(ctx);
+  size_t cnt = (size_t)ncells * n_b;
+  GHB_CUDA(ctx, cudaMalloc((void**)&ctx->as.d_ids, cnt * sizeof(int64_t)));
+  GHB_CUDA(ctx, cudaMemcpyAsync(ctx->as.d_ids, cell_ids, cnt * sizeof(int64_t),
+                                is_device_ptr(cell_ids) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+  int rc = asm_symbolic(ctx, ncells, 0, 0, n_b, ctx->as.d_ids, nrows, 0, nrows);
+  if (rc != GHB_OK) { asm_free(ctx); return rc; }
+  if (nnz_out) *nnz_out = ctx->as.nnz;
+  return GHB_OK;
+}
+
+int ghb_assemble_symbolic_slab(ghb_ctx* ctx, int64_t ncells_local, int64_t nghost, int ghost_ncols, int n_b,
+                               const int64_t* cell_ids, int64_t nrows_global, int64_t col_begin, int64_t col_end,
+                               int64_t* nnz_out) {
+  if (!ctx) return GHB_EINVAL;
+  if (ncells_local <= 0 || nghost < 0 || n_b <= 0 || n_b > 255 || !cell_ids || nrows_global <= 0 || col_begin < 1 ||
+      col_end < col_begin || col_end > nrows_global + 1 || ghost_ncols < 0 || ghost_ncols > n_b)
+    return fail(ctx, GHB_EINVAL, "ghb_assemble_symbolic_slab: bad argument");
+  if (col_end == col_begin) return fail(ctx, GHB_EINVAL, "ghb_assemble_symbolic_slab: empty owned column range");
+  cudaSetDevice(ctx->device);
+  asm_free(ctx);
+  size_t cnt = (size_t)(ncells_local + nghost) * n_b;
+  GHB_CUDA(ctx, cudaMalloc((void**)&ctx->as.d_ids, cnt * sizeof(int64_t)));
+  GHB_CUDA(ctx, cudaMemcpyAsync(ctx->as.d_ids, cell_ids, cnt * sizeof(int64_t),
+                                is_device_ptr(cell_ids) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+  int rc = asm_symbolic(ctx, ncells_local, nghost, ghost_ncols, n_b, ctx->as.d_ids, nrows_global, col_begin - 1,
+                        col_end - col_begin);
+  if (rc != GHB_OK) { asm_free(ctx); return rc; }
+  if (nnz_out) *nnz_out = ctx->as.nnz;
+  return GHB_OK;
+}
+
+int ghb_pack_cut_plane_f64(ghb_ctx* ctx, int64_t ncut, int n_b, int ncols, const double* S, const double* g,
+                           const int64_t* cell_ids, const double* dirichlet_vals, double* out) {
+  if (!ctx) return GHB_EINVAL;
+  if (ncut < 0 || n_b <= 0 || ncols <= 0 || ncols > n_b || !S || !g || !out || (dirichlet_vals && !cell_ids))
+    return fail(ctx, GHB_EINVAL, "ghb_pack_cut_plane_f64: bad argument");
+  cudaSetDevice(ctx->device);
+  if (!is_device_ptr(S) || !is_device_ptr(g) || !is_device_ptr(out) || (cell_ids && !is_device_ptr(cell_ids)) ||
+      (dirichlet_vals && !is_device_ptr(dirichlet_vals)))
+    return fail(ctx, GHB_EUNSUPPORTED, "ghb_pack_cut_plane_f64: device pointers required (feeds NCCL)");
+  return asm_pack_cut_plane(ctx, ncut, n_b, ncols, S, g, cell_ids, dirichlet_vals, out);
+}
+
+int ghb_assemble_numeric_slab_f64(ghb_ctx* ctx, const double* S, const double* g, const double* ghost,
+                                  const double* dirichlet_vals, double* nzval, double* rhs) {
+  if (!ctx) return GHB_EINVAL;
+  if (!ctx->as.valid) return fail(ctx, GHB_ESTATE, "ghb_assemble_numeric_slab_f64: call ghb_assemble_symbolic_slab first");
+  if (!S || !g || !nzval || !rhs || (ctx->as.nghost > 0 && !ghost))
+    return fail(ctx, GHB_EINVAL, "ghb_assemble_numeric_slab_f64: null array");
+  cudaSetDevice(ctx->device);
+  if (!is_device_ptr(S) || !is_device_ptr(g) || !is_device_ptr(nzval) || !is_device_ptr(rhs) ||
+      (ghost && !is_device_ptr(ghost)) || (dirichlet_vals && !is_device_ptr(dirichlet_vals)))
+    return fail(ctx, GHB_EUNSUPPORTED, "ghb_assemble_numeric_slab_f64: device pointers required");
+  return asm_numeric(ctx, S, g, ghost, dirichlet_vals, nzval, rhs);
+}
+
+int ghb_assemble_pattern(ghb_ctx* ctx, int64_t* colptr, int64_t* rowval) {
+  if (!ctx) return GHB_EINVAL;
+  if (!ctx->as.valid) return fail(ctx, GHB_ESTATE, "ghb_assemble_pattern: no symbolic phase cached");
+  cudaSetDevice(ctx->device);
+  if (colptr)
+    GHB_CUDA(ctx, cudaMemcpyAsync(colptr, ctx->as.d_colptr, (ctx->as.nrows + 1) * sizeof(int64_t), cudaMemcpyDefault, ctx->stream));
+  if (rowval)
+    GHB_CUDA(ctx, cudaMemcpyAsync(rowval, ctx->as.d_rowval, ctx->as.nnz * sizeof(int64_t), cudaMemcpyDefault, ctx->stream));
+  GHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return GHB_OK;
+}
+
+int ghb_assemble_numeric_f64(ghb_ctx* ctx, const double* S, const double* g, const double* dirichlet_vals,
+                             double* nzval, double* rhs) {
+  if (!ctx) return GHB_EINVAL;
+  if (!ctx->as.valid) return fail(ctx, GHB_ESTATE, "ghb_assemble_numeric_f64: call ghb_assemble_symbolic first");
+  if (ctx->as.nghost) return fail(ctx, GHB_ESTATE, "ghb_assemble_numeric_f64: the cached pattern has ghost cells; use ghb_assemble_numeric_slab_f64");
+  if (!S || !g || !nzval || !rhs) return fail(ctx, GHB_EINVAL, "ghb_assemble_numeric_f64: null array");
+  cudaSetDevice(ctx->device);
+  const AsmState& as = ctx->as;
+  if (dirichlet_vals && !is_device_ptr(dirichlet_vals))
+    return fail(ctx, GHB_EUNSUPPORTED, "ghb_assemble_numeric_f64: dirichlet_vals must be a device pointer (its length is not passed)");
+  Arg<double> dS(ctx, S, (size_t)as.ncells * as.n_b * as.n_b, true, false); GHB_TRY(dS.rc);
+  Arg<double> dg(ctx, g, (size_t)as.ncells * as.n_b, true, false); GHB_TRY(dg.rc);
+  Arg<double> dz(ctx, nzval, (size_t)as.nnz, false, true); GHB_TRY(dz.rc);
+  Arg<double> dr(ctx, rhs, (size_t)as.nrows, false, true); GHB_TRY(dr.rc);
+  GHB_TRY(asm_numeric(ctx, dS.dev, dg.dev, nullptr, dirichlet_vals, dz.dev, dr.dev));
+  GHB_TRY(dz.finish()); GHB_TRY(dr.finish());
+  return GHB_OK;
+}
+
+int ghb_condense_assemble_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A, const double* b,
+                              const double* dirichlet_vals, double* nzval, double* rhs, int32_t* info) {
+  Plan* p = get_plan(ctx, plan_id);
+  if (!p) return fail(ctx, GHB_EINVAL, "ghb_condense_assemble_f64: bad plan id");
+  if (!ctx->as.valid) return fail(ctx, GHB_ESTATE, "ghb_condense_assemble_f64: call ghb_assemble_symbolic first");
+  const AsmState& as = ctx->as;
+  if (as.nghost) return fail(ctx, GHB_ESTATE, "ghb_condense_assemble_f64: the cached pattern has ghost cells (slab mode)");
+  if (ncells != as.ncells || p->n_b != as.n_b)
+    return fail(ctx, GHB_EINVAL, "ghb_condense_assemble_f64: ncells / n_b differ from the symbolic phase");
+  if (!A || !b || !nzval || !rhs) return fail(ctx, GHB_EINVAL, "ghb_condense_assemble_f64: null array");
+  if (dirichlet_vals && !is_device_ptr(dirichlet_vals))
+    return fail(ctx, GHB_EUNSUPPORTED, "ghb_condense_assemble_f64: dirichlet_vals must be a device pointer");
+  cudaSetDevice(ctx->device);
+  const bool hostA = !is_device_ptr(A), hostb = !is_device_ptr(b);
+  if (hostA != hostb) return fail(ctx, GHB_EINVAL, "ghb_condense_assemble_f64: A and b must both be host or both device");
+  double *dS = nullptr, *dg = nullptr;
+  GHB_CUDA(ctx, cudaMallocAsync((void**)&dS, (size_t)ncells * p->n_b * p->n_b * sizeof(double), ctx->stream));
+  GHB_CUDA(ctx, cudaMallocAsync((void**)&dg, (size_t)ncells * p->n_b * sizeof(double), ctx->stream));
+  Arg<int32_t> di(ctx, info, info ? (size_t)ncells : 0, false, true); GHB_TRY(di.rc);
+  int rc = GHB_OK;
+  if (!hostA) {
+    rc = launch_condense_generic(ctx, *p, ncells, A, b, dS, dg, di.dev, nullptr);
+  } else {
+    // stream host records through two device chunk buffers: H2D of chunk k+1 overlaps condensation of chunk k
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(ncells, (int64_t)(256u << 20) / ((p->lenA + p->lenb) * 8)));
+    double* dA[2] = {nullptr, nullptr};
+    double* db[2] = {nullptr, nullptr};
+    cudaEvent_t h2d_done[2], k_done[2];
+    for (int i = 0; i < 2; ++i) {
+      GHB_CUDA(ctx, cudaMallocAsync((void**)&dA[i], (size_t)chunk * p->lenA * 8, ctx->stream));
+      GHB_CUDA(ctx, cudaMallocAsync((void**)&db[i], (size_t)chunk * p->lenb * 8, ctx->stream));
+      GHB_CUDA(ctx, cudaEventCreateWithFlags(&h2d_done[i], cudaEventDisableTiming));
+      GHB_CUDA(ctx, cudaEventCreateWithFlags(&k_done[i], cudaEventDisableTiming));
+    }
+    GHB_CUDA(ctx, cudaEventRecord(k_done[0], ctx->stream));
+    GHB_CUDA(ctx, cudaEventRecord(k_done[1], ctx->stream));
+    int64_t c0 = 0;
+    for (int it = 0; c0 < ncells && rc == GHB_OK; ++it, c0 += chunk) {
+      int s = it & 1;
+      int64_t nc = std::min(chunk, ncells - c0);
+      GHB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, k_done[s], 0));
+      GHB_CUDA(ctx, cudaMemcpyAsync(dA[s], A + c0 * p->lenA, (size_t)nc * p->lenA * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+      GHB_CUDA(ctx, cudaMemcpyAsync(db[s], b + c0 * p->lenb, (size_t)nc * p->lenb * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+      GHB_CUDA(ctx, cudaEventRecord(h2d_done[s], ctx->copy_stream));
+      GHB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, h2d_done[s], 0));
+      rc = launch_condense_generic(ctx, *p, nc, dA[s], db[s], dS + c0 * p->n_b * p->n_b, dg + c0 * p->n_b,
+                                   di.dev ? di.dev + c0 : nullptr, nullptr);
+      GHB_CUDA(ctx, cudaEventRecord(k_done[s], ctx->stream));
+    }
+    for (int i = 0; i < 2; ++i) {
+      cudaFreeAsync(dA[i], ctx->stream); cudaFreeAsync(db[i], ctx->stream);
+      cudaEventDestroy(h2d_done[i]); cudaEventDestroy(k_done[i]);
+    }
+  }
+  if (rc == GHB_OK) {
+    Arg<double> dz(ctx, nzval, (size_t)as.nnz, false, true); rc = dz.rc;
+    Arg<double> dr(ctx, rhs, (size_t)as.nrows, false, true); if (rc == GHB_OK) rc = dr.rc;
+    if (rc == GHB_OK) rc = asm_numeric(ctx, dS, dg, nullptr, dirichlet_vals, dz.dev, dr.dev);
+    if (rc == GHB_OK) rc = dz.finish();
+    if (rc == GHB_OK) rc = dr.finish();
+  }
+  cudaFreeAsync(dS, ctx->stream);
+  cudaFreeAsync(dg, ctx->stream);
+  if (rc == GHB_OK) rc = di.finish();
+  return rc;
+}
+
+int ghb_backsub_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A, const double* b,
+                    const double* lambda_free, const double* lambda_dirichlet, const int64_t* cell_ids,
+                    double* u, int32_t* info) {
+  Plan* p = get_plan(ctx, plan_id);
+  if (!p) return fail(ctx, GHB_EINVAL, "ghb_backsub_f64: bad plan id");
+  if (ncells < 0) return fail(ctx, GHB_EINVAL, "ghb_backsub_f64: ncells < 0");
+  if (ncells == 0) return GHB_OK;
+  if (!cell_ids || !u || !lambda_free) return fail(ctx, GHB_EINVAL, "ghb_backsub_f64: null array");
+  cudaSetDevice(ctx->device);
+  if (!is_device_ptr(lambda_free) || (lambda_dirichlet && !is_device_ptr(lambda_dirichlet)))
+    return fail(ctx, GHB_EUNSUPPORTED, "ghb_backsub_f64: lambda vectors must be device pointers (their lengths are not passed)");
+  Arg<int64_t> dids(ctx, cell_ids, (size_t)ncells * p->n_b, true, false); GHB_TRY(dids.rc);
+  Arg<double> du(ctx, u, (size_t)ncells * p->n_i, false, true); GHB_TRY(du.rc);
+  Arg<int32_t> di(ctx, info, info ? (size_t)ncells : 0, false, true); GHB_TRY(di.rc);
+  if (!A && !b) {
+    if (ctx->fac.plan_id != plan_id || ctx->fac.ncells != ncells)
+      return fail(ctx, GHB_ESTATE, "ghb_backsub_f64: A,b are NULL but no matching keep_factors condensation is stored");
+    GHB_TRY(launch_backsub_factors(ctx, *p, ncells, ctx->fac.d_X, lambda_free, lambda_dirichlet, dids.dev, du.dev));
+    if (di.dev) GHB_CUDA(ctx, cudaMemsetAsync(di.dev, 0, ncells * sizeof(int32_t), ctx->stream));
+  } else {
+    if (!A || !b) return fail(ctx, GHB_EINVAL, "ghb_backsub_f64: A and b must both be given or both NULL");
+    Arg<double> dA(ctx, A, (size_t)ncells * p->lenA, true, false); GHB_TRY(dA.rc);
+    Arg<double> db(ctx, b, (size_t)ncells * p->lenb, true, false); GHB_TRY(db.rc);
+    GHB_TRY(launch_backsub_generic(ctx, *p, ncells, dA.dev, db.dev, lambda_free, lambda_dirichlet, dids.dev, du.dev, di.dev));
+    GHB_TRY(du.finish()); GHB_TRY(di.finish());
+    return GHB_OK;
+  }
+  GHB_TRY(du.finish()); GHB_TRY(di.finish());
+  return GHB_OK;
+}
+
+int ghb_scatter_free_dof_values(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* u,
+                                const double* lambda_free, int64_t nlambda, double* x) {
+  Plan* p = get_plan(ctx, plan_id);
+  if (!p) return fail(ctx, GHB_EINVAL, "ghb_scatter_free_dof_values: bad plan id");
+  if (ncells < 0 || nlambda < 0 || !u || !x || (nlambda > 0 && !lambda_free))
+    return fail(ctx, GHB_EINVAL, "ghb_scatter_free_dof_values: bad argument");
+  cudaSetDevice(ctx->device);
+  Arg<double> du(ctx, u, (size_t)ncells * p->n_i, true, false); GHB_TRY(du.rc);
+  Arg<double> dl(ctx, lambda_free, (size_t)nlambda, true, false); GHB_TRY(dl.rc);
+  Arg<double> dx(ctx, x, (size_t)ncells * p->n_i + nlambda, false, true); GHB_TRY(dx.rc);
+  GHB_TRY(launch_scatter_free(ctx, *p, ncells, du.dev, dl.dev, nlambda, dx.dev));
+  GHB_TRY(dx.finish());
+  return GHB_OK;
+}
+
+int ghb_synth_fill_f64(ghb_ctx* ctx, int plan_id, int64_t cell_start, int64_t ncells, uint64_t seed, double* A,
+                       double* b) {
+  Plan* p = get_plan(ctx, plan_id);
+  if (!p) return fail(ctx, GHB_EINVAL, "ghb_synth_fill_f64: bad plan id");
+  if (ncells < 0 || cell_start < 0 || !A || !b) return fail(ctx, GHB_EINVAL, "ghb_synth_fill_f64: bad argument");
+  if (ncells == 0) return GHB_OK;
+  cudaSetDevice(ctx->device);
+  Arg<double> dA(ctx, A, (size_t)ncells * p->lenA, false, true); GHB_TRY(dA.rc);
+  Arg<double> db(ctx, b, (size_t)ncells * p->lenb, false, true); GHB_TRY(db.rc);
+  GHB_TRY(launch_synth_fill(ctx, *p, cell_start, ncells, seed, dA.dev, db.dev));
+  GHB_TRY(dA.finish()); GHB_TRY(db.finish());
+  return GHB_OK;
+}
+
+int ghb_cartesian_cell_wise_facets(ghb_ctx* ctx, int D, const int64_t* dims, int64_t cell_start, int64_t ncells,
+                                   int64_t* cell_wise_facets) {
+  if (!ctx) return GHB_EINVAL;
+  if ((D != 2 && D != 3) || !dims || ncells < 0 || cell_start < 0 || !cell_wise_facets)
+    return fail(ctx, GHB_EINVAL, "ghb_cartesian_cell_wise_facets: bad argument (D must be 2 or 3)");
+  int64_t tot = 1;
+  for (int d = 0; d < D; ++d) { if (dims[d] <= 0) return fail(ctx, GHB_EINVAL, "dims must be positive"); tot *= dims[d]; }
+  if (cell_start + ncells > tot) return fail(ctx, GHB_EINVAL, "cell range exceeds the mesh");
+  if (ncells == 0) return GHB_OK;
+  cudaSetDevice(ctx->device);
+  Arg<int64_t> dout(ctx, cell_wise_facets, (size_t)ncells * 2 * D, false, true); GHB_TRY(dout.rc);
+  GHB_TRY(launch_cartesian_facets(ctx, D, dims, cell_start, ncells, dout.dev));
+  GHB_TRY(dout.finish());
+  return GHB_OK;
+}
+
+}  // extern "C"

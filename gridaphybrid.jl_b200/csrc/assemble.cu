@@ -1,0 +1,430 @@
+// assemble.cu -- skeleton assembly: symbolic phase (CSC pattern of Julia's sparse(I,J,V,m,n)) and the
+// atomic-free, owner-computes numeric phase.
+//
+// Reference semantics (Gridap SparseMatrixAssembler; call sites
+// /root/reference/src/HybridAffineFEOperators.jl:38,46 and src/HybridLinearSolvers.jl:43-44):
+//   cells ascending, `for lj, for li`: push (ids[li], ids[lj], S[li,lj]) when both ids > 0;
+//   b[ids[li]] += g[li]; then sparse(I,J,V,m,n): columns ascending, rows ascending inside a column,
+//   duplicates summed, stored zeros kept.
+// Facet dofs belong to at most two cells, so column j of the result is the sorted union of the positive
+// ids of the (<=2) cells that contain j.  The symbolic phase stores, per dof, its <=2 occurrences
+// (cell ascending) and, per cell, the order of its positive ids; a column is then a two-pointer merge.
+// The numeric phase *gathers*: the thread that owns a stored entry adds its <=2 contributions in cell
+// order -- no atomics, bitwise reproducible, and identical to the reference's left-to-right sum.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace ghb {
+
+namespace {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;  // per thread
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+// ---- exclusive scan of int32 counts into int64 offsets (three small kernels) ------------------
+__global__ void scan_tile_sums(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ tile_sums) {
+  __shared__ int64_t red[kScanThreads / 32];
+  int64_t base = (int64_t)blockIdx.x * kScanTile;
+  int64_t s = 0;
+  for (int k = 0; k < kScanItems; ++k) {
+    int64_t i = base + threadIdx.x + (int64_t)k * kScanThreads;
+    if (i < n) s += in[i];
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int64_t t = 0;
+    for (int w = 0; w < kScanThreads / 32; ++w) t += red[w];
+    tile_sums[blockIdx.x] = t;
+  }
+}
+
+__global__ void scan_tile_offsets(int64_t* tile_sums, int64_t ntiles, int64_t* total) {
+  // single block: sequential chunks of blockDim.x with a block-wide scan each
+  __shared__ int64_t buf[1024];
+  __shared__ int64_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < ntiles; base += blockDim.x) {
+    int64_t i = base + threadIdx.x;
+    int64_t v = i < ntiles ? tile_sums[i] : 0;
+    buf[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < (int)blockDim.x; o <<= 1) {
+      int64_t t = threadIdx.x >= o ? buf[threadIdx.x - o] : 0;
+      __syncthreads();
+      buf[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < ntiles) tile_sums[i] = carry + buf[threadIdx.x] - v;  // exclusive
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry += buf[threadIdx.x];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+// out[i] = one_based + exclusive prefix; also writes out[n] = one_based + total
+__global__ void scan_apply(const int32_t* __restrict__ in, int64_t n, const int64_t* __restrict__ tile_offsets,
+                           int64_t* __restrict__ out, int64_t one_based) {
+  __shared__ int64_t wsum[kScanThreads / 32];
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  int64_t v[kScanItems];
+  int64_t s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    int64_t i = base + k;
+    v[k] = i < n ? in[i] : 0;
+    s += v[k];
+  }
+  // warp inclusive scan of thread sums
+  int64_t inc = s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) {
+    int64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  int64_t woff = 0;
+  for (int w = 0; w < warp; ++w) woff += wsum[w];
+  int64_t run = tile_offsets[blockIdx.x] + woff + inc - s + one_based;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    int64_t i = base + k;
+    if (i < n) out[i] = run;
+    run += v[k];
+    if (i == n - 1) out[n] = run;
+  }
+}
+
+// ---- symbolic kernels --------------------------------------------------------------------------
+// occurrences of every positive dof: at most two cells, kept cell-ascending; also per-cell checks
+// Columns [col0, col0+ncols) (0-based dof index) are owned by this slab; ids outside are rows only.
+// Ghost cells (index >= ncells_local) may touch an owned column only through their leading ghost_ncols
+// local dofs (the cut-plane facet block whose S columns were exchanged).
+__global__ void occ_count_kernel(int64_t ncells, int64_t ncells_local, int ghost_ncols, int n_b,
+                                 const int64_t* __restrict__ ids, int64_t nrows, int64_t col0, int64_t ncols,
+                                 int32_t* __restrict__ cnt, int* __restrict__ err) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ncells * n_b) return;
+  int64_t id = ids[t];
+  if (id > 0) {
+    if (id > nrows) { atomicExch(err, 1); return; }
+    int64_t k = id - 1 - col0;
+    if (k < 0 || k >= ncols) return;
+    int64_t cell = t / n_b;
+    if (cell >= ncells_local && (int)(t - cell * n_b) >= ghost_ncols) { atomicExch(err, 4); return; }
+    int old = atomicAdd(&cnt[k], 1);
+    if (old >= 2) atomicExch(err, 2);
+  }
+}
+
+__global__ void occ_fill_kernel(int64_t ncells, int n_b, const int64_t* __restrict__ ids, int64_t col0,
+                                int64_t ncols, unsigned long long* __restrict__ occ) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ncells * n_b) return;
+  int64_t id = ids[t] - col0;
+  if (id > 0 && id <= ncols) {
+    // two slots per dof, initialised to ~0; smaller (cell*n_b+l) ends in slot 0: deterministic
+    unsigned long long v = (unsigned long long)t;
+    unsigned long long prev = atomicMin(&occ[2 * (id - 1)], v);
+    if (prev != ~0ull) {
+      unsigned long long larger = prev > v ? prev : v;
+      atomicMin(&occ[2 * (id - 1) + 1], larger);
+    }
+  }
+}
+
+// per cell: order of positive ids (rank by counting), Dirichlet flag, duplicate check
+__global__ void cell_sort_kernel(int64_t ncells, int n_b, const int64_t* __restrict__ ids,
+                                 uint8_t* __restrict__ sorted, uint8_t* __restrict__ npos,
+                                 uint8_t* __restrict__ celldir, int* __restrict__ err) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ncells * n_b) return;
+  int64_t cell = t / n_b;
+  int li = (int)(t - cell * n_b);
+  const int64_t* cid = ids + cell * n_b;
+  int64_t id = cid[li];
+  int rank = 0, np = 0, dir = 0;
+  for (int l = 0; l < n_b; ++l) {
+    int64_t o = cid[l];
+    if (o > 0) {
+      ++np;
+      if (o < id) ++rank;
+      if (o == id && l != li) atomicExch(err, 3);
+    } else if (o < 0) {
+      dir = 1;
+    }
+  }
+  if (id > 0) sorted[cell * n_b + rank] = (uint8_t)li;
+  if (li == 0) { npos[cell] = (uint8_t)np; celldir[cell] = (uint8_t)dir; }
+}
+
+// Column merge.  FILL=false: count distinct rows of column j.  FILL=true: write rowval and the gather map.
+template <bool FILL>
+__global__ void column_merge_kernel(int64_t nrows, int n_b, const int64_t* __restrict__ ids,
+                                    const unsigned long long* __restrict__ occ, const uint8_t* __restrict__ sorted,
+                                    const uint8_t* __restrict__ npos, int32_t* __restrict__ colcnt,
+                                    const int64_t* __restrict__ colptr, int64_t* __restrict__ rowval,
+                                    uint8_t* __restrict__ src) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nrows) return;
+  unsigned long long o0 = occ[2 * j], o1 = occ[2 * j + 1];
+  if (o0 == ~0ull) { if (!FILL) colcnt[j] = 0; return; }
+  int64_t c0 = (int64_t)(o0 / n_b);
+  const int64_t* id0 = ids + c0 * n_b;
+  const uint8_t* s0 = sorted + c0 * n_b;
+  int n0 = npos[c0];
+  int64_t p = FILL ? colptr[j] - 1 : 0;
+  if (o1 == ~0ull) {
+    if constexpr (!FILL) {
+      colcnt[j] = n0;
+    } else {
+      for (int a = 0; a < n0; ++a) {
+        rowval[p] = id0[s0[a]];
+        src[2 * p] = s0[a]; src[2 * p + 1] = 255;
+        ++p;
+      }
+    }
+    return;
+  }
+  int64_t c1 = (int64_t)(o1 / n_b);
+  const int64_t* id1 = ids + c1 * n_b;
+  const uint8_t* s1 = sorted + c1 * n_b;
+  int n1 = npos[c1];
+  int a = 0, bq = 0, cnt = 0;
+  while (a < n0 || bq < n1) {
+    int64_t va = a < n0 ? id0[s0[a]] : INT64_MAX;
+    int64_t vb = bq < n1 ? id1[s1[bq]] : INT64_MAX;
+    int64_t v = va < vb ? va : vb;
+    if (FILL) {
+      rowval[p] = v;
+      src[2 * p] = va == v ? s0[a] : 255;
+      src[2 * p + 1] = vb == v ? s1[bq] : 255;
+      ++p;
+    }
+    if (va == v) ++a;
+    if (vb == v) ++bq;
+    ++cnt;
+  }
+  if (!FILL) colcnt[j] = cnt;
+}
+
+// ---- numeric kernels ---------------------------------------------------------------------------
+// one warp per column: lanes own the stored entries of the column
+struct GhostView {
+  int64_t ncells_local;   // cells >= ncells_local are ghosts
+  const double* G;        // [nghost][stride]: leading ghost_ncols columns of S (n_b x ghost_ncols), then g[0:ghost_ncols]
+  int64_t stride;
+};
+
+__device__ __forceinline__ const double* s_column(const double* S, const GhostView& gv, int64_t c, int l, int n_b) {
+  return c < gv.ncells_local ? S + c * (int64_t)n_b * n_b + (int64_t)l * n_b
+                             : gv.G + (c - gv.ncells_local) * gv.stride + (int64_t)l * n_b;
+}
+
+__global__ void __launch_bounds__(256) gather_nzval_kernel(int64_t nrows, int n_b, const int64_t* __restrict__ colptr,
+                                                           const unsigned long long* __restrict__ occ,
+                                                           const uint8_t* __restrict__ src,
+                                                           const double* __restrict__ S, GhostView gv,
+                                                           double* __restrict__ nzval) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t j = warp; j < nrows; j += nwarps) {
+    int64_t p0 = colptr[j] - 1, p1 = colptr[j + 1] - 1;
+    if (p0 == p1) continue;
+    unsigned long long o0 = occ[2 * j], o1 = occ[2 * j + 1];
+    int64_t c0 = (int64_t)(o0 / n_b);
+    int l0 = (int)(o0 - (unsigned long long)c0 * n_b);
+    const double* col0 = s_column(S, gv, c0, l0, n_b);
+    const double* col1 = nullptr;
+    if (o1 != ~0ull) {
+      int64_t c1 = (int64_t)(o1 / n_b);
+      int l1 = (int)(o1 - (unsigned long long)c1 * n_b);
+      col1 = s_column(S, gv, c1, l1, n_b);
+    }
+    for (int64_t p = p0 + lane; p < p1; p += 32) {
+      uint8_t a = src[2 * p], bq = src[2 * p + 1];
+      double v;
+      if (a != 255) {
+        v = col0[a];
+        if (bq != 255) v += col1[bq];  // cell-ascending order, as the reference's COO sum
+      } else {
+        v = col1[bq];
+      }
+      nzval[p] = v;
+    }
+  }
+}
+
+// rhs gather with the Dirichlet lift g_K - S_K*vals_K (AttachDirichletMap)
+// (ghost contributions arrive already lifted by the sender, see pack_cut_plane_kernel)
+__global__ void gather_rhs_kernel(int64_t nrows, int n_b, const unsigned long long* __restrict__ occ,
+                                  const int64_t* __restrict__ ids, const uint8_t* __restrict__ celldir,
+                                  const double* __restrict__ S, const double* __restrict__ g, GhostView gv,
+                                  int ghost_ncols, const double* __restrict__ dvals, double* __restrict__ rhs) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  double acc = 0.0;
+  bool first = true;
+  for (int q = 0; q < 2; ++q) {
+    unsigned long long o = occ[2 * i + q];
+    if (o == ~0ull) break;
+    int64_t c = (int64_t)(o / n_b);
+    int l = (int)(o - (unsigned long long)c * n_b);
+    double v;
+    if (c >= gv.ncells_local) {
+      v = gv.G[(c - gv.ncells_local) * gv.stride + (int64_t)n_b * ghost_ncols + l];
+    } else {
+      v = g[c * n_b + l];
+    }
+    if (c < gv.ncells_local && dvals && celldir[c]) {
+      const int64_t* cid = ids + c * n_b;
+      const double* Sc = S + c * (int64_t)n_b * n_b;
+      for (int lj = 0; lj < n_b; ++lj) {
+        int64_t id = cid[lj];
+        if (id < 0) v = fma(-dvals[-id - 1], Sc[l + (int64_t)lj * n_b], v);
+      }
+    }
+    acc = first ? v : acc + v;
+    first = false;
+  }
+  rhs[i] = acc;
+}
+
+// Cut-plane export of a slab's bottom-layer cells to the slab below (collective 1): the
+// leading `ncols` columns of S_K (the dofs of local facet 0, which the lower slab owns) and the matching
+// entries of g_K with the Dirichlet lift already applied.
+__global__ void pack_cut_plane_kernel(int64_t ncut, int n_b, int ncols, const double* __restrict__ S,
+                                      const double* __restrict__ g, const int64_t* __restrict__ ids,
+                                      const double* __restrict__ dvals, double* __restrict__ out) {
+  const int64_t stride = (int64_t)n_b * ncols + ncols;
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ncut * stride) return;
+  int64_t c = t / stride;
+  int r = (int)(t - c * stride);
+  const double* Sc = S + c * (int64_t)n_b * n_b;
+  if (r < n_b * ncols) { out[t] = Sc[r]; return; }
+  int l = r - n_b * ncols;
+  double v = g[c * n_b + l];
+  if (dvals) {
+    const int64_t* cid = ids + c * n_b;
+    for (int lj = 0; lj < n_b; ++lj) {
+      int64_t id = cid[lj];
+      if (id < 0) v = fma(-dvals[-id - 1], Sc[l + (int64_t)lj * n_b], v);
+    }
+  }
+  out[t] = v;
+}
+
+int exclusive_scan(ghb_ctx* ctx, const int32_t* d_in, int64_t n, int64_t* d_out, int64_t one_based, int64_t* h_total) {
+  int64_t ntiles = (n + kScanTile - 1) / kScanTile;
+  int64_t* d_tiles = nullptr;
+  GHB_CUDA(ctx, cudaMallocAsync((void**)&d_tiles, (ntiles + 1) * sizeof(int64_t), ctx->stream));
+  scan_tile_sums<<<(unsigned)ntiles, kScanThreads, 0, ctx->stream>>>(d_in, n, d_tiles);
+  GHB_LAUNCHED(ctx);
+  scan_tile_offsets<<<1, 1024, 0, ctx->stream>>>(d_tiles, ntiles, d_tiles + ntiles);
+  GHB_LAUNCHED(ctx);
+  scan_apply<<<(unsigned)ntiles, kScanThreads, 0, ctx->stream>>>(d_in, n, d_tiles, d_out, one_based);
+  GHB_LAUNCHED(ctx);
+  if (h_total) {
+    GHB_CUDA(ctx, cudaMemcpyAsync(h_total, d_tiles + ntiles, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  cudaFreeAsync(d_tiles, ctx->stream);
+  return GHB_OK;
+}
+
+}  // namespace
+
+void asm_free(ghb_ctx* ctx) {
+  AsmState& as = ctx->as;
+  cudaFree(as.d_ids); cudaFree(as.d_occ); cudaFree(as.d_sorted); cudaFree(as.d_npos); cudaFree(as.d_celldir);
+  cudaFree(as.d_colptr); cudaFree(as.d_rowval); cudaFree(as.d_src);
+  as = AsmState();
+}
+
+int asm_symbolic(ghb_ctx* ctx, int64_t ncells_local, int64_t nghost, int ghost_ncols, int n_b, const int64_t* d_ids,
+                 int64_t nrows_global, int64_t col0, int64_t ncols) {
+  AsmState& as = ctx->as;
+  const int64_t ncells = ncells_local + nghost;
+  const int64_t nrows = ncols;   // owned columns (== rows of the local rhs)
+  as.ncells = ncells; as.ncells_local = ncells_local; as.nghost = nghost; as.ghost_ncols = ghost_ncols;
+  as.n_b = n_b; as.nrows = nrows; as.nrows_global = nrows_global; as.col0 = col0;
+  const int64_t nent = ncells * n_b;
+  const unsigned eb = (unsigned)((nent + 255) / 256), rb = (unsigned)((nrows + 255) / 256);
+  int32_t* d_cnt = nullptr;
+  int* d_err = nullptr;
+  GHB_CUDA(ctx, cudaMallocAsync((void**)&d_cnt, nrows * sizeof(int32_t), ctx->stream));
+  GHB_CUDA(ctx, cudaMallocAsync((void**)&d_err, sizeof(int), ctx->stream));
+  GHB_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, nrows * sizeof(int32_t), ctx->stream));
+  GHB_CUDA(ctx, cudaMemsetAsync(d_err, 0, sizeof(int), ctx->stream));
+  GHB_CUDA(ctx, cudaMalloc((void**)&as.d_occ, 2 * nrows * sizeof(int64_t)));
+  GHB_CUDA(ctx, cudaMalloc((void**)&as.d_sorted, nent));
+  GHB_CUDA(ctx, cudaMalloc((void**)&as.d_npos, ncells));
+  GHB_CUDA(ctx, cudaMalloc((void**)&as.d_celldir, ncells));
+  GHB_CUDA(ctx, cudaMalloc((void**)&as.d_colptr, (nrows + 1) * sizeof(int64_t)));
+  GHB_CUDA(ctx, cudaMemsetAsync(as.d_occ, 0xff, 2 * nrows * sizeof(int64_t), ctx->stream));
+  occ_count_kernel<<<eb, 256, 0, ctx->stream>>>(ncells, ncells_local, ghost_ncols, n_b, d_ids, nrows_global, col0, ncols, d_cnt, d_err);
+  GHB_LAUNCHED(ctx);
+  cell_sort_kernel<<<eb, 256, 0, ctx->stream>>>(ncells, n_b, d_ids, as.d_sorted, as.d_npos, as.d_celldir, d_err);
+  GHB_LAUNCHED(ctx);
+  int h_err = 0;
+  GHB_CUDA(ctx, cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  GHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h_err) {
+    cudaFreeAsync(d_cnt, ctx->stream); cudaFreeAsync(d_err, ctx->stream);
+    if (h_err == 1) return fail(ctx, GHB_EINVAL, "ghb_assemble_symbolic: a cell id exceeds nrows");
+    if (h_err == 2) return fail(ctx, GHB_EUNSUPPORTED, "ghb_assemble_symbolic: a dof belongs to more than 2 cells (only facet dofs are supported)");
+    if (h_err == 4) return fail(ctx, GHB_EINVAL, "ghb_assemble_symbolic_slab: a ghost cell touches an owned column outside its leading ghost_ncols dofs");
+    return fail(ctx, GHB_EUNSUPPORTED, "ghb_assemble_symbolic: a dof id repeats inside one cell");
+  }
+  occ_fill_kernel<<<eb, 256, 0, ctx->stream>>>(ncells, n_b, d_ids, col0, ncols, (unsigned long long*)as.d_occ);
+  GHB_LAUNCHED(ctx);
+  // pass 1: column counts (reuse d_cnt), scan -> colptr (1-based)
+  column_merge_kernel<false><<<rb, 256, 0, ctx->stream>>>(nrows, n_b, d_ids, (const unsigned long long*)as.d_occ,
+                                                          as.d_sorted, as.d_npos, d_cnt, nullptr, nullptr, nullptr);
+  GHB_LAUNCHED(ctx);
+  int64_t nnz = 0;
+  GHB_TRY(exclusive_scan(ctx, d_cnt, nrows, as.d_colptr, 1, &nnz));
+  as.nnz = nnz;
+  GHB_CUDA(ctx, cudaMalloc((void**)&as.d_rowval, std::max<int64_t>(nnz, 1) * sizeof(int64_t)));
+  GHB_CUDA(ctx, cudaMalloc((void**)&as.d_src, std::max<int64_t>(nnz, 1) * 2));
+  column_merge_kernel<true><<<rb, 256, 0, ctx->stream>>>(nrows, n_b, d_ids, (const unsigned long long*)as.d_occ,
+                                                         as.d_sorted, as.d_npos, nullptr, as.d_colptr, as.d_rowval, as.d_src);
+  GHB_LAUNCHED(ctx);
+  cudaFreeAsync(d_cnt, ctx->stream); cudaFreeAsync(d_err, ctx->stream);
+  GHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  as.valid = true;
+  return GHB_OK;
+}
+
+int asm_pack_cut_plane(ghb_ctx* ctx, int64_t ncut, int n_b, int ncols, const double* S, const double* g,
+                       const int64_t* ids, const double* dvals, double* out) {
+  int64_t tot = ncut * ((int64_t)n_b * ncols + ncols);
+  if (tot == 0) return GHB_OK;
+  pack_cut_plane_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ncut, n_b, ncols, S, g, ids, dvals, out);
+  GHB_LAUNCHED(ctx);
+  return GHB_OK;
+}
+
+int asm_numeric(ghb_ctx* ctx, const double* S, const double* g, const double* ghost, const double* dvals,
+                double* nzval, double* rhs) {
+  const AsmState& as = ctx->as;
+  GhostView gv{as.ncells_local, ghost, (int64_t)as.n_b * as.ghost_ncols + as.ghost_ncols};
+  int64_t blocks = std::min<int64_t>((as.nrows + 7) / 8, (int64_t)ctx->sm_count * 16);
+  gather_nzval_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(as.nrows, as.n_b, as.d_colptr,
+                                                                 (const unsigned long long*)as.d_occ, as.d_src, S, gv, nzval);
+  GHB_LAUNCHED(ctx);
+  gather_rhs_kernel<<<(unsigned)((as.nrows + 255) / 256), 256, 0, ctx->stream>>>(
+      as.nrows, as.n_b, (const unsigned long long*)as.d_occ, as.d_ids, as.d_celldir, S, g, gv, as.ghost_ncols, dvals, rhs);
+  GHB_LAUNCHED(ctx);
+  return GHB_OK;
+}
+
+}  // namespace ghb

@@ -1,0 +1,168 @@
+// common.cuh -- context, block plan and launch helpers shared by all kernels of libgridaphybrid_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/ghb.h"
+
+namespace ghb {
+
+// Device view of a block plan (mirrors StaticCondensationMap + touched mask,
+// /root/reference/src/StaticCondensationMap.jl:3-34,72-84).
+struct PlanDev {
+  int n_i, n_b, n;      // interior / boundary / total dofs per cell
+  int lenA, lenb;       // doubles per packed record
+  const int32_t* emap;  // [n*(n+1)] condensed-order (interior rows first) col-major element -> record
+                        // offset; -1 = structural zero; column n maps into the b record
+};
+
+struct Plan {
+  int nfields = 0;
+  std::vector<int32_t> ndofs, interior, boundary;
+  std::vector<uint8_t> touched;        // col-major nfields x nfields
+  std::vector<int64_t> block_offset;   // [i + nfields*j] -> offset in record or -1
+  std::vector<int32_t> field_offset_b; // offset of field f inside the b record
+  std::vector<int32_t> row_field, row_local;  // condensed row -> (field index 0-based, local dof)
+  int n_i = 0, n_b = 0, n = 0, lenA = 0, lenb = 0;
+  int32_t* d_emap = nullptr;
+  bool all_touched = false;
+  const char* kernel_name = "generic";
+  PlanDev dev() const { return PlanDev{n_i, n_b, n, lenA, lenb, d_emap}; }
+};
+
+// Cached symbolic phase of the assembler (pattern of sparse(I,J,V) + gather map).
+struct AsmState {
+  bool valid = false;
+  int64_t ncells = 0, nrows = 0, nnz = 0;   // ncells = local + ghost; nrows = owned columns
+  int64_t ncells_local = 0, nghost = 0, nrows_global = 0, col0 = 0;
+  int n_b = 0, ghost_ncols = 0;
+  int64_t* d_ids = nullptr;      // [ncells][n_b] copy of cell ids
+  int64_t* d_occ = nullptr;      // [nrows][2]  cell*n_b + l of the (<=2) occurrences, cell ascending; -1 none
+  uint8_t* d_sorted = nullptr;   // [ncells][n_b] local indices of positive ids sorted by id
+  uint8_t* d_npos = nullptr;     // [ncells] number of positive ids
+  uint8_t* d_celldir = nullptr;  // [ncells] 1 if the cell has a Dirichlet dof
+  int64_t* d_colptr = nullptr;   // [nrows+1] 1-based
+  int64_t* d_rowval = nullptr;   // [nnz] 1-based
+  uint8_t* d_src = nullptr;      // [nnz][2] local row index inside occurrence 0 / 1, 255 = none
+};
+
+struct Factors {
+  int plan_id = -1;
+  int64_t ncells = 0;
+  double* d_X = nullptr;  // [ncells][n_i*(n_b+1)] col-major n_i x (n_b+1): A11^-1 [A12 | b1]
+  size_t bytes = 0;
+};
+
+}  // namespace ghb
+
+struct ghb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  cudaStream_t copy_stream = nullptr;  // H2D/D2H staging of host-pointer calls
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  int64_t launches = 0;
+  std::string err;
+  std::vector<ghb::Plan*> plans;
+  ghb::AsmState as;
+  ghb::Factors fac;
+  // pinned staging for host-pointer streaming
+  void* pinned[2] = {nullptr, nullptr};
+  size_t pinned_bytes = 0;
+};
+
+namespace ghb {
+
+int fail(ghb_ctx* ctx, int code, const std::string& msg);
+
+#define GHB_CUDA(ctx, expr)                                                                      \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      return ghb::fail(ctx, GHB_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+  } while (0)
+
+#define GHB_TRY(expr)            \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != GHB_OK) return _rc; \
+  } while (0)
+
+// After a kernel launch: count it and surface launch errors.
+#define GHB_LAUNCHED(ctx)                                                                        \
+  do {                                                                                           \
+    (ctx)->launches++;                                                                           \
+    cudaError_t _e = cudaGetLastError();                                                         \
+    if (_e != cudaSuccess)                                                                       \
+      return ghb::fail(ctx, GHB_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(_e)); \
+  } while (0)
+
+bool is_device_ptr(const void* p);
+
+// RAII device view of a caller array that may live on host or device.
+template <typename T>
+struct Arg {
+  ghb_ctx* ctx;
+  T* host = nullptr;   // non-null if the caller pointer is a host pointer
+  T* dev = nullptr;
+  size_t count = 0;
+  bool out = false, owned = false;
+  int rc = GHB_OK;
+  Arg(ghb_ctx* c, const T* p, size_t n, bool in, bool out_) : ctx(c), count(n), out(out_) {
+    if (p == nullptr || n == 0) { dev = const_cast<T*>(p); return; }
+    if (is_device_ptr(p)) { dev = const_cast<T*>(p); return; }
+    host = const_cast<T*>(p);
+    cudaError_t e = cudaMallocAsync((void**)&dev, n * sizeof(T), c->stream);
+    if (e != cudaSuccess) { rc = fail(c, GHB_ENOMEM, std::string("cudaMallocAsync: ") + cudaGetErrorString(e)); dev = nullptr; return; }
+    owned = true;
+    if (in) {
+      e = cudaMemcpyAsync(dev, host, n * sizeof(T), cudaMemcpyHostToDevice, c->stream);
+      if (e != cudaSuccess) rc = fail(c, GHB_ECUDA, std::string("H2D: ") + cudaGetErrorString(e));
+    }
+  }
+  // copy results back (if host) -- call explicitly so errors can be returned
+  int finish() {
+    if (owned && out && rc == GHB_OK) {
+      cudaError_t e = cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream);
+      if (e != cudaSuccess) return fail(ctx, GHB_ECUDA, std::string("D2H: ") + cudaGetErrorString(e));
+      e = cudaStreamSynchronize(ctx->stream);
+      if (e != cudaSuccess) return fail(ctx, GHB_ECUDA, std::string("sync: ") + cudaGetErrorString(e));
+    }
+    return GHB_OK;
+  }
+  ~Arg() {
+    if (owned && dev) cudaFreeAsync(dev, ctx->stream);
+  }
+  Arg(const Arg&) = delete;
+  Arg& operator=(const Arg&) = delete;
+};
+
+// kernels / launchers implemented in the other translation units
+int launch_condense_generic(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b,
+                            double* S, double* g, int32_t* info, double* X);
+int launch_backsub_generic(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b,
+                           const double* lam_free, const double* lam_dir, const int64_t* ids, double* u,
+                           int32_t* info);
+int launch_backsub_factors(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* X, const double* lam_free,
+                           const double* lam_dir, const int64_t* ids, double* u);
+int asm_symbolic(ghb_ctx* ctx, int64_t ncells_local, int64_t nghost, int ghost_ncols, int n_b, const int64_t* d_ids,
+                 int64_t nrows_global, int64_t col0, int64_t ncols);
+int asm_numeric(ghb_ctx* ctx, const double* S, const double* g, const double* ghost, const double* dvals,
+                double* nzval, double* rhs);
+int asm_pack_cut_plane(ghb_ctx* ctx, int64_t ncut, int n_b, int ncols, const double* S, const double* g,
+                       const int64_t* ids, const double* dvals, double* out);
+void asm_free(ghb_ctx* ctx);
+int launch_restrict_facet_dofs(ghb_ctx* ctx, int64_t ncells, int nlf, int nf, const int64_t* cwf,
+                               const int64_t* fdata, int64_t* out);
+int launch_scatter_free(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* u, const double* lam,
+                        int64_t nlam, double* x);
+int launch_synth_fill(ghb_ctx* ctx, const Plan& p, int64_t cell_start, int64_t ncells, uint64_t seed, double* A,
+                      double* b);
+int launch_cartesian_facets(ghb_ctx* ctx, int D, const int64_t* dims, int64_t cell_start, int64_t ncells,
+                            int64_t* out);
+
+}  // namespace ghb

@@ -1,0 +1,159 @@
+/* ghb.h -- C ABI of libgridaphybrid_b200.so: B200 (sm_100a) implementation of GridapHybrid.jl's
+ * per-cell hybridisation hot path (static condensation -> skeleton assembly -> backward recovery).
+ *
+ * The reference has no FFI; its "plugin API" is Gridap's Map protocol (return_cache / evaluate! /
+ * lazy_map).  These entry points are what a thin Julia glue binds with `ccall` at the three
+ * array-level sites of the reference (INTEGRATION.md shows the glue):
+ *
+ *   lazy_map(StaticCondensationMap(bf,sf), t)          src/HybridAffineFEOperators.jl:338  -> ghb_condense_f64
+ *   assemble_matrix_and_vector(assem, data)            src/HybridAffineFEOperators.jl:46,
+ *                                                      src/HybridLinearSolvers.jl:43-44   -> ghb_assemble_symbolic,
+ *                                                                                            ghb_assemble_numeric_f64,
+ *                                                                                            ghb_condense_assemble_f64
+ *   lazy_map(BackwardStaticCondensationMap(bf,sf),t,l) src/HybridAffineFEOperators.jl:117-118 -> ghb_backsub_f64
+ *   assemble_vector(assem, ...)                        src/HybridAffineFEOperators.jl:149  -> ghb_scatter_free_dof_values
+ *
+ * Conventions (Julia side): all ids are Int64 and 1-based; a dof id < 0 is a Dirichlet dof
+ * (-k = k-th Dirichlet value); dense matrices are column-major; all floating data is FP64.
+ *
+ * Pointers: every array argument may be a device pointer or a host pointer (pageable or pinned);
+ * the library asks cudaPointerGetAttributes.  The caller owns every array; the library keeps no
+ * caller pointer past the call (the symbolic phase copies what it caches).
+ * Errors: every function returns GHB_OK (0) or a negative GHB_E*; ghb_last_error(ctx) holds text.
+ * Per-cell factorisation failures are NOT errors: they are reported in info[] with LAPACK dgetrf
+ * semantics (info[c] = k > 0: U(k,k) is exactly zero), mirroring `@check info==0`
+ * (src/StaticCondensationMap.jl:180); outputs of such a cell are NaN.
+ * Threading: one caller thread per ctx (the reference is serial); distinct ctxs are independent.
+ * There is no CPU fallback: without a CUDA device ghb_create fails with GHB_ENODEVICE.
+ */
+#ifndef GHB_H
+#define GHB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GHB_OK 0
+#define GHB_EINVAL (-1)     /* bad argument (message in ghb_last_error) */
+#define GHB_ECUDA (-2)      /* CUDA runtime error */
+#define GHB_ENODEVICE (-3)  /* no usable CUDA device: there is no CPU fallback */
+#define GHB_ENOMEM (-4)
+#define GHB_EUNSUPPORTED (-5) /* valid input the library does not handle (e.g. a dof shared by >2 cells) */
+#define GHB_ESTATE (-6)     /* call order violated (e.g. numeric before symbolic) */
+
+typedef struct ghb_ctx ghb_ctx; /* opaque: device, stream, plans, cached symbolic pattern, scratch */
+
+/* ---- context ------------------------------------------------------------------------------ */
+int ghb_create(int device_id, ghb_ctx** out);
+void ghb_destroy(ghb_ctx* ctx);
+const char* ghb_last_error(const ghb_ctx* ctx);
+/* Run on a caller-provided cudaStream_t (e.g. torch's current stream); NULL = ctx-owned stream. */
+int ghb_set_stream(ghb_ctx* ctx, void* cuda_stream);
+int ghb_synchronize(ghb_ctx* ctx);
+/* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
+int64_t ghb_launch_count(const ghb_ctx* ctx);
+/* Name of the condensation kernel variant chosen for a plan ("generic", "dmma_c3", ...). */
+const char* ghb_plan_kernel_name(ghb_ctx* ctx, int plan_id);
+
+/* ---- block plan: mirrors StaticCondensationMap{IFT,BFT} + the touched mask ------------------
+ * (src/StaticCondensationMap.jl:3-34 struct + preconditions, :72-84 block sizes)
+ * nfields        number of fields of the cell-wise block system
+ * ndofs[f]       per-cell dofs of field f (for a skeleton field: nlfacets * ndofs per facet)
+ * touched        nfields x nfields, column-major, 1 = block present in the packed record
+ * interior[]     1-based field ids condensed out (bulk), boundary[] kept (skeleton); together a
+ *                disjoint cover of 1:nfields, else GHB_EINVAL.  A touched mask leaving a block row of
+ *                the interior without any touched block is rejected.
+ * Packed record of one cell: the touched blocks in block-column-major order (j outer, i inner), each
+ * block column-major ndofs[i] x ndofs[j]  => lenA doubles;  b: all field vectors concatenated => lenb.
+ */
+int ghb_plan_blocks(ghb_ctx* ctx, int nfields, const int32_t* ndofs, const uint8_t* touched, int n_int,
+                    const int32_t* interior, int n_bnd, const int32_t* boundary, int* plan_id);
+/* out[0..3] = n_i, n_b, lenA, lenb */
+int ghb_plan_query(ghb_ctx* ctx, int plan_id, int64_t out[4]);
+
+/* ---- (a3) static condensation: (A_K, b_K) -> (S_K, g_K) for a batch of cells -----------------
+ * replaces evaluate!(cache, ::StaticCondensationMap, A, b)   src/StaticCondensationMap.jl:152-196
+ * A [ncells][lenA], b [ncells][lenb]  packed records;  S [ncells][n_b*n_b] col-major; g [ncells][n_b];
+ * info [ncells] (may be NULL).  keep_factors != 0 additionally stores X = A11^-1 A12 and y = A11^-1 b1
+ * inside the ctx for ghb_backsub_f64 (factor reuse); 0 follows the reference (recompute).
+ */
+int ghb_condense_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A, const double* b, double* S,
+                     double* g, int32_t* info, int keep_factors);
+
+/* ---- (a6) id glue: facet dofs -> cell boundary ids ------------------------------------------
+ * replaces RestrictFacetDoFsToSkeleton / restrict_facet_dof_ids_to_cell_boundary
+ * (src/HybridAffineFEOperators.jl:388-439): out[c][lf*ndofs_f + d] = facet_data[cell_wise_facets[c][lf]-1][d]
+ */
+int ghb_restrict_facet_dofs_i64(ghb_ctx* ctx, int64_t ncells, int nlfacets, int ndofs_f,
+                                const int64_t* cell_wise_facets, const int64_t* facet_data, int64_t* out);
+
+/* ---- (a8) assembly --------------------------------------------------------------------------
+ * replaces assemble_matrix_and_vector(SparseMatrixAssembler(M,L), data)
+ * (src/HybridAffineFEOperators.jl:38,46) producing SparseMatrixCSC{Float64,Int64} + Vector{Float64}.
+ * Symbolic: builds and caches the CSC pattern of  sparse(I,J,V,nrows,nrows)  and the gather map.
+ * cell_ids [ncells][n_b] 1-based, <=0 = Dirichlet (not assembled).  A dof may belong to at most 2
+ * cells (facet dofs; else GHB_EUNSUPPORTED) and may not repeat inside a cell.
+ */
+int ghb_assemble_symbolic(ghb_ctx* ctx, int64_t ncells, int n_b, const int64_t* cell_ids, int64_t nrows,
+                          int64_t* nnz_out);
+/* Copies the cached pattern out: colptr [nrows+1], rowval [nnz]; 1-based Int64 (Julia CSC). */
+int ghb_assemble_pattern(ghb_ctx* ctx, int64_t* colptr, int64_t* rowval);
+/* Numeric: nzval [nnz], rhs [nrows].  dirichlet_vals (may be NULL) applies the lift of
+ * _attach_dirichlet (src/HybridAffineFEOperators.jl:41-42): g_K <- g_K - S_K * vals_K on cells that
+ * have a Dirichlet dof, vals_K[l] = dirichlet_vals[-id-1] for id<0, else 0. */
+int ghb_assemble_numeric_f64(ghb_ctx* ctx, const double* S, const double* g, const double* dirichlet_vals,
+                             double* nzval, double* rhs);
+/* ---- (e) multi-GPU slabs: cells are partitioned in contiguous slabs, one process per GPU --------
+ * A slab owns the dofs of the facets first touched by its cells = a contiguous range of
+ * global columns [col_begin, col_end) (1-based, end exclusive).  Its cell list is its own cells followed
+ * by `nghost` ghost cells (the bottom layer of the slab above), whose local facet 0 lies on the cut
+ * plane.  Only the leading `ghost_ncols` columns of a ghost cell's S_K (and entries of g_K) exist on
+ * this rank: they arrive through ghb_pack_cut_plane_f64 on the sender + an NCCL send/recv.
+ * The pattern holds the owned columns only: colptr [ncols_owned+1], rowval = GLOBAL row ids. */
+int ghb_assemble_symbolic_slab(ghb_ctx* ctx, int64_t ncells_local, int64_t nghost, int ghost_ncols, int n_b,
+                               const int64_t* cell_ids /* [(ncells_local+nghost)][n_b] */, int64_t nrows_global,
+                               int64_t col_begin, int64_t col_end, int64_t* nnz_out);
+/* Sender side of the cut-plane exchange: for `ncut` consecutive cells starting at S/g/cell_ids, packs
+ * out[c] = { S_K[:, 0:ncols] (n_b*ncols, col-major), g_K[0:ncols] - (S_K*vals_K)[0:ncols] }. */
+int ghb_pack_cut_plane_f64(ghb_ctx* ctx, int64_t ncut, int n_b, int ncols, const double* S, const double* g,
+                           const int64_t* cell_ids, const double* dirichlet_vals, double* out);
+/* nzval [nnz owned], rhs [ncols_owned]; `ghost` = the received packed buffer [nghost][n_b*ghost_ncols+ghost_ncols]. */
+int ghb_assemble_numeric_slab_f64(ghb_ctx* ctx, const double* S, const double* g, const double* ghost,
+                                  const double* dirichlet_vals, double* nzval, double* rhs);
+
+/* Fused condensation + numeric assembly (S_K, g_K never stored by the caller). Host pointers are
+ * streamed through pinned staging in chunks (H2D, kernels and the final D2H overlap). */
+int ghb_condense_assemble_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A, const double* b,
+                              const double* dirichlet_vals, double* nzval, double* rhs, int32_t* info);
+
+/* ---- (a11)+(a12) backward static condensation -----------------------------------------------
+ * replaces evaluate!(cache, ::BackwardStaticCondensationMap, A, b, x)
+ * (src/BackwardStaticCondensationMap.jl:61-102) fed by get_cell_dof_values(lh, dK)
+ * (src/HybridAffineFEOperators.jl:113): lambda_K[l] = lambda_free[id-1] (id>0) or lambda_dirichlet[-id-1].
+ * u [ncells][n_i] = interior fields concatenated in `interior` order.  If the last condense call used
+ * keep_factors on the same cells, A and b may be NULL and the stored X, y are used.
+ */
+int ghb_backsub_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A, const double* b,
+                    const double* lambda_free, const double* lambda_dirichlet, const int64_t* cell_ids,
+                    double* u, int32_t* info);
+/* (a12) full-space free-dof vector (src/HybridAffineFEOperators.jl:134-149):
+ * x = [bulk field 1 cell-major | bulk field 2 | ... | lambda_free].  x has sum(n_i)*ncells + nlambda entries. */
+int ghb_scatter_free_dof_values(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* u,
+                                const double* lambda_free, int64_t nlambda, double* x);
+
+/* ---- synthetic workload (bench / tests): counter-based Philox4x32-10, bit-identical to oracle ---
+ * Fills records of cells [cell_start, cell_start+ncells) (oracle.synth_cell_records). */
+int ghb_synth_fill_f64(ghb_ctx* ctx, int plan_id, int64_t cell_start, int64_t ncells, uint64_t seed, double* A,
+                       double* b);
+/* Cartesian mesh glue for the synthetic workload (closed form of Gridap's first-touch facet numbering,
+ * SURVEY A1-A3): writes cell_wise_facets [ncells][2*D] for cells [cell_start, cell_start+ncells) of a
+ * dims[0] x ... x dims[D-1] mesh (x fastest), 1-based Int64. */
+int ghb_cartesian_cell_wise_facets(ghb_ctx* ctx, int D, const int64_t* dims, int64_t cell_start, int64_t ncells,
+                                   int64_t* cell_wise_facets);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GHB_H */

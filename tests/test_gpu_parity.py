@@ -1,0 +1,395 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances: integer/index outputs bit-exact; FP64 values <= 1e-11 relative per cell (Frobenius), the
+bar BASELINE.json's north_star states."""
+import numpy as np
+import pytest
+import torch
+
+import gridaphybrid_b200 as gh
+from oracle import oracle as o
+from oracle import oracle_c as oc
+from tests.helpers import CONFIGS, DarcyProblem, oracle_plan, rel_err_cells
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-11
+
+
+def _dev_plan(ctx, name):
+    c = CONFIGS[name]
+    return ctx.plan_blocks(c["ndofs"], c["touched"], c["interior"], c["boundary"])
+
+
+def _synth(ctx, plan, cell_start, ncells):
+    A = torch.empty((ncells, plan.lenA), dtype=torch.float64, device="cuda")
+    b = torch.empty((ncells, plan.lenb), dtype=torch.float64, device="cuda")
+    ctx.synth_fill(plan, cell_start, ncells, A, b)
+    return A, b
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_synth_bitwise_equal_to_oracle(ctx, name):
+    plan, op = _dev_plan(ctx, name), oracle_plan(name)
+    assert (plan.n_i, plan.n_b, plan.lenA, plan.lenb) == (op.n_i, op.n_b, op.lenA, op.lenb)
+    A, b = _synth(ctx, plan, 123456789012, 17)
+    A0, b0 = o.synth_cell_records(op, 123456789012, 17)
+    assert np.array_equal(A.cpu().numpy(), A0) and np.array_equal(b.cpu().numpy(), b0)
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+@pytest.mark.parametrize("ncells", [1, 37, 700])
+def test_condense_parity(ctx, name, ncells):
+    plan, op = _dev_plan(ctx, name), oracle_plan(name)
+    A, b = _synth(ctx, plan, 1000, ncells)
+    S = torch.empty((ncells, plan.n_b ** 2), dtype=torch.float64, device="cuda")
+    g = torch.empty((ncells, plan.n_b), dtype=torch.float64, device="cuda")
+    info = torch.empty(ncells, dtype=torch.int32, device="cuda")
+    ctx.condense(plan, ncells, A, b, S, g, info)
+    An, bn = A.cpu().numpy(), b.cpu().numpy()
+    if ncells <= 64:
+        S0, g0, info0 = o.condense_records(op, An, bn)      # SciPy LAPACK
+    else:
+        S0, g0, info0 = oc.condense(op, An, bn)             # C twin (pinned to LAPACK in test_oracle.py)
+    assert not info.cpu().numpy().any() and not info0.any()
+    assert rel_err_cells(S.cpu().numpy(), S0) < TOL
+    assert rel_err_cells(g.cpu().numpy(), g0) < TOL
+
+
+def test_condense_host_pointers_and_empty(ctx):
+    plan, op = _dev_plan(ctx, "C1_hdg_k1_2d"), oracle_plan("C1_hdg_k1_2d")
+    A0, b0 = o.synth_cell_records(op, 0, 50)
+    S = np.empty((50, plan.n_b ** 2)); g = np.empty((50, plan.n_b)); info = np.empty(50, dtype=np.int32)
+    ctx.condense(plan, 50, A0, b0, S, g, info)              # numpy host arrays straight through the ABI
+    S0, g0, _ = o.condense_records(op, A0, b0)
+    assert rel_err_cells(S, S0) < TOL and rel_err_cells(g, g0) < TOL and not info.any()
+    ctx.condense(plan, 0, A0, b0, S, g, info)               # empty batch is a no-op
+
+
+def test_singular_cell_info(ctx):
+    plan, op = _dev_plan(ctx, "C1_hdg_k1_2d"), oracle_plan("C1_hdg_k1_2d")
+    A0, b0 = o.synth_cell_records(op, 0, 5)
+    A0[2, :] = 0.0
+    S = np.empty((5, plan.n_b ** 2)); g = np.empty((5, plan.n_b)); info = np.empty(5, dtype=np.int32)
+    ctx.condense(plan, 5, A0, b0, S, g, info)
+    _, _, info0 = o.condense_records(op, A0, b0)
+    assert info.tolist() == info0.tolist() == [0, 0, 1, 0, 0]
+    assert np.isnan(S[2]).all() and np.isfinite(S[[0, 1, 3, 4]]).all()
+
+
+def test_pivoting_is_exercised(ctx):
+    """zero diagonal block (RT-H saddle point): only partial pivoting gets through."""
+    plan, op = _dev_plan(ctx, "C2_rth_k1_2d"), oracle_plan("C2_rth_k1_2d")
+    rng = np.random.default_rng(11)
+    A0 = rng.standard_normal((40, plan.lenA)); b0 = rng.standard_normal((40, plan.lenb))
+    S = np.empty((40, plan.n_b ** 2)); g = np.empty((40, plan.n_b)); info = np.empty(40, dtype=np.int32)
+    ctx.condense(plan, 40, A0, b0, S, g, info)
+    S0, g0, info0 = o.condense_records(op, A0, b0)
+    assert not info.any() and not info0.any()
+    assert rel_err_cells(S, S0) < 1e-9 and rel_err_cells(g, g0) < 1e-9   # unconditioned random saddle points
+
+
+@pytest.mark.parametrize("name", ["C1_hdg_k1_2d", "C3_hdg_k2_3d", "multifield_2skel", "odd_shapes"])
+def test_backsub_parity_and_factor_reuse(ctx, name):
+    plan, op = _dev_plan(ctx, name), oracle_plan(name)
+    n = 33
+    A, b = _synth(ctx, plan, 5, n)
+    rng = np.random.default_rng(2)
+    # ids: mix of free (positive) and Dirichlet (negative) dofs
+    nfree, ndir = 40, 9
+    ids = rng.integers(1, nfree + 1, (n, plan.n_b))
+    neg = rng.random((n, plan.n_b)) < 0.2
+    ids[neg] = -rng.integers(1, ndir + 1, int(neg.sum()))
+    lam_f, lam_d = rng.standard_normal(nfree), rng.standard_normal(ndir)
+    xk = o.cell_dof_values(lam_f, lam_d, ids)
+    u0, info0 = oc.backsub(op, A.cpu().numpy(), b.cpu().numpy(), xk)
+    ids_d = torch.as_tensor(ids, device="cuda")
+    lf, ld = torch.as_tensor(lam_f, device="cuda"), torch.as_tensor(lam_d, device="cuda")
+    u = torch.empty((n, plan.n_i), dtype=torch.float64, device="cuda")
+    info = torch.empty(n, dtype=torch.int32, device="cuda")
+    ctx.backsub(plan, n, A, b, lf, ld, ids_d, u, info)
+    assert not info.cpu().numpy().any()
+    assert rel_err_cells(u.cpu().numpy(), u0) < TOL
+    # factor reuse: keep_factors condensation, then backsub without A,b
+    S = torch.empty((n, plan.n_b ** 2), dtype=torch.float64, device="cuda")
+    g = torch.empty((n, plan.n_b), dtype=torch.float64, device="cuda")
+    ctx.condense(plan, n, A, b, S, g, None, keep_factors=True)
+    u2 = torch.empty_like(u)
+    ctx.backsub(plan, n, None, None, lf, ld, ids_d, u2, None)
+    assert rel_err_cells(u2.cpu().numpy(), u0) < TOL
+    # full-space scatter
+    x = torch.empty(n * plan.n_i + nfree, dtype=torch.float64, device="cuda")
+    ctx.scatter_free_dof_values(plan, n, u, lf, x)
+    ibrs = [op.ndofs[f - 1] for f in op.interior]
+    assert np.array_equal(x.cpu().numpy(), o.hybridizable_free_dof_values(u.cpu().numpy(), ibrs, lam_f))
+
+
+@pytest.mark.parametrize("dims", [(2, 1), (2, 2), (5, 3), (1, 4), (3, 2, 2), (4, 5, 3), (1, 1, 3), (7, 1, 2)])
+def test_cartesian_facets_closed_form_bit_exact(ctx, dims):
+    """device closed form == literal first-touch loop of the oracle (incl. the reference's golden vector)."""
+    ref = o.cartesian_cell_wise_facets(dims)
+    sk = gh.CartesianSkeleton(dims, ctx)
+    assert np.array_equal(sk.cell_wise_facets.cpu().numpy(), ref)
+    assert sk.nfacets == ref.max()
+    assert np.array_equal(sk.facet_is_boundary().cpu().numpy(), o.facet_is_boundary(ref))
+    # a slab (multi-GPU partition) reproduces the rows of the global table
+    nc = ref.shape[0]
+    if nc >= 4:
+        slab = gh.CartesianSkeleton(dims, ctx, cell_start=nc // 2, ncells=nc - nc // 2)
+        assert np.array_equal(slab.cell_wise_facets.cpu().numpy(), ref[nc // 2:])
+
+
+@pytest.mark.parametrize("dims,ndofs_f", [((2, 2), 2), ((6, 5), 3), ((3, 3, 3), 6), ((4, 2, 3), 1)])
+def test_ids_and_pattern_bit_exact(ctx, dims, ndofs_f):
+    """cell ids (RestrictFacetDoFsToSkeleton) and the CSC pattern/values vs the restated Gridap assembler."""
+    cwf = o.cartesian_cell_wise_facets(dims)
+    isb = o.facet_is_boundary(cwf)
+    fids, nfree, ndir = o.facet_dof_ids(isb, ndofs_f)
+    ids0 = o.restrict_facet_dofs_to_skeleton(cwf, fids)
+    sk = gh.CartesianSkeleton(dims, ctx)
+    sp_ = gh.FacetFESpace(sk, ndofs_f, sk.facet_is_boundary())
+    assert (sp_.num_free_dofs, sp_.num_dirichlet_dofs) == (nfree, ndir)
+    assert np.array_equal(sp_.facet_dof_ids.cpu().numpy(), fids)
+    assem = gh.SparseMatrixAssembler(sp_)
+    assert np.array_equal(assem.cell_ids.cpu().numpy(), ids0)
+    nc, nb = ids0.shape
+    rng = np.random.default_rng(4)
+    S = rng.standard_normal((nc, nb * nb)); g = rng.standard_normal((nc, nb)); dv = rng.standard_normal(max(ndir, 1))
+    Sc = [S[c].reshape((nb, nb), order="F") for c in range(nc)]
+    gl = [o.attach_dirichlet(Sc[c], g[c], ids0[c], dv) for c in range(nc)]
+    colptr0, rowval0, nzval0, rhs0 = o.assemble_matrix_and_vector(Sc, gl, ids0, nfree)
+    cond = gh.CondensedCells(torch.as_tensor(S, device="cuda"), torch.as_tensor(g, device="cuda"), None, nb, None)
+    Amat, rhs = gh.assemble_matrix_and_vector(assem, cond, torch.as_tensor(dv, device="cuda"))
+    assert np.array_equal(Amat.colptr.cpu().numpy(), colptr0)
+    assert np.array_equal(Amat.rowval.cpu().numpy(), rowval0)
+    assert np.array_equal(Amat.nzval.cpu().numpy(), nzval0)          # <=2 summands in cell order: bitwise
+    assert np.allclose(rhs.cpu().numpy(), rhs0, rtol=1e-13, atol=1e-13)
+    # no lift (Newton path)
+    _, _, _, rhs1 = o.assemble_matrix_and_vector(Sc, list(g), ids0, nfree)
+    _, rhs_nl = gh.assemble_matrix_and_vector(assem, cond, None)
+    assert np.array_equal(rhs_nl.cpu().numpy(), rhs1)
+
+
+def test_symbolic_rejects_unsupported(ctx):
+    ids = np.array([[1, 2], [1, 3], [1, 4]], dtype=np.int64)   # dof 1 in three cells
+    with pytest.raises(gh.GhbError) as e:
+        ctx.assemble_symbolic(3, 2, ids, 4)
+    assert e.value.code == gh._lib.GHB_EUNSUPPORTED
+    ids = np.array([[1, 1]], dtype=np.int64)                    # repeated inside a cell
+    with pytest.raises(gh.GhbError):
+        ctx.assemble_symbolic(1, 2, ids, 1)
+    ids = np.array([[1, 9]], dtype=np.int64)                    # id beyond nrows
+    with pytest.raises(gh.GhbError):
+        ctx.assemble_symbolic(1, 2, ids, 2)
+
+
+def test_plan_rejects_bad_fields(ctx):
+    with pytest.raises(gh.GhbError):
+        ctx.plan_blocks([2, 2, 2], np.ones((3, 3), bool), [1, 2], [2])
+    with pytest.raises(gh.GhbError):   # block row with no touched block
+        ctx.plan_blocks([2, 2, 2], np.array([[1, 0, 1], [0, 0, 0], [1, 0, 1]], bool), [1, 2], [3])
+
+
+def test_reference_unit_test_shape_through_map_api(ctx):
+    """test/StaticCondensationMapTests.jl:6-46 driven through the mirrored Map API (per-cell evaluate)."""
+    rng = np.random.default_rng(3)
+    x = rng.random((3, 3))
+    y = [[x, x + 3, x + 5], [x + 1, None, None], [x + 2, None, None]]
+    touched = np.ones((3, 3), bool); touched[1:, 1:] = False
+    xv = rng.random(3)
+    k = gh.StaticCondensationMap([1, 2], [3])
+    A, b = gh.ArrayBlock(y, touched), gh.ArrayBlock([xv, xv + 1, xv + 2], [True] * 3)
+    cache = k.return_cache(A, b)
+    S, g = k.evaluate(cache, A, b)
+    S0, g0, _ = o.static_condensation(o.ArrayBlock(y, touched), o.ArrayBlock([xv, xv + 1, xv + 2], [True] * 3), [1, 2], [3])
+    assert np.allclose(S, S0, rtol=1e-9, atol=1e-11) and np.allclose(g, g0, rtol=1e-9, atol=1e-11)
+    kb = gh.BackwardStaticCondensationMap([1, 2], [3])
+    blk = kb.evaluate(kb.return_cache(A, b, g), A, b, g)
+    blk0, _ = o.backward_static_condensation(o.ArrayBlock(y, touched), o.ArrayBlock([xv, xv + 1, xv + 2], [True] * 3), g0, [1, 2], [3])
+    for v, v0 in zip(blk.array, blk0.array):
+        assert np.allclose(v, v0, rtol=1e-8, atol=1e-10)
+    # Scalar2ArrayBlockMap golden (test/Scalar2ArrayBlockMapTests.jl:16-19) on the condensed batch
+    A24, b24 = torch.rand(24, 24, dtype=torch.float64), torch.rand(24, dtype=torch.float64)
+    Ab, bb = gh.Scalar2ArrayBlockMap().evaluate(None, A24, b24, [8, 16])
+    assert torch.equal(Ab.array[1][0], A24[8:24, 0:8]) and torch.equal(Ab.array[0][1], A24[0:8, 8:24])
+
+
+@pytest.mark.parametrize("dims,order", [((2, 2), 1), ((5, 4), 1), ((3, 3), 2), ((2, 2, 2), 1), ((3, 2, 2), 2)])
+def test_darcy_hdg_exact_solution_gpu(ctx, dims, order):
+    """test/DarcyHDGTests.jl:137-142 through the mirrored HybridAffineFEOperator: ||u-uh||_L2 < 1e-12,
+    and every intermediate (S, g, pattern, nzval, rhs, u) against the oracle pipeline."""
+    prob = DarcyProblem(dims, order)
+    ref = prob.oracle_solve()
+    sk = gh.CartesianSkeleton(dims, ctx)
+    dv = torch.as_tensor(prob.dir_vals, device="cuda")
+    M = gh.FacetFESpace(sk, prob.prob.Nl, sk.facet_is_boundary(), dv)
+    mats = [[torch.as_tensor(m) for m in row] for row in prob.mats]
+    vecs = [torch.as_tensor(v) for v in prob.vecs]
+    cells = gh.PackedCells.from_blocks(mats, vecs, prob.touched, device="cuda")
+    assert np.array_equal(cells.A.cpu().numpy(), prob.A)
+    trial = [prob.prob.ndofs[0], prob.prob.ndofs[1], M]
+    op = gh.HybridAffineFEOperator(lambda: cells, trial, trial, [1, 2], [3])
+    A = op.skeleton_op.matrix
+    assert np.array_equal(A.colptr.cpu().numpy(), ref["colptr"]) and np.array_equal(A.rowval.cpu().numpy(), ref["rowval"])
+    scale = np.abs(ref["nzval"]).max()
+    assert np.abs(A.nzval.cpu().numpy() - ref["nzval"]).max() < 1e-11 * scale
+    assert np.abs(op.skeleton_op.vector.cpu().numpy() - ref["rhs"]).max() < 1e-11 * max(1.0, np.abs(ref["rhs"]).max())
+    x = op.solve().cpu().numpy()
+    nc, p = prob.prob.ncells, prob.prob
+    nu = p.D * p.Nu
+    u_cells = x[:nc * nu].reshape(nc, nu)
+    assert p.l2_error_u(u_cells) < 1e-12
+    lam = x[nc * (nu + p.Np):]
+    assert np.allclose(lam.reshape(-1, p.Nl)[:, 0], -3.14, atol=1e-10)
+    assert np.abs(u_cells - ref["u"][:, :nu]).max() < 1e-10
+
+
+def test_multifield_two_skeleton_fields_gpu(ctx):
+    """test/MultiFieldLagrangeMultipliersTests.jl shape: two decoupled problems, fields (u1,u2,p1,p2,l1,l2),
+    bulk 1:4, skeleton 5:6 -- exercises touched masks, field-major boundary order and the multi-field
+    skeleton space; the solution of each copy must equal the single-problem solution."""
+    dims = (3, 3)
+    prob = DarcyProblem(dims, 1)
+    ref = prob.oracle_solve()
+    m, v = prob.mats, prob.vecs
+    T = lambda a: torch.as_tensor(a)
+    Z = None
+    mats = [[T(m[0][0]), Z, T(m[0][1]), Z, T(m[0][2]), Z],
+            [Z, T(m[0][0]), Z, T(m[0][1]), Z, T(m[0][2])],
+            [T(m[1][0]), Z, T(m[1][1]), Z, T(m[1][2]), Z],
+            [Z, T(m[1][0]), Z, T(m[1][1]), Z, T(m[1][2])],
+            [T(m[2][0]), Z, T(m[2][1]), Z, T(m[2][2]), Z],
+            [Z, T(m[2][0]), Z, T(m[2][1]), Z, T(m[2][2])]]
+    touched = np.array([[x is not None for x in row] for row in mats])
+    vecs = [T(v[0]), T(v[0]), T(v[1]), T(v[1]), T(v[2]), T(v[2])]
+    cells = gh.PackedCells.from_blocks(mats, vecs, touched, device="cuda")
+    sk = gh.CartesianSkeleton(dims, ctx)
+    dv = torch.as_tensor(prob.dir_vals, device="cuda")
+    M1 = gh.FacetFESpace(sk, prob.prob.Nl, sk.facet_is_boundary(), dv)
+    M2 = gh.FacetFESpace(sk, prob.prob.Nl, sk.facet_is_boundary(), dv)
+    nd = prob.prob.ndofs
+    trial = [nd[0], nd[0], nd[1], nd[1], M1, M2]
+    op = gh.HybridAffineFEOperator(lambda: cells, trial, trial, [1, 2, 3, 4], [5, 6])
+    assert op.assem.nrows == 2 * prob.nfree
+    x = op.solve().cpu().numpy()
+    nc = prob.prob.ncells
+    u1 = x[:nc * nd[0]].reshape(nc, nd[0]); u2 = x[nc * nd[0]:2 * nc * nd[0]].reshape(nc, nd[0])
+    assert prob.prob.l2_error_u(u1) < 1e-12 and prob.prob.l2_error_u(u2) < 1e-12
+    lam = x[nc * 2 * (nd[0] + nd[1]):]
+    assert np.allclose(lam[:prob.nfree], ref["lam"], atol=1e-10) and np.allclose(lam[prob.nfree:], ref["lam"], atol=1e-10)
+
+
+def test_fused_condense_assemble_host_streaming(ctx):
+    """ghb_condense_assemble_f64 with HOST records (chunk-streamed) == separate device calls."""
+    dims = (6, 5, 4)
+    c = CONFIGS["C3_hdg_k2_3d"]
+    plan = ctx.plan_blocks(c["ndofs"], c["touched"], c["interior"], c["boundary"])
+    sk = gh.CartesianSkeleton(dims, ctx)
+    M = gh.FacetFESpace(sk, 6, sk.facet_is_boundary())
+    assem = gh.SparseMatrixAssembler(M)
+    n = sk.ncells
+    A, b = _synth(ctx, plan, 0, n)
+    cells = gh.PackedCells(A, b, c["ndofs"], c["touched"])
+    cond = gh.lazy_map(gh.StaticCondensationMap(c["interior"], c["boundary"]), cells)
+    dv = torch.linspace(-1, 1, max(M.num_dirichlet_dofs, 1), dtype=torch.float64, device="cuda")
+    A1, r1 = gh.assemble_matrix_and_vector(assem, cond, dv)
+    host = gh.PackedCells(A.cpu().numpy(), b.cpu().numpy(), c["ndofs"], c["touched"])
+    nz = np.empty(A1.nnz); rhs = np.empty(assem.nrows); info = np.empty(n, dtype=np.int32)
+    ctx.condense_assemble(plan, n, host.A, host.b, dv, nz, rhs, info)
+    assert np.array_equal(nz, A1.nzval.cpu().numpy()) and np.array_equal(rhs, r1.cpu().numpy()) and not info.any()
+
+
+def test_full_size_properties_c3(ctx):
+    """BASELINE-size property checks (size-independent, no oracle at this scale): linearity of g in b,
+    Schur identity S*lam + A21*u = A22*lam - ... via back-substitution, idempotent re-run."""
+    name = "C3_hdg_k2_3d"
+    plan, op = _dev_plan(ctx, name), oracle_plan(name)
+    n = 32 * 32 * 32
+    A, b = _synth(ctx, plan, 10 ** 6, n)
+    S = torch.empty((n, plan.n_b ** 2), dtype=torch.float64, device="cuda"); g = torch.empty((n, plan.n_b), dtype=torch.float64, device="cuda")
+    info = torch.empty(n, dtype=torch.int32, device="cuda")
+    ctx.condense(plan, n, A, b, S, g, info)
+    assert int(info.abs().sum()) == 0 and bool(torch.isfinite(S).all())
+    S2 = torch.empty_like(S); g2 = torch.empty_like(g)
+    ctx.condense(plan, n, A, b, S2, g2, info)
+    assert torch.equal(S, S2) and torch.equal(g, g2)                        # deterministic
+    ctx.condense(plan, n, A, 2.0 * b, S2, g2, info)
+    assert torch.equal(S, S2) and torch.allclose(g2, 2.0 * g, rtol=1e-12, atol=1e-12)   # S independent of b, g linear
+    # consistency of forward and backward maps: with lam arbitrary and u = A11^-1(b1 - A12 lam):
+    #   A21 u + A22 lam - b2 == S lam - g     (definition of the Schur complement)
+    lam = torch.randn(n * plan.n_b, dtype=torch.float64, device="cuda")
+    ids = torch.arange(1, n * plan.n_b + 1, dtype=torch.int64, device="cuda")
+    u = torch.empty((n, plan.n_i), dtype=torch.float64, device="cuda")
+    ctx.backsub(plan, n, A, b, lam, None, ids, u, info)
+    nI, nB = plan.n_i, plan.n_b
+    # dense views of A21, A22, b2 from the packed record of the all-touched 3-field plan (u30,p4 | l36)
+    nd = CONFIGS[name]["ndofs"]
+    off, _ = gh.PackedCells.layout(nd, CONFIGS[name]["touched"])
+    blk = lambda i, j: A[:, off[i, j]:off[i, j] + nd[i] * nd[j]].view(n, nd[j], nd[i]).transpose(1, 2)
+    A21 = torch.cat([blk(2, 0), blk(2, 1)], dim=2); A22 = blk(2, 2); b2 = b[:, nd[0] + nd[1]:]
+    lamK = lam.view(n, nB)
+    lhs = torch.einsum("cij,cj->ci", A21, u) + torch.einsum("cij,cj->ci", A22, lamK) - b2
+    rhs_ = torch.einsum("cij,cj->ci", S.view(n, nB, nB).transpose(1, 2), lamK) - g
+    scale = rhs_.abs().max()
+    assert float((lhs - rhs_).abs().max() / scale) < 1e-11
+    # spot-check a sample of cells against the C oracle at full size
+    idx = torch.randint(0, n, (64,), device="cuda")
+    S0, g0, _ = oc.condense(op, A[idx].cpu().numpy(), b[idx].cpu().numpy())
+    assert rel_err_cells(S[idx].cpu().numpy(), S0) < TOL and rel_err_cells(g[idx].cpu().numpy(), g0) < TOL
+
+
+@pytest.mark.parametrize("gdims,world", [((4, 3, 4), 2), ((3, 3, 6), 3), ((5, 4), 2), ((2, 2, 4), 4)])
+def test_slab_assembly_matches_global(ctx, gdims, world):
+    """Multi-GPU path on one device: P slab assemblers (one Context each, the cut-plane exchange replaced by
+    a copy) must reproduce the global CSC bit-for-bit: colptr segments concatenate, rowval/nzval/rhs equal."""
+    from gridaphybrid_b200.distributed import SlabAssembler, SlabLayout
+    nf = 3
+    D = len(gdims)
+    nb = 2 * D * nf
+    L0 = SlabLayout(gdims, nf, 0, 1)
+    n = L0.ncells_global
+    rng = np.random.default_rng(9)
+    S = torch.as_tensor(rng.standard_normal((n, nb * nb)), device="cuda")
+    g = torch.as_tensor(rng.standard_normal((n, nb)), device="cuda")
+    ids = L0.cell_dof_ids(torch.arange(n, device="cuda"))
+    ndir = int((-ids).max().item())
+    dv = torch.as_tensor(rng.standard_normal(ndir), device="cuda")
+    # global reference through the single-GPU entry points
+    nnz = ctx.assemble_symbolic(n, nb, ids, L0.nrows_global)
+    colptr = torch.empty(L0.nrows_global + 1, dtype=torch.int64, device="cuda"); rowval = torch.empty(nnz, dtype=torch.int64, device="cuda")
+    ctx.assemble_pattern(colptr, rowval)
+    nz = torch.empty(nnz, dtype=torch.float64, device="cuda"); rhs = torch.empty(L0.nrows_global, dtype=torch.float64, device="cuda")
+    ctx.assemble_numeric(S, g, dv, nz, rhs)
+    # and against the oracle's restated assembler
+    Sn, gn, idn = S.cpu().numpy(), g.cpu().numpy(), ids.cpu().numpy()
+    Sc = [Sn[c].reshape((nb, nb), order="F") for c in range(n)]
+    gl = [o.attach_dirichlet(Sc[c], gn[c], idn[c], dv.cpu().numpy()) for c in range(n)]
+    cp0, rv0, nz0, rhs0 = o.assemble_matrix_and_vector(Sc, gl, idn, L0.nrows_global)
+    assert np.array_equal(colptr.cpu().numpy(), cp0) and np.array_equal(rowval.cpu().numpy(), rv0)
+    assert np.array_equal(nz.cpu().numpy(), nz0)
+    # slabs
+    ctxs = [gh.Context(0) for _ in range(world)]
+    asms = [SlabAssembler(ctxs[r], gdims, nf, r, world, dirichlet_values=dv) for r in range(world)]
+    for r, a in enumerate(asms):
+        L = a.layout
+        a.pack(S[L.cell_start:L.cell_start + L.ncells], g[L.cell_start:L.cell_start + L.ncells])
+    torch.cuda.synchronize()
+    cps, rvs, nzs, rhss = [], [], [], []
+    for r, a in enumerate(asms):
+        L = a.layout
+        fake = lambda send, recv, rank, w, group: recv.copy_(asms[rank + 1].send_buf) if recv is not None else None
+        z = torch.empty(a.nnz, dtype=torch.float64, device="cuda"); rr = torch.empty(a.nrows_local, dtype=torch.float64, device="cuda")
+        a.assemble(S[L.cell_start:L.cell_start + L.ncells].contiguous(), g[L.cell_start:L.cell_start + L.ncells].contiguous(), z, rr, exchange=fake)
+        cp, rv = a.pattern()
+        cps.append(cp.cpu().numpy()); rvs.append(rv.cpu().numpy()); nzs.append(z.cpu().numpy()); rhss.append(rr.cpu().numpy())
+    # concatenate the column segments
+    off = 0
+    cat = [np.array([1], dtype=np.int64)]
+    for cp in cps:
+        cat.append(cp[1:] + off)
+        off += cp[-1] - 1
+    assert np.array_equal(np.concatenate(cat), cp0)
+    assert np.array_equal(np.concatenate(rvs), rv0)
+    assert np.array_equal(np.concatenate(nzs), nz0)
+    assert np.array_equal(np.concatenate(rhss), rhs.cpu().numpy())
+    for c in ctxs:
+        c.close()
