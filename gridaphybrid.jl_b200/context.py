@@ -68,6 +68,8 @@ class Context:
             raise GhbError(rc, "ghb_create failed")
         self._h = h
         self.device = int(device)
+        if torch is not None and torch.cuda.is_available():
+            self.use_torch_stream()   # stream-ordered with the caller's torch work from the start
 
     def close(self):
         if getattr(self, "_h", None):

@@ -1,4 +1,5 @@
 // api.cu -- C ABI entry points (include/ghb.h): context, block plans, argument staging, dispatch.
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -16,6 +17,12 @@ bool is_device_ptr(const void* p) {
   cudaError_t e = cudaPointerGetAttributes(&at, p);
   if (e != cudaSuccess) { cudaGetLastError(); return false; }
   return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+int launch_condense(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
+                    double* g, int32_t* info, double* X) {
+  if (p.use_dmma && X == nullptr) return launch_condense_dmma(ctx, p, ncells, A, b, S, g, info);
+  return launch_condense_generic(ctx, p, ncells, A, b, S, g, info, X);
 }
 
 static Plan* get_plan(ghb_ctx* ctx, int id) {
@@ -62,6 +69,8 @@ void ghb_destroy(ghb_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (Plan* p : ctx->plans) {
     if (p && p->d_emap) cudaFree(p->d_emap);
+    if (p && p->d_colbase) cudaFree(p->d_colbase);
+    if (p && p->d_rowf) cudaFree(p->d_rowf);
     delete p;
   }
   asm_free(ctx);
@@ -79,13 +88,9 @@ int ghb_set_stream(ghb_ctx* ctx, void* s) {
   if (!ctx) return GHB_EINVAL;
   cudaSetDevice(ctx->device);
   if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
-  if (s == nullptr) {
-    GHB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    ctx->own_stream = true;
-  } else {
-    ctx->stream = (cudaStream_t)s;
-    ctx->own_stream = false;
-  }
+  // NULL is a valid handle: the legacy default stream (what torch uses unless told otherwise)
+  ctx->stream = (cudaStream_t)s;
+  ctx->own_stream = false;
   return GHB_OK;
 }
 
@@ -168,6 +173,12 @@ int ghb_plan_blocks(ghb_ctx* ctx, int nfields, const int32_t* ndofs, const uint8
   cudaSetDevice(ctx->device);
   if (cudaMalloc((void**)&p->d_emap, emap.size() * sizeof(int32_t)) != cudaSuccess) { delete p; return fail(ctx, GHB_ENOMEM, "emap alloc"); }
   cudaMemcpy(p->d_emap, emap.data(), emap.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+  const char* force = getenv("GHB_FORCE_GENERIC");
+  if (dmma_supported(*p) && !(force && force[0] == '1')) {
+    int rc = dmma_prepare(ctx, *p);
+    if (rc != GHB_OK) { cudaFree(p->d_emap); delete p; return rc; }
+    p->use_dmma = true;
+  }
   ctx->plans.push_back(p);
   *plan_id = (int)ctx->plans.size() - 1;
   return GHB_OK;
@@ -207,7 +218,7 @@ int ghb_condense_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A,
   Arg<double> dS(ctx, S, (size_t)ncells * p->n_b * p->n_b, false, true); GHB_TRY(dS.rc);
   Arg<double> dg(ctx, g, (size_t)ncells * p->n_b, false, true); GHB_TRY(dg.rc);
   Arg<int32_t> di(ctx, info, info ? (size_t)ncells : 0, false, true); GHB_TRY(di.rc);
-  GHB_TRY(launch_condense_generic(ctx, *p, ncells, dA.dev, db.dev, dS.dev, dg.dev, di.dev, X));
+  GHB_TRY(launch_condense(ctx, *p, ncells, dA.dev, db.dev, dS.dev, dg.dev, di.dev, X));
   GHB_TRY(dS.finish()); GHB_TRY(dg.finish()); GHB_TRY(di.finish());
   return GHB_OK;
 }
@@ -339,7 +350,7 @@ int ghb_condense_assemble_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const d
   Arg<int32_t> di(ctx, info, info ? (size_t)ncells : 0, false, true); GHB_TRY(di.rc);
   int rc = GHB_OK;
   if (!hostA) {
-    rc = launch_condense_generic(ctx, *p, ncells, A, b, dS, dg, di.dev, nullptr);
+    rc = launch_condense(ctx, *p, ncells, A, b, dS, dg, di.dev, nullptr);
   } else {
     // stream host records through two device chunk buffers: H2D of chunk k+1 overlaps condensation of chunk k
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(ncells, (int64_t)(256u << 20) / ((p->lenA + p->lenb) * 8)));
@@ -363,7 +374,7 @@ int ghb_condense_assemble_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const d
       GHB_CUDA(ctx, cudaMemcpyAsync(db[s], b + c0 * p->lenb, (size_t)nc * p->lenb * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
       GHB_CUDA(ctx, cudaEventRecord(h2d_done[s], ctx->copy_stream));
       GHB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, h2d_done[s], 0));
-      rc = launch_condense_generic(ctx, *p, nc, dA[s], db[s], dS + c0 * p->n_b * p->n_b, dg + c0 * p->n_b,
+      rc = launch_condense(ctx, *p, nc, dA[s], db[s], dS + c0 * p->n_b * p->n_b, dg + c0 * p->n_b,
                                    di.dev ? di.dev + c0 : nullptr, nullptr);
       GHB_CUDA(ctx, cudaEventRecord(k_done[s], ctx->stream));
     }

@@ -28,6 +28,10 @@ struct Plan {
   std::vector<int32_t> row_field, row_local;  // condensed row -> (field index 0-based, local dof)
   int n_i = 0, n_b = 0, n = 0, lenA = 0, lenb = 0;
   int32_t* d_emap = nullptr;
+  int32_t* d_colbase = nullptr;   // tables of the DMMA kernel's on-the-fly re-layout (condense_dmma.cu)
+  uint8_t* d_rowf = nullptr;
+  uint8_t* d_rowl = nullptr;
+  bool use_dmma = false;
   bool all_touched = false;
   const char* kernel_name = "generic";
   PlanDev dev() const { return PlanDev{n_i, n_b, n, lenA, lenb, d_emap}; }
@@ -144,6 +148,13 @@ struct Arg {
 // kernels / launchers implemented in the other translation units
 int launch_condense_generic(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b,
                             double* S, double* g, int32_t* info, double* X);
+bool dmma_supported(const Plan& p);
+int dmma_prepare(ghb_ctx* ctx, Plan& p);
+int launch_condense_dmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
+                         double* g, int32_t* info);
+// dispatch: tuned kernel when the plan has one and no factors are requested, else the generic kernel
+int launch_condense(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
+                    double* g, int32_t* info, double* X);
 int launch_backsub_generic(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b,
                            const double* lam_free, const double* lam_dir, const int64_t* ids, double* u,
                            int32_t* info);

@@ -49,7 +49,10 @@ typedef struct ghb_ctx ghb_ctx; /* opaque: device, stream, plans, cached symboli
 int ghb_create(int device_id, ghb_ctx** out);
 void ghb_destroy(ghb_ctx* ctx);
 const char* ghb_last_error(const ghb_ctx* ctx);
-/* Run on a caller-provided cudaStream_t (e.g. torch's current stream); NULL = ctx-owned stream. */
+/* Streams: a new ctx owns a non-blocking stream.  ghb_set_stream makes it launch on a caller-provided
+ * cudaStream_t instead (e.g. torch's current stream; NULL = the legacy default stream).  Calls whose
+ * outputs are device pointers return without waiting (stream-ordered); outputs to host pointers are
+ * complete on return. */
 int ghb_set_stream(ghb_ctx* ctx, void* cuda_stream);
 int ghb_synchronize(ghb_ctx* ctx);
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
