@@ -61,137 +61,132 @@ struct Cfg {
   static_assert(NI % 2 == 0 && NB % 2 == 0, "16-byte cp.async needs even block heights");
   static constexpr int WT_DOUBLES = NCP * LDW;
   static constexpr int BT_DOUBLES = NCP * LDB;
-  static constexpr int MAXCHG = 16;
-  static constexpr size_t SMEM = (size_t)(WT_DOUBLES + BT_DOUBLES + NP * 64) * 8 + 1024;
+  static size_t smem_bytes(int nf) {   // arrays + Dinv + rinv + control block + re-layout tables
+    return (size_t)(WT_DOUBLES + BT_DOUBLES + NP * 64 + 8) * 8 + 512 + (size_t)(N + 1) * nf * 4 + N + 64;
+  }
 };
 
-struct Shared {
+struct Shared {   // sizeof <= 512
   // small control block placed after the big arrays
-  int perm_n;            // number of changed positions of the current panel
   int info;
-  int chg_pos[16];
-  int chg_src[16];
+  int ndisp;             // displaced rows of the current panel
+  int psrc[8];           // physical row (before this panel's permutation) of the k-th pivot row
+  int dsrc[8];           // displaced rows: old position (inside the diagonal block) ...
+  int ddst[8];           // ... and the vacated position they move to
+  int vac[40];           // scratch: vacated positions by rank
 };
 
-// ---- panel factorisation: one warp, one row per lane -------------------------------------------
-// Factorises columns [c0, c0+NPIV) of Wt over rows [c0, NI); also carries the other 8-NPIV columns of the
-// column tile through the eliminations.  Writes L\U back, publishes the net row permutation as
-// (position <- source row) pairs and the reciprocals of the pivots.
-template <int NI, int LDW, int C0, int NPIV>
-__device__ __forceinline__ void panel_factor(double* __restrict__ Wt, Shared* sh, double* __restrict__ rinv_out) {
+// ---- panel factorisation: one warp, one row per lane, implicit pivoting --------------------------
+// Factorises columns [c0, c0+npiv) of Wt over rows [c0, NI) and carries the other columns of the 8-wide
+// column tile through the eliminations.  Rows are not exchanged while factorising: a lane keeps its row
+// and remembers at which step it was chosen.  On write-back the k-th pivot row goes to position c0+k and
+// the rows it displaces from the diagonal block go to the vacated positions (any consistent row order is
+// a valid row-permuted LU; S does not depend on it).  Publishes that permutation for the trailing columns.
+template <int NI, int LDW, bool TWO>
+__device__ __forceinline__ void panel_factor(double* __restrict__ Wt, const int c0, const int npiv, Shared* sh,
+                                             double* __restrict__ rinv_out) {
   const int lane = threadIdx.x & 31;
-  constexpr int NROWS = NI - C0;              // candidate rows
-  constexpr bool TWO = NROWS > 32;            // a second register set for rows beyond 32 lanes
-  static_assert(NROWS <= 64, "panel rows exceed two register sets");
-  const bool v1 = lane < NROWS;
-  const bool v2 = TWO && (lane + 32 < NROWS);
+  const int nrows = NI - c0;
+  const bool v1 = lane < nrows;
+  const bool v2 = TWO && (lane + 32 < nrows);
   double a[8], a2[8];
-  int org = C0 + lane, org2 = C0 + 32 + lane;
+  int ch1 = -1, ch2 = -1;                       // step at which this lane's row became the pivot row
+  double* base = Wt + c0 + lane + LDW * c0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    a[j] = v1 ? Wt[C0 + lane + LDW * (C0 + j)] : 0.0;
-    a2[j] = v2 ? Wt[C0 + 32 + lane + LDW * (C0 + j)] : 0.0;
+    a[j] = v1 ? base[LDW * j] : 0.0;
+    a2[j] = v2 ? base[32 + LDW * j] : 0.0;
   }
-  bool failed = false;
 #pragma unroll
-  for (int k = 0; k < NPIV; ++k) {
-    // ---- pivot search: first max of |a[k]| over positions >= k
-    const bool c1 = v1 && lane >= k;
-    const bool c2 = v2;
-    unsigned long long key1 = c1 ? ((unsigned long long)__double_as_longlong(a[k]) & 0x7fffffffffffffffull) : 0ull;
-    unsigned long long key2 = c2 ? ((unsigned long long)__double_as_longlong(a2[k]) & 0x7fffffffffffffffull) : 0ull;
-    double rc1 = 1.0 / a[k];                  // speculative reciprocal, overlaps the reduction
-    double rc2 = TWO ? 1.0 / a2[k] : 0.0;
-    unsigned long long km = TWO ? (key1 > key2 ? key1 : key2) : key1;
-    unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)(km >> 32));
-    unsigned lo = __reduce_max_sync(0xffffffffu, (unsigned)(km >> 32) == hi ? (unsigned)km : 0u);
-    const unsigned long long kmax = ((unsigned long long)hi << 32) | lo;
-    unsigned b1 = __ballot_sync(0xffffffffu, c1 && key1 == kmax);
-    unsigned b2 = TWO ? __ballot_sync(0xffffffffu, c2 && key2 == kmax) : 0u;
-    if (kmax == 0ull) {                       // exact zero pivot: LAPACK info = k+1 (uniform branch)
-      if (lane == 0 && sh->info == 0) sh->info = C0 + k + 1;
-      failed = true;
-      break;
-    }
-    const bool from2 = TWO && (b1 == 0u);
-    const int q = from2 ? (__ffs(b2) - 1) : (__ffs(b1) - 1);
-    const double rinv = __shfl_sync(0xffffffffu, from2 ? rc2 : rc1, q);
-    if (lane == 0) rinv_out[k] = rinv;
-    // ---- exchange row at position k (lane k, set 1) with the pivot row (lane q, set 1 or 2)
-    const int oq = __shfl_sync(0xffffffffu, from2 ? org2 : org, q);
-    const int ok = __shfl_sync(0xffffffffu, org, k);
-    double prow[8];
+  for (int k = 0; k < 8; ++k) {
+    if (k < npiv) {
+      // ---- pivot search: max |a[k]| over the rows not chosen yet (lowest lane wins ties)
+      const bool c1 = v1 && ch1 < 0;
+      const bool c2 = v2 && ch2 < 0;
+      const unsigned long long key1 = c1 ? ((unsigned long long)__double_as_longlong(a[k]) & 0x7fffffffffffffffull) : 0ull;
+      const unsigned long long key2 = c2 ? ((unsigned long long)__double_as_longlong(a2[k]) & 0x7fffffffffffffffull) : 0ull;
+      const double rc1 = __drcp_rn(a[k]);       // speculative reciprocal, overlaps the reduction
+      const double rc2 = TWO ? __drcp_rn(a2[k]) : 0.0;
+      const unsigned long long km = TWO ? (key1 > key2 ? key1 : key2) : key1;
+      const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)(km >> 32));
+      const unsigned lo = __reduce_max_sync(0xffffffffu, (unsigned)(km >> 32) == hi ? (unsigned)km : 0u);
+      const unsigned long long kmax = ((unsigned long long)hi << 32) | lo;
+      if (kmax == 0ull) {                       // exact zero pivot column: LAPACK info = k+1 (uniform branch)
+        if (lane == 0 && sh->info == 0) sh->info = c0 + k + 1;
+        break;
+      }
+      const unsigned b1 = __ballot_sync(0xffffffffu, c1 && key1 == kmax);
+      const unsigned b2 = TWO ? __ballot_sync(0xffffffffu, c2 && key2 == kmax) : 0u;
+      const bool from2 = TWO && (b1 == 0u);
+      const int q = from2 ? (__ffs(b2) - 1) : (__ffs(b1) - 1);
+      const double rinv = __shfl_sync(0xffffffffu, from2 ? rc2 : rc1, q);
+      if (lane == 0) rinv_out[k] = rinv;
+      const bool me1 = !from2 && lane == q, me2 = from2 && lane == q;
+      if (me1) ch1 = k;
+      if (me2) ch2 = k;
+      // ---- multipliers and rank-1 update of the rows still in play
+      const bool u1 = c1 && !me1, u2 = TWO && c2 && !me2;
+      const double l1 = a[k] * rinv, l2 = a2[k] * rinv;   // dgetf2: scale by the reciprocal
+      if (u1) a[k] = l1;
+      if (u2) a2[k] = l2;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const double pj = __shfl_sync(0xffffffffu, from2 ? a2[j] : a[j], q);   // pivot row, to everyone
-      const double kj = __shfl_sync(0xffffffffu, a[j], k);                    // row at position k
-      prow[j] = pj;
-      if (from2) { if (lane == q) a2[j] = kj; }
-      else       { if (lane == q) a[j] = kj; }
-      if (lane == k) a[j] = pj;
-    }
-    if (from2) { if (lane == q) org2 = ok; }
-    else       { if (lane == q) org = ok; }
-    if (lane == k) org = oq;
-    // ---- multipliers and rank-1 update of the rest of the tile
-    if (v1 && lane > k) {
-      const double l = a[k] * rinv;           // dgetf2: scale by the reciprocal
-      a[k] = l;
-#pragma unroll
-      for (int j = k + 1; j < 8; ++j) a[j] = fma(-l, prow[j], a[j]);
-    }
-    if (TWO && v2) {
-      const double l = a2[k] * rinv;
-      a2[k] = l;
-#pragma unroll
-      for (int j = k + 1; j < 8; ++j) a2[j] = fma(-l, prow[j], a2[j]);
+      for (int j = k + 1; j < 8; ++j) {
+        const double pj = __shfl_sync(0xffffffffu, from2 ? a2[j] : a[j], q);   // pivot row entry, to everyone
+        if (u1) a[j] = fma(-l1, pj, a[j]);
+        if (u2) a2[j] = fma(-l2, pj, a2[j]);
+      }
     }
   }
-  (void)failed;
-  // ---- write back and publish the permutation
+  // ---- new positions: pivot rows first, displaced rows into the vacated slots
+  const bool disp = v1 && lane < 8 && ch1 < 0 && lane < npiv + 0 * nrows;   // rows of the diagonal block not chosen
+  const bool vc1 = v1 && lane >= npiv && ch1 >= 0;
+  const bool vc2 = v2 && ch2 >= 0;
+  const unsigned mdisp = __ballot_sync(0xffffffffu, disp);
+  const unsigned mv1 = __ballot_sync(0xffffffffu, vc1);
+  const unsigned mv2 = __ballot_sync(0xffffffffu, vc2);
+  const unsigned lt = (1u << lane) - 1u;
+  if (vc1) sh->vac[__popc(mv1 & lt)] = c0 + lane;
+  if (vc2) sh->vac[__popc(mv1) + __popc(mv2 & lt)] = c0 + 32 + lane;
+  __syncwarp();
+  int np1 = c0 + lane, np2 = c0 + 32 + lane;
+  if (ch1 >= 0) np1 = c0 + ch1;
+  else if (disp) np1 = sh->vac[__popc(mdisp & lt)];
+  if (ch2 >= 0) np2 = c0 + ch2;
+  if (ch1 >= 0) sh->psrc[ch1] = c0 + lane;
+  if (ch2 >= 0) sh->psrc[ch2] = c0 + 32 + lane;
+  if (disp) {
+    const int t = __popc(mdisp & lt);
+    sh->dsrc[t] = c0 + lane;
+    sh->ddst[t] = np1;
+  }
+  if (lane == 0) sh->ndisp = __popc(mdisp);
+  double* wb = Wt + LDW * c0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    if (v1) Wt[C0 + lane + LDW * (C0 + j)] = a[j];
-    if (v2) Wt[C0 + 32 + lane + LDW * (C0 + j)] = a2[j];
+    if (v1) wb[np1 + LDW * j] = a[j];
+    if (v2) wb[np2 + LDW * j] = a2[j];
   }
-  const bool ch1 = v1 && org != C0 + lane;
-  const bool ch2 = v2 && org2 != C0 + 32 + lane;
-  const unsigned m1 = __ballot_sync(0xffffffffu, ch1);
-  const unsigned m2 = __ballot_sync(0xffffffffu, ch2);
-  const int n1 = __popc(m1);
-  if (ch1) {
-    int t = __popc(m1 & ((1u << lane) - 1u));
-    sh->chg_pos[t] = C0 + lane;
-    sh->chg_src[t] = org;
-  }
-  if (ch2) {
-    int t = n1 + __popc(m2 & ((1u << lane) - 1u));
-    sh->chg_pos[t] = C0 + 32 + lane;
-    sh->chg_src[t] = org2;
-  }
-  if (lane == 0) sh->perm_n = n1 + __popc(m2);
 }
 
-// inverse of the NPIV x NPIV upper-triangular diagonal block, stored as the 8x8 B-operand
-// Dinv[k + 8*n] (column-major), zero outside the NPIV block.  Lane n < 8 computes column n.
-template <int LDW, int C0, int NPIV>
-__device__ __forceinline__ void invert_upper(const double* __restrict__ Wt, const double* __restrict__ rinv,
-                                             double* __restrict__ Dinv) {
+// inverse of the npiv x npiv upper-triangular diagonal block, stored as the 8x8 B-operand
+// Dinv[k + 8*n] (column-major), zero outside the npiv block.  Lane n < 8 computes column n.
+template <int LDW>
+__device__ __forceinline__ void invert_upper(const double* __restrict__ Wt, const int c0, const int npiv,
+                                             const double* __restrict__ rinv, double* __restrict__ Dinv) {
   const int n = threadIdx.x & 31;
   if (n >= 8) return;
   double x[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) x[i] = 0.0;
-  if (n < NPIV) {
+  const double* U = Wt + c0 + LDW * c0;
 #pragma unroll
-    for (int i = NPIV - 1; i >= 0; --i) {
-      if (i <= n) {
-        double s = (i == n) ? 1.0 : 0.0;
+  for (int i = 7; i >= 0; --i) {
+    if (i < npiv && i <= n && n < npiv) {
+      double s = (i == n) ? 1.0 : 0.0;
 #pragma unroll
-        for (int m = i + 1; m < NPIV; ++m)
-          if (m <= n) s = fma(-Wt[C0 + i + LDW * (C0 + m)], x[m], s);
-        x[i] = s * rinv[i];
-      }
+      for (int m = i + 1; m < 8; ++m)
+        if (m <= n) s = fma(-U[i + LDW * m], x[m], s);
+      x[i] = s * rinv[i];
     }
   }
 #pragma unroll
@@ -205,18 +200,24 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
                      int32_t* __restrict__ info) {
   using C = Cfg<NI, NB>;
   constexpr int N = C::N, NC = C::NC, LDW = C::LDW, LDB = C::LDB, RT = C::RT, BT = C::BT, CT = C::CT, NP = C::NP;
+  constexpr int NF = 8;                          // max fields handled by the smem tables
   extern __shared__ __align__(16) double smem[];
   double* Wt = smem;
   double* Bt = Wt + C::WT_DOUBLES;
   double* Dinv = Bt + C::BT_DOUBLES;            // [NP][64]
-  Shared* sh = reinterpret_cast<Shared*>(Dinv + NP * 64);
-  double* rinv = reinterpret_cast<double*>(sh + 1);  // [8]
+  double* rinv = Dinv + NP * 64;                // [8]
+  Shared* sh = reinterpret_cast<Shared*>(rinv + 8);
+  int* s_colbase = reinterpret_cast<int*>(sh + 1);           // [(N+1)*nf]
+  unsigned short* s_rowinfo = reinterpret_cast<unsigned short*>(s_colbase + (N + 1) * tb.nf);  // [N/2]: f<<8 | local row
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gid = lane >> 2, tig = lane & 3;    // fragment coordinates
+  (void)NF;
 
   // padding never written by the loader: zero it once (rows NI.. of Wt, rows NB.. of Bt, column NC)
   for (int i = tid; i < C::WT_DOUBLES; i += 128) Wt[i] = 0.0;
   for (int i = tid; i < C::BT_DOUBLES; i += 128) Bt[i] = 0.0;
+  for (int i = tid; i < (N + 1) * tb.nf; i += 128) s_colbase[i] = tb.colbase[i];
+  for (int i = tid; i < N / 2; i += 128) s_rowinfo[i] = (unsigned short)((tb.rowf[2 * i] << 8) | tb.rowl[2 * i]);
   __syncthreads();
 
   for (int64_t cell = blockIdx.x; cell < ncells; cell += gridDim.x) {
@@ -225,17 +226,21 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
       const double* Arec = A + cell * lenA;
       const double* brec = b + cell * lenb;
       constexpr int HP = N / 2;  // row pairs per column
-      for (int idx = tid; idx < HP * NC; idx += 128) {
-        const int c = idx / HP, r = 2 * (idx - c * HP);
-        const int f = tb.rowf[r];
-        const int off = tb.colbase[c * tb.nf + f];
+      // idx = tid + 128*m  ->  (c, rp) advanced incrementally (no division)
+      int c = tid / HP, rp = tid - c * HP;
+      constexpr int DC = 128 / HP, DR = 128 - DC * HP;
+      for (; c < NC;) {
+        const int ri = s_rowinfo[rp];
+        const int off = s_colbase[c * tb.nf + (ri >> 8)];
+        const int r = 2 * rp;
         double* dst = r < NI ? Wt + r + LDW * c : Bt + (r - NI) + LDB * c;
         if (off >= 0) {
-          const double* src = (c < N ? Arec : brec) + off + tb.rowl[r];
-          cp_async16(dst, src);
+          cp_async16(dst, (c < N ? Arec : brec) + off + (ri & 0xff));
         } else {
           dst[0] = 0.0; dst[1] = 0.0;
         }
+        c += DC; rp += DR;
+        if (rp >= HP) { rp -= HP; ++c; }
       }
       if (tid == 0) sh->info = 0;
       cp_async_commit_wait_all();
@@ -244,77 +249,56 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
 
     // ------------------------------------------------------------------ phase 1: blocked LU of Wt
     bool ok = true;
-#pragma unroll
+#pragma unroll 1
     for (int p = 0; p < NP; ++p) {
-      constexpr int dummy = 0; (void)dummy;
       const int c0 = 8 * p;
       const int npiv = (NI - c0) < 8 ? (NI - c0) : 8;
       if (warp == 0) {
-        // compile-time dispatch on the panel index
-        switch (p) {
-          case 0: panel_factor<NI, LDW, 0, (NI - 0 < 8 ? NI - 0 : 8)>(Wt, sh, rinv); break;
-          case 1: if constexpr (NP > 1) panel_factor<NI, LDW, 8, (NI - 8 < 8 ? NI - 8 : 8)>(Wt, sh, rinv); break;
-          case 2: if constexpr (NP > 2) panel_factor<NI, LDW, 16, (NI - 16 < 8 ? NI - 16 : 8)>(Wt, sh, rinv); break;
-          case 3: if constexpr (NP > 3) panel_factor<NI, LDW, 24, (NI - 24 < 8 ? NI - 24 : 8)>(Wt, sh, rinv); break;
-          case 4: if constexpr (NP > 4) panel_factor<NI, LDW, 32, (NI - 32 < 8 ? NI - 32 : 8)>(Wt, sh, rinv); break;
-          default: break;
-        }
+        if ((NI - c0) > 32) panel_factor<NI, LDW, true>(Wt, c0, npiv, sh, rinv);
+        else panel_factor<NI, LDW, false>(Wt, c0, npiv, sh, rinv);
       }
       __syncthreads();
       if (sh->info != 0) { ok = false; break; }
-      // ---- row interchanges + unit-lower solve on the trailing columns: one column per thread;
-      //      warp 3 inverts the diagonal block meanwhile
+      // ---- warp 3 inverts the diagonal block; warps 0-2: one trailing column per thread: gather the pivot
+      //      rows, move the displaced rows, unit-lower solve
       if (warp == 3) {
-        switch (p) {
-          case 0: invert_upper<LDW, 0, (NI - 0 < 8 ? NI - 0 : 8)>(Wt, rinv, Dinv + 0 * 64); break;
-          case 1: if constexpr (NP > 1) invert_upper<LDW, 8, (NI - 8 < 8 ? NI - 8 : 8)>(Wt, rinv, Dinv + 1 * 64); break;
-          case 2: if constexpr (NP > 2) invert_upper<LDW, 16, (NI - 16 < 8 ? NI - 16 : 8)>(Wt, rinv, Dinv + 2 * 64); break;
-          case 3: if constexpr (NP > 3) invert_upper<LDW, 24, (NI - 24 < 8 ? NI - 24 : 8)>(Wt, rinv, Dinv + 3 * 64); break;
-          case 4: if constexpr (NP > 4) invert_upper<LDW, 32, (NI - 32 < 8 ? NI - 32 : 8)>(Wt, rinv, Dinv + 4 * 64); break;
-          default: break;
-        }
-      }
-      {
+        invert_upper<LDW>(Wt, c0, npiv, rinv, Dinv + p * 64);
+      } else {
         const int c = c0 + 8 + tid;             // trailing column of this thread
-        if (c < NC && warp < 3) {
+        if (c < NC) {
           double* col = Wt + LDW * c;
-          const int nchg = sh->perm_n;
-          double vals[C::MAXCHG];
+          double u[8], dv[8];
+          const int nd = sh->ndisp;
 #pragma unroll
-          for (int t = 0; t < C::MAXCHG; ++t)
-            if (t < nchg) vals[t] = col[sh->chg_src[t]];
+          for (int k = 0; k < 8; ++k) u[k] = k < npiv ? col[sh->psrc[k]] : 0.0;
 #pragma unroll
-          for (int t = 0; t < C::MAXCHG; ++t)
-            if (t < nchg) col[sh->chg_pos[t]] = vals[t];
-          // u = L_pp^-1 u  (rows c0 .. c0+nr-1 of this column)
-          const int nr = (NI - c0) < 8 ? (NI - c0) : 8;
-          double u[8];
+          for (int t = 0; t < 8; ++t) dv[t] = t < nd ? col[sh->dsrc[t]] : 0.0;
+          const double* Lp = Wt + c0 + LDW * c0;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) u[i] = i < nr ? col[c0 + i] : 0.0;
+          for (int j = 0; j < 7; ++j) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (j < npiv) {
-#pragma unroll
-              for (int i = j + 1; i < 8; ++i)
-                if (i < nr) u[i] = fma(-Wt[c0 + i + LDW * (c0 + j)], u[j], u[i]);
-            }
+            for (int i = j + 1; i < 8; ++i)
+              if (i < npiv) u[i] = fma(-Lp[i + LDW * j], u[j], u[i]);
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (i < nr) col[c0 + i] = u[i];
+          for (int k = 0; k < 8; ++k)
+            if (k < npiv) col[c0 + k] = u[k];
+#pragma unroll
+          for (int t = 0; t < 8; ++t)
+            if (t < nd) col[sh->ddst[t]] = dv[t];
         }
       }
       __syncthreads();
       // ---- trailing update of the top block: C[I][J] -= L[I][p] * U[p][J],  I > p, J > p
       if (p + 1 < RT) {
         for (int J = p + 1 + warp; J < CT; J += 4) {
-          double bf0 = neg(Wt[c0 + tig + LDW * (8 * J + gid)]);
-          double bf1 = neg(Wt[c0 + 4 + tig + LDW * (8 * J + gid)]);
+          const double bf0 = neg(Wt[c0 + tig + LDW * (8 * J + gid)]);
+          const double bf1 = neg(Wt[c0 + 4 + tig + LDW * (8 * J + gid)]);
           for (int I = p + 1; I < RT; ++I) {
             const int r = 8 * I + gid;
             const bool rv = r < NI;
-            double a0 = rv ? Wt[r + LDW * (c0 + tig)] : 0.0;
-            double a1 = rv ? Wt[r + LDW * (c0 + 4 + tig)] : 0.0;
+            const double a0 = rv ? Wt[r + LDW * (c0 + tig)] : 0.0;
+            const double a1 = rv ? Wt[r + LDW * (c0 + 4 + tig)] : 0.0;
             double* cp0 = Wt + r + LDW * (8 * J + 2 * tig);
             double d0 = rv ? cp0[0] : 0.0, d1 = rv ? cp0[LDW] : 0.0;
             dmma(d0, d1, a0, bf0);
@@ -322,8 +306,8 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
             if (rv) { cp0[0] = d0; cp0[LDW] = d1; }
           }
         }
+        __syncthreads();
       }
-      __syncthreads();
     }
 
     // ------------------------------------------------------------------ phase 2: bottom block
@@ -347,7 +331,6 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
           }
           if (J < NP) {
             // L = X * Dinv_J  (C fragment -> A fragment through shared memory: the tile is private to the warp)
-            constexpr int dummy2 = 0; (void)dummy2;
             const int npv = (NI - 8 * J) < 8 ? (NI - 8 * J) : 8;
             if (rv) { cp0[0] = x0; cp0[LDB] = x1; }
             __syncwarp();
@@ -459,11 +442,12 @@ int launch_condense_dmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const doub
                          double* g, int32_t* info) {
   using C = Cfg<34, 36>;
   auto kern = condense_dmma_kernel<34, 36>;
-  GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+  const size_t smem = C::smem_bytes(p.nfields);
+  GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   DmmaTables tb{p.d_colbase, p.d_rowf, p.d_rowl, p.nfields};
   int64_t grid = std::min<int64_t>(ncells, (int64_t)ctx->sm_count * 5);
-  kern<<<(unsigned)grid, 128, C::SMEM, ctx->stream>>>(tb, p.lenA, p.lenb, ncells, A, b, S, g, info);
+  kern<<<(unsigned)grid, 128, smem, ctx->stream>>>(tb, p.lenA, p.lenb, ncells, A, b, S, g, info);
   GHB_LAUNCHED(ctx);
   return GHB_OK;
 }
