@@ -6,14 +6,17 @@
 // (/root/reference/src/StaticCondensationMap.jl:152-196):
 //   * the packed record is re-laid out on the fly by 16-byte cp.async into two dense column-major
 //     images in shared memory: Wt = [A11 A12 b1] (n_i rows) and Bt = [A21 A22 b2] (n_b rows);
-//   * phase 1 (getrf! :179 + the L-solve half of getrs! :183,:189): blocked right-looking LU of Wt with
-//     partial pivoting, panel width 8.  The panel is factorised by one warp with one row per lane
-//     (pivot = first max |.| like idamax, found with two REDUX.MAX on the 64-bit magnitude), row
-//     interchanges and the unit-lower solve run one column per lane, the trailing update is DMMA;
-//   * phase 2 (the U-solve half of getrs!, gemm! :186, gemv! :192 re-associated as
-//     S = A22 - (A21 U^-1)(L^-1 P A12)): left-looking sweep over the column tiles of Bt with the
-//     accumulators in registers: L21 = (A21 - L21 U) * inv(U_pp) and S = A22 - L21 * U12, all DMMA.
-// The pivot sequence is LAPACK's; only the association/rounding of the updates differs (parity bar 1e-11).
+//   * top block (getrf! :179 + the L-solve half of getrs! :183,:189): blocked right-looking LU of Wt with
+//     partial pivoting, panel width 8, with look-ahead: warp 0 only factorises panels (one row per lane,
+//     pivot found with one REDUX.MAX on a packed magnitude|row key), warps 1-3 own the column tiles:
+//     row gather + unit-lower solve (DMMA with the inverted diagonal block) + trailing update (DMMA);
+//     the next panel's column tile is done first and handed back to warp 0 through a named barrier;
+//   * bottom block (the U-solve half of getrs!, gemm! :186, gemv! :192 re-associated as
+//     S = A22 - (A21 U^-1)(L^-1 P A12)): warps 1-3 own row tiles of Bt; per panel
+//     L21 = X * inv(U_pp) and S -= L21 * U12 (DMMA, S accumulators in registers), overlapped with the
+//     factorisation of the following panels.
+// Pivoting: the pivot of a column is an entry whose magnitude equals the column maximum to 2^-15 relative
+// (lowest row among those); S does not depend on the pivot order, only rounding does (parity bar 1e-11).
 #include <algorithm>
 
 #include "common.cuh"
@@ -61,36 +64,62 @@ struct Cfg {
   static_assert(NI % 2 == 0 && NB % 2 == 0, "16-byte cp.async needs even block heights");
   static constexpr int WT_DOUBLES = NCP * LDW;
   static constexpr int BT_DOUBLES = NCP * LDB;
-  static size_t smem_bytes(int nf) {   // arrays + Dinv + rinv + control block + re-layout tables
-    return (size_t)(WT_DOUBLES + BT_DOUBLES + NP * 64 + 8) * 8 + 512 + (size_t)(N + 1) * nf * 4 + N + 64;
+  static size_t smem_bytes(int nf) {   // arrays + 2 panel control blocks + info + re-layout tables
+    return (size_t)(WT_DOUBLES + BT_DOUBLES) * 8 + 2 * 1232 + 16 + (size_t)(N + 1) * nf * 4 + N + 16;
   }
 };
 
-struct Shared {   // sizeof <= 512
-  // small control block placed after the big arrays
-  int info;
-  int ndisp;             // displaced rows of the current panel
+// per-panel control block written by the panel warp (double buffered by panel parity)
+struct PanelCtl {
+  int ndisp;             // rows displaced out of the diagonal block
   int psrc[8];           // physical row (before this panel's permutation) of the k-th pivot row
   int dsrc[8];           // displaced rows: old position (inside the diagonal block) ...
   int ddst[8];           // ... and the vacated position they move to
-  int vac[40];           // scratch: vacated positions by rank
+  int vac[8];            // scratch: vacated positions by rank
+  int pad[3];
+  double rinv[8];        // reciprocals of the pivots
+  double Linv[64];       // inverse of the unit-lower diagonal block, A operand: Linv[i + 8*k]
+  double Dinv[64];       // inverse of the upper diagonal block (npiv x npiv, zero padded), B operand: Dinv[k + 8*n]
 };
+
+static_assert(sizeof(PanelCtl) == 1232, "smem_bytes() assumes this");
+// named barriers: ids are immediates (a register id makes ptxas reserve all 16 and caps occupancy)
+enum { BAR_PANEL = 1, BAR_COL = 3, BAR_UDONE = 5, BAR_UW = 7 };   // + panel parity
+template <int ID, int COUNT>
+__device__ __forceinline__ void bar_sync_i() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
+template <int ID, int COUNT>
+__device__ __forceinline__ void bar_arrive_i() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
+template <int ID, int COUNT>
+__device__ __forceinline__ void bar_sync(int parity) { if (parity) bar_sync_i<ID + 1, COUNT>(); else bar_sync_i<ID, COUNT>(); }
+template <int ID, int COUNT>
+__device__ __forceinline__ void bar_arrive(int parity) { if (parity) bar_arrive_i<ID + 1, COUNT>(); else bar_arrive_i<ID, COUNT>(); }
+
+// fast reciprocal: MUFU.RCP64H seed + two Newton steps (branch free; ~1 ulp)
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
 
 // ---- panel factorisation: one warp, one row per lane, implicit pivoting --------------------------
 // Factorises columns [c0, c0+npiv) of Wt over rows [c0, NI) and carries the other columns of the 8-wide
 // column tile through the eliminations.  Rows are not exchanged while factorising: a lane keeps its row
 // and remembers at which step it was chosen.  On write-back the k-th pivot row goes to position c0+k and
 // the rows it displaces from the diagonal block go to the vacated positions (any consistent row order is
-// a valid row-permuted LU; S does not depend on it).  Publishes that permutation for the trailing columns.
+// a valid row-permuted LU; S does not depend on it).  Publishes that permutation, inv(L_pp) and inv(U_pp).
 template <int NI, int LDW, bool TWO>
-__device__ __forceinline__ void panel_factor(double* __restrict__ Wt, const int c0, const int npiv, Shared* sh,
-                                             double* __restrict__ rinv_out) {
+__device__ __forceinline__ void panel_factor(double* __restrict__ Wt, const int c0, const int npiv, PanelCtl* ctl,
+                                             int* __restrict__ info) {
   const int lane = threadIdx.x & 31;
   const int nrows = NI - c0;
   const bool v1 = lane < nrows;
   const bool v2 = TWO && (lane + 32 < nrows);
   double a[8], a2[8];
   int ch1 = -1, ch2 = -1;                       // step at which this lane's row became the pivot row
+  double myrinv = 0.0;                          // lane k keeps 1/pivot of step k
   double* base = Wt + c0 + lane + LDW * c0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -100,97 +129,135 @@ __device__ __forceinline__ void panel_factor(double* __restrict__ Wt, const int 
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     if (k < npiv) {
-      // ---- pivot search: max |a[k]| over the rows not chosen yet (lowest lane wins ties)
+      // ---- pivot search: one REDUX.MAX over key = |a| (exponent + 15 mantissa bits) << 6 | (63 - row)
       const bool c1 = v1 && ch1 < 0;
       const bool c2 = v2 && ch2 < 0;
-      const unsigned long long key1 = c1 ? ((unsigned long long)__double_as_longlong(a[k]) & 0x7fffffffffffffffull) : 0ull;
-      const unsigned long long key2 = c2 ? ((unsigned long long)__double_as_longlong(a2[k]) & 0x7fffffffffffffffull) : 0ull;
-      const double rc1 = __drcp_rn(a[k]);       // speculative reciprocal, overlaps the reduction
-      const double rc2 = TWO ? __drcp_rn(a2[k]) : 0.0;
-      const unsigned long long km = TWO ? (key1 > key2 ? key1 : key2) : key1;
-      const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)(km >> 32));
-      const unsigned lo = __reduce_max_sync(0xffffffffu, (unsigned)(km >> 32) == hi ? (unsigned)km : 0u);
-      const unsigned long long kmax = ((unsigned long long)hi << 32) | lo;
-      if (kmax == 0ull) {                       // exact zero pivot column: LAPACK info = k+1 (uniform branch)
-        if (lane == 0 && sh->info == 0) sh->info = c0 + k + 1;
-        break;
+      const unsigned h1 = (unsigned)(__double_as_longlong(a[k]) >> 32) & 0x7fffffffu;
+      const unsigned h2 = (unsigned)(__double_as_longlong(a2[k]) >> 32) & 0x7fffffffu;
+      unsigned key = c1 ? (((h1 >> 5) << 6) | (unsigned)(63 - lane)) : 0u;
+      if (TWO) {
+        const unsigned key2 = c2 ? (((h2 >> 5) << 6) | (unsigned)(31 - lane)) : 0u;
+        key = key > key2 ? key : key2;
       }
-      const unsigned b1 = __ballot_sync(0xffffffffu, c1 && key1 == kmax);
-      const unsigned b2 = TWO ? __ballot_sync(0xffffffffu, c2 && key2 == kmax) : 0u;
-      const bool from2 = TWO && (b1 == 0u);
-      const int q = from2 ? (__ffs(b2) - 1) : (__ffs(b1) - 1);
+      const double rc1 = fast_rcp(a[k]);        // speculative reciprocal, overlaps the reduction
+      const double rc2 = TWO ? fast_rcp(a2[k]) : 0.0;
+      unsigned kmax = __reduce_max_sync(0xffffffffu, key);
+      if ((kmax >> 6) == 0u) {
+        // all candidates below 2^-1017: decide exactly (zero column => LAPACK info = k+1)
+        const unsigned long long e1 = c1 ? ((unsigned long long)__double_as_longlong(a[k]) & 0x7fffffffffffffffull) : 0ull;
+        const unsigned long long e2 = c2 ? ((unsigned long long)__double_as_longlong(a2[k]) & 0x7fffffffffffffffull) : 0ull;
+        const unsigned lo1 = __reduce_max_sync(0xffffffffu, (unsigned)(e1 >> 32) | (unsigned)(e2 >> 32));
+        const unsigned lo2 = __reduce_max_sync(0xffffffffu, (unsigned)e1 | (unsigned)e2);
+        if ((lo1 | lo2) == 0u) {
+          if (lane == 0 && *info == 0) *info = c0 + k + 1;
+        }
+        // keep going with the first candidate row (results of a failed cell are overwritten with NaN)
+        const unsigned bb1 = __ballot_sync(0xffffffffu, c1);
+        const unsigned bb2 = __ballot_sync(0xffffffffu, c2);
+        const int row = bb1 ? (__ffs(bb1) - 1) : (32 + __ffs(bb2) - 1);
+        kmax = (unsigned)(63 - row);
+      }
+      const int prow = 63 - (int)(kmax & 63u);  // row of the pivot inside the panel (0..63)
+      const bool from2 = TWO && prow >= 32;
+      const int q = prow & 31;
       const double rinv = __shfl_sync(0xffffffffu, from2 ? rc2 : rc1, q);
-      if (lane == 0) rinv_out[k] = rinv;
+      if (lane == k) myrinv = rinv;
       const bool me1 = !from2 && lane == q, me2 = from2 && lane == q;
       if (me1) ch1 = k;
       if (me2) ch2 = k;
       // ---- multipliers and rank-1 update of the rows still in play
       const bool u1 = c1 && !me1, u2 = TWO && c2 && !me2;
       const double l1 = a[k] * rinv, l2 = a2[k] * rinv;   // dgetf2: scale by the reciprocal
-      if (u1) a[k] = l1;
-      if (u2) a2[k] = l2;
+      a[k] = u1 ? l1 : a[k];
+      const double nl1 = u1 ? -l1 : 0.0;                  // rows out of play: a + 0*p = a
+      double nl2 = 0.0;
+      if (TWO) { a2[k] = u2 ? l2 : a2[k]; nl2 = u2 ? -l2 : 0.0; }
 #pragma unroll
       for (int j = k + 1; j < 8; ++j) {
         const double pj = __shfl_sync(0xffffffffu, from2 ? a2[j] : a[j], q);   // pivot row entry, to everyone
-        if (u1) a[j] = fma(-l1, pj, a[j]);
-        if (u2) a2[j] = fma(-l2, pj, a2[j]);
+        a[j] = fma(nl1, pj, a[j]);
+        if (TWO) a2[j] = fma(nl2, pj, a2[j]);
       }
     }
   }
   // ---- new positions: pivot rows first, displaced rows into the vacated slots
-  const bool disp = v1 && lane < 8 && ch1 < 0 && lane < npiv + 0 * nrows;   // rows of the diagonal block not chosen
+  const bool disp = v1 && lane < npiv && ch1 < 0;          // rows of the diagonal block not chosen
   const bool vc1 = v1 && lane >= npiv && ch1 >= 0;
   const bool vc2 = v2 && ch2 >= 0;
   const unsigned mdisp = __ballot_sync(0xffffffffu, disp);
   const unsigned mv1 = __ballot_sync(0xffffffffu, vc1);
-  const unsigned mv2 = __ballot_sync(0xffffffffu, vc2);
+  const unsigned mv2 = TWO ? __ballot_sync(0xffffffffu, vc2) : 0u;
   const unsigned lt = (1u << lane) - 1u;
-  if (vc1) sh->vac[__popc(mv1 & lt)] = c0 + lane;
-  if (vc2) sh->vac[__popc(mv1) + __popc(mv2 & lt)] = c0 + 32 + lane;
+  if (vc1) ctl->vac[__popc(mv1 & lt)] = c0 + lane;
+  if (vc2) ctl->vac[__popc(mv1) + __popc(mv2 & lt)] = c0 + 32 + lane;
   __syncwarp();
   int np1 = c0 + lane, np2 = c0 + 32 + lane;
   if (ch1 >= 0) np1 = c0 + ch1;
-  else if (disp) np1 = sh->vac[__popc(mdisp & lt)];
+  else if (disp) np1 = ctl->vac[__popc(mdisp & lt)];
   if (ch2 >= 0) np2 = c0 + ch2;
-  if (ch1 >= 0) sh->psrc[ch1] = c0 + lane;
-  if (ch2 >= 0) sh->psrc[ch2] = c0 + 32 + lane;
+  if (ch1 >= 0) ctl->psrc[ch1] = c0 + lane;
+  if (ch2 >= 0) ctl->psrc[ch2] = c0 + 32 + lane;
   if (disp) {
     const int t = __popc(mdisp & lt);
-    sh->dsrc[t] = c0 + lane;
-    sh->ddst[t] = np1;
+    ctl->dsrc[t] = c0 + lane;
+    ctl->ddst[t] = np1;
   }
-  if (lane == 0) sh->ndisp = __popc(mdisp);
+  if (lane == 0) ctl->ndisp = __popc(mdisp);
   double* wb = Wt + LDW * c0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     if (v1) wb[np1 + LDW * j] = a[j];
     if (v2) wb[np2 + LDW * j] = a2[j];
   }
+  if (lane < 8) ctl->rinv[lane] = myrinv;
 }
 
-// inverse of the npiv x npiv upper-triangular diagonal block, stored as the 8x8 B-operand
-// Dinv[k + 8*n] (column-major), zero outside the npiv block.  Lane n < 8 computes column n.
+// ---- inverses of the 8x8 diagonal block of a factorised panel, by the (otherwise idle) update warps:
+// lanes 0-7 each own one column and run the same branch-free substitution; entries of L\U are uniform
+// (broadcast) shared-memory loads.  Rows/columns >= npiv are treated as identity (L) / zero (U^-1).
 template <int LDW>
-__device__ __forceinline__ void invert_upper(const double* __restrict__ Wt, const int c0, const int npiv,
-                                             const double* __restrict__ rinv, double* __restrict__ Dinv) {
-  const int n = threadIdx.x & 31;
-  if (n >= 8) return;
+__device__ __forceinline__ void invert_unit_lower(const double* __restrict__ D, const int npiv, double* __restrict__ Linv) {
+  const int n = threadIdx.x & 31;              // column (only lanes 0-7 store)
   double x[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) x[i] = 0.0;
-  const double* U = Wt + c0 + LDW * c0;
+  for (int i = 0; i < 8; ++i) x[i] = (i == n) ? 1.0 : 0.0;
 #pragma unroll
-  for (int i = 7; i >= 0; --i) {
-    if (i < npiv && i <= n && n < npiv) {
-      double s = (i == n) ? 1.0 : 0.0;
+  for (int i = 1; i < 8; ++i) {
+    double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-      for (int m = i + 1; m < 8; ++m)
-        if (m <= n) s = fma(-U[i + LDW * m], x[m], s);
-      x[i] = s * rinv[i];
+    for (int m = 0; m < i; ++m) {
+      const double lim = i < npiv ? D[i + LDW * m] : 0.0;
+      if (m & 1) s1 = fma(-lim, x[m], s1); else s0 = fma(-lim, x[m], s0);
     }
+    x[i] = (i > n) ? (s0 + s1) : x[i];
   }
+  if (n < 8) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) Dinv[i + 8 * n] = x[i];
+    for (int i = 0; i < 8; ++i) Linv[i + 8 * n] = x[i];
+  }
+}
+
+template <int LDW>
+__device__ __forceinline__ void invert_upper(const double* __restrict__ D, const int npiv, const double* __restrict__ rinv,
+                                             double* __restrict__ Dinv) {
+  const int n = threadIdx.x & 31;              // column (only lanes 0-7 store)
+  double x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = (i == n && n < npiv) ? rinv[i] : 0.0;
+#pragma unroll
+  for (int i = 6; i >= 0; --i) {
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int m = i + 1; m < 8; ++m) {
+      const double uim = m < npiv ? D[i + LDW * m] : 0.0;
+      if (m & 1) s1 = fma(uim, x[m], s1); else s0 = fma(uim, x[m], s0);
+    }
+    x[i] = (i < n && n < npiv) ? -(s0 + s1) * rinv[i] : x[i];
+  }
+  if (n < 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) Dinv[i + 8 * n] = x[i];
+  }
 }
 
 template <int NI, int NB>
@@ -200,18 +267,18 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
                      int32_t* __restrict__ info) {
   using C = Cfg<NI, NB>;
   constexpr int N = C::N, NC = C::NC, LDW = C::LDW, LDB = C::LDB, RT = C::RT, BT = C::BT, CT = C::CT, NP = C::NP;
-  constexpr int NF = 8;                          // max fields handled by the smem tables
+  constexpr int SJ0 = NI / 8;                   // first column tile holding S columns
+  constexpr int NSJ = CT - SJ0;                 // S column tiles
+  constexpr int MAXROWS = (BT + 2) / 3;         // bottom row tiles per update warp
   extern __shared__ __align__(16) double smem[];
   double* Wt = smem;
   double* Bt = Wt + C::WT_DOUBLES;
-  double* Dinv = Bt + C::BT_DOUBLES;            // [NP][64]
-  double* rinv = Dinv + NP * 64;                // [8]
-  Shared* sh = reinterpret_cast<Shared*>(rinv + 8);
-  int* s_colbase = reinterpret_cast<int*>(sh + 1);           // [(N+1)*nf]
-  unsigned short* s_rowinfo = reinterpret_cast<unsigned short*>(s_colbase + (N + 1) * tb.nf);  // [N/2]: f<<8 | local row
+  PanelCtl* ctl2 = reinterpret_cast<PanelCtl*>(Bt + C::BT_DOUBLES);   // [2]
+  int* s_info = reinterpret_cast<int*>(ctl2 + 2);
+  int* s_colbase = s_info + 4;                                         // [(N+1)*nf]
+  unsigned short* s_rowinfo = reinterpret_cast<unsigned short*>(s_colbase + (N + 1) * tb.nf);  // [N/2]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gid = lane >> 2, tig = lane & 3;    // fragment coordinates
-  (void)NF;
 
   // padding never written by the loader: zero it once (rows NI.. of Wt, rows NB.. of Bt, column NC)
   for (int i = tid; i < C::WT_DOUBLES; i += 128) Wt[i] = 0.0;
@@ -220,177 +287,207 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
   for (int i = tid; i < N / 2; i += 128) s_rowinfo[i] = (unsigned short)((tb.rowf[2 * i] << 8) | tb.rowl[2 * i]);
   __syncthreads();
 
+  // loader: a thread owns one row pair and walks the columns
+  constexpr int HP = N / 2;                     // row pairs per column
+  constexpr int LG = 128 / HP;                  // column groups
+  const int l_grp = tid / HP, l_rp = tid - l_grp * HP;
+  const bool l_on = l_grp < LG;
+  const int l_ri = l_on ? s_rowinfo[l_rp] : 0;
+  const int l_f = l_ri >> 8, l_lr = l_ri & 0xff;
+  double* const l_dst0 = (2 * l_rp < NI) ? Wt + 2 * l_rp : Bt + (2 * l_rp - NI);
+
   for (int64_t cell = blockIdx.x; cell < ncells; cell += gridDim.x) {
     // ------------------------------------------------------------------ load + re-layout
-    {
-      const double* Arec = A + cell * lenA;
-      const double* brec = b + cell * lenb;
-      constexpr int HP = N / 2;  // row pairs per column
-      // idx = tid + 128*m  ->  (c, rp) advanced incrementally (no division)
-      int c = tid / HP, rp = tid - c * HP;
-      constexpr int DC = 128 / HP, DR = 128 - DC * HP;
-      for (; c < NC;) {
-        const int ri = s_rowinfo[rp];
-        const int off = s_colbase[c * tb.nf + (ri >> 8)];
-        const int r = 2 * rp;
-        double* dst = r < NI ? Wt + r + LDW * c : Bt + (r - NI) + LDB * c;
-        if (off >= 0) {
-          cp_async16(dst, (c < N ? Arec : brec) + off + (ri & 0xff));
-        } else {
-          dst[0] = 0.0; dst[1] = 0.0;
-        }
-        c += DC; rp += DR;
-        if (rp >= HP) { rp -= HP; ++c; }
+    if (l_on) {
+      const double* Arec = A + cell * lenA + l_lr;
+      const double* brec = b + cell * lenb + l_lr;
+      for (int c = l_grp; c < NC; c += LG) {
+        const int off = s_colbase[c * tb.nf + l_f];
+        double* dst = l_dst0 + LDW * c;
+        if (off >= 0) cp_async16(dst, (c < N ? Arec : brec) + off);
+        else { dst[0] = 0.0; dst[1] = 0.0; }
       }
-      if (tid == 0) sh->info = 0;
-      cp_async_commit_wait_all();
-      __syncthreads();
     }
+    if (tid == 0) *s_info = 0;
+    cp_async_commit_wait_all();
+    __syncthreads();
 
-    // ------------------------------------------------------------------ phase 1: blocked LU of Wt
-    bool ok = true;
+    if (warp == 0) {
+      // ================================================================ panel warp
 #pragma unroll 1
-    for (int p = 0; p < NP; ++p) {
-      const int c0 = 8 * p;
-      const int npiv = (NI - c0) < 8 ? (NI - c0) : 8;
-      if (warp == 0) {
-        if ((NI - c0) > 32) panel_factor<NI, LDW, true>(Wt, c0, npiv, sh, rinv);
-        else panel_factor<NI, LDW, false>(Wt, c0, npiv, sh, rinv);
-      }
-      __syncthreads();
-      if (sh->info != 0) { ok = false; break; }
-      // ---- warp 3 inverts the diagonal block; warps 0-2: one trailing column per thread: gather the pivot
-      //      rows, move the displaced rows, unit-lower solve
-      if (warp == 3) {
-        invert_upper<LDW>(Wt, c0, npiv, rinv, Dinv + p * 64);
-      } else {
-        const int c = c0 + 8 + tid;             // trailing column of this thread
-        if (c < NC) {
-          double* col = Wt + LDW * c;
-          double u[8], dv[8];
-          const int nd = sh->ndisp;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) u[k] = k < npiv ? col[sh->psrc[k]] : 0.0;
-#pragma unroll
-          for (int t = 0; t < 8; ++t) dv[t] = t < nd ? col[sh->dsrc[t]] : 0.0;
-          const double* Lp = Wt + c0 + LDW * c0;
-#pragma unroll
-          for (int j = 0; j < 7; ++j) {
-#pragma unroll
-            for (int i = j + 1; i < 8; ++i)
-              if (i < npiv) u[i] = fma(-Lp[i + LDW * j], u[j], u[i]);
-          }
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            if (k < npiv) col[c0 + k] = u[k];
-#pragma unroll
-          for (int t = 0; t < 8; ++t)
-            if (t < nd) col[sh->ddst[t]] = dv[t];
-        }
-      }
-      __syncthreads();
-      // ---- trailing update of the top block: C[I][J] -= L[I][p] * U[p][J],  I > p, J > p
-      if (p + 1 < RT) {
-        for (int J = p + 1 + warp; J < CT; J += 4) {
-          const double bf0 = neg(Wt[c0 + tig + LDW * (8 * J + gid)]);
-          const double bf1 = neg(Wt[c0 + 4 + tig + LDW * (8 * J + gid)]);
-          for (int I = p + 1; I < RT; ++I) {
-            const int r = 8 * I + gid;
-            const bool rv = r < NI;
-            const double a0 = rv ? Wt[r + LDW * (c0 + tig)] : 0.0;
-            const double a1 = rv ? Wt[r + LDW * (c0 + 4 + tig)] : 0.0;
-            double* cp0 = Wt + r + LDW * (8 * J + 2 * tig);
-            double d0 = rv ? cp0[0] : 0.0, d1 = rv ? cp0[LDW] : 0.0;
-            dmma(d0, d1, a0, bf0);
-            dmma(d0, d1, a1, bf1);
-            if (rv) { cp0[0] = d0; cp0[LDW] = d1; }
-          }
-        }
-        __syncthreads();
-      }
-    }
-
-    // ------------------------------------------------------------------ phase 2: bottom block
-    double* Sc = S + cell * (int64_t)NB * NB;
-    double* gc = g + cell * (int64_t)NB;
-    if (ok) {
-      for (int I = warp; I < BT; I += 4) {
-        const int r = 8 * I + gid;               // row inside Bt
-        const bool rv = r < NB;
-        double la[2 * NP];                        // A fragments of L21[I][K], K < NP (two k-steps each)
-#pragma unroll
-        for (int J = 0; J < CT; ++J) {
-          double* cp0 = Bt + r + LDB * (8 * J + 2 * tig);
-          double x0 = rv ? cp0[0] : 0.0, x1 = rv ? cp0[LDB] : 0.0;
-#pragma unroll
-          for (int K = 0; K < NP; ++K) {
-            if (K < J) {
-              dmma(x0, x1, la[2 * K], neg(Wt[8 * K + tig + LDW * (8 * J + gid)]));
-              if (8 * K + 4 < NI) dmma(x0, x1, la[2 * K + 1], neg(Wt[8 * K + 4 + tig + LDW * (8 * J + gid)]));
-            }
-          }
-          if (J < NP) {
-            // L = X * Dinv_J  (C fragment -> A fragment through shared memory: the tile is private to the warp)
-            const int npv = (NI - 8 * J) < 8 ? (NI - 8 * J) : 8;
-            if (rv) { cp0[0] = x0; cp0[LDB] = x1; }
-            __syncwarp();
-            double xa0 = rv ? Bt[r + LDB * (8 * J + tig)] : 0.0;
-            double xa1 = rv ? Bt[r + LDB * (8 * J + 4 + tig)] : 0.0;
-            double l0 = 0.0, l1 = 0.0;
-            const double* Dj = Dinv + J * 64;
-            dmma(l0, l1, xa0, Dj[tig + 8 * gid]);
-            if (npv > 4) dmma(l0, l1, xa1, Dj[4 + tig + 8 * gid]);
-            if (npv < 8) {
-              // partial panel: columns >= npv of this tile are trailing columns: X -= L * U_pp[:, npv..]
-              // (L is zero outside its first npv columns because Dinv is)
-              __syncwarp();
-              if (rv) { cp0[0] = l0; cp0[LDB] = l1; }   // park L to read it back as an A fragment
-              __syncwarp();
-              double lt0 = rv ? Bt[r + LDB * (8 * J + tig)] : 0.0;
-              // B operand: rows < npv of the U tile, zero for columns < npv (those hold L\U of the panel)
-              const int kk = tig, nn = gid;
-              double ub = (kk < npv && nn >= npv) ? neg(Wt[8 * J + kk + LDW * (8 * J + nn)]) : 0.0;
-              dmma(x0, x1, lt0, ub);
-              la[2 * J] = lt0;
-              la[2 * J + 1] = 0.0;
-              // final S values of this tile's trailing columns
-              __syncwarp();
-              if (rv) {
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                  const int c = 8 * J + 2 * tig + e;
-                  const double v = e ? x1 : x0;
-                  if (c >= NI) {
-                    if (c < N) Sc[r + (int64_t)NB * (c - NI)] = v;
-                    else if (c == N) gc[r] = v;
-                  }
-                }
-              }
-            } else {
-              __syncwarp();
-              if (rv) { cp0[0] = l0; cp0[LDB] = l1; }
-              __syncwarp();
-              la[2 * J] = rv ? Bt[r + LDB * (8 * J + tig)] : 0.0;
-              la[2 * J + 1] = rv ? Bt[r + LDB * (8 * J + 4 + tig)] : 0.0;
-            }
-          } else if (rv) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int c = 8 * J + 2 * tig + e;
-              const double v = e ? x1 : x0;
-              if (c < N) Sc[r + (int64_t)NB * (c - NI)] = v;
-              else if (c == N) gc[r] = v;
-            }
-          }
-        }
+      for (int p = 0; p < NP; ++p) {
+        const int c0 = 8 * p;
+        const int npiv = (NI - c0) < 8 ? (NI - c0) : 8;
+        if (p > 0) bar_sync<BAR_COL, 64>(p & 1);             // column tile p is up to date
+        PanelCtl* ctl = ctl2 + (p & 1);
+        if ((NI - c0) > 32) panel_factor<NI, LDW, true>(Wt, c0, npiv, ctl, s_info);
+        else panel_factor<NI, LDW, false>(Wt, c0, npiv, ctl, s_info);
+        bar_arrive<BAR_PANEL, 128>(p & 1);
       }
     } else {
+      // ================================================================ update warps
+      const int uw = warp - 1;                    // 0..2
+      // S accumulators of the owned bottom row tiles (column tiles SJ0..CT-1), C fragments
+      double acc[MAXROWS][NSJ][2];
+#pragma unroll
+      for (int ri = 0; ri < MAXROWS; ++ri) {
+        const int I = uw * MAXROWS + ri;
+        const int r = 8 * I + gid;
+        const bool rv = I < BT && r < NB;
+#pragma unroll
+        for (int js = 0; js < NSJ; ++js) {
+          const double* cp0 = Bt + r + LDB * (8 * (SJ0 + js) + 2 * tig);
+          acc[ri][js][0] = rv ? cp0[0] : 0.0;
+          acc[ri][js][1] = rv ? cp0[LDB] : 0.0;
+        }
+      }
+#pragma unroll 1
+      for (int p = 0; p < NP; ++p) {
+        const int c0 = 8 * p;
+        const int npiv = (NI - c0) < 8 ? (NI - c0) : 8;
+        PanelCtl* ctl = ctl2 + (p & 1);
+        bar_sync<BAR_PANEL, 128>(p & 1);
+        // ---- the owner of the next panel's column tile inverts L_pp (critical path), its neighbour U_pp
+        {
+          const int own = (p + 1) % 3;
+          const double* D = Wt + c0 + LDW * c0;
+          if (uw == own) invert_unit_lower<LDW>(D, npiv, ctl->Linv);
+          else if (uw == (own + 1) % 3) invert_upper<LDW>(D, npiv, ctl->rinv, ctl->Dinv);
+        }
+        bar_sync<BAR_UW, 96>(p & 1);
+        // ---- owned column tiles J > p (J = uw mod 3); the next panel's tile first
+        const int nd = ctl->ndisp;
+        const int ps0 = tig < npiv ? ctl->psrc[tig] : -1;
+        const int ps1 = 4 + tig < npiv ? ctl->psrc[4 + tig] : -1;
+        const int dsr = gid < nd ? ctl->dsrc[gid] : -1;
+        const int dds = gid < nd ? ctl->ddst[gid] : -1;
+        const double li0 = ctl->Linv[gid + 8 * tig], li1 = ctl->Linv[gid + 8 * (4 + tig)];
+        int Jfirst = p + 1;
+        while (Jfirst % 3 != uw) ++Jfirst;        // first owned tile > p
+#pragma unroll 1
+        for (int J = Jfirst; J < CT; J += 3) {
+          double* colg = Wt + LDW * (8 * J + gid);     // B-fragment column of this lane
+          double* colt = Wt + LDW * (8 * J + tig);     // displaced rows: lane (t=gid) moves columns tig, tig+4
+          const double g0 = ps0 >= 0 ? colg[ps0] : 0.0;
+          const double g1 = ps1 >= 0 ? colg[ps1] : 0.0;
+          const double dv0 = dsr >= 0 ? colt[dsr] : 0.0;
+          const double dv1 = dsr >= 0 ? colt[dsr + 4 * LDW] : 0.0;
+          __syncwarp();
+          double u0 = 0.0, u1 = 0.0;              // U12 tile = inv(L_pp) * gathered rows
+          dmma(u0, u1, li0, g0);
+          dmma(u0, u1, li1, g1);
+          double* cu = Wt + c0 + gid + LDW * (8 * J + 2 * tig);
+          if (c0 + gid < NI) { cu[0] = u0; cu[LDW] = u1; }
+          if (dds >= 0) { colt[dds] = dv0; colt[dds + 4 * LDW] = dv1; }
+          __syncwarp();
+          if (p + 1 < RT) {
+            const double bf0 = neg(colg[c0 + tig]);
+            const double bf1 = neg(colg[c0 + 4 + tig]);
+#pragma unroll 1
+            for (int I = p + 1; I < RT; ++I) {
+              const int r = 8 * I + gid;
+              const bool rv = r < NI;
+              const double a0 = rv ? Wt[r + LDW * (c0 + tig)] : 0.0;
+              const double a1 = rv ? Wt[r + LDW * (c0 + 4 + tig)] : 0.0;
+              double* cp0 = Wt + r + LDW * (8 * J + 2 * tig);
+              double d0 = rv ? cp0[0] : 0.0, d1 = rv ? cp0[LDW] : 0.0;
+              dmma(d0, d1, a0, bf0);
+              dmma(d0, d1, a1, bf1);
+              if (rv) { cp0[0] = d0; cp0[LDW] = d1; }
+            }
+          }
+          if (J == p + 1 && p + 1 < NP) bar_arrive<BAR_COL, 64>((p + 1) & 1);
+        }
+        // ---- bottom block, owned row tiles: needs every U[p][J] and Dinv_p
+        bar_sync<BAR_UDONE, 96>(p & 1);
+        const double dj0 = ctl->Dinv[tig + 8 * gid], dj1 = ctl->Dinv[4 + tig + 8 * gid];
+#pragma unroll
+        for (int ri = 0; ri < MAXROWS; ++ri) {
+          const int I = uw * MAXROWS + ri;
+          if (I < BT) {
+            const int r = 8 * I + gid;
+            const bool rv = r < NB;
+            double* bp = Bt + r + LDB * (8 * p + 2 * tig);
+            if (npiv == 8) {
+              // L = X * Dinv with X = Bt tile (I,p) (already updated right-looking): A fragments straight from smem
+              const double xa0 = rv ? Bt[r + LDB * (8 * p + tig)] : 0.0;
+              const double xa1 = rv ? Bt[r + LDB * (8 * p + 4 + tig)] : 0.0;
+              double l0 = 0.0, l1 = 0.0;
+              dmma(l0, l1, xa0, dj0);
+              dmma(l0, l1, xa1, dj1);
+              __syncwarp();
+              if (rv) { bp[0] = l0; bp[LDB] = l1; }     // park L to read it back as A fragments
+              __syncwarp();
+              const double la0 = rv ? Bt[r + LDB * (8 * p + tig)] : 0.0;
+              const double la1 = rv ? Bt[r + LDB * (8 * p + 4 + tig)] : 0.0;
+              // A21 part still in shared memory: tiles p < J < SJ0
+#pragma unroll 1
+              for (int J = p + 1; J < SJ0; ++J) {
+                double* cp0 = Bt + r + LDB * (8 * J + 2 * tig);
+                double d0 = rv ? cp0[0] : 0.0, d1 = rv ? cp0[LDB] : 0.0;
+                dmma(d0, d1, la0, neg(Wt[c0 + tig + LDW * (8 * J + gid)]));
+                dmma(d0, d1, la1, neg(Wt[c0 + 4 + tig + LDW * (8 * J + gid)]));
+                if (rv) { cp0[0] = d0; cp0[LDB] = d1; }
+              }
+              // S part in registers
+#pragma unroll
+              for (int js = 0; js < NSJ; ++js) {
+                const int J = SJ0 + js;
+                dmma(acc[ri][js][0], acc[ri][js][1], la0, neg(Wt[c0 + tig + LDW * (8 * J + gid)]));
+                dmma(acc[ri][js][0], acc[ri][js][1], la1, neg(Wt[c0 + 4 + tig + LDW * (8 * J + gid)]));
+              }
+            } else {
+              // partial last panel (npiv < 8): its column tile is the first S tile, held in registers.
+              // X (C fragment) -> A fragment through the (dead) Bt tile; L = X * Dinv (zero outside npiv cols)
+              __syncwarp();
+              if (rv) { bp[0] = acc[ri][0][0]; bp[LDB] = acc[ri][0][1]; }
+              __syncwarp();
+              const double xa0 = rv ? Bt[r + LDB * (8 * p + tig)] : 0.0;
+              double l0 = 0.0, l1 = 0.0;
+              dmma(l0, l1, xa0, dj0);
+              __syncwarp();
+              if (rv) { bp[0] = l0; bp[LDB] = l1; }
+              __syncwarp();
+              const double lt0 = rv ? Bt[r + LDB * (8 * p + tig)] : 0.0;
+              // trailing columns of the panel's own tile: B = U_pp rows < npiv, columns >= npiv
+              const double ub = (tig < npiv && gid >= npiv) ? neg(Wt[c0 + tig + LDW * (c0 + gid)]) : 0.0;
+              dmma(acc[ri][0][0], acc[ri][0][1], lt0, ub);
+#pragma unroll
+              for (int js = 1; js < NSJ; ++js) {
+                const int J = SJ0 + js;
+                dmma(acc[ri][js][0], acc[ri][js][1], lt0, neg(Wt[c0 + tig + LDW * (8 * J + gid)]));
+              }
+            }
+          }
+        }
+      }
+      // ---- store S, g
+      const bool failed = *s_info != 0;
       const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-      for (int i = tid; i < NB * NB; i += 128) Sc[i] = qnan;
-      for (int i = tid; i < NB; i += 128) gc[i] = qnan;
+      double* Sc = S + cell * (int64_t)NB * NB;
+      double* gc = g + cell * (int64_t)NB;
+#pragma unroll
+      for (int ri = 0; ri < MAXROWS; ++ri) {
+        const int I = uw * MAXROWS + ri;
+        const int r = 8 * I + gid;
+        if (I < BT && r < NB) {
+#pragma unroll
+          for (int js = 0; js < NSJ; ++js) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int c = 8 * (SJ0 + js) + 2 * tig + e;
+              const double v = failed ? qnan : acc[ri][js][e];
+              if (c >= NI) {
+                if (c < N) Sc[r + (int64_t)NB * (c - NI)] = v;
+                else if (c == N) gc[r] = v;
+              }
+            }
+          }
+        }
+      }
     }
-    if (info && tid == 0) info[cell] = sh->info;
     __syncthreads();
+    if (info && tid == 0) info[cell] = *s_info;
   }
 }
 
