@@ -41,6 +41,11 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
 
 __device__ __forceinline__ double neg(double x) { return -x; }
 
+// Shared-memory column permutation inside every 8-column tile (logical columns 4<->5 and 6<->7 swapped):
+// with a leading dimension of 36 doubles it makes the A, B *and* C fragment access patterns of
+// mma.m8n8k4.f64 bank-conflict free at the same time (C fragments touch columns 2t, 2t+1; A/B touch t, t+4).
+__device__ __host__ __forceinline__ constexpr int pc(int c) { return c ^ ((c >> 2) & 1); }
+
 // tables of a plan for the on-the-fly re-layout (built on the host, tiny)
 struct DmmaTables {
   const int32_t* colbase;  // [(n+1)*nf]: record offset of (first row of field f, column c) or -1; c==n: offset in b
@@ -123,8 +128,8 @@ __device__ __forceinline__ void panel_factor(double* __restrict__ Wt, const int 
   double* base = Wt + c0 + lane + LDW * c0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    a[j] = v1 ? base[LDW * j] : 0.0;
-    a2[j] = v2 ? base[32 + LDW * j] : 0.0;
+    a[j] = v1 ? base[LDW * pc(j)] : 0.0;
+    a2[j] = v2 ? base[32 + LDW * pc(j)] : 0.0;
   }
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -206,8 +211,8 @@ __device__ __forceinline__ void panel_factor(double* __restrict__ Wt, const int 
   double* wb = Wt + LDW * c0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    if (v1) wb[np1 + LDW * j] = a[j];
-    if (v2) wb[np2 + LDW * j] = a2[j];
+    if (v1) wb[np1 + LDW * pc(j)] = a[j];
+    if (v2) wb[np2 + LDW * pc(j)] = a2[j];
   }
   if (lane < 8) ctl->rinv[lane] = myrinv;
 }
@@ -226,7 +231,7 @@ __device__ __forceinline__ void invert_unit_lower(const double* __restrict__ D, 
     double s0 = 0.0, s1 = 0.0;
 #pragma unroll
     for (int m = 0; m < i; ++m) {
-      const double lim = i < npiv ? D[i + LDW * m] : 0.0;
+      const double lim = i < npiv ? D[i + LDW * pc(m)] : 0.0;
       if (m & 1) s1 = fma(-lim, x[m], s1); else s0 = fma(-lim, x[m], s0);
     }
     x[i] = (i > n) ? (s0 + s1) : x[i];
@@ -249,7 +254,7 @@ __device__ __forceinline__ void invert_upper(const double* __restrict__ D, const
     double s0 = 0.0, s1 = 0.0;
 #pragma unroll
     for (int m = i + 1; m < 8; ++m) {
-      const double uim = m < npiv ? D[i + LDW * m] : 0.0;
+      const double uim = m < npiv ? D[i + LDW * pc(m)] : 0.0;
       if (m & 1) s1 = fma(uim, x[m], s1); else s0 = fma(uim, x[m], s0);
     }
     x[i] = (i < n && n < npiv) ? -(s0 + s1) * rinv[i] : x[i];
@@ -279,6 +284,10 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
   unsigned short* s_rowinfo = reinterpret_cast<unsigned short*>(s_colbase + (N + 1) * tb.nf);  // [N/2]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gid = lane >> 2, tig = lane & 3;    // fragment coordinates
+  // memory columns (inside a tile) of this lane's fragment elements, see pc()
+  const int ce0 = pc(2 * tig), ce1 = pc(2 * tig + 1);   // C fragment
+  const int ka0 = tig, ka1 = pc(4 + tig);               // A fragment (k-steps 0, 1)
+  const int nb = pc(gid);                               // B fragment column
 
   // padding never written by the loader: zero it once (rows NI.. of Wt, rows NB.. of Bt, column NC)
   for (int i = tid; i < C::WT_DOUBLES; i += 128) Wt[i] = 0.0;
@@ -287,7 +296,7 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
   for (int i = tid; i < N / 2; i += 128) s_rowinfo[i] = (unsigned short)((tb.rowf[2 * i] << 8) | tb.rowl[2 * i]);
   __syncthreads();
 
-  // loader: a thread owns one row pair and walks the columns
+  // loader: a thread owns one row pair (interior pairs -> Wt, boundary pairs -> Bt) and walks the columns
   constexpr int HP = N / 2;                     // row pairs per column
   constexpr int LG = 128 / HP;                  // column groups
   const int l_grp = tid / HP, l_rp = tid - l_grp * HP;
@@ -301,12 +310,15 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
     if (l_on) {
       const double* Arec = A + cell * lenA + l_lr;
       const double* brec = b + cell * lenb + l_lr;
-      for (int c = l_grp; c < NC; c += LG) {
-        const int off = s_colbase[c * tb.nf + l_f];
-        double* dst = l_dst0 + LDW * c;
-        if (off >= 0) cp_async16(dst, (c < N ? Arec : brec) + off);
+      const int* cb = s_colbase + l_f;
+#pragma unroll 4
+      for (int c = l_grp; c < N; c += LG) {
+        const int off = cb[c * tb.nf];
+        double* dst = l_dst0 + LDW * pc(c);
+        if (off >= 0) cp_async16(dst, Arec + off);
         else { dst[0] = 0.0; dst[1] = 0.0; }
       }
+      if (l_grp == N % LG) cp_async16(l_dst0 + LDW * pc(N), brec + cb[N * tb.nf]);   // rhs column
     }
     if (tid == 0) *s_info = 0;
     cp_async_commit_wait_all();
@@ -323,6 +335,9 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
         if ((NI - c0) > 32) panel_factor<NI, LDW, true>(Wt, c0, npiv, ctl, s_info);
         else panel_factor<NI, LDW, false>(Wt, c0, npiv, ctl, s_info);
         bar_arrive<BAR_PANEL, 128>(p & 1);
+        // inv(U_pp) for the bottom block, computed while the update warps prepare the next column tile
+        invert_upper<LDW>(Wt + c0 + LDW * c0, npiv, ctl->rinv, ctl->Dinv);
+        bar_arrive<BAR_UDONE, 128>(p & 1);
       }
     } else {
       // ================================================================ update warps
@@ -336,9 +351,9 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
         const bool rv = I < BT && r < NB;
 #pragma unroll
         for (int js = 0; js < NSJ; ++js) {
-          const double* cp0 = Bt + r + LDB * (8 * (SJ0 + js) + 2 * tig);
-          acc[ri][js][0] = rv ? cp0[0] : 0.0;
-          acc[ri][js][1] = rv ? cp0[LDB] : 0.0;
+          const double* cp0 = Bt + r + LDB * 8 * (SJ0 + js);
+          acc[ri][js][0] = rv ? cp0[LDB * ce0] : 0.0;
+          acc[ri][js][1] = rv ? cp0[LDB * ce1] : 0.0;
         }
       }
 #pragma unroll 1
@@ -347,13 +362,8 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
         const int npiv = (NI - c0) < 8 ? (NI - c0) : 8;
         PanelCtl* ctl = ctl2 + (p & 1);
         bar_sync<BAR_PANEL, 128>(p & 1);
-        // ---- the owner of the next panel's column tile inverts L_pp (critical path), its neighbour U_pp
-        {
-          const int own = (p + 1) % 3;
-          const double* D = Wt + c0 + LDW * c0;
-          if (uw == own) invert_unit_lower<LDW>(D, npiv, ctl->Linv);
-          else if (uw == (own + 1) % 3) invert_upper<LDW>(D, npiv, ctl->rinv, ctl->Dinv);
-        }
+        // ---- the owner of the next panel's column tile inverts L_pp (on the critical path)
+        if (uw == (p + 1) % 3) invert_unit_lower<LDW>(Wt + c0 + LDW * c0, npiv, ctl->Linv);
         bar_sync<BAR_UW, 96>(p & 1);
         // ---- owned column tiles J > p (J = uw mod 3); the next panel's tile first
         const int nd = ctl->ndisp;
@@ -362,11 +372,19 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
         const int dsr = gid < nd ? ctl->dsrc[gid] : -1;
         const int dds = gid < nd ? ctl->ddst[gid] : -1;
         const double li0 = ctl->Linv[gid + 8 * tig], li1 = ctl->Linv[gid + 8 * (4 + tig)];
-        int Jfirst = p + 1;
-        while (Jfirst % 3 != uw) ++Jfirst;        // first owned tile > p
+        // A fragments of the panel's multipliers L[I][p], I > p, shared by all owned column tiles
+        double lt[RT][2];
+#pragma unroll
+        for (int I = 1; I < RT; ++I) {
+          const int r = 8 * I + gid;
+          const bool rv = I > p && r < NI;
+          lt[I][0] = rv ? Wt[r + LDW * (c0 + ka0)] : 0.0;
+          lt[I][1] = rv ? Wt[r + LDW * (c0 + ka1)] : 0.0;
+        }
+        int Jfirst = p + 1 + (uw + 3 - (p + 1) % 3) % 3;   // first owned tile > p
 #pragma unroll 1
         for (int J = Jfirst; J < CT; J += 3) {
-          double* colg = Wt + LDW * (8 * J + gid);     // B-fragment column of this lane
+          double* colg = Wt + LDW * (8 * J + nb);      // B-fragment column of this lane
           double* colt = Wt + LDW * (8 * J + tig);     // displaced rows: lane (t=gid) moves columns tig, tig+4
           const double g0 = ps0 >= 0 ? colg[ps0] : 0.0;
           const double g1 = ps1 >= 0 ? colg[ps1] : 0.0;
@@ -376,88 +394,112 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
           double u0 = 0.0, u1 = 0.0;              // U12 tile = inv(L_pp) * gathered rows
           dmma(u0, u1, li0, g0);
           dmma(u0, u1, li1, g1);
-          double* cu = Wt + c0 + gid + LDW * (8 * J + 2 * tig);
-          if (c0 + gid < NI) { cu[0] = u0; cu[LDW] = u1; }
+          double* cc0 = Wt + gid + LDW * (8 * J + ce0);      // C-fragment columns of this lane in tile J
+          double* cc1 = Wt + gid + LDW * (8 * J + ce1);
+          if (c0 + gid < NI) { cc0[c0] = u0; cc1[c0] = u1; }
           if (dds >= 0) { colt[dds] = dv0; colt[dds + 4 * LDW] = dv1; }
           __syncwarp();
           if (p + 1 < RT) {
             const double bf0 = neg(colg[c0 + tig]);
             const double bf1 = neg(colg[c0 + 4 + tig]);
-#pragma unroll 1
-            for (int I = p + 1; I < RT; ++I) {
-              const int r = 8 * I + gid;
-              const bool rv = r < NI;
-              const double a0 = rv ? Wt[r + LDW * (c0 + tig)] : 0.0;
-              const double a1 = rv ? Wt[r + LDW * (c0 + 4 + tig)] : 0.0;
-              double* cp0 = Wt + r + LDW * (8 * J + 2 * tig);
-              double d0 = rv ? cp0[0] : 0.0, d1 = rv ? cp0[LDW] : 0.0;
-              dmma(d0, d1, a0, bf0);
-              dmma(d0, d1, a1, bf1);
-              if (rv) { cp0[0] = d0; cp0[LDW] = d1; }
+#pragma unroll
+            for (int I = 1; I < RT; ++I) {
+              if (I > p) {
+                const bool rv = 8 * I + gid < NI;
+                double d0 = rv ? cc0[8 * I] : 0.0, d1 = rv ? cc1[8 * I] : 0.0;
+                dmma(d0, d1, lt[I][0], bf0);
+                dmma(d0, d1, lt[I][1], bf1);
+                if (rv) { cc0[8 * I] = d0; cc1[8 * I] = d1; }
+              }
             }
           }
           if (J == p + 1 && p + 1 < NP) bar_arrive<BAR_COL, 64>((p + 1) & 1);
         }
-        // ---- bottom block, owned row tiles: needs every U[p][J] and Dinv_p
-        bar_sync<BAR_UDONE, 96>(p & 1);
+        // ---- bottom block, owned row tiles: needs every U[p][J] and Dinv_p (from the panel warp)
+        bar_sync<BAR_UDONE, 128>(p & 1);
         const double dj0 = ctl->Dinv[tig + 8 * gid], dj1 = ctl->Dinv[4 + tig + 8 * gid];
+        const double* ub0 = Wt + c0 + tig + LDW * nb;        // B fragment of U[p][J]: ub0[LDW*8*J], ub0[4 + LDW*8*J]
+        if (npiv == 8) {
+          double la[MAXROWS][2];
 #pragma unroll
-        for (int ri = 0; ri < MAXROWS; ++ri) {
-          const int I = uw * MAXROWS + ri;
-          if (I < BT) {
+          for (int ri = 0; ri < MAXROWS; ++ri) {
+            const int I = uw * MAXROWS + ri;
             const int r = 8 * I + gid;
-            const bool rv = r < NB;
-            double* bp = Bt + r + LDB * (8 * p + 2 * tig);
-            if (npiv == 8) {
-              // L = X * Dinv with X = Bt tile (I,p) (already updated right-looking): A fragments straight from smem
-              const double xa0 = rv ? Bt[r + LDB * (8 * p + tig)] : 0.0;
-              const double xa1 = rv ? Bt[r + LDB * (8 * p + 4 + tig)] : 0.0;
-              double l0 = 0.0, l1 = 0.0;
-              dmma(l0, l1, xa0, dj0);
-              dmma(l0, l1, xa1, dj1);
-              __syncwarp();
-              if (rv) { bp[0] = l0; bp[LDB] = l1; }     // park L to read it back as A fragments
-              __syncwarp();
-              const double la0 = rv ? Bt[r + LDB * (8 * p + tig)] : 0.0;
-              const double la1 = rv ? Bt[r + LDB * (8 * p + 4 + tig)] : 0.0;
-              // A21 part still in shared memory: tiles p < J < SJ0
+            const bool rv = I < BT && r < NB;
+            // L = X * Dinv with X = Bt tile (I,p) (already updated right-looking): A fragments straight from smem
+            const double xa0 = rv ? Bt[r + LDB * (c0 + ka0)] : 0.0;
+            const double xa1 = rv ? Bt[r + LDB * (c0 + ka1)] : 0.0;
+            double l0 = 0.0, l1 = 0.0;
+            dmma(l0, l1, xa0, dj0);
+            dmma(l0, l1, xa1, dj1);
+            __syncwarp();
+            double* bp = Bt + r + LDB * c0;
+            if (rv) { bp[LDB * ce0] = l0; bp[LDB * ce1] = l1; }   // park L to read it back as A fragments
+            __syncwarp();
+            la[ri][0] = rv ? bp[LDB * ka0] : 0.0;
+            la[ri][1] = rv ? bp[LDB * ka1] : 0.0;
+          }
+          // A21 part still in shared memory: tiles p < J < SJ0
 #pragma unroll 1
-              for (int J = p + 1; J < SJ0; ++J) {
-                double* cp0 = Bt + r + LDB * (8 * J + 2 * tig);
-                double d0 = rv ? cp0[0] : 0.0, d1 = rv ? cp0[LDB] : 0.0;
-                dmma(d0, d1, la0, neg(Wt[c0 + tig + LDW * (8 * J + gid)]));
-                dmma(d0, d1, la1, neg(Wt[c0 + 4 + tig + LDW * (8 * J + gid)]));
-                if (rv) { cp0[0] = d0; cp0[LDB] = d1; }
-              }
-              // S part in registers
+          for (int J = p + 1; J < SJ0; ++J) {
+            const double bf0 = neg(ub0[LDW * 8 * J]), bf1 = neg(ub0[4 + LDW * 8 * J]);
 #pragma unroll
-              for (int js = 0; js < NSJ; ++js) {
-                const int J = SJ0 + js;
-                dmma(acc[ri][js][0], acc[ri][js][1], la0, neg(Wt[c0 + tig + LDW * (8 * J + gid)]));
-                dmma(acc[ri][js][0], acc[ri][js][1], la1, neg(Wt[c0 + 4 + tig + LDW * (8 * J + gid)]));
-              }
-            } else {
-              // partial last panel (npiv < 8): its column tile is the first S tile, held in registers.
-              // X (C fragment) -> A fragment through the (dead) Bt tile; L = X * Dinv (zero outside npiv cols)
-              __syncwarp();
-              if (rv) { bp[0] = acc[ri][0][0]; bp[LDB] = acc[ri][0][1]; }
-              __syncwarp();
-              const double xa0 = rv ? Bt[r + LDB * (8 * p + tig)] : 0.0;
-              double l0 = 0.0, l1 = 0.0;
-              dmma(l0, l1, xa0, dj0);
-              __syncwarp();
-              if (rv) { bp[0] = l0; bp[LDB] = l1; }
-              __syncwarp();
-              const double lt0 = rv ? Bt[r + LDB * (8 * p + tig)] : 0.0;
-              // trailing columns of the panel's own tile: B = U_pp rows < npiv, columns >= npiv
-              const double ub = (tig < npiv && gid >= npiv) ? neg(Wt[c0 + tig + LDW * (c0 + gid)]) : 0.0;
-              dmma(acc[ri][0][0], acc[ri][0][1], lt0, ub);
+            for (int ri = 0; ri < MAXROWS; ++ri) {
+              const int I = uw * MAXROWS + ri;
+              const int r = 8 * I + gid;
+              const bool rv = I < BT && r < NB;
+              double* cp0 = Bt + r + LDB * 8 * J;
+              double d0 = rv ? cp0[LDB * ce0] : 0.0, d1 = rv ? cp0[LDB * ce1] : 0.0;
+              dmma(d0, d1, la[ri][0], bf0);
+              dmma(d0, d1, la[ri][1], bf1);
+              if (rv) { cp0[LDB * ce0] = d0; cp0[LDB * ce1] = d1; }
+            }
+          }
+          // S part in registers
 #pragma unroll
-              for (int js = 1; js < NSJ; ++js) {
-                const int J = SJ0 + js;
-                dmma(acc[ri][js][0], acc[ri][js][1], lt0, neg(Wt[c0 + tig + LDW * (8 * J + gid)]));
+          for (int js = 0; js < NSJ; ++js) {
+            const int J = SJ0 + js;
+            const double bf0 = neg(ub0[LDW * 8 * J]), bf1 = neg(ub0[4 + LDW * 8 * J]);
+#pragma unroll
+            for (int ri = 0; ri < MAXROWS; ++ri) {
+              if (uw * MAXROWS + ri < BT) {
+                dmma(acc[ri][js][0], acc[ri][js][1], la[ri][0], bf0);
+                dmma(acc[ri][js][0], acc[ri][js][1], la[ri][1], bf1);
               }
             }
+          }
+        } else {
+          // partial last panel (npiv < 8): its column tile is the first S tile, held in registers.
+          // X (C fragment) -> A fragment through the (dead) Bt tile; L = X * Dinv (zero outside npiv cols)
+          double lq[MAXROWS];
+#pragma unroll
+          for (int ri = 0; ri < MAXROWS; ++ri) {
+            const int I = uw * MAXROWS + ri;
+            const int r = 8 * I + gid;
+            const bool rv = I < BT && r < NB;
+            double* bp = Bt + r + LDB * c0;
+            __syncwarp();
+            if (rv) { bp[LDB * ce0] = acc[ri][0][0]; bp[LDB * ce1] = acc[ri][0][1]; }
+            __syncwarp();
+            const double xa0 = rv ? bp[LDB * ka0] : 0.0;
+            double l0 = 0.0, l1 = 0.0;
+            dmma(l0, l1, xa0, dj0);
+            __syncwarp();
+            if (rv) { bp[LDB * ce0] = l0; bp[LDB * ce1] = l1; }
+            __syncwarp();
+            lq[ri] = rv ? bp[LDB * ka0] : 0.0;
+          }
+          // trailing columns of the panel's own tile: B = U_pp rows < npiv, columns >= npiv
+          const double ub = (tig < npiv && gid >= npiv) ? neg(Wt[c0 + tig + LDW * (c0 + nb)]) : 0.0;
+#pragma unroll
+          for (int ri = 0; ri < MAXROWS; ++ri)
+            if (uw * MAXROWS + ri < BT) dmma(acc[ri][0][0], acc[ri][0][1], lq[ri], ub);
+#pragma unroll
+          for (int js = 1; js < NSJ; ++js) {
+            const double bf0 = neg(ub0[LDW * 8 * (SJ0 + js)]);
+#pragma unroll
+            for (int ri = 0; ri < MAXROWS; ++ri)
+              if (uw * MAXROWS + ri < BT) dmma(acc[ri][js][0], acc[ri][js][1], lq[ri], bf0);
           }
         }
       }
