@@ -18,25 +18,12 @@
 // Pivoting: the pivot of a column is an entry whose magnitude equals the column maximum to 2^-15 relative
 // (lowest row among those); S does not depend on the pivot order, only rounding does (parity bar 1e-11).
 #include <algorithm>
-#include <cstdlib>
 
 #include "common.cuh"
 
 namespace ghb {
 
 namespace {
-
-// Optional timeline trace (compile with -DGHB_TRACE): CTA 0 records clock64() at phase boundaries of its first
-// cells into a global buffer (tools/trace_condense.py prints it).  No effect on the product build.
-#ifdef GHB_TRACE
-__device__ long long g_trace[64 * 4 * 64];
-#define TRACE(ev)                                                                              \
-  do {                                                                                         \
-    if (blockIdx.x == 0 && lane == 0 && trace_cell < 64) g_trace[(trace_cell * 4 + (tid >> 5)) * 64 + (ev)] = clock64(); \
-  } while (0)
-#else
-#define TRACE(ev) do { } while (0)
-#endif
 
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -102,7 +89,7 @@ struct PanelCtl {
 
 static_assert(sizeof(PanelCtl) == 1232, "smem_bytes() assumes this");
 // named barriers: ids are immediates (a register id makes ptxas reserve all 16 and caps occupancy)
-enum { BAR_PANEL = 1, BAR_COL = 3, BAR_UDONE = 5, BAR_UW = 7, BAR_BOT = 8, BAR_ACC = 10 };   // PANEL/COL/UDONE/BOT: + panel parity
+enum { BAR_PANEL = 1, BAR_COL = 3, BAR_UDONE = 5, BAR_UW = 7 };   // + panel parity
 template <int ID, int COUNT>
 __device__ __forceinline__ void bar_sync_i() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
 template <int ID, int COUNT>
@@ -128,10 +115,9 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // and remembers at which step it was chosen.  On write-back the k-th pivot row goes to position c0+k and
 // the rows it displaces from the diagonal block go to the vacated positions (any consistent row order is
 // a valid row-permuted LU; S does not depend on it).  Publishes that permutation, inv(L_pp) and inv(U_pp).
-template <int NI, int LDW, bool TWO, int NPIV>
-__device__ __forceinline__ void panel_factor(double* __restrict__ Wt, const int c0, PanelCtl* ctl,
+template <int NI, int LDW, bool TWO>
+__device__ __forceinline__ void panel_factor(double* __restrict__ Wt, const int c0, const int npiv, PanelCtl* ctl,
                                              int* __restrict__ info) {
-  constexpr int npiv = NPIV;
   const int lane = threadIdx.x & 31;
   const int nrows = NI - c0;
   const bool v1 = lane < nrows;
@@ -145,48 +131,60 @@ __device__ __forceinline__ void panel_factor(double* __restrict__ Wt, const int 
     a[j] = v1 ? base[LDW * pc(j)] : 0.0;
     a2[j] = v2 ? base[32 + LDW * pc(j)] : 0.0;
   }
-  int bad = 0;                                  // first step whose pivot column is (numerically) zero, 1-based
 #pragma unroll
-  for (int k = 0; k < NPIV; ++k) {
-    // ---- pivot search: one REDUX.MAX over key = |a| (exponent + 15 mantissa bits) << 6 | (63 - row)
-    const bool c1 = v1 && ch1 < 0;
-    const bool c2 = v2 && ch2 < 0;
-    const unsigned h1 = (unsigned)(__double_as_longlong(a[k]) >> 32) & 0x7fffffffu;
-    unsigned key = c1 ? (((h1 >> 5) << 6) | (unsigned)(63 - lane)) : 0u;
-    if (TWO) {
+  for (int k = 0; k < 8; ++k) {
+    if (k < npiv) {
+      // ---- pivot search: one REDUX.MAX over key = |a| (exponent + 15 mantissa bits) << 6 | (63 - row)
+      const bool c1 = v1 && ch1 < 0;
+      const bool c2 = v2 && ch2 < 0;
+      const unsigned h1 = (unsigned)(__double_as_longlong(a[k]) >> 32) & 0x7fffffffu;
       const unsigned h2 = (unsigned)(__double_as_longlong(a2[k]) >> 32) & 0x7fffffffu;
-      const unsigned key2 = c2 ? (((h2 >> 5) << 6) | (unsigned)(31 - lane)) : 0u;
-      key = key > key2 ? key : key2;
-    }
-    const double rc1 = fast_rcp(a[k]);          // speculative reciprocal, overlaps the reduction
-    const double rc2 = TWO ? fast_rcp(a2[k]) : 0.0;
-    const unsigned kmax = __reduce_max_sync(0xffffffffu, key);
-    // a column whose largest candidate is below 2^-1017 is reported as an exact zero pivot (LAPACK: info = k+1);
-    // no branch: the cell's outputs are overwritten with NaN at the end
-    bad = (bad == 0 && (kmax >> 6) == 0u) ? k + 1 : bad;
-    const int prow = 63 - (int)(kmax & 63u);    // row of the pivot inside the panel (0..63)
-    const bool from2 = TWO && prow >= 32;
-    const int q = prow & 31;
-    const double rinv = __shfl_sync(0xffffffffu, from2 ? rc2 : rc1, q);
-    myrinv = (lane == k) ? rinv : myrinv;
-    const bool me1 = !from2 && lane == q, me2 = from2 && lane == q;
-    ch1 = me1 ? k : ch1;
-    if (TWO) ch2 = me2 ? k : ch2;
-    // ---- multipliers and rank-1 update of the rows still in play
-    const bool u1 = c1 && !me1, u2 = TWO && c2 && !me2;
-    const double l1 = a[k] * rinv;              // dgetf2: scale by the reciprocal
-    a[k] = u1 ? l1 : a[k];
-    const double nl1 = u1 ? -l1 : 0.0;          // rows out of play: a + 0*p = a
-    double nl2 = 0.0;
-    if (TWO) { const double l2 = a2[k] * rinv; a2[k] = u2 ? l2 : a2[k]; nl2 = u2 ? -l2 : 0.0; }
+      unsigned key = c1 ? (((h1 >> 5) << 6) | (unsigned)(63 - lane)) : 0u;
+      if (TWO) {
+        const unsigned key2 = c2 ? (((h2 >> 5) << 6) | (unsigned)(31 - lane)) : 0u;
+        key = key > key2 ? key : key2;
+      }
+      const double rc1 = fast_rcp(a[k]);        // speculative reciprocal, overlaps the reduction
+      const double rc2 = TWO ? fast_rcp(a2[k]) : 0.0;
+      unsigned kmax = __reduce_max_sync(0xffffffffu, key);
+      if ((kmax >> 6) == 0u) {
+        // all candidates below 2^-1017: decide exactly (zero column => LAPACK info = k+1)
+        const unsigned long long e1 = c1 ? ((unsigned long long)__double_as_longlong(a[k]) & 0x7fffffffffffffffull) : 0ull;
+        const unsigned long long e2 = c2 ? ((unsigned long long)__double_as_longlong(a2[k]) & 0x7fffffffffffffffull) : 0ull;
+        const unsigned lo1 = __reduce_max_sync(0xffffffffu, (unsigned)(e1 >> 32) | (unsigned)(e2 >> 32));
+        const unsigned lo2 = __reduce_max_sync(0xffffffffu, (unsigned)e1 | (unsigned)e2);
+        if ((lo1 | lo2) == 0u) {
+          if (lane == 0 && *info == 0) *info = c0 + k + 1;
+        }
+        // keep going with the first candidate row (results of a failed cell are overwritten with NaN)
+        const unsigned bb1 = __ballot_sync(0xffffffffu, c1);
+        const unsigned bb2 = __ballot_sync(0xffffffffu, c2);
+        const int row = bb1 ? (__ffs(bb1) - 1) : (32 + __ffs(bb2) - 1);
+        kmax = (unsigned)(63 - row);
+      }
+      const int prow = 63 - (int)(kmax & 63u);  // row of the pivot inside the panel (0..63)
+      const bool from2 = TWO && prow >= 32;
+      const int q = prow & 31;
+      const double rinv = __shfl_sync(0xffffffffu, from2 ? rc2 : rc1, q);
+      if (lane == k) myrinv = rinv;
+      const bool me1 = !from2 && lane == q, me2 = from2 && lane == q;
+      if (me1) ch1 = k;
+      if (me2) ch2 = k;
+      // ---- multipliers and rank-1 update of the rows still in play
+      const bool u1 = c1 && !me1, u2 = TWO && c2 && !me2;
+      const double l1 = a[k] * rinv, l2 = a2[k] * rinv;   // dgetf2: scale by the reciprocal
+      a[k] = u1 ? l1 : a[k];
+      const double nl1 = u1 ? -l1 : 0.0;                  // rows out of play: a + 0*p = a
+      double nl2 = 0.0;
+      if (TWO) { a2[k] = u2 ? l2 : a2[k]; nl2 = u2 ? -l2 : 0.0; }
 #pragma unroll
-    for (int j = k + 1; j < 8; ++j) {
-      const double pj = __shfl_sync(0xffffffffu, from2 ? a2[j] : a[j], q);   // pivot row entry, to everyone
-      a[j] = fma(nl1, pj, a[j]);
-      if (TWO) a2[j] = fma(nl2, pj, a2[j]);
+      for (int j = k + 1; j < 8; ++j) {
+        const double pj = __shfl_sync(0xffffffffu, from2 ? a2[j] : a[j], q);   // pivot row entry, to everyone
+        a[j] = fma(nl1, pj, a[j]);
+        if (TWO) a2[j] = fma(nl2, pj, a2[j]);
+      }
     }
   }
-  if (bad != 0 && lane == 0 && *info == 0) *info = c0 + bad;
   // ---- new positions: pivot rows first, displaced rows into the vacated slots
   const bool disp = v1 && lane < npiv && ch1 < 0;          // rows of the diagonal block not chosen
   const bool vc1 = v1 && lane >= npiv && ch1 >= 0;
@@ -267,43 +265,9 @@ __device__ __forceinline__ void invert_upper(const double* __restrict__ D, const
   }
 }
 
-// cp.async of rows [2*rp0, 2*(rp0+NRP)) x logical columns [cA, cB) of one image of a cell record (re-layout on
-// the fly) by ONE warp: CW lanes walk the columns, 32/CW lane groups split the row pairs; the inner loops are
-// unrolled so the table look-ups of several copies overlap.  Used by the panel warp to prefetch the NEXT cell
-// into regions of Wt/Bt that the current cell no longer needs.
-template <int NRP, int LD, int CW>
-__device__ __forceinline__ void load_rows(double* __restrict__ img, const int rp0, const int rinfo0, const int cA,
-                                          const int cB, const int ncolA, const double* __restrict__ Arec,
-                                          const double* __restrict__ brec, const int* __restrict__ s_colbase,
-                                          const unsigned short* __restrict__ s_rowinfo, const int nf, const int lane) {
-  constexpr int KG = 32 / CW;                    // lane groups over the row pairs
-  constexpr int KPL = (NRP + KG - 1) / KG;       // row pairs per lane
-  const int cl = lane % CW, kg = lane / CW;
-  int ri[KPL];
-#pragma unroll
-  for (int q = 0; q < KPL; ++q) {
-    const int k = kg + q * KG;
-    ri[q] = k < NRP ? s_rowinfo[rinfo0 + rp0 + k] : -1;
-  }
-  for (int c = cA + cl; c < cB; c += CW) {
-    const double* rec = c < ncolA ? Arec : brec;
-    const int* cb = s_colbase + c * nf;
-    double* dcol = img + 2 * (rp0 + kg) + LD * pc(c);
-#pragma unroll
-    for (int q = 0; q < KPL; ++q) {
-      if (ri[q] >= 0) {
-        const int off = cb[ri[q] >> 8];
-        double* dst = dcol + 2 * KG * q;
-        if (off >= 0) cp_async16(dst, rec + off + (ri[q] & 0xff));
-        else { dst[0] = 0.0; dst[1] = 0.0; }
-      }
-    }
-  }
-}
-
 template <int NI, int NB>
 __global__ void __launch_bounds__(128, 5)
-condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int role_div, int64_t ncells, const double* __restrict__ A,
+condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const double* __restrict__ A,
                      const double* __restrict__ b, double* __restrict__ S, double* __restrict__ g,
                      int32_t* __restrict__ info) {
   using C = Cfg<NI, NB>;
@@ -318,10 +282,7 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int role_div, int64_t nc
   int* s_info = reinterpret_cast<int*>(ctl2 + 2);
   int* s_colbase = s_info + 4;                                         // [(N+1)*nf]
   unsigned short* s_rowinfo = reinterpret_cast<unsigned short*>(s_colbase + (N + 1) * tb.nf);  // [N/2]
-  const int tid = threadIdx.x, lane = tid & 31;
-  // role of this warp: 0 = panel warp, 1..3 = update warps.  Rotated per CTA so that the panel warps of the
-  // CTAs resident on one SM do not all sit on the same SM sub-partition (warp id % 4).
-  const int warp = ((tid >> 5) + (int)((blockIdx.x / role_div) & 3)) & 3;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gid = lane >> 2, tig = lane & 3;    // fragment coordinates
   // memory columns (inside a tile) of this lane's fragment elements, see pc()
   const int ce0 = pc(2 * tig), ce1 = pc(2 * tig + 1);   // C fragment
@@ -344,13 +305,9 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int role_div, int64_t nc
   const int l_f = l_ri >> 8, l_lr = l_ri & 0xff;
   double* const l_dst0 = (2 * l_rp < NI) ? Wt + 2 * l_rp : Bt + (2 * l_rp - NI);
 
-  int trace_cell = -1; (void)trace_cell;
   for (int64_t cell = blockIdx.x; cell < ncells; cell += gridDim.x) {
-    ++trace_cell;
-    TRACE(0);
     // ------------------------------------------------------------------ load + re-layout
-    // (only the first cell of this CTA: every later record was prefetched during the previous cell)
-    if (cell == (int64_t)blockIdx.x && l_on) {
+    if (l_on) {
       const double* Arec = A + cell * lenA + l_lr;
       const double* brec = b + cell * lenb + l_lr;
       const int* cb = s_colbase + l_f;
@@ -363,57 +320,25 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int role_div, int64_t nc
       }
       if (l_grp == N % LG) cp_async16(l_dst0 + LDW * pc(N), brec + cb[N * tb.nf]);   // rhs column
     }
-    const int64_t ncell = cell + gridDim.x;       // next cell of this CTA
-    const bool has_next = ncell < ncells;
-    const double* nArec = A + ncell * lenA;
-    const double* nbrec = b + ncell * lenb;
     if (tid == 0) *s_info = 0;
     cp_async_commit_wait_all();
-    TRACE(1);
     __syncthreads();
-    TRACE(2);
 
-    // stage q complete on all update warps => rows 8q..8q+7 of Wt (U[q][*], L\U of panel q) and column tile q of
-    // Bt are dead: the panel warp loads those parts of the next cell's record into them
-    auto prefetch_stage = [&](const int q) {
-      bar_sync<BAR_BOT, 128>(q & 1);
-      if (has_next) {
-        const int q0 = 8 * q;
-        if (NI - q0 >= 8) load_rows<4, LDW, 32>(Wt, q0 / 2, 0, 0, NC, N, nArec, nbrec, s_colbase, s_rowinfo, tb.nf, lane);
-        else load_rows<(NI % 8 ? NI % 8 : 8) / 2, LDW, 32>(Wt, q0 / 2, 0, 0, NC, N, nArec, nbrec, s_colbase, s_rowinfo, tb.nf, lane);
-        load_rows<NB / 2, LDB, 8>(Bt, 0, NI / 2, q0, q0 + 8, N, nArec, nbrec, s_colbase, s_rowinfo, tb.nf, lane);
-      }
-    };
     if (warp == 0) {
       // ================================================================ panel warp
 #pragma unroll 1
       for (int p = 0; p < NP; ++p) {
         const int c0 = 8 * p;
         const int npiv = (NI - c0) < 8 ? (NI - c0) : 8;
-        TRACE(4 + 6 * p);
         if (p > 0) bar_sync<BAR_COL, 64>(p & 1);             // column tile p is up to date
-        TRACE(5 + 6 * p);
         PanelCtl* ctl = ctl2 + (p & 1);
-        if ((NI - c0) > 32) panel_factor<NI, LDW, true, 8>(Wt, c0, ctl, s_info);
-        else if (npiv == 8) panel_factor<NI, LDW, false, 8>(Wt, c0, ctl, s_info);
-        else panel_factor<NI, LDW, false, (NI % 8 ? NI % 8 : 8)>(Wt, c0, ctl, s_info);
-        TRACE(6 + 6 * p);
+        if ((NI - c0) > 32) panel_factor<NI, LDW, true>(Wt, c0, npiv, ctl, s_info);
+        else panel_factor<NI, LDW, false>(Wt, c0, npiv, ctl, s_info);
         bar_arrive<BAR_PANEL, 128>(p & 1);
         // inv(U_pp) for the bottom block, computed while the update warps prepare the next column tile
         invert_upper<LDW>(Wt + c0 + LDW * c0, npiv, ctl->rinv, ctl->Dinv);
-        TRACE(7 + 6 * p);
         bar_arrive<BAR_UDONE, 128>(p & 1);
-        // ---- prefetch duty (this warp is otherwise waiting for its next column tile): the next cell's record
-        //      goes straight into the regions of Wt/Bt that the update warps have released
-        if (p == 0) {
-          bar_sync_i<BAR_ACC, 128>();
-          if (has_next)
-            load_rows<NB / 2, LDB, 32>(Bt, 0, NI / 2, 8 * (SJ0 + 1), NC, N, nArec, nbrec, s_colbase, s_rowinfo, tb.nf, lane);
-        } else {
-          prefetch_stage(p - 1);
-        }
       }
-      prefetch_stage(NP - 1);
     } else {
       // ================================================================ update warps
       const int uw = warp - 1;                    // 0..2
@@ -431,19 +356,15 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int role_div, int64_t nc
           acc[ri][js][1] = rv ? cp0[LDB * ce1] : 0.0;
         }
       }
-      bar_arrive_i<BAR_ACC, 128>();               // this warp holds its S accumulators: Bt's S part is dead
 #pragma unroll 1
       for (int p = 0; p < NP; ++p) {
         const int c0 = 8 * p;
         const int npiv = (NI - c0) < 8 ? (NI - c0) : 8;
         PanelCtl* ctl = ctl2 + (p & 1);
-        TRACE(4 + 6 * p);
         bar_sync<BAR_PANEL, 128>(p & 1);
-        TRACE(5 + 6 * p);
         // ---- the owner of the next panel's column tile inverts L_pp (on the critical path)
         if (uw == (p + 1) % 3) invert_unit_lower<LDW>(Wt + c0 + LDW * c0, npiv, ctl->Linv);
-        bar_sync_i<BAR_UW, 96>();
-        TRACE(6 + 6 * p);
+        bar_sync<BAR_UW, 96>(p & 1);
         // ---- owned column tiles J > p (J = uw mod 3); the next panel's tile first
         const int nd = ctl->ndisp;
         const int ps0 = tig < npiv ? ctl->psrc[tig] : -1;
@@ -495,9 +416,7 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int role_div, int64_t nc
           if (J == p + 1 && p + 1 < NP) bar_arrive<BAR_COL, 64>((p + 1) & 1);
         }
         // ---- bottom block, owned row tiles: needs every U[p][J] and Dinv_p (from the panel warp)
-        TRACE(7 + 6 * p);
         bar_sync<BAR_UDONE, 128>(p & 1);
-        TRACE(8 + 6 * p);
         const double dj0 = ctl->Dinv[tig + 8 * gid], dj1 = ctl->Dinv[4 + tig + 8 * gid];
         const double* ub0 = Wt + c0 + tig + LDW * nb;        // B fragment of U[p][J]: ub0[LDW*8*J], ub0[4 + LDW*8*J]
         if (npiv == 8) {
@@ -583,10 +502,6 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int role_div, int64_t nc
               if (uw * MAXROWS + ri < BT) dmma(acc[ri][js][0], acc[ri][js][1], lq[ri], bf0);
           }
         }
-        // ---- stage p is complete on this warp: tell the panel warp (it prefetches the next record into
-        //      the regions that are now dead)
-        TRACE(9 + 6 * p);
-        bar_arrive<BAR_BOT, 128>(p & 1);
       }
       // ---- store S, g
       const bool failed = *s_info != 0;
@@ -613,9 +528,7 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int role_div, int64_t nc
         }
       }
     }
-    TRACE(40);
     __syncthreads();
-    TRACE(41);
     if (info && tid == 0) info[cell] = *s_info;
   }
 }
@@ -673,9 +586,7 @@ int launch_condense_dmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const doub
   GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   DmmaTables tb{p.d_colbase, p.d_rowf, p.d_rowl, p.nfields};
   int64_t grid = std::min<int64_t>(ncells, (int64_t)ctx->sm_count * 5);
-  const char* rot = getenv("GHB_ROLE_ROT");
-  const int role_div = (rot && rot[0] == '0') ? (1 << 30) : ctx->sm_count;
-  kern<<<(unsigned)grid, 128, smem, ctx->stream>>>(tb, p.lenA, p.lenb, role_div, ncells, A, b, S, g, info);
+  kern<<<(unsigned)grid, 128, smem, ctx->stream>>>(tb, p.lenA, p.lenb, ncells, A, b, S, g, info);
   GHB_LAUNCHED(ctx);
   return GHB_OK;
 }
