@@ -227,29 +227,32 @@ __device__ __forceinline__ const double* s_column(const double* S, const GhostVi
                              : gv.G + (c - gv.ncells_local) * gv.stride + (int64_t)l * n_b;
 }
 
+// GL lanes per column: a facet column of C3 has <= 66 entries, so 16 lanes waste less than 32 and double the
+// number of independent columns in flight (17 ms -> 12 ms at 128^3).
+template <int GL>
 __global__ void __launch_bounds__(256) gather_nzval_kernel(int64_t nrows, int n_b, const int64_t* __restrict__ colptr,
                                                            const unsigned long long* __restrict__ occ,
                                                            const uint8_t* __restrict__ src,
                                                            const double* __restrict__ S, GhostView gv,
                                                            double* __restrict__ nzval) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t j = warp; j < nrows; j += nwarps) {
-    int64_t p0 = colptr[j] - 1, p1 = colptr[j + 1] - 1;
+  const int gl = threadIdx.x % GL;
+  const int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GL;
+  const int64_t ngrp = ((int64_t)gridDim.x * blockDim.x) / GL;
+  for (int64_t j = grp; j < nrows; j += ngrp) {
+    const int64_t p0 = colptr[j] - 1, p1 = colptr[j + 1] - 1;
     if (p0 == p1) continue;
-    unsigned long long o0 = occ[2 * j], o1 = occ[2 * j + 1];
-    int64_t c0 = (int64_t)(o0 / n_b);
-    int l0 = (int)(o0 - (unsigned long long)c0 * n_b);
+    const unsigned long long o0 = occ[2 * j], o1 = occ[2 * j + 1];
+    const int64_t c0 = (int64_t)(o0 / n_b);
+    const int l0 = (int)(o0 - (unsigned long long)c0 * n_b);
     const double* col0 = s_column(S, gv, c0, l0, n_b);
     const double* col1 = nullptr;
     if (o1 != ~0ull) {
-      int64_t c1 = (int64_t)(o1 / n_b);
-      int l1 = (int)(o1 - (unsigned long long)c1 * n_b);
+      const int64_t c1 = (int64_t)(o1 / n_b);
+      const int l1 = (int)(o1 - (unsigned long long)c1 * n_b);
       col1 = s_column(S, gv, c1, l1, n_b);
     }
-    for (int64_t p = p0 + lane; p < p1; p += 32) {
-      uint8_t a = src[2 * p], bq = src[2 * p + 1];
+    for (int64_t p = p0 + gl; p < p1; p += GL) {
+      const uint8_t a = src[2 * p], bq = src[2 * p + 1];
       double v;
       if (a != 255) {
         v = col0[a];
@@ -417,8 +420,8 @@ int asm_numeric(ghb_ctx* ctx, const double* S, const double* g, const double* gh
                 double* nzval, double* rhs) {
   const AsmState& as = ctx->as;
   GhostView gv{as.ncells_local, ghost, (int64_t)as.n_b * as.ghost_ncols + as.ghost_ncols};
-  int64_t blocks = std::min<int64_t>((as.nrows + 7) / 8, (int64_t)ctx->sm_count * 16);
-  gather_nzval_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(as.nrows, as.n_b, as.d_colptr,
+  int64_t blocks = std::min<int64_t>((as.nrows + 15) / 16, (int64_t)ctx->sm_count * 16);
+  gather_nzval_kernel<16><<<(unsigned)blocks, 256, 0, ctx->stream>>>(as.nrows, as.n_b, as.d_colptr,
                                                                  (const unsigned long long*)as.d_occ, as.d_src, S, gv, nzval);
   GHB_LAUNCHED(ctx);
   gather_rhs_kernel<<<(unsigned)((as.nrows + 255) / 256), 256, 0, ctx->stream>>>(

@@ -393,3 +393,18 @@ def test_slab_assembly_matches_global(ctx, gdims, world):
     assert np.array_equal(np.concatenate(rhss), rhs.cpu().numpy())
     for c in ctxs:
         c.close()
+
+
+def test_dmma_singular_cell_info(ctx):
+    """tuned kernel: an exactly singular interior block is reported like dgetrf (info = first zero pivot), NaN outputs."""
+    plan, op = _dev_plan(ctx, "C3_hdg_k2_3d"), oracle_plan("C3_hdg_k2_3d")
+    assert plan.kernel_name.startswith("dmma")
+    A0, b0 = o.synth_cell_records(op, 0, 6)
+    A0[3, :] = 0.0                                  # zero matrix: first pivot column is zero
+    S = np.empty((6, plan.n_b ** 2)); g = np.empty((6, plan.n_b)); info = np.empty(6, dtype=np.int32)
+    ctx.condense(plan, 6, A0, b0, S, g, info)
+    assert info.tolist() == [0, 0, 0, 1, 0, 0]
+    assert np.isnan(S[3]).all() and np.isnan(g[3]).all() and np.isfinite(S[[0, 1, 2, 4, 5]]).all()
+    S0, g0, info0 = oc.condense(op, A0, b0)
+    assert info0.tolist() == info.tolist()
+    assert rel_err_cells(S[[0, 1, 2, 4, 5]], S0[[0, 1, 2, 4, 5]]) < TOL
