@@ -332,6 +332,10 @@ def run_ours(args):
 
 
 def main():
+    # keep stdout clean for the ONE JSON line: libraries (NCCL's version banner, ...) write to fd 1 too
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

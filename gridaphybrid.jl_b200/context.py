@@ -128,6 +128,11 @@ class Context:
             self._h, int(ncells), int(nlfacets), int(ndofs_f), _ptr(cell_wise_facets, np.int64, ncells * nlfacets),
             _ptr(facet_data, np.int64), _ptr(out, np.int64, ncells * nlfacets * ndofs_f)))
 
+    def sum_facets(self, ncells, nlfacets, length, a, out):
+        self._check(self._L.ghb_sum_facets_f64(self._h, int(ncells), int(nlfacets), int(length),
+                                               _ptr(a, np.float64, ncells * nlfacets * length, "in"),
+                                               _ptr(out, np.float64, ncells * length, "out")))
+
     def assemble_symbolic(self, ncells, n_b, cell_ids, nrows) -> int:
         nnz = ctypes.c_int64(0)
         self._check(self._L.ghb_assemble_symbolic(self._h, int(ncells), int(n_b),

@@ -22,6 +22,7 @@ bool is_device_ptr(const void* p) {
 int launch_condense(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
                     double* g, int32_t* info, double* X) {
   if (p.use_dmma && X == nullptr) return launch_condense_dmma(ctx, p, ncells, A, b, S, g, info);
+  if (p.use_warp && X == nullptr) return launch_condense_warp(ctx, p, ncells, A, b, S, g, info);
   return launch_condense_generic(ctx, p, ncells, A, b, S, g, info, X);
 }
 
@@ -178,6 +179,9 @@ int ghb_plan_blocks(ghb_ctx* ctx, int nfields, const int32_t* ndofs, const uint8
     int rc = dmma_prepare(ctx, *p);
     if (rc != GHB_OK) { cudaFree(p->d_emap); delete p; return rc; }
     p->use_dmma = true;
+  } else if (warp_kernel_name(*p) && !(force && force[0] == '1')) {
+    p->use_warp = true;
+    p->kernel_name = warp_kernel_name(*p);
   }
   ctx->plans.push_back(p);
   *plan_id = (int)ctx->plans.size() - 1;
@@ -233,6 +237,18 @@ int ghb_restrict_facet_dofs_i64(ghb_ctx* ctx, int64_t ncells, int nlfacets, int 
   if (!is_device_ptr(facet_data) || !is_device_ptr(cell_wise_facets) || !is_device_ptr(out))
     return fail(ctx, GHB_EUNSUPPORTED, "ghb_restrict_facet_dofs_i64: device pointers required (facet table size is not passed)");
   return launch_restrict_facet_dofs(ctx, ncells, nlfacets, ndofs_f, cell_wise_facets, facet_data, out);
+}
+
+int ghb_sum_facets_f64(ghb_ctx* ctx, int64_t ncells, int nlfacets, int64_t len, const double* in, double* out) {
+  if (!ctx) return GHB_EINVAL;
+  if (ncells < 0 || nlfacets <= 0 || len <= 0 || !in || !out) return fail(ctx, GHB_EINVAL, "ghb_sum_facets_f64: bad argument");
+  if (ncells == 0) return GHB_OK;
+  cudaSetDevice(ctx->device);
+  Arg<double> din(ctx, in, (size_t)ncells * nlfacets * len, true, false); GHB_TRY(din.rc);
+  Arg<double> dout(ctx, out, (size_t)ncells * len, false, true); GHB_TRY(dout.rc);
+  GHB_TRY(launch_sum_facets(ctx, ncells, nlfacets, len, din.dev, dout.dev));
+  GHB_TRY(dout.finish());
+  return GHB_OK;
 }
 
 int ghb_assemble_symbolic(ghb_ctx* ctx, int64_t ncells, int n_b, const int64_t* cell_ids, int64_t nrows,
@@ -419,7 +435,10 @@ int ghb_backsub_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A, 
     if (!A || !b) return fail(ctx, GHB_EINVAL, "ghb_backsub_f64: A and b must both be given or both NULL");
     Arg<double> dA(ctx, A, (size_t)ncells * p->lenA, true, false); GHB_TRY(dA.rc);
     Arg<double> db(ctx, b, (size_t)ncells * p->lenb, true, false); GHB_TRY(db.rc);
-    GHB_TRY(launch_backsub_generic(ctx, *p, ncells, dA.dev, db.dev, lambda_free, lambda_dirichlet, dids.dev, du.dev, di.dev));
+    if (p->use_warp)
+      GHB_TRY(launch_backsub_warp(ctx, *p, ncells, dA.dev, db.dev, lambda_free, lambda_dirichlet, dids.dev, du.dev, di.dev));
+    else
+      GHB_TRY(launch_backsub_generic(ctx, *p, ncells, dA.dev, db.dev, lambda_free, lambda_dirichlet, dids.dev, du.dev, di.dev));
     GHB_TRY(du.finish()); GHB_TRY(di.finish());
     return GHB_OK;
   }

@@ -32,6 +32,7 @@ struct Plan {
   uint8_t* d_rowf = nullptr;
   uint8_t* d_rowl = nullptr;
   bool use_dmma = false;
+  bool use_warp = false;          // register-resident warp kernels for small cells (condense_warp.cu)
   bool all_touched = false;
   const char* kernel_name = "generic";
   PlanDev dev() const { return PlanDev{n_i, n_b, n, lenA, lenb, d_emap}; }
@@ -148,6 +149,11 @@ struct Arg {
 // kernels / launchers implemented in the other translation units
 int launch_condense_generic(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b,
                             double* S, double* g, int32_t* info, double* X);
+const char* warp_kernel_name(const Plan& p);
+int launch_condense_warp(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
+                         double* g, int32_t* info);
+int launch_backsub_warp(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b,
+                        const double* lam_free, const double* lam_dir, const int64_t* ids, double* u, int32_t* info);
 bool dmma_supported(const Plan& p);
 int dmma_prepare(ghb_ctx* ctx, Plan& p);
 int launch_condense_dmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
@@ -169,6 +175,7 @@ int asm_pack_cut_plane(ghb_ctx* ctx, int64_t ncut, int n_b, int ncols, const dou
 void asm_free(ghb_ctx* ctx);
 int launch_restrict_facet_dofs(ghb_ctx* ctx, int64_t ncells, int nlf, int nf, const int64_t* cwf,
                                const int64_t* fdata, int64_t* out);
+int launch_sum_facets(ghb_ctx* ctx, int64_t ncells, int nlf, int64_t len, const double* in, double* out);
 int launch_scatter_free(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* u, const double* lam,
                         int64_t nlam, double* x);
 int launch_synth_fill(ghb_ctx* ctx, const Plan& p, int64_t cell_start, int64_t ncells, uint64_t seed, double* A,

@@ -1,0 +1,195 @@
+// condense_warp.cu -- static condensation and backward static condensation for SMALL cells (n = n_i + n_b <= 32:
+// Darcy HDG k=1 on quads (7,8), RT-H k=1 on quads (16,8)): one warp per cell, one row of the augmented system per
+// lane, the whole cell in registers, no shared memory.  These configurations are HBM-bound (AI 0.85 - 1.8 flop/B), so
+// what matters is coalesced record loads and enough cells in flight; the elimination itself is the FMA-warp-tile
+// path of BASELINE.json's north_star ("plain FMA warp tiles otherwise").
+//
+// Replaces evaluate!(cache, ::StaticCondensationMap, A, b) (/root/reference/src/StaticCondensationMap.jl:152-196) and
+// evaluate!(cache, ::BackwardStaticCondensationMap, A, b, x) (src/BackwardStaticCondensationMap.jl:61-102).
+// Pivoting: partial pivoting over the interior rows with implicit row exchange (a lane keeps its row); the pivot is
+// the row of largest magnitude to 2^-15 relative (one REDUX.MAX on a packed key), exact-zero columns give LAPACK's info.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace ghb {
+
+namespace {
+
+__device__ __forceinline__ double fast_rcp_w(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+
+// pivot search among `cand` lanes on value v: returns the lane (lowest among the maxima at key resolution) and
+// sets zero=true when every candidate is below 2^-1017 (reported as an exact zero pivot)
+__device__ __forceinline__ int pivot_lane(double v, bool cand, int lane, bool& zero) {
+  const unsigned h = (unsigned)(__double_as_longlong(v) >> 32) & 0x7fffffffu;
+  const unsigned key = cand ? (((h >> 5) << 5) | (unsigned)(31 - lane)) : 0u;
+  const unsigned kmax = __reduce_max_sync(0xffffffffu, key);
+  zero = (kmax >> 5) == 0u;
+  return 31 - (int)(kmax & 31u);
+}
+
+// One warp per cell.  Lane r < N holds row r of W = [A11 A12 b1; A21 A22 b2] (condensed order).
+template <int NI, int NB>
+__global__ void __launch_bounds__(128) condense_warp_kernel(PlanDev p, int64_t ncells, const double* __restrict__ A,
+                                                            const double* __restrict__ b, double* __restrict__ S,
+                                                            double* __restrict__ g, int32_t* __restrict__ info) {
+  constexpr int N = NI + NB;
+  static_assert(N <= 32, "one row per lane");
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool rowok = lane < N;
+  const int32_t* em = p.emap + (rowok ? lane : 0);   // record offsets of this lane's row (L1-resident table)
+  for (int64_t cell = warp; cell < ncells; cell += nwarps) {
+    const double* Arec = A + cell * p.lenA;
+    const double* brec = b + cell * p.lenb;
+    double a[N + 1];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const int o = rowok ? em[N * j] : -1;
+      a[j] = o >= 0 ? Arec[o] : 0.0;
+    }
+    a[N] = rowok ? brec[em[N * N]] : 0.0;
+    bool chosen = false;
+    int bad = 0;
+#pragma unroll
+    for (int k = 0; k < NI; ++k) {
+      const bool cand = lane < NI && !chosen;
+      const double rc = fast_rcp_w(a[k]);
+      bool zero;
+      const int q = pivot_lane(a[k], cand, lane, zero);
+      bad = (bad == 0 && zero) ? k + 1 : bad;
+      const double rinv = __shfl_sync(0xffffffffu, rc, q);
+      const bool me = lane == q;
+      const bool upd = rowok && !chosen && !me;       // interior rows still in play and every boundary row
+      chosen = chosen || me;
+      const double nl = upd ? -(a[k] * rinv) : 0.0;
+#pragma unroll
+      for (int j = k + 1; j <= N; ++j) {
+        const double pj = __shfl_sync(0xffffffffu, a[j], q);
+        a[j] = fma(nl, pj, a[j]);
+      }
+    }
+    // boundary rows now hold S (columns NI..N-1) and g (column N)
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    if (lane >= NI && lane < N) {
+      double* Sc = S + cell * (int64_t)NB * NB + (lane - NI);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) Sc[(int64_t)NB * j] = bad ? qnan : a[NI + j];
+      g[cell * (int64_t)NB + (lane - NI)] = bad ? qnan : a[N];
+    }
+    if (info && lane == 0) info[cell] = bad;
+  }
+}
+
+// Backward map: lane r < NI holds row r of [A11 | b1 - A12*lambda_K]; Gauss-Jordan with partial pivoting, so the
+// lane whose row was chosen at step k ends up holding u[k].
+template <int NI, int NB>
+__global__ void __launch_bounds__(128) backsub_warp_kernel(PlanDev p, int64_t ncells, const double* __restrict__ A,
+                                                           const double* __restrict__ b,
+                                                           const double* __restrict__ lam_free,
+                                                           const double* __restrict__ lam_dir,
+                                                           const int64_t* __restrict__ ids, double* __restrict__ u,
+                                                           int32_t* __restrict__ info) {
+  constexpr int N = NI + NB;
+  static_assert(NI <= 32, "one interior row per lane");
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool rowok = lane < NI;
+  const int32_t* em = p.emap + (rowok ? lane : 0);
+  for (int64_t cell = warp; cell < ncells; cell += nwarps) {
+    const double* Arec = A + cell * p.lenA;
+    const double* brec = b + cell * p.lenb;
+    double a[NI + 1];
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+      const int o = rowok ? em[N * j] : -1;
+      a[j] = o >= 0 ? Arec[o] : 0.0;
+    }
+    double r = rowok ? brec[em[N * N]] : 0.0;
+    // r -= A12 * lambda_K  (gemv!('N',-1,A12,x,1,b1), ascending columns)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int64_t id = ids[cell * NB + j];        // uniform across the warp
+      const double lj = id > 0 ? lam_free[id - 1] : (id < 0 && lam_dir ? lam_dir[-id - 1] : 0.0);
+      const int o = rowok ? em[N * (NI + j)] : -1;
+      if (o >= 0) r = fma(-Arec[o], lj, r);
+    }
+    a[NI] = r;
+    bool chosen = false;
+    int step = -1, bad = 0;
+#pragma unroll
+    for (int k = 0; k < NI; ++k) {
+      const bool cand = rowok && !chosen;
+      const double rc = fast_rcp_w(a[k]);
+      bool zero;
+      const int q = pivot_lane(a[k], cand, lane, zero);
+      bad = (bad == 0 && zero) ? k + 1 : bad;
+      const double rinv = __shfl_sync(0xffffffffu, rc, q);
+      const bool me = lane == q;
+      if (me) { chosen = true; step = k; }
+      // Gauss-Jordan: normalise the pivot row, eliminate column k from every other row
+      const double scale = me ? rinv : 1.0;
+      const double nl = (rowok && !me) ? -a[k] : 0.0;
+#pragma unroll
+      for (int j = k + 1; j <= NI; ++j) {
+        const double pj = __shfl_sync(0xffffffffu, a[j], q) * rinv;
+        a[j] = me ? a[j] * scale : fma(nl, pj, a[j]);
+      }
+    }
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    if (rowok && step >= 0) u[cell * (int64_t)NI + step] = bad ? qnan : a[NI];
+    if (info && lane == 0) info[cell] = bad;
+  }
+}
+
+template <int NI, int NB>
+int launch_cw(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S, double* g,
+              int32_t* info) {
+  const int64_t blocks = std::min<int64_t>((ncells + 3) / 4, (int64_t)ctx->sm_count * 16);
+  condense_warp_kernel<NI, NB><<<(unsigned)blocks, 128, 0, ctx->stream>>>(p.dev(), ncells, A, b, S, g, info);
+  GHB_LAUNCHED(ctx);
+  return GHB_OK;
+}
+
+template <int NI, int NB>
+int launch_bw(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, const double* lf,
+              const double* ld, const int64_t* ids, double* u, int32_t* info) {
+  const int64_t blocks = std::min<int64_t>((ncells + 3) / 4, (int64_t)ctx->sm_count * 16);
+  backsub_warp_kernel<NI, NB><<<(unsigned)blocks, 128, 0, ctx->stream>>>(p.dev(), ncells, A, b, lf, ld, ids, u, info);
+  GHB_LAUNCHED(ctx);
+  return GHB_OK;
+}
+
+}  // namespace
+
+// shapes with a register-resident warp kernel (BASELINE.json C1 and C2 k=1)
+const char* warp_kernel_name(const Plan& p) {
+  if (p.n_i == 7 && p.n_b == 8) return "warp_7_8";
+  if (p.n_i == 16 && p.n_b == 8) return "warp_16_8";
+  return nullptr;
+}
+
+int launch_condense_warp(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
+                         double* g, int32_t* info) {
+  if (p.n_i == 7 && p.n_b == 8) return launch_cw<7, 8>(ctx, p, ncells, A, b, S, g, info);
+  if (p.n_i == 16 && p.n_b == 8) return launch_cw<16, 8>(ctx, p, ncells, A, b, S, g, info);
+  return fail(ctx, GHB_EUNSUPPORTED, "no warp kernel for this shape");
+}
+
+int launch_backsub_warp(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b,
+                        const double* lam_free, const double* lam_dir, const int64_t* ids, double* u, int32_t* info) {
+  if (p.n_i == 7 && p.n_b == 8) return launch_bw<7, 8>(ctx, p, ncells, A, b, lam_free, lam_dir, ids, u, info);
+  if (p.n_i == 16 && p.n_b == 8) return launch_bw<16, 8>(ctx, p, ncells, A, b, lam_free, lam_dir, ids, u, info);
+  return fail(ctx, GHB_EUNSUPPORTED, "no warp kernel for this shape");
+}
+
+}  // namespace ghb

@@ -3,6 +3,7 @@
 //   * full-space free-dof scatter              (/root/reference/src/HybridAffineFEOperators.jl:134-149)
 //   * Cartesian cell_wise_facets, closed form of Gridap's first-touch numbering
 //   * Philox4x32-10 synthetic records, bit-identical to oracle/oracle.py::synth_cell_records
+#include <algorithm>
 #include <cmath>
 
 #include "common.cuh"
@@ -39,6 +40,34 @@ __global__ void scatter_free_kernel(int64_t ncells, int n_i, int nint, const int
     x[(int64_t)foff[f] * ncells + cell * fsize[f] + l] = u[t];
   } else if (t < nu + nlam) {
     x[t] = lam[t - nu];
+  }
+}
+
+// SumFacetsMap (/root/reference/src/SumFacetsMap.jl:19-30) on the batch: out[c][e] = in[c][0][e] + in[c][1][e] + ...
+// summed left to right like the reference's chained BroadcastingFieldOpMap(+).  16-byte vector accesses when len is even.
+__global__ void sum_facets_kernel(int64_t ncells, int nlf, int64_t len, const double* __restrict__ in,
+                                  double* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if ((len & 1) == 0) {
+    const int64_t len2 = len >> 1, tot = ncells * len2;
+    const double2* in2 = reinterpret_cast<const double2*>(in);
+    double2* out2 = reinterpret_cast<double2*>(out);
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += stride) {
+      const int64_t c = t / len2, e = t - c * len2;
+      const double2* p = in2 + c * nlf * len2 + e;
+      double2 acc = p[0];
+      for (int f = 1; f < nlf; ++f) { const double2 v = p[f * len2]; acc.x += v.x; acc.y += v.y; }
+      out2[t] = acc;
+    }
+  } else {
+    const int64_t tot = ncells * len;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += stride) {
+      const int64_t c = t / len, e = t - c * len;
+      const double* p = in + c * nlf * len + e;
+      double acc = p[0];
+      for (int f = 1; f < nlf; ++f) acc += p[f * len];
+      out[t] = acc;
+    }
   }
 }
 
@@ -136,6 +165,16 @@ int launch_restrict_facet_dofs(ghb_ctx* ctx, int64_t ncells, int nlf, int nf, co
   int64_t tot = ncells * nlf * nf;
   restrict_facet_dofs_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ncells, nlf, nf, cwf, fdata, out);
   GHB_LAUNCHED(ctx);
+  return GHB_OK;
+}
+
+int launch_sum_facets(ghb_ctx* ctx, int64_t ncells, int nlf, int64_t len, const double* in, double* out) {
+  const int64_t work = ncells * ((len & 1) ? len : len / 2);
+  const int64_t blocks = std::min<int64_t>((work + 255) / 256, (int64_t)ctx->sm_count * 32);
+  if (blocks > 0) {
+    sum_facets_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(ncells, nlf, len, in, out);
+    GHB_LAUNCHED(ctx);
+  }
   return GHB_OK;
 }
 

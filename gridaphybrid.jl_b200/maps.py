@@ -144,7 +144,14 @@ class SumFacetsMap:
             for i in range(2, len(a.array)):
                 res = _add(res, a.array[i])
             return res
-        return a.sum(dim=1)
+        # batched: [ncells, nlfacets, ...] on the device -> ghb_sum_facets_f64
+        ctx = default_context()
+        a = a.contiguous()
+        n, nlf = int(a.shape[0]), int(a.shape[1])
+        out = torch.empty((n,) + tuple(a.shape[2:]), dtype=torch.float64, device=a.device)
+        ctx.use_torch_stream()
+        ctx.sum_facets(n, nlf, a[0, 0].numel(), a, out)
+        return out
 
 
 def _add(x, y):

@@ -92,6 +92,13 @@ int ghb_condense_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A,
 int ghb_restrict_facet_dofs_i64(ghb_ctx* ctx, int64_t ncells, int nlfacets, int ndofs_f,
                                 const int64_t* cell_wise_facets, const int64_t* facet_data, int64_t* out);
 
+/* ---- (a9) in-cell sum over local facets -------------------------------------------------------
+ * replaces SumFacetsMap.evaluate! (src/SumFacetsMap.jl:19-30, wired in at src/GridapAPIExtensions.jl:442-451) on the
+ * batch: in [ncells][nlfacets][len] = the dK contributions of every local facet already laid out on the cell record
+ * (facet-field blocks are disjoint, so their "sum" is placement); out [ncells][len] = in[:,0,:] + in[:,1,:] + ...
+ * added left to right like the reference. */
+int ghb_sum_facets_f64(ghb_ctx* ctx, int64_t ncells, int nlfacets, int64_t len, const double* in, double* out);
+
 /* ---- (a8) assembly --------------------------------------------------------------------------
  * replaces assemble_matrix_and_vector(SparseMatrixAssembler(M,L), data)
  * (src/HybridAffineFEOperators.jl:38,46) producing SparseMatrixCSC{Float64,Int64} + Vector{Float64}.

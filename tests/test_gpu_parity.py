@@ -408,3 +408,18 @@ def test_dmma_singular_cell_info(ctx):
     S0, g0, info0 = oc.condense(op, A0, b0)
     assert info0.tolist() == info.tolist()
     assert rel_err_cells(S[[0, 1, 2, 4, 5]], S0[[0, 1, 2, 4, 5]]) < TOL
+
+
+@pytest.mark.parametrize("shape", [(100, 4, 2, 4), (37, 6, 71), (5, 6, 4900)])
+def test_sum_facets_device(ctx, shape):
+    """SumFacetsMap on the batch (test/SumFacetMapTests.jl:10-29: four equal facet blocks sum to 4a) and vs the oracle."""
+    rng = np.random.default_rng(8)
+    a = rng.standard_normal(shape)
+    out = gh.SumFacetsMap().evaluate(None, torch.as_tensor(a, device="cuda"))
+    ref = a[:, 0].copy()
+    for f in range(1, shape[1]):
+        ref = ref + a[:, f]                      # left to right, like the reference
+    assert np.array_equal(out.cpu().numpy(), ref)
+    same = np.repeat(rng.random((shape[0], 1) + shape[2:]), 4, axis=1)
+    out4 = gh.SumFacetsMap().evaluate(None, torch.as_tensor(same, device="cuda"))
+    assert np.allclose(out4.cpu().numpy(), 4 * same[:, 0])
