@@ -35,6 +35,10 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc));
 }
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc));
+}
 __device__ __forceinline__ void cp_async_commit_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
@@ -54,6 +58,10 @@ struct DmmaTables {
   int nf;
 };
 
+// smallest leading dimension >= x with LD = 4 (mod 8): 2*LD = 8 or 24 (mod 32) words, the condition for
+// conflict-free A/B/C fragment accesses (together with the in-tile column permutation pc())
+constexpr int ld_for(int x) { return ((x + 3) / 8) * 8 + 4 >= x ? ((x + 3) / 8) * 8 + 4 : ((x + 3) / 8) * 8 + 12; }
+
 template <int NI, int NB>
 struct Cfg {
   static constexpr int N = NI + NB;
@@ -62,15 +70,15 @@ struct Cfg {
   static constexpr int BT = (NB + 7) / 8;      // row tiles of the bottom block
   static constexpr int CT = (NC + 7) / 8;      // column tiles
   static constexpr int NP = (NI + 7) / 8;      // panels
-  static constexpr int LDW = 36;               // leading dims: 2*LD = 8 (mod 32) words -> conflict-free fragments
-  static constexpr int LDB = 36;
+  static constexpr int LDW = ld_for(NI);       // leading dimensions of the two images
+  static constexpr int LDB = ld_for(NB);
   static constexpr int NCP = CT * 8;
-  static_assert(NI <= LDW && NB <= LDB, "leading dimension too small");
-  static_assert(NI % 2 == 0 && NB % 2 == 0, "16-byte cp.async needs even block heights");
+  static_assert(NI <= LDW && NB <= LDB && LDW % 8 == 4 && LDB % 8 == 4, "bad leading dimension");
+  static_assert(NI <= 64, "the panel warp holds at most two rows per lane");
   static constexpr int WT_DOUBLES = NCP * LDW;
   static constexpr int BT_DOUBLES = NCP * LDB;
   static size_t smem_bytes(int nf) {   // arrays + 2 panel control blocks + info + re-layout tables
-    return (size_t)(WT_DOUBLES + BT_DOUBLES) * 8 + 2 * 1232 + 16 + (size_t)(N + 1) * nf * 4 + N + 16;
+    return (size_t)(WT_DOUBLES + BT_DOUBLES) * 8 + 2 * 1232 + 16 + (size_t)(N + 1) * nf * 4 + 2 * N + 16;
   }
 };
 
@@ -265,8 +273,10 @@ __device__ __forceinline__ void invert_upper(const double* __restrict__ D, const
   }
 }
 
-template <int NI, int NB>
-__global__ void __launch_bounds__(128, 5)
+// RPC = rows per cp.async: 2 (16 bytes) when every vertical pair of the condensed matrix is contiguous and aligned in
+// the packed record (all block heights even), else 1 (8 bytes).
+template <int NI, int NB, int RPC>
+__global__ void __launch_bounds__(128, (NI > 40 ? 4 : 5))
 condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const double* __restrict__ A,
                      const double* __restrict__ b, double* __restrict__ S, double* __restrict__ g,
                      int32_t* __restrict__ info) {
@@ -281,7 +291,8 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
   PanelCtl* ctl2 = reinterpret_cast<PanelCtl*>(Bt + C::BT_DOUBLES);   // [2]
   int* s_info = reinterpret_cast<int*>(ctl2 + 2);
   int* s_colbase = s_info + 4;                                         // [(N+1)*nf]
-  unsigned short* s_rowinfo = reinterpret_cast<unsigned short*>(s_colbase + (N + 1) * tb.nf);  // [N/2]
+  unsigned short* s_rowinfo = reinterpret_cast<unsigned short*>(s_colbase + (N + 1) * tb.nf);  // [N/RPC]
+  static_assert(RPC == 1 || (NI % 2 == 0 && NB % 2 == 0), "16-byte cp.async needs even block heights");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gid = lane >> 2, tig = lane & 3;    // fragment coordinates
   // memory columns (inside a tile) of this lane's fragment elements, see pc()
@@ -293,17 +304,20 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
   for (int i = tid; i < C::WT_DOUBLES; i += 128) Wt[i] = 0.0;
   for (int i = tid; i < C::BT_DOUBLES; i += 128) Bt[i] = 0.0;
   for (int i = tid; i < (N + 1) * tb.nf; i += 128) s_colbase[i] = tb.colbase[i];
-  for (int i = tid; i < N / 2; i += 128) s_rowinfo[i] = (unsigned short)((tb.rowf[2 * i] << 8) | tb.rowl[2 * i]);
+  for (int i = tid; i < N / RPC; i += 128) s_rowinfo[i] = (unsigned short)((tb.rowf[RPC * i] << 8) | tb.rowl[RPC * i]);
   __syncthreads();
 
-  // loader: a thread owns one row pair (interior pairs -> Wt, boundary pairs -> Bt) and walks the columns
-  constexpr int HP = N / 2;                     // row pairs per column
+  // loader: a thread owns one copy unit (RPC rows; interior rows -> Wt, boundary rows -> Bt) and walks the columns
+  constexpr int HP = N / RPC;                   // copy units per column
   constexpr int LG = 128 / HP;                  // column groups
+  static_assert(LG >= 1, "cell too tall for the loader");
   const int l_grp = tid / HP, l_rp = tid - l_grp * HP;
   const bool l_on = l_grp < LG;
   const int l_ri = l_on ? s_rowinfo[l_rp] : 0;
   const int l_f = l_ri >> 8, l_lr = l_ri & 0xff;
-  double* const l_dst0 = (2 * l_rp < NI) ? Wt + 2 * l_rp : Bt + (2 * l_rp - NI);
+  const bool l_top = RPC * l_rp < NI;
+  double* const l_dst0 = l_top ? Wt + RPC * l_rp : Bt + (RPC * l_rp - NI);
+  const int l_ld = l_top ? LDW : LDB;
 
   for (int64_t cell = blockIdx.x; cell < ncells; cell += gridDim.x) {
     // ------------------------------------------------------------------ load + re-layout
@@ -314,11 +328,14 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
 #pragma unroll 4
       for (int c = l_grp; c < N; c += LG) {
         const int off = cb[c * tb.nf];
-        double* dst = l_dst0 + LDW * pc(c);
-        if (off >= 0) cp_async16(dst, Arec + off);
-        else { dst[0] = 0.0; dst[1] = 0.0; }
+        double* dst = l_dst0 + l_ld * pc(c);
+        if (off >= 0) { if (RPC == 2) cp_async16(dst, Arec + off); else cp_async8(dst, Arec + off); }
+        else { dst[0] = 0.0; if (RPC == 2) dst[1] = 0.0; }
       }
-      if (l_grp == N % LG) cp_async16(l_dst0 + LDW * pc(N), brec + cb[N * tb.nf]);   // rhs column
+      if (l_grp == N % LG) {                                                       // rhs column
+        if (RPC == 2) cp_async16(l_dst0 + l_ld * pc(N), brec + cb[N * tb.nf]);
+        else cp_async8(l_dst0 + l_ld * pc(N), brec + cb[N * tb.nf]);
+      }
     }
     if (tid == 0) *s_info = 0;
     cp_async_commit_wait_all();
@@ -536,21 +553,27 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
 }  // namespace
 
 // host side -----------------------------------------------------------------------------------------
-bool dmma_supported(const Plan& p) {
-  if (!(p.n_i == 34 && p.n_b == 36)) return false;
-  if (p.lenA % 2 || p.lenb % 2) return false;
-  // every vertical pair (2q, 2q+1) of the condensed matrix must be contiguous and 16-byte aligned in the record
-  const int n = p.n;
-  for (int r = 0; r < n; r += 2) {
+// every vertical pair (2q, 2q+1) of the condensed matrix contiguous and 16-byte aligned in the packed record?
+static bool pairs_aligned(const Plan& p) {
+  if (p.lenA % 2 || p.lenb % 2 || p.n % 2 || p.n_i % 2) return false;
+  for (int r = 0; r + 1 < p.n; r += 2)
     if (p.row_field[r] != p.row_field[r + 1] || p.row_local[r] + 1 != p.row_local[r + 1] || p.row_local[r] % 2) return false;
-  }
   for (int f = 0; f < p.nfields; ++f) {
-    if (p.ndofs[f] % 2) return false;
-    if (p.field_offset_b[f] % 2) return false;
+    if (p.ndofs[f] % 2 || p.field_offset_b[f] % 2) return false;
     for (int q = 0; q < p.nfields; ++q)
       if (p.block_offset[f + p.nfields * q] >= 0 && p.block_offset[f + p.nfields * q] % 2) return false;
   }
-  return p.nfields <= 8;
+  return true;
+}
+
+// shapes with a DMMA instantiation: 3-D HDG k=2 (34,36) and RT-H k=2, k=3 on quads (33,12), (56,16)
+bool dmma_supported(const Plan& p) {
+  if (p.nfields > 8) return false;
+  for (int r = 0; r < p.n; ++r) if (p.row_local[r] > 255) return false;
+  if (p.n_i == 34 && p.n_b == 36) return pairs_aligned(p);
+  if (p.n_i == 56 && p.n_b == 16) return pairs_aligned(p);
+  if (p.n_i == 33 && p.n_b == 12) return true;            // 8-byte copies
+  return false;
 }
 
 int dmma_prepare(ghb_ctx* ctx, Plan& p) {
@@ -573,22 +596,33 @@ int dmma_prepare(ghb_ctx* ctx, Plan& p) {
   GHB_CUDA(ctx, cudaMemcpy(p.d_colbase, colbase.data(), colbase.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   GHB_CUDA(ctx, cudaMemcpy(p.d_rowf, rowf.data(), n, cudaMemcpyHostToDevice));
   GHB_CUDA(ctx, cudaMemcpy(p.d_rowl, rowl.data(), n, cudaMemcpyHostToDevice));
-  p.kernel_name = "dmma_34_36";
+  p.kernel_name = p.n_i == 34 ? "dmma_34_36" : (p.n_i == 33 ? "dmma_33_12" : "dmma_56_16");
+  return GHB_OK;
+}
+
+template <int NI, int NB, int RPC>
+static int launch_dmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
+                       double* g, int32_t* info) {
+  using C = Cfg<NI, NB>;
+  auto kern = condense_dmma_kernel<NI, NB, RPC>;
+  const size_t smem = C::smem_bytes(p.nfields);
+  GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  int per_sm = 0;
+  GHB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
+  if (per_sm < 1) return fail(ctx, GHB_ECUDA, "condense_dmma_kernel does not fit on an SM");
+  DmmaTables tb{p.d_colbase, p.d_rowf, p.d_rowl, p.nfields};
+  int64_t grid = std::min<int64_t>(ncells, (int64_t)ctx->sm_count * per_sm);
+  kern<<<(unsigned)grid, 128, smem, ctx->stream>>>(tb, p.lenA, p.lenb, ncells, A, b, S, g, info);
+  GHB_LAUNCHED(ctx);
   return GHB_OK;
 }
 
 int launch_condense_dmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
                          double* g, int32_t* info) {
-  using C = Cfg<34, 36>;
-  auto kern = condense_dmma_kernel<34, 36>;
-  const size_t smem = C::smem_bytes(p.nfields);
-  GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  DmmaTables tb{p.d_colbase, p.d_rowf, p.d_rowl, p.nfields};
-  int64_t grid = std::min<int64_t>(ncells, (int64_t)ctx->sm_count * 5);
-  kern<<<(unsigned)grid, 128, smem, ctx->stream>>>(tb, p.lenA, p.lenb, ncells, A, b, S, g, info);
-  GHB_LAUNCHED(ctx);
-  return GHB_OK;
+  if (p.n_i == 34) return launch_dmma<34, 36, 2>(ctx, p, ncells, A, b, S, g, info);
+  if (p.n_i == 56) return launch_dmma<56, 16, 2>(ctx, p, ncells, A, b, S, g, info);
+  return launch_dmma<33, 12, 1>(ctx, p, ncells, A, b, S, g, info);
 }
 
 }  // namespace ghb

@@ -13,6 +13,8 @@ CONFIGS = {
                          interior=[1, 2], boundary=[3]),
     "C2_rth_k2_2d": dict(ndofs=[24, 9, 12], touched=np.array([[1, 1, 1], [1, 0, 0], [1, 0, 0]], bool),
                          interior=[1, 2], boundary=[3]),
+    "C2_rth_k3_2d": dict(ndofs=[40, 16, 16], touched=np.array([[1, 1, 1], [1, 0, 0], [1, 0, 0]], bool),
+                         interior=[1, 2], boundary=[3]),
     "C3_hdg_k2_3d": dict(ndofs=[30, 4, 36], touched=np.ones((3, 3), bool), interior=[1, 2], boundary=[3]),
     "multifield_2skel": dict(ndofs=[4, 4, 1, 1, 4, 4],
                              touched=np.array([[1, 0, 1, 0, 1, 0], [0, 1, 0, 1, 0, 1], [1, 0, 0, 0, 0, 0],
