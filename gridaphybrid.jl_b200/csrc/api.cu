@@ -435,7 +435,9 @@ int ghb_backsub_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A, 
     if (!A || !b) return fail(ctx, GHB_EINVAL, "ghb_backsub_f64: A and b must both be given or both NULL");
     Arg<double> dA(ctx, A, (size_t)ncells * p->lenA, true, false); GHB_TRY(dA.rc);
     Arg<double> db(ctx, b, (size_t)ncells * p->lenb, true, false); GHB_TRY(db.rc);
-    if (p->use_warp)
+    if (p->use_dmma && !getenv("GHB_FORCE_GENERIC"))
+      GHB_TRY(launch_backsub_dmma(ctx, *p, ncells, dA.dev, db.dev, lambda_free, lambda_dirichlet, dids.dev, du.dev, di.dev));
+    else if (p->use_warp)
       GHB_TRY(launch_backsub_warp(ctx, *p, ncells, dA.dev, db.dev, lambda_free, lambda_dirichlet, dids.dev, du.dev, di.dev));
     else
       GHB_TRY(launch_backsub_generic(ctx, *p, ncells, dA.dev, db.dev, lambda_free, lambda_dirichlet, dids.dev, du.dev, di.dev));

@@ -152,6 +152,8 @@ int launch_condense_generic(ghb_ctx* ctx, const Plan& p, int64_t ncells, const d
 const char* warp_kernel_name(const Plan& p);
 int launch_condense_warp(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
                          double* g, int32_t* info);
+int launch_backsub_dmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b,
+                        const double* lam_free, const double* lam_dir, const int64_t* ids, double* u, int32_t* info);
 int launch_backsub_warp(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b,
                         const double* lam_free, const double* lam_dir, const int64_t* ids, double* u, int32_t* info);
 bool dmma_supported(const Plan& p);

@@ -98,6 +98,7 @@ struct PanelCtl {
 static_assert(sizeof(PanelCtl) == 1232, "smem_bytes() assumes this");
 // named barriers: ids are immediates (a register id makes ptxas reserve all 16 and caps occupancy)
 enum { BAR_PANEL = 1, BAR_COL = 3, BAR_UDONE = 5, BAR_UW = 7 };   // + panel parity
+enum { BAR_UW_BACK = 6 };   // the backward kernel uses BAR_UDONE once (id 5): 8 barriers -> 8 CTAs per SM
 template <int ID, int COUNT>
 __device__ __forceinline__ void bar_sync_i() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
 template <int ID, int COUNT>
@@ -550,6 +551,189 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
   }
 }
 
+// ---- backward static condensation on the same machinery ------------------------------------------
+// u_K = A11^-1 (b1 - A12 lambda_K)   (/root/reference/src/BackwardStaticCondensationMap.jl:84-99; the LU is
+// recomputed from the record, as the reference does).  Image W = [A11 | r] (n_i rows, n_i+1 columns): the same
+// panel warp and column-tile owners as the condensation kernel factorise it (there is no bottom block), then
+// warp 0 back-substitutes with U column by column.  Only A11, A12 and b1 are read from the record:
+// B_back = 8(n_i^2 + n_i n_b + 2 n_i) + 16 n_b bytes per cell (ids and gathered lambda included).
+template <int NI, int NB>
+struct BackCfg {
+  using C = Cfg<NI, NB>;
+  static constexpr int CTB = (NI + 1 + 7) / 8;          // column tiles of [A11 | r]
+  static constexpr int NBP = (NB + 1) & ~1;
+  static size_t smem_bytes(int nf) {
+    return (size_t)(CTB * 8 * C::LDW + NBP + C::NP * 8) * 8 + 2 * sizeof(PanelCtl) + 16 +
+           (size_t)(C::N + 1) * nf * 4 + 2 * NI + 16;
+  }
+};
+
+template <int NI, int NB, int RPC>
+__global__ void __launch_bounds__(128, 8)
+backsub_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const double* __restrict__ A,
+                    const double* __restrict__ b, const double* __restrict__ lam_free,
+                    const double* __restrict__ lam_dir, const int64_t* __restrict__ ids, double* __restrict__ u,
+                    int32_t* __restrict__ info) {
+  using C = Cfg<NI, NB>;
+  using BC = BackCfg<NI, NB>;
+  constexpr int N = C::N, LDW = C::LDW, RT = C::RT, NP = C::NP, CTB = BC::CTB;
+  static_assert(RPC == 1 || NI % 2 == 0, "16-byte cp.async needs an even interior height");
+  extern __shared__ __align__(16) double smem[];
+  double* Wt = smem;                                               // [CTB*8][LDW]
+  double* s_lam = Wt + CTB * 8 * LDW;                              // [NB]
+  double* s_rinv = s_lam + BC::NBP;                                // [NP*8]
+  PanelCtl* ctl2 = reinterpret_cast<PanelCtl*>(s_rinv + NP * 8);   // [2]
+  int* s_info = reinterpret_cast<int*>(ctl2 + 2);
+  int* s_colbase = s_info + 4;                                     // [(N+1)*nf]
+  unsigned short* s_rowinfo = reinterpret_cast<unsigned short*>(s_colbase + (N + 1) * tb.nf);  // [NI/RPC]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int ce0 = pc(2 * tig), ce1 = pc(2 * tig + 1);
+  const int ka0 = tig, ka1 = pc(4 + tig);
+  const int nb = pc(gid);
+  constexpr int HP = (NI + RPC - 1) / RPC;      // copy units per column of A11
+  constexpr int LG = 128 / HP;                  // column groups
+  static_assert(LG >= 1, "cell too tall for the loader");
+  for (int i = tid; i < CTB * 8 * LDW; i += 128) Wt[i] = 0.0;
+  for (int i = tid; i < (N + 1) * tb.nf; i += 128) s_colbase[i] = tb.colbase[i];
+  for (int i = tid; i < HP; i += 128) s_rowinfo[i] = (unsigned short)((tb.rowf[RPC * i] << 8) | tb.rowl[RPC * i]);
+  __syncthreads();
+  const int l_grp = tid / HP, l_rp = tid - l_grp * HP;
+  const bool l_on = l_grp < LG;
+  const int l_ri = l_on ? s_rowinfo[l_rp] : 0;
+  const int l_f = l_ri >> 8, l_lr = l_ri & 0xff;
+  // the thread that forms r for interior row tid
+  const int r_f = tid < NI ? tb.rowf[tid] : 0, r_lr = tid < NI ? tb.rowl[tid] : 0;
+
+  for (int64_t cell = blockIdx.x; cell < ncells; cell += gridDim.x) {
+    const double* Arec = A + cell * lenA;
+    const double* brec = b + cell * lenb;
+    if (l_on) {
+      const int* cb = s_colbase + l_f;
+#pragma unroll 4
+      for (int c = l_grp; c < NI; c += LG) {
+        const int off = cb[c * tb.nf];
+        double* dst = Wt + RPC * l_rp + LDW * pc(c);
+        if (off >= 0) { if (RPC == 2) cp_async16(dst, Arec + l_lr + off); else cp_async8(dst, Arec + l_lr + off); }
+        else { dst[0] = 0.0; if (RPC == 2) dst[1] = 0.0; }
+      }
+    }
+    // lambda_K through the cell ids (get_cell_dof_values, src/HybridAffineFEOperators.jl:113)
+    if (tid < NB) {
+      const int64_t id = ids[cell * NB + tid];
+      s_lam[tid] = id > 0 ? lam_free[id - 1] : (id < 0 && lam_dir ? lam_dir[-id - 1] : 0.0);
+    }
+    if (tid == 0) *s_info = 0;
+    __syncthreads();
+    // r = b1 - A12 * lambda_K, ascending columns (gemv!('N',-1,A12,x,1,b1)): one interior row per thread, A12 read
+    // straight from the record (consecutive threads read consecutive rows of a column)
+    if (tid < NI) {
+      double r = brec[s_colbase[N * tb.nf + r_f] + r_lr];
+#pragma unroll 4
+      for (int j = 0; j < NB; ++j) {
+        const int off = s_colbase[(NI + j) * tb.nf + r_f];
+        if (off >= 0) r = fma(-Arec[off + r_lr], s_lam[j], r);
+      }
+      Wt[tid + LDW * pc(NI)] = r;
+    }
+    cp_async_commit_wait_all();
+    __syncthreads();
+
+    if (warp == 0) {
+      // ================================================================ panel warp
+#pragma unroll 1
+      for (int p = 0; p < NP; ++p) {
+        const int c0 = 8 * p;
+        const int npiv = (NI - c0) < 8 ? (NI - c0) : 8;
+        if (p > 0) bar_sync<BAR_COL, 64>(p & 1);
+        PanelCtl* ctl = ctl2 + (p & 1);
+        if ((NI - c0) > 32) panel_factor<NI, LDW, true>(Wt, c0, npiv, ctl, s_info);
+        else panel_factor<NI, LDW, false>(Wt, c0, npiv, ctl, s_info);
+        __syncwarp();
+        if (lane < 8) s_rinv[c0 + lane] = ctl->rinv[lane];
+        bar_arrive<BAR_PANEL, 128>(p & 1);
+      }
+      // ---- every column tile is final: back substitution U x = y, rows lane and lane+32 in registers
+      bar_sync<BAR_UDONE, 128>(0);
+      const double* ycol = Wt + LDW * pc(NI);
+      double y1 = lane < NI ? ycol[lane] : 0.0;
+      double y2 = lane + 32 < NI ? ycol[lane + 32] : 0.0;
+#pragma unroll 1
+      for (int k = NI - 1; k >= 0; --k) {
+        const double* uk = Wt + LDW * pc(k);
+        const double u1k = uk[lane];
+        const double u2k = lane + 32 < NI ? uk[lane + 32] : 0.0;
+        const double yk = __shfl_sync(0xffffffffu, k >= 32 ? y2 : y1, k & 31);
+        const double xk = yk * s_rinv[k];
+        if (lane == (k & 31)) { if (k >= 32) y2 = xk; else y1 = xk; }
+        if (lane < k) y1 = fma(-u1k, xk, y1);
+        if (NI > 32 && lane + 32 < k) y2 = fma(-u2k, xk, y2);
+      }
+      const bool failed = *s_info != 0;
+      const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+      double* uc = u + cell * (int64_t)NI;
+      if (lane < NI) uc[lane] = failed ? qnan : y1;
+      if (lane + 32 < NI) uc[lane + 32] = failed ? qnan : y2;
+    } else {
+      // ================================================================ update warps: column tiles J > p
+      const int uw = warp - 1;
+#pragma unroll 1
+      for (int p = 0; p < NP; ++p) {
+        const int c0 = 8 * p;
+        const int npiv = (NI - c0) < 8 ? (NI - c0) : 8;
+        PanelCtl* ctl = ctl2 + (p & 1);
+        bar_sync<BAR_PANEL, 128>(p & 1);
+        if (uw == (p + 1) % 3) invert_unit_lower<LDW>(Wt + c0 + LDW * c0, npiv, ctl->Linv);
+        bar_sync<BAR_UW_BACK, 96>(p & 1);
+        const int nd = ctl->ndisp;
+        const int ps0 = tig < npiv ? ctl->psrc[tig] : -1;
+        const int ps1 = 4 + tig < npiv ? ctl->psrc[4 + tig] : -1;
+        const int dsr = gid < nd ? ctl->dsrc[gid] : -1;
+        const int dds = gid < nd ? ctl->ddst[gid] : -1;
+        const double li0 = ctl->Linv[gid + 8 * tig], li1 = ctl->Linv[gid + 8 * (4 + tig)];
+        const int Jfirst = p + 1 + (uw + 3 - (p + 1) % 3) % 3;
+#pragma unroll 1
+        for (int J = Jfirst; J < CTB; J += 3) {
+          double* colg = Wt + LDW * (8 * J + nb);
+          double* colt = Wt + LDW * (8 * J + tig);
+          const double g0 = ps0 >= 0 ? colg[ps0] : 0.0;
+          const double g1 = ps1 >= 0 ? colg[ps1] : 0.0;
+          const double dv0 = dsr >= 0 ? colt[dsr] : 0.0;
+          const double dv1 = dsr >= 0 ? colt[dsr + 4 * LDW] : 0.0;
+          __syncwarp();
+          double u0 = 0.0, u1 = 0.0;              // U12 tile = inv(L_pp) * gathered rows
+          dmma(u0, u1, li0, g0);
+          dmma(u0, u1, li1, g1);
+          double* cc0 = Wt + gid + LDW * (8 * J + ce0);
+          double* cc1 = Wt + gid + LDW * (8 * J + ce1);
+          if (c0 + gid < NI) { cc0[c0] = u0; cc1[c0] = u1; }
+          if (dds >= 0) { colt[dds] = dv0; colt[dds + 4 * LDW] = dv1; }
+          __syncwarp();
+          if (p + 1 < RT) {
+            const double bf0 = neg(colg[c0 + tig]);
+            const double bf1 = neg(colg[c0 + 4 + tig]);
+#pragma unroll 1
+            for (int I = p + 1; I < RT; ++I) {
+              const int r = 8 * I + gid;
+              const bool rv = r < NI;
+              const double a0 = rv ? Wt[r + LDW * (c0 + ka0)] : 0.0;
+              const double a1 = rv ? Wt[r + LDW * (c0 + ka1)] : 0.0;
+              double d0 = rv ? cc0[8 * I] : 0.0, d1 = rv ? cc1[8 * I] : 0.0;
+              dmma(d0, d1, a0, bf0);
+              dmma(d0, d1, a1, bf1);
+              if (rv) { cc0[8 * I] = d0; cc1[8 * I] = d1; }
+            }
+          }
+          if (J == p + 1 && p + 1 < NP) bar_arrive<BAR_COL, 64>((p + 1) & 1);
+        }
+      }
+      bar_arrive<BAR_UDONE, 128>(0);
+    }
+    __syncthreads();
+    if (info && tid == 0) info[cell] = *s_info;
+  }
+}
+
 }  // namespace
 
 // host side -----------------------------------------------------------------------------------------
@@ -616,6 +800,31 @@ static int launch_dmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double
   kern<<<(unsigned)grid, 128, smem, ctx->stream>>>(tb, p.lenA, p.lenb, ncells, A, b, S, g, info);
   GHB_LAUNCHED(ctx);
   return GHB_OK;
+}
+
+template <int NI, int NB, int RPC>
+static int launch_bdmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b,
+                        const double* lam_free, const double* lam_dir, const int64_t* ids, double* u, int32_t* info) {
+  auto kern = backsub_dmma_kernel<NI, NB, RPC>;
+  const size_t smem = BackCfg<NI, NB>::smem_bytes(p.nfields);
+  GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  int per_sm = 0;
+  GHB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
+  if (per_sm < 1) return fail(ctx, GHB_ECUDA, "backsub_dmma_kernel does not fit on an SM");
+  if (getenv("GHB_DEBUG")) fprintf(stderr, "backsub_dmma<%d,%d>: %d CTAs/SM, %zu B smem\n", NI, NB, per_sm, smem);
+  DmmaTables tb{p.d_colbase, p.d_rowf, p.d_rowl, p.nfields};
+  int64_t grid = std::min<int64_t>(ncells, (int64_t)ctx->sm_count * per_sm);
+  kern<<<(unsigned)grid, 128, smem, ctx->stream>>>(tb, p.lenA, p.lenb, ncells, A, b, lam_free, lam_dir, ids, u, info);
+  GHB_LAUNCHED(ctx);
+  return GHB_OK;
+}
+
+int launch_backsub_dmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b,
+                        const double* lam_free, const double* lam_dir, const int64_t* ids, double* u, int32_t* info) {
+  if (p.n_i == 34) return launch_bdmma<34, 36, 2>(ctx, p, ncells, A, b, lam_free, lam_dir, ids, u, info);
+  if (p.n_i == 56) return launch_bdmma<56, 16, 2>(ctx, p, ncells, A, b, lam_free, lam_dir, ids, u, info);
+  return launch_bdmma<33, 12, 1>(ctx, p, ncells, A, b, lam_free, lam_dir, ids, u, info);
 }
 
 int launch_condense_dmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
