@@ -56,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every .cu under csrc/ for sm_100a into one in-tree shared library."""
     if force or needs_build():
         nvcc = os.environ.get("NVCC", "nvcc")
-        cmd = [nvcc] + NVCC_FLAGS + ["-o", SO_PATH] + sources()
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("GHB_NVCC_EXTRA", "").split() + ["-o", SO_PATH] + sources()
         if verbose:
             cmd += ["-Xptxas", "-v"]
         res = subprocess.run(cmd, capture_output=True, text=True)

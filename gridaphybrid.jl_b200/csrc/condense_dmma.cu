@@ -21,6 +21,17 @@
 
 #include "common.cuh"
 
+// resident CTAs per SM the condensation kernels are compiled for (tuning knobs; see profiles/)
+#ifndef GHB_MINB34
+#define GHB_MINB34 5
+#endif
+#ifndef GHB_LTREGS
+#define GHB_LTREGS 0
+#endif
+#ifndef GHB_MINB33
+#define GHB_MINB33 7
+#endif
+
 namespace ghb {
 
 namespace {
@@ -76,9 +87,13 @@ struct Cfg {
   static_assert(NI <= LDW && NB <= LDB && LDW % 8 == 4 && LDB % 8 == 4, "bad leading dimension");
   static_assert(NI <= 64, "the panel warp holds at most two rows per lane");
   static constexpr int WT_DOUBLES = NCP * LDW;
-  static constexpr int BT_DOUBLES = NCP * LDB;
+  // DIRECT_S: A22 and b2 go from the record straight into the S accumulators (registers) and Bt keeps only the
+  // A21 tiles; pays off where the smaller footprint buys resident CTAs ((33,12): 5 -> 7 per SM, +16%), loses for
+  // (34,36) where registers cap the occupancy anyway (profiles/r01_condense_dmma_timeline.md)
+  static constexpr bool DIRECT_S = NI != 34;
+  static constexpr int BT_DOUBLES = (DIRECT_S ? RT * 8 : NCP) * LDB;
   static size_t smem_bytes(int nf) {   // arrays + 2 panel control blocks + info + re-layout tables
-    return (size_t)(WT_DOUBLES + BT_DOUBLES) * 8 + 2 * 1232 + 16 + (size_t)(N + 1) * nf * 4 + 2 * N + 16;
+    return (size_t)(WT_DOUBLES + BT_DOUBLES) * 8 + 2 * 1232 + 16 + (size_t)(N + 1) * nf * 4 + 2 * N + 2 * NB + 16;
   }
 };
 
@@ -277,7 +292,7 @@ __device__ __forceinline__ void invert_upper(const double* __restrict__ D, const
 // RPC = rows per cp.async: 2 (16 bytes) when every vertical pair of the condensed matrix is contiguous and aligned in
 // the packed record (all block heights even), else 1 (8 bytes).
 template <int NI, int NB, int RPC>
-__global__ void __launch_bounds__(128, (NI > 40 ? 4 : 5))
+__global__ void __launch_bounds__(128, (NI > 40 ? 4 : (NI == 34 ? GHB_MINB34 : GHB_MINB33)))
 condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const double* __restrict__ A,
                      const double* __restrict__ b, double* __restrict__ S, double* __restrict__ g,
                      int32_t* __restrict__ info) {
@@ -286,6 +301,7 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
   constexpr int SJ0 = NI / 8;                   // first column tile holding S columns
   constexpr int NSJ = CT - SJ0;                 // S column tiles
   constexpr int MAXROWS = (BT + 2) / 3;         // bottom row tiles per update warp
+  constexpr bool LT_REGS = NI != 33 || GHB_LTREGS;             // keep the panel's multipliers in registers across column tiles
   extern __shared__ __align__(16) double smem[];
   double* Wt = smem;
   double* Bt = Wt + C::WT_DOUBLES;
@@ -293,6 +309,7 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
   int* s_info = reinterpret_cast<int*>(ctl2 + 2);
   int* s_colbase = s_info + 4;                                         // [(N+1)*nf]
   unsigned short* s_rowinfo = reinterpret_cast<unsigned short*>(s_colbase + (N + 1) * tb.nf);  // [N/RPC]
+  unsigned short* s_rowinfo2 = s_rowinfo + N / RPC;                                            // [NB] boundary rows
   static_assert(RPC == 1 || (NI % 2 == 0 && NB % 2 == 0), "16-byte cp.async needs even block heights");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gid = lane >> 2, tig = lane & 3;    // fragment coordinates
@@ -306,6 +323,7 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
   for (int i = tid; i < C::BT_DOUBLES; i += 128) Bt[i] = 0.0;
   for (int i = tid; i < (N + 1) * tb.nf; i += 128) s_colbase[i] = tb.colbase[i];
   for (int i = tid; i < N / RPC; i += 128) s_rowinfo[i] = (unsigned short)((tb.rowf[RPC * i] << 8) | tb.rowl[RPC * i]);
+  for (int i = tid; i < NB; i += 128) s_rowinfo2[i] = (unsigned short)((tb.rowf[NI + i] << 8) | tb.rowl[NI + i]);
   __syncthreads();
 
   // loader: a thread owns one copy unit (RPC rows; interior rows -> Wt, boundary rows -> Bt) and walks the columns
@@ -326,16 +344,41 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
       const double* Arec = A + cell * lenA + l_lr;
       const double* brec = b + cell * lenb + l_lr;
       const int* cb = s_colbase + l_f;
+      const int cend = (l_top || !C::DIRECT_S) ? N : 8 * SJ0;   // DIRECT_S: only the A21 tiles of boundary rows live in Bt
 #pragma unroll 4
-      for (int c = l_grp; c < N; c += LG) {
+      for (int c = l_grp; c < cend; c += LG) {
         const int off = cb[c * tb.nf];
         double* dst = l_dst0 + l_ld * pc(c);
         if (off >= 0) { if (RPC == 2) cp_async16(dst, Arec + off); else cp_async8(dst, Arec + off); }
         else { dst[0] = 0.0; if (RPC == 2) dst[1] = 0.0; }
       }
-      if (l_grp == N % LG) {                                                       // rhs column
+      if ((l_top || !C::DIRECT_S) && l_grp == N % LG) {                                              // rhs column
         if (RPC == 2) cp_async16(l_dst0 + l_ld * pc(N), brec + cb[N * tb.nf]);
         else cp_async8(l_dst0 + l_ld * pc(N), brec + cb[N * tb.nf]);
+      }
+    }
+    // S accumulators of the owned bottom row tiles (column tiles SJ0..CT-1) as C fragments, straight from the
+    // record: 8 consecutive rows x 4 columns per load instruction, i.e. full 64-byte runs of the packed columns
+    double acc[MAXROWS][NSJ][2];
+    if (C::DIRECT_S && warp != 0) {
+      const double* Arec = A + cell * lenA;
+      const double* brec = b + cell * lenb;
+#pragma unroll
+      for (int ri = 0; ri < MAXROWS; ++ri) {
+        const int I = (warp - 1) * MAXROWS + ri;
+        const int r = 8 * I + gid;
+        const bool rv = I < BT && r < NB;
+        const int ri_ = rv ? s_rowinfo2[r] : 0;
+        const int f = ri_ >> 8, lr = ri_ & 0xff;
+#pragma unroll
+        for (int js = 0; js < NSJ; ++js) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int c = 8 * (SJ0 + js) + 2 * tig + e;
+            const int off = (rv && c <= N) ? s_colbase[c * tb.nf + f] : -1;
+            acc[ri][js][e] = off >= 0 ? (c < N ? Arec : brec)[off + lr] : 0.0;
+          }
+        }
       }
     }
     if (tid == 0) *s_info = 0;
@@ -360,18 +403,18 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
     } else {
       // ================================================================ update warps
       const int uw = warp - 1;                    // 0..2
-      // S accumulators of the owned bottom row tiles (column tiles SJ0..CT-1), C fragments
-      double acc[MAXROWS][NSJ][2];
+      if (!C::DIRECT_S) {
 #pragma unroll
-      for (int ri = 0; ri < MAXROWS; ++ri) {
-        const int I = uw * MAXROWS + ri;
-        const int r = 8 * I + gid;
-        const bool rv = I < BT && r < NB;
+        for (int ri = 0; ri < MAXROWS; ++ri) {
+          const int I = uw * MAXROWS + ri;
+          const int r = 8 * I + gid;
+          const bool rv = I < BT && r < NB;
 #pragma unroll
-        for (int js = 0; js < NSJ; ++js) {
-          const double* cp0 = Bt + r + LDB * 8 * (SJ0 + js);
-          acc[ri][js][0] = rv ? cp0[LDB * ce0] : 0.0;
-          acc[ri][js][1] = rv ? cp0[LDB * ce1] : 0.0;
+          for (int js = 0; js < NSJ; ++js) {
+            const double* cp0 = Bt + r + LDB * 8 * (SJ0 + js);
+            acc[ri][js][0] = rv ? cp0[LDB * ce0] : 0.0;
+            acc[ri][js][1] = rv ? cp0[LDB * ce1] : 0.0;
+          }
         }
       }
 #pragma unroll 1
@@ -391,13 +434,15 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
         const int dds = gid < nd ? ctl->ddst[gid] : -1;
         const double li0 = ctl->Linv[gid + 8 * tig], li1 = ctl->Linv[gid + 8 * (4 + tig)];
         // A fragments of the panel's multipliers L[I][p], I > p, shared by all owned column tiles
-        double lt[RT][2];
+        double lt[LT_REGS ? RT : 1][2];
+        if (LT_REGS) {
 #pragma unroll
-        for (int I = 1; I < RT; ++I) {
-          const int r = 8 * I + gid;
-          const bool rv = I > p && r < NI;
-          lt[I][0] = rv ? Wt[r + LDW * (c0 + ka0)] : 0.0;
-          lt[I][1] = rv ? Wt[r + LDW * (c0 + ka1)] : 0.0;
+          for (int I = 1; I < RT; ++I) {
+            const int r = 8 * I + gid;
+            const bool rv = I > p && r < NI;
+            lt[I][0] = rv ? Wt[r + LDW * (c0 + ka0)] : 0.0;
+            lt[I][1] = rv ? Wt[r + LDW * (c0 + ka1)] : 0.0;
+          }
         }
         int Jfirst = p + 1 + (uw + 3 - (p + 1) % 3) % 3;   // first owned tile > p
 #pragma unroll 1
@@ -420,13 +465,27 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
           if (p + 1 < RT) {
             const double bf0 = neg(colg[c0 + tig]);
             const double bf1 = neg(colg[c0 + 4 + tig]);
+            if (LT_REGS) {
 #pragma unroll
-            for (int I = 1; I < RT; ++I) {
-              if (I > p) {
-                const bool rv = 8 * I + gid < NI;
+              for (int I = 1; I < RT; ++I) {
+                if (I > p) {
+                  const bool rv = 8 * I + gid < NI;
+                  double d0 = rv ? cc0[8 * I] : 0.0, d1 = rv ? cc1[8 * I] : 0.0;
+                  dmma(d0, d1, lt[I][0], bf0);
+                  dmma(d0, d1, lt[I][1], bf1);
+                  if (rv) { cc0[8 * I] = d0; cc1[8 * I] = d1; }
+                }
+              }
+            } else {
+#pragma unroll 1
+              for (int I = p + 1; I < RT; ++I) {
+                const int r = 8 * I + gid;
+                const bool rv = r < NI;
+                const double a0 = rv ? Wt[r + LDW * (c0 + ka0)] : 0.0;
+                const double a1 = rv ? Wt[r + LDW * (c0 + ka1)] : 0.0;
                 double d0 = rv ? cc0[8 * I] : 0.0, d1 = rv ? cc1[8 * I] : 0.0;
-                dmma(d0, d1, lt[I][0], bf0);
-                dmma(d0, d1, lt[I][1], bf1);
+                dmma(d0, d1, a0, bf0);
+                dmma(d0, d1, a1, bf1);
                 if (rv) { cc0[8 * I] = d0; cc1[8 * I] = d1; }
               }
             }
@@ -795,6 +854,7 @@ static int launch_dmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double
   int per_sm = 0;
   GHB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
   if (per_sm < 1) return fail(ctx, GHB_ECUDA, "condense_dmma_kernel does not fit on an SM");
+  if (getenv("GHB_DEBUG")) fprintf(stderr, "condense_dmma<%d,%d>: %d CTAs/SM, %zu B smem\n", NI, NB, per_sm, smem);
   DmmaTables tb{p.d_colbase, p.d_rowf, p.d_rowl, p.nfields};
   int64_t grid = std::min<int64_t>(ncells, (int64_t)ctx->sm_count * per_sm);
   kern<<<(unsigned)grid, 128, smem, ctx->stream>>>(tb, p.lenA, p.lenb, ncells, A, b, S, g, info);
