@@ -28,6 +28,9 @@
 #ifndef GHB_LTREGS
 #define GHB_LTREGS 0
 #endif
+#ifndef GHB_L2PREFETCH
+#define GHB_L2PREFETCH 1
+#endif
 #ifndef GHB_MINB33
 #define GHB_MINB33 7
 #endif
@@ -55,6 +58,16 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
 }
 
 __device__ __forceinline__ double neg(double x) { return -x; }
+
+// one-instruction L2 prefetch of a contiguous global range (UBLKPF): issued by one thread for the record the CTA
+// will process next, so that its cp.async loads hit L2 instead of paying the DRAM latency at the head of the cell
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, unsigned bytes) {
+  // the instruction wants a 16-byte aligned address and size: shrink the range to whole granules (the cut-off
+  // head/tail, at most 15 bytes each, is fetched by the ordinary loads)
+  const unsigned long long a0 = ((unsigned long long)gptr + 15ull) & ~15ull;
+  const unsigned long long a1 = ((unsigned long long)gptr + bytes) & ~15ull;
+  if (a1 > a0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((unsigned)(a1 - a0)) : "memory");
+}
 
 // Shared-memory column permutation inside every 8-column tile (logical columns 4<->5 and 6<->7 swapped):
 // with a leading dimension of 36 doubles it makes the A, B *and* C fragment access patterns of
@@ -382,6 +395,12 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
       }
     }
     if (tid == 0) *s_info = 0;
+#if GHB_L2PREFETCH
+    if (tid == 32 && cell + gridDim.x < ncells) {
+      l2_prefetch_bulk(A + (cell + gridDim.x) * lenA, (unsigned)(lenA * 8));
+      l2_prefetch_bulk(b + (cell + gridDim.x) * lenb, (unsigned)(lenb * 8));
+    }
+#endif
     cp_async_commit_wait_all();
     __syncthreads();
 
@@ -683,6 +702,12 @@ backsub_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const dou
       s_lam[tid] = id > 0 ? lam_free[id - 1] : (id < 0 && lam_dir ? lam_dir[-id - 1] : 0.0);
     }
     if (tid == 0) *s_info = 0;
+#if GHB_L2PREFETCH
+    if (tid == 64 && cell + gridDim.x < ncells) {   // A11 and A12 lead the record; b is small
+      l2_prefetch_bulk(A + (cell + gridDim.x) * lenA, (unsigned)(lenA * 8));
+      l2_prefetch_bulk(b + (cell + gridDim.x) * lenb, (unsigned)(lenb * 8));
+    }
+#endif
     __syncthreads();
     // r = b1 - A12 * lambda_K, ascending columns (gemv!('N',-1,A12,x,1,b1)): one interior row per thread, A12 read
     // straight from the record (consecutive threads read consecutive rows of a column)

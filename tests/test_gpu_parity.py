@@ -88,7 +88,32 @@ def test_pivoting_is_exercised(ctx):
     assert rel_err_cells(S, S0) < 1e-9 and rel_err_cells(g, g0) < 1e-9   # unconditioned random saddle points
 
 
-@pytest.mark.parametrize("name", ["C1_hdg_k1_2d", "C3_hdg_k2_3d", "multifield_2skel", "odd_shapes"])
+@pytest.mark.parametrize("name", ["C2_rth_k2_2d", "C2_rth_k3_2d", "C3_hdg_k2_3d"])
+def test_persistent_grid_wraps(ctx, name):
+    """more cells than resident CTAs (148 SMs x 8): every CTA loops, the next record is prefetched into L2."""
+    plan, op = _dev_plan(ctx, name), oracle_plan(name)
+    n = 2600
+    A, b = _synth(ctx, plan, 77, n)
+    S = torch.empty((n, plan.n_b ** 2), dtype=torch.float64, device="cuda")
+    g = torch.empty((n, plan.n_b), dtype=torch.float64, device="cuda")
+    info = torch.empty(n, dtype=torch.int32, device="cuda")
+    ctx.condense(plan, n, A, b, S, g, info)
+    An, bn = A.cpu().numpy(), b.cpu().numpy()
+    S0, g0, info0 = oc.condense(op, An, bn)
+    assert not info.cpu().numpy().any() and not info0.any()
+    assert rel_err_cells(S.cpu().numpy(), S0) < TOL and rel_err_cells(g.cpu().numpy(), g0) < TOL
+    rng = np.random.default_rng(4)
+    ids = rng.integers(1, 101, (n, plan.n_b))
+    lam = rng.standard_normal(100)
+    u0, _ = oc.backsub(op, An, bn, o.cell_dof_values(lam, np.zeros(0), ids))
+    u = torch.empty((n, plan.n_i), dtype=torch.float64, device="cuda")
+    ctx.backsub(plan, n, A, b, torch.as_tensor(lam, device="cuda"), None, torch.as_tensor(ids, device="cuda"), u, info)
+    assert not info.cpu().numpy().any()
+    assert rel_err_cells(u.cpu().numpy(), u0) < TOL
+
+
+@pytest.mark.parametrize("name", ["C1_hdg_k1_2d", "C2_rth_k2_2d", "C2_rth_k3_2d", "C3_hdg_k2_3d", "multifield_2skel",
+                                  "odd_shapes"])
 def test_backsub_parity_and_factor_reuse(ctx, name):
     plan, op = _dev_plan(ctx, name), oracle_plan(name)
     n = 33
