@@ -39,6 +39,19 @@ namespace ghb {
 
 namespace {
 
+// Optional timeline trace (compile with -DGHB_TRACE, see tools/trace_condense.cu): CTA 0 records clock64() at the
+// phase boundaries of its first cells into a global buffer.  No effect on the product build.
+#ifdef GHB_TRACE
+__device__ long long g_trace[64 * 4 * 64];
+#define TRACE(ev)                                                                                      \
+  do {                                                                                                 \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && trace_cell < 64)                                 \
+      g_trace[(trace_cell * 4 + (threadIdx.x >> 5)) * 64 + (ev)] = clock64();                          \
+  } while (0)
+#else
+#define TRACE(ev) do { } while (0)
+#endif
+
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(d0), "+d"(d1)
@@ -52,6 +65,15 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc));
+}
+// zero-filling variants: `ok == false` writes zeros without reading (src-size 0), so the loader has no branch
+__device__ __forceinline__ void cp_async16_z(void* smem_dst, const void* gsrc, bool ok) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gsrc), "r"(ok ? 16 : 0));
+}
+__device__ __forceinline__ void cp_async8_z(void* smem_dst, const void* gsrc, bool ok) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gsrc), "r"(ok ? 8 : 0));
 }
 __device__ __forceinline__ void cp_async_commit_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
@@ -343,6 +365,7 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
   constexpr int HP = N / RPC;                   // copy units per column
   constexpr int LG = 128 / HP;                  // column groups
   static_assert(LG >= 1, "cell too tall for the loader");
+  constexpr int LB = 6;                         // loader batch: look-ups in flight per thread
   const int l_grp = tid / HP, l_rp = tid - l_grp * HP;
   const bool l_on = l_grp < LG;
   const int l_ri = l_on ? s_rowinfo[l_rp] : 0;
@@ -351,19 +374,29 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
   double* const l_dst0 = l_top ? Wt + RPC * l_rp : Bt + (RPC * l_rp - NI);
   const int l_ld = l_top ? LDW : LDB;
 
-  for (int64_t cell = blockIdx.x; cell < ncells; cell += gridDim.x) {
+  int trace_cell = 0; (void)trace_cell;
+  for (int64_t cell = blockIdx.x; cell < ncells; cell += gridDim.x, ++trace_cell) {
     // ------------------------------------------------------------------ load + re-layout
+    TRACE(0);
     if (l_on) {
       const double* Arec = A + cell * lenA + l_lr;
       const double* brec = b + cell * lenb + l_lr;
       const int* cb = s_colbase + l_f;
       const int cend = (l_top || !C::DIRECT_S) ? N : 8 * SJ0;   // DIRECT_S: only the A21 tiles of boundary rows live in Bt
-#pragma unroll 4
-      for (int c = l_grp; c < cend; c += LG) {
-        const int off = cb[c * tb.nf];
-        double* dst = l_dst0 + l_ld * pc(c);
-        if (off >= 0) { if (RPC == 2) cp_async16(dst, Arec + off); else cp_async8(dst, Arec + off); }
-        else { dst[0] = 0.0; if (RPC == 2) dst[1] = 0.0; }
+      // batches of LB columns: all table look-ups first, then the copies, so that the shared-memory latency of the
+      // look-up is paid once per batch instead of once per copy (the copies are volatile asm and do not reorder)
+#pragma unroll 1
+      for (int cb0 = l_grp; cb0 < cend; cb0 += LB * LG) {
+        int off[LB];
+#pragma unroll
+        for (int q = 0; q < LB; ++q) { const int c = cb0 + q * LG; off[q] = c < cend ? cb[c * tb.nf] : -2; }
+#pragma unroll
+        for (int q = 0; q < LB; ++q) {
+          const int c = cb0 + q * LG;
+          double* dst = l_dst0 + l_ld * pc(c);
+          const double* src = Arec + (off[q] >= 0 ? off[q] : 0);   // untouched block: zero fill, nothing read
+          if (off[q] != -2) { if (RPC == 2) cp_async16_z(dst, src, off[q] >= 0); else cp_async8_z(dst, src, off[q] >= 0); }
+        }
       }
       if ((l_top || !C::DIRECT_S) && l_grp == N % LG) {                                              // rhs column
         if (RPC == 2) cp_async16(l_dst0 + l_ld * pc(N), brec + cb[N * tb.nf]);
@@ -394,6 +427,7 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
         }
       }
     }
+    TRACE(1);
     if (tid == 0) *s_info = 0;
 #if GHB_L2PREFETCH
     if (tid == 32 && cell + gridDim.x < ncells) {
@@ -403,6 +437,7 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
 #endif
     cp_async_commit_wait_all();
     __syncthreads();
+    TRACE(2);
 
     if (warp == 0) {
       // ================================================================ panel warp
@@ -411,12 +446,15 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
         const int c0 = 8 * p;
         const int npiv = (NI - c0) < 8 ? (NI - c0) : 8;
         if (p > 0) bar_sync<BAR_COL, 64>(p & 1);             // column tile p is up to date
+        TRACE(4 + 6 * p);
         PanelCtl* ctl = ctl2 + (p & 1);
         if ((NI - c0) > 32) panel_factor<NI, LDW, true>(Wt, c0, npiv, ctl, s_info);
         else panel_factor<NI, LDW, false>(Wt, c0, npiv, ctl, s_info);
+        TRACE(5 + 6 * p);
         bar_arrive<BAR_PANEL, 128>(p & 1);
         // inv(U_pp) for the bottom block, computed while the update warps prepare the next column tile
         invert_upper<LDW>(Wt + c0 + LDW * c0, npiv, ctl->rinv, ctl->Dinv);
+        TRACE(6 + 6 * p);
         bar_arrive<BAR_UDONE, 128>(p & 1);
       }
     } else {
@@ -442,9 +480,11 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
         const int npiv = (NI - c0) < 8 ? (NI - c0) : 8;
         PanelCtl* ctl = ctl2 + (p & 1);
         bar_sync<BAR_PANEL, 128>(p & 1);
+        TRACE(4 + 6 * p);
         // ---- the owner of the next panel's column tile inverts L_pp (on the critical path)
         if (uw == (p + 1) % 3) invert_unit_lower<LDW>(Wt + c0 + LDW * c0, npiv, ctl->Linv);
         bar_sync<BAR_UW, 96>(p & 1);
+        TRACE(5 + 6 * p);
         // ---- owned column tiles J > p (J = uw mod 3); the next panel's tile first
         const int nd = ctl->ndisp;
         const int ps0 = tig < npiv ? ctl->psrc[tig] : -1;
@@ -512,7 +552,9 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
           if (J == p + 1 && p + 1 < NP) bar_arrive<BAR_COL, 64>((p + 1) & 1);
         }
         // ---- bottom block, owned row tiles: needs every U[p][J] and Dinv_p (from the panel warp)
+        TRACE(6 + 6 * p);
         bar_sync<BAR_UDONE, 128>(p & 1);
+        TRACE(7 + 6 * p);
         const double dj0 = ctl->Dinv[tig + 8 * gid], dj1 = ctl->Dinv[4 + tig + 8 * gid];
         const double* ub0 = Wt + c0 + tig + LDW * nb;        // B fragment of U[p][J]: ub0[LDW*8*J], ub0[4 + LDW*8*J]
         if (npiv == 8) {
@@ -598,7 +640,9 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
               if (uw * MAXROWS + ri < BT) dmma(acc[ri][js][0], acc[ri][js][1], lq[ri], bf0);
           }
         }
+        TRACE(8 + 6 * p);
       }
+      TRACE(40);
       // ---- store S, g
       const bool failed = *s_info != 0;
       const double qnan = __longlong_as_double(0x7ff8000000000000LL);
@@ -624,7 +668,9 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
         }
       }
     }
+    TRACE(41);
     __syncthreads();
+    TRACE(42);
     if (info && tid == 0) info[cell] = *s_info;
   }
 }
@@ -672,6 +718,7 @@ backsub_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const dou
   constexpr int HP = (NI + RPC - 1) / RPC;      // copy units per column of A11
   constexpr int LG = 128 / HP;                  // column groups
   static_assert(LG >= 1, "cell too tall for the loader");
+  constexpr int LB = 6;                         // loader batch: look-ups in flight per thread
   for (int i = tid; i < CTB * 8 * LDW; i += 128) Wt[i] = 0.0;
   for (int i = tid; i < (N + 1) * tb.nf; i += 128) s_colbase[i] = tb.colbase[i];
   for (int i = tid; i < HP; i += 128) s_rowinfo[i] = (unsigned short)((tb.rowf[RPC * i] << 8) | tb.rowl[RPC * i]);
@@ -688,12 +735,18 @@ backsub_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const dou
     const double* brec = b + cell * lenb;
     if (l_on) {
       const int* cb = s_colbase + l_f;
-#pragma unroll 4
-      for (int c = l_grp; c < NI; c += LG) {
-        const int off = cb[c * tb.nf];
-        double* dst = Wt + RPC * l_rp + LDW * pc(c);
-        if (off >= 0) { if (RPC == 2) cp_async16(dst, Arec + l_lr + off); else cp_async8(dst, Arec + l_lr + off); }
-        else { dst[0] = 0.0; if (RPC == 2) dst[1] = 0.0; }
+#pragma unroll 1
+      for (int cb0 = l_grp; cb0 < NI; cb0 += LB * LG) {      // look-ups first, then the copies (see the forward kernel)
+        int off[LB];
+#pragma unroll
+        for (int q = 0; q < LB; ++q) { const int c = cb0 + q * LG; off[q] = c < NI ? cb[c * tb.nf] : -2; }
+#pragma unroll
+        for (int q = 0; q < LB; ++q) {
+          const int c = cb0 + q * LG;
+          double* dst = Wt + RPC * l_rp + LDW * pc(c);
+          const double* src = Arec + l_lr + (off[q] >= 0 ? off[q] : 0);
+          if (off[q] != -2) { if (RPC == 2) cp_async16_z(dst, src, off[q] >= 0); else cp_async8_z(dst, src, off[q] >= 0); }
+        }
       }
     }
     // lambda_K through the cell ids (get_cell_dof_values, src/HybridAffineFEOperators.jl:113)
@@ -713,10 +766,11 @@ backsub_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const dou
     // straight from the record (consecutive threads read consecutive rows of a column)
     if (tid < NI) {
       double r = brec[s_colbase[N * tb.nf + r_f] + r_lr];
-#pragma unroll 4
+#pragma unroll 12
       for (int j = 0; j < NB; ++j) {
         const int off = s_colbase[(NI + j) * tb.nf + r_f];
-        if (off >= 0) r = fma(-Arec[off + r_lr], s_lam[j], r);
+        const double a = Arec[(off >= 0 ? off : 0) + r_lr];
+        r = fma(off >= 0 ? -a : 0.0, s_lam[j], r);
       }
       Wt[tid + LDW * pc(NI)] = r;
     }
@@ -879,6 +933,7 @@ static int launch_dmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double
   int per_sm = 0;
   GHB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
   if (per_sm < 1) return fail(ctx, GHB_ECUDA, "condense_dmma_kernel does not fit on an SM");
+  if (const char* cap = getenv("GHB_MAX_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(cap)));   // profiling knob
   if (getenv("GHB_DEBUG")) fprintf(stderr, "condense_dmma<%d,%d>: %d CTAs/SM, %zu B smem\n", NI, NB, per_sm, smem);
   DmmaTables tb{p.d_colbase, p.d_rowf, p.d_rowl, p.nfields};
   int64_t grid = std::min<int64_t>(ncells, (int64_t)ctx->sm_count * per_sm);
@@ -897,6 +952,7 @@ static int launch_bdmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const doubl
   int per_sm = 0;
   GHB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
   if (per_sm < 1) return fail(ctx, GHB_ECUDA, "backsub_dmma_kernel does not fit on an SM");
+  if (const char* cap = getenv("GHB_MAX_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(cap)));   // profiling knob
   if (getenv("GHB_DEBUG")) fprintf(stderr, "backsub_dmma<%d,%d>: %d CTAs/SM, %zu B smem\n", NI, NB, per_sm, smem);
   DmmaTables tb{p.d_colbase, p.d_rowf, p.d_rowl, p.nfields};
   int64_t grid = std::min<int64_t>(ncells, (int64_t)ctx->sm_count * per_sm);
