@@ -31,6 +31,9 @@
 #ifndef GHB_L2PREFETCH
 #define GHB_L2PREFETCH 1
 #endif
+#ifndef GHB_LTREGS34
+#define GHB_LTREGS34 0
+#endif
 #ifndef GHB_MINB33
 #define GHB_MINB33 7
 #endif
@@ -336,7 +339,7 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
   constexpr int SJ0 = NI / 8;                   // first column tile holding S columns
   constexpr int NSJ = CT - SJ0;                 // S column tiles
   constexpr int MAXROWS = (BT + 2) / 3;         // bottom row tiles per update warp
-  constexpr bool LT_REGS = NI != 33 || GHB_LTREGS;             // keep the panel's multipliers in registers across column tiles
+  constexpr bool LT_REGS = (NI != 33 && GHB_LTREGS34) || GHB_LTREGS;             // keep the panel's multipliers in registers across column tiles
   extern __shared__ __align__(16) double smem[];
   double* Wt = smem;
   double* Bt = Wt + C::WT_DOUBLES;
@@ -524,20 +527,43 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
           if (p + 1 < RT) {
             const double bf0 = neg(colg[c0 + tig]);
             const double bf1 = neg(colg[c0 + 4 + tig]);
+            // two row tiles per step with independent accumulators, DMMAs interleaved (the asm statements keep
+            // their order): a single accumulator serialises the whole column tile on the 26-cycle DMMA latency
             if (LT_REGS) {
 #pragma unroll
-              for (int I = 1; I < RT; ++I) {
-                if (I > p) {
-                  const bool rv = 8 * I + gid < NI;
-                  double d0 = rv ? cc0[8 * I] : 0.0, d1 = rv ? cc1[8 * I] : 0.0;
-                  dmma(d0, d1, lt[I][0], bf0);
-                  dmma(d0, d1, lt[I][1], bf1);
-                  if (rv) { cc0[8 * I] = d0; cc1[8 * I] = d1; }
+              for (int I = 1; I < RT; I += 2) {
+                const bool two = I + 1 < RT;
+                if ((two ? I + 1 : I) > p) {
+                  const bool vA = I > p && 8 * I + gid < NI;
+                  const bool vB = two && 8 * (I + 1) + gid < NI;           // I + 1 > p holds here
+                  double dA0 = vA ? cc0[8 * I] : 0.0, dA1 = vA ? cc1[8 * I] : 0.0;
+                  double dB0 = vB ? cc0[8 * I + 8] : 0.0, dB1 = vB ? cc1[8 * I + 8] : 0.0;
+                  dmma(dA0, dA1, lt[I][0], bf0);
+                  if (two) dmma(dB0, dB1, lt[two ? I + 1 : I][0], bf0);
+                  dmma(dA0, dA1, lt[I][1], bf1);
+                  if (two) dmma(dB0, dB1, lt[two ? I + 1 : I][1], bf1);
+                  if (vA) { cc0[8 * I] = dA0; cc1[8 * I] = dA1; }
+                  if (vB) { cc0[8 * I + 8] = dB0; cc1[8 * I + 8] = dB1; }
                 }
               }
             } else {
+              int I = p + 1;
 #pragma unroll 1
-              for (int I = p + 1; I < RT; ++I) {
+              for (; I + 1 < RT; I += 2) {
+                const int rA = 8 * I + gid, rB = rA + 8;
+                const bool vA = rA < NI, vB = rB < NI;
+                const double aA0 = vA ? Wt[rA + LDW * (c0 + ka0)] : 0.0, aA1 = vA ? Wt[rA + LDW * (c0 + ka1)] : 0.0;
+                const double aB0 = vB ? Wt[rB + LDW * (c0 + ka0)] : 0.0, aB1 = vB ? Wt[rB + LDW * (c0 + ka1)] : 0.0;
+                double dA0 = vA ? cc0[8 * I] : 0.0, dA1 = vA ? cc1[8 * I] : 0.0;
+                double dB0 = vB ? cc0[8 * I + 8] : 0.0, dB1 = vB ? cc1[8 * I + 8] : 0.0;
+                dmma(dA0, dA1, aA0, bf0);
+                dmma(dB0, dB1, aB0, bf0);
+                dmma(dA0, dA1, aA1, bf1);
+                dmma(dB0, dB1, aB1, bf1);
+                if (vA) { cc0[8 * I] = dA0; cc1[8 * I] = dA1; }
+                if (vB) { cc0[8 * I + 8] = dB0; cc1[8 * I + 8] = dB1; }
+              }
+              if (I < RT) {
                 const int r = 8 * I + gid;
                 const bool rv = r < NI;
                 const double a0 = rv ? Wt[r + LDW * (c0 + ka0)] : 0.0;
@@ -558,53 +584,84 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
         const double dj0 = ctl->Dinv[tig + 8 * gid], dj1 = ctl->Dinv[4 + tig + 8 * gid];
         const double* ub0 = Wt + c0 + tig + LDW * nb;        // B fragment of U[p][J]: ub0[LDW*8*J], ub0[4 + LDW*8*J]
         if (npiv == 8) {
+          // (every DMMA sequence below is written k-step outermost so that consecutive instructions belong to
+          // independent accumulators: a warp issues in order, and the asm statements keep their order)
           double la[MAXROWS][2];
-#pragma unroll
-          for (int ri = 0; ri < MAXROWS; ++ri) {
-            const int I = uw * MAXROWS + ri;
-            const int r = 8 * I + gid;
-            const bool rv = I < BT && r < NB;
+          {
             // L = X * Dinv with X = Bt tile (I,p) (already updated right-looking): A fragments straight from smem
-            const double xa0 = rv ? Bt[r + LDB * (c0 + ka0)] : 0.0;
-            const double xa1 = rv ? Bt[r + LDB * (c0 + ka1)] : 0.0;
-            double l0 = 0.0, l1 = 0.0;
-            dmma(l0, l1, xa0, dj0);
-            dmma(l0, l1, xa1, dj1);
+            double xa[MAXROWS][2], l[MAXROWS][2];
+#pragma unroll
+            for (int ri = 0; ri < MAXROWS; ++ri) {
+              const int r = 8 * (uw * MAXROWS + ri) + gid;
+              const bool rv = uw * MAXROWS + ri < BT && r < NB;
+              xa[ri][0] = rv ? Bt[r + LDB * (c0 + ka0)] : 0.0;
+              xa[ri][1] = rv ? Bt[r + LDB * (c0 + ka1)] : 0.0;
+              l[ri][0] = 0.0; l[ri][1] = 0.0;
+            }
+#pragma unroll
+            for (int ri = 0; ri < MAXROWS; ++ri) dmma(l[ri][0], l[ri][1], xa[ri][0], dj0);
+#pragma unroll
+            for (int ri = 0; ri < MAXROWS; ++ri) dmma(l[ri][0], l[ri][1], xa[ri][1], dj1);
             __syncwarp();
-            double* bp = Bt + r + LDB * c0;
-            if (rv) { bp[LDB * ce0] = l0; bp[LDB * ce1] = l1; }   // park L to read it back as A fragments
+#pragma unroll
+            for (int ri = 0; ri < MAXROWS; ++ri) {
+              const int r = 8 * (uw * MAXROWS + ri) + gid;
+              const bool rv = uw * MAXROWS + ri < BT && r < NB;
+              double* bp = Bt + r + LDB * c0;
+              if (rv) { bp[LDB * ce0] = l[ri][0]; bp[LDB * ce1] = l[ri][1]; }   // park L to read it back as A fragments
+            }
             __syncwarp();
-            la[ri][0] = rv ? bp[LDB * ka0] : 0.0;
-            la[ri][1] = rv ? bp[LDB * ka1] : 0.0;
+#pragma unroll
+            for (int ri = 0; ri < MAXROWS; ++ri) {
+              const int r = 8 * (uw * MAXROWS + ri) + gid;
+              const bool rv = uw * MAXROWS + ri < BT && r < NB;
+              const double* bp = Bt + r + LDB * c0;
+              la[ri][0] = rv ? bp[LDB * ka0] : 0.0;
+              la[ri][1] = rv ? bp[LDB * ka1] : 0.0;
+            }
           }
           // A21 part still in shared memory: tiles p < J < SJ0
 #pragma unroll 1
           for (int J = p + 1; J < SJ0; ++J) {
             const double bf0 = neg(ub0[LDW * 8 * J]), bf1 = neg(ub0[4 + LDW * 8 * J]);
+            double d[MAXROWS][2];
 #pragma unroll
             for (int ri = 0; ri < MAXROWS; ++ri) {
-              const int I = uw * MAXROWS + ri;
-              const int r = 8 * I + gid;
-              const bool rv = I < BT && r < NB;
+              const int r = 8 * (uw * MAXROWS + ri) + gid;
+              const bool rv = uw * MAXROWS + ri < BT && r < NB;
+              const double* cp0 = Bt + r + LDB * 8 * J;
+              d[ri][0] = rv ? cp0[LDB * ce0] : 0.0; d[ri][1] = rv ? cp0[LDB * ce1] : 0.0;
+            }
+#pragma unroll
+            for (int ri = 0; ri < MAXROWS; ++ri) dmma(d[ri][0], d[ri][1], la[ri][0], bf0);
+#pragma unroll
+            for (int ri = 0; ri < MAXROWS; ++ri) dmma(d[ri][0], d[ri][1], la[ri][1], bf1);
+#pragma unroll
+            for (int ri = 0; ri < MAXROWS; ++ri) {
+              const int r = 8 * (uw * MAXROWS + ri) + gid;
+              const bool rv = uw * MAXROWS + ri < BT && r < NB;
               double* cp0 = Bt + r + LDB * 8 * J;
-              double d0 = rv ? cp0[LDB * ce0] : 0.0, d1 = rv ? cp0[LDB * ce1] : 0.0;
-              dmma(d0, d1, la[ri][0], bf0);
-              dmma(d0, d1, la[ri][1], bf1);
-              if (rv) { cp0[LDB * ce0] = d0; cp0[LDB * ce1] = d1; }
+              if (rv) { cp0[LDB * ce0] = d[ri][0]; cp0[LDB * ce1] = d[ri][1]; }
             }
           }
           // S part in registers
+          // (rows beyond the block have la = 0: their DMMAs leave the unused accumulators alone)
 #pragma unroll
-          for (int js = 0; js < NSJ; ++js) {
-            const int J = SJ0 + js;
-            const double bf0 = neg(ub0[LDW * 8 * J]), bf1 = neg(ub0[4 + LDW * 8 * J]);
+          for (int js = 0; js < NSJ; js += 2) {
+            constexpr int W = 2;
+            double bf[W][2];
 #pragma unroll
-            for (int ri = 0; ri < MAXROWS; ++ri) {
-              if (uw * MAXROWS + ri < BT) {
-                dmma(acc[ri][js][0], acc[ri][js][1], la[ri][0], bf0);
-                dmma(acc[ri][js][0], acc[ri][js][1], la[ri][1], bf1);
-              }
+            for (int q = 0; q < W; ++q) {
+              const int J = SJ0 + (js + q < NSJ ? js + q : js);
+              bf[q][0] = neg(ub0[LDW * 8 * J]); bf[q][1] = neg(ub0[4 + LDW * 8 * J]);
             }
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+#pragma unroll
+              for (int q = 0; q < W; ++q)
+#pragma unroll
+                for (int ri = 0; ri < MAXROWS; ++ri)
+                  if (js + q < NSJ) dmma(acc[ri][js + q < NSJ ? js + q : js][0], acc[ri][js + q < NSJ ? js + q : js][1], la[ri][k], bf[q][k]);
           }
         } else {
           // partial last panel (npiv < 8): its column tile is the first S tile, held in registers.
