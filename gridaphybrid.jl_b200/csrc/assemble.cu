@@ -227,41 +227,73 @@ __device__ __forceinline__ const double* s_column(const double* S, const GhostVi
                              : gv.G + (c - gv.ncells_local) * gv.stride + (int64_t)l * n_b;
 }
 
+#ifndef GHB_GATHER_MINB
+#define GHB_GATHER_MINB 8
+#endif
+#ifndef GHB_GATHER_UNR
+#define GHB_GATHER_UNR 5
+#endif
+
+// (cell, local dof) of an occurrence code o = cell*n_b + l without a 64-bit division: M = ceil(2^64 / n_b),
+// exact for o < 2^56 and n_b <= 255 (the error term o*(M*n_b - 2^64) stays below 2^64)
+__device__ __forceinline__ void occ_decode(unsigned long long o, unsigned long long M, int n_b, int64_t& c, int& l) {
+  const unsigned long long q = n_b == 1 ? o : __umul64hi(o, M);
+  c = (int64_t)q;
+  l = (int)(o - q * (unsigned long long)n_b);
+}
+
 // GL lanes per column: a facet column of C3 has <= 66 entries, so 16 lanes waste less than 32 and double the
-// number of independent columns in flight (17 ms -> 12 ms at 128^3).
+// number of independent columns in flight (17 ms -> 12 ms at 128^3).  The kernel is a chain of dependent DRAM
+// accesses per column (colptr/occ -> gather map -> S -> store): the metadata of the group's next column is fetched
+// while the current one is processed, the gather-map bytes of UNR entries are read before their S values, and the
+// kernel is compiled for 8 resident blocks per SM (tools/time_assembly.py: 13.8 -> 11.7 ms at 128^3).  Loading the
+// two S columns whole and permuting them through shared memory measured no better (13.9 ms).
 template <int GL>
-__global__ void __launch_bounds__(256) gather_nzval_kernel(int64_t nrows, int n_b, const int64_t* __restrict__ colptr,
+__global__ void __launch_bounds__(256, GHB_GATHER_MINB) gather_nzval_kernel(int64_t nrows, int n_b, const int64_t* __restrict__ colptr,
                                                            const unsigned long long* __restrict__ occ,
                                                            const uint8_t* __restrict__ src,
                                                            const double* __restrict__ S, GhostView gv,
                                                            double* __restrict__ nzval) {
+  constexpr int UNR = GHB_GATHER_UNR;
   const int gl = threadIdx.x % GL;
-  const int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GL;
   const int64_t ngrp = ((int64_t)gridDim.x * blockDim.x) / GL;
-  for (int64_t j = grp; j < nrows; j += ngrp) {
-    const int64_t p0 = colptr[j] - 1, p1 = colptr[j + 1] - 1;
-    if (p0 == p1) continue;
-    const unsigned long long o0 = occ[2 * j], o1 = occ[2 * j + 1];
-    const int64_t c0 = (int64_t)(o0 / n_b);
-    const int l0 = (int)(o0 - (unsigned long long)c0 * n_b);
-    const double* col0 = s_column(S, gv, c0, l0, n_b);
-    const double* col1 = nullptr;
-    if (o1 != ~0ull) {
-      const int64_t c1 = (int64_t)(o1 / n_b);
-      const int l1 = (int)(o1 - (unsigned long long)c1 * n_b);
-      col1 = s_column(S, gv, c1, l1, n_b);
-    }
-    for (int64_t p = p0 + gl; p < p1; p += GL) {
-      const uint8_t a = src[2 * p], bq = src[2 * p + 1];
-      double v;
-      if (a != 255) {
-        v = col0[a];
-        if (bq != 255) v += col1[bq];  // cell-ascending order, as the reference's COO sum
-      } else {
-        v = col1[bq];
+  int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GL;
+  if (j >= nrows) return;
+  const unsigned long long M = n_b > 1 ? 0xffffffffffffffffull / (unsigned)n_b + 1ull : 0ull;
+  const unsigned short* __restrict__ src16 = reinterpret_cast<const unsigned short*>(src);   // (a, b) byte pairs
+  int64_t p0 = colptr[j] - 1, p1 = colptr[j + 1] - 1;
+  unsigned long long o0 = occ[2 * j], o1 = occ[2 * j + 1];
+  while (true) {
+    const int64_t jn = j + ngrp;
+    int64_t np0 = 0, np1 = 0;
+    unsigned long long no0 = ~0ull, no1 = ~0ull;
+    if (jn < nrows) { np0 = colptr[jn] - 1; np1 = colptr[jn + 1] - 1; no0 = occ[2 * jn]; no1 = occ[2 * jn + 1]; }
+    if (p0 != p1) {
+      int64_t c0, c1 = 0;
+      int l0, l1 = 0;
+      occ_decode(o0, M, n_b, c0, l0);
+      const double* col0 = s_column(S, gv, c0, l0, n_b);
+      const double* col1 = col0;
+      if (o1 != ~0ull) { occ_decode(o1, M, n_b, c1, l1); col1 = s_column(S, gv, c1, l1, n_b); }
+      const int len = (int)(p1 - p0);                      // entries of this column
+      const unsigned short* sp = src16 + p0;
+      double* nz = nzval + p0;
+      for (int pb = gl; pb < len; pb += UNR * GL) {
+        unsigned sc[UNR];
+#pragma unroll
+        for (int q = 0; q < UNR; ++q) sc[q] = pb + q * GL < len ? sp[pb + q * GL] : 0xffffu;
+#pragma unroll
+        for (int q = 0; q < UNR; ++q) {
+          const unsigned a = sc[q] & 0xffu, bq = sc[q] >> 8;
+          const double va = a != 255u ? col0[a] : 0.0;
+          const double vb = bq != 255u ? col1[bq] : 0.0;
+          // cell-ascending order, as the reference's COO sum
+          if (pb + q * GL < len) nz[pb + q * GL] = a != 255u ? (bq != 255u ? va + vb : va) : vb;
+        }
       }
-      nzval[p] = v;
     }
+    if (jn >= nrows) break;
+    j = jn; p0 = np0; p1 = np1; o0 = no0; o1 = no1;
   }
 }
 
