@@ -80,6 +80,7 @@ void ghb_destroy(ghb_ctx* ctx) {
     if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
   delete ctx;
 }
 
@@ -367,21 +368,42 @@ int ghb_condense_assemble_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const d
   int rc = GHB_OK;
   if (!hostA) {
     rc = launch_condense(ctx, *p, ncells, A, b, dS, dg, di.dev, nullptr);
+    if (rc == GHB_OK) {
+      Arg<double> dz(ctx, nzval, (size_t)as.nnz, false, true); rc = dz.rc;
+      Arg<double> dr(ctx, rhs, (size_t)as.nrows, false, true); if (rc == GHB_OK) rc = dr.rc;
+      if (rc == GHB_OK) rc = asm_numeric(ctx, dS, dg, nullptr, dirichlet_vals, dz.dev, dr.dev);
+      if (rc == GHB_OK) rc = dz.finish();
+      if (rc == GHB_OK) rc = dr.finish();
+    }
   } else {
-    // stream host records through two device chunk buffers: H2D of chunk k+1 overlaps condensation of chunk k
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(ncells, (int64_t)(256u << 20) / ((p->lenA + p->lenb) * 8)));
+    // Host records are streamed through two device chunk buffers: the H2D copy of chunk k+1 overlaps the
+    // condensation of chunk k.  After chunk k the columns whose cells have all been condensed are assembled and, if
+    // nzval/rhs are host arrays, copied back on a third stream, so that the D2H traffic overlaps the H2D traffic.
+    int64_t chunk_bytes = (int64_t)(256u << 20);
+    if (const char* e = getenv("GHB_STREAM_CHUNK_BYTES")) chunk_bytes = std::max<int64_t>(1, atoll(e));   // tests: force many chunks
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(ncells, chunk_bytes / ((p->lenA + p->lenb) * 8)));
+    const int nchunks = (int)((ncells + chunk - 1) / chunk);
+    rc = asm_ready_columns(ctx, chunk, nchunks);
+    Arg<double> dz(ctx, nzval, (size_t)as.nnz, false, false); if (rc == GHB_OK) rc = dz.rc;   // copied back piecewise
+    Arg<double> dr(ctx, rhs, (size_t)as.nrows, false, false); if (rc == GHB_OK) rc = dr.rc;
+    if (rc == GHB_OK && (dz.host || dr.host) && !ctx->d2h_stream &&
+        cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking) != cudaSuccess)
+      rc = fail(ctx, GHB_ECUDA, "ghb_condense_assemble_f64: cannot create the D2H stream");
     double* dA[2] = {nullptr, nullptr};
     double* db[2] = {nullptr, nullptr};
-    cudaEvent_t h2d_done[2], k_done[2];
-    for (int i = 0; i < 2; ++i) {
-      GHB_CUDA(ctx, cudaMallocAsync((void**)&dA[i], (size_t)chunk * p->lenA * 8, ctx->stream));
-      GHB_CUDA(ctx, cudaMallocAsync((void**)&db[i], (size_t)chunk * p->lenb * 8, ctx->stream));
-      GHB_CUDA(ctx, cudaEventCreateWithFlags(&h2d_done[i], cudaEventDisableTiming));
-      GHB_CUDA(ctx, cudaEventCreateWithFlags(&k_done[i], cudaEventDisableTiming));
+    cudaEvent_t h2d_done[2] = {nullptr, nullptr}, k_done[2] = {nullptr, nullptr}, g_done = nullptr;
+    if (rc == GHB_OK) {
+      for (int i = 0; i < 2; ++i) {
+        GHB_CUDA(ctx, cudaMallocAsync((void**)&dA[i], (size_t)chunk * p->lenA * 8, ctx->stream));
+        GHB_CUDA(ctx, cudaMallocAsync((void**)&db[i], (size_t)chunk * p->lenb * 8, ctx->stream));
+        GHB_CUDA(ctx, cudaEventCreateWithFlags(&h2d_done[i], cudaEventDisableTiming));
+        GHB_CUDA(ctx, cudaEventCreateWithFlags(&k_done[i], cudaEventDisableTiming));
+      }
+      GHB_CUDA(ctx, cudaEventCreateWithFlags(&g_done, cudaEventDisableTiming));
+      GHB_CUDA(ctx, cudaEventRecord(k_done[0], ctx->stream));
+      GHB_CUDA(ctx, cudaEventRecord(k_done[1], ctx->stream));
     }
-    GHB_CUDA(ctx, cudaEventRecord(k_done[0], ctx->stream));
-    GHB_CUDA(ctx, cudaEventRecord(k_done[1], ctx->stream));
-    int64_t c0 = 0;
+    int64_t c0 = 0, jprev = 0, pprev = 0;
     for (int it = 0; c0 < ncells && rc == GHB_OK; ++it, c0 += chunk) {
       int s = it & 1;
       int64_t nc = std::min(chunk, ncells - c0);
@@ -391,20 +413,34 @@ int ghb_condense_assemble_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const d
       GHB_CUDA(ctx, cudaEventRecord(h2d_done[s], ctx->copy_stream));
       GHB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, h2d_done[s], 0));
       rc = launch_condense(ctx, *p, nc, dA[s], db[s], dS + c0 * p->n_b * p->n_b, dg + c0 * p->n_b,
-                                   di.dev ? di.dev + c0 : nullptr, nullptr);
+                           di.dev ? di.dev + c0 : nullptr, nullptr);
       GHB_CUDA(ctx, cudaEventRecord(k_done[s], ctx->stream));
+      // columns completed by this chunk
+      const int64_t jnow = as.ready_J[it], pnow = it + 1 < nchunks ? as.ready_p[it] : as.nnz;
+      if (rc == GHB_OK && jnow > jprev) {
+        rc = asm_numeric_range(ctx, dS, dg, nullptr, dirichlet_vals, dz.dev, dr.dev, jprev, jnow);
+        if (rc == GHB_OK && (dz.host || dr.host)) {
+          GHB_CUDA(ctx, cudaEventRecord(g_done, ctx->stream));
+          GHB_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, g_done, 0));
+          if (dz.host && pnow > pprev)
+            GHB_CUDA(ctx, cudaMemcpyAsync(dz.host + pprev, dz.dev + pprev, (size_t)(pnow - pprev) * 8, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+          if (dr.host)
+            GHB_CUDA(ctx, cudaMemcpyAsync(dr.host + jprev, dr.dev + jprev, (size_t)(jnow - jprev) * 8, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        }
+        jprev = jnow; pprev = pnow;
+      }
+    }
+    if (ctx->d2h_stream && (dz.host || dr.host)) {
+      cudaError_t e = cudaStreamSynchronize(ctx->d2h_stream);
+      if (e != cudaSuccess && rc == GHB_OK) rc = fail(ctx, GHB_ECUDA, std::string("D2H: ") + cudaGetErrorString(e));
     }
     for (int i = 0; i < 2; ++i) {
-      cudaFreeAsync(dA[i], ctx->stream); cudaFreeAsync(db[i], ctx->stream);
-      cudaEventDestroy(h2d_done[i]); cudaEventDestroy(k_done[i]);
+      if (dA[i]) cudaFreeAsync(dA[i], ctx->stream);
+      if (db[i]) cudaFreeAsync(db[i], ctx->stream);
+      if (h2d_done[i]) cudaEventDestroy(h2d_done[i]);
+      if (k_done[i]) cudaEventDestroy(k_done[i]);
     }
-  }
-  if (rc == GHB_OK) {
-    Arg<double> dz(ctx, nzval, (size_t)as.nnz, false, true); rc = dz.rc;
-    Arg<double> dr(ctx, rhs, (size_t)as.nrows, false, true); if (rc == GHB_OK) rc = dr.rc;
-    if (rc == GHB_OK) rc = asm_numeric(ctx, dS, dg, nullptr, dirichlet_vals, dz.dev, dr.dev);
-    if (rc == GHB_OK) rc = dz.finish();
-    if (rc == GHB_OK) rc = dr.finish();
+    if (g_done) cudaEventDestroy(g_done);
   }
   cudaFreeAsync(dS, ctx->stream);
   cudaFreeAsync(dg, ctx->stream);

@@ -249,7 +249,7 @@ __device__ __forceinline__ void occ_decode(unsigned long long o, unsigned long l
 // kernel is compiled for 8 resident blocks per SM (tools/time_assembly.py: 13.8 -> 11.7 ms at 128^3).  Loading the
 // two S columns whole and permuting them through shared memory measured no better (13.9 ms).
 template <int GL>
-__global__ void __launch_bounds__(256, GHB_GATHER_MINB) gather_nzval_kernel(int64_t nrows, int n_b, const int64_t* __restrict__ colptr,
+__global__ void __launch_bounds__(256, GHB_GATHER_MINB) gather_nzval_kernel(int64_t j0, int64_t nrows, int n_b, const int64_t* __restrict__ colptr,
                                                            const unsigned long long* __restrict__ occ,
                                                            const uint8_t* __restrict__ src,
                                                            const double* __restrict__ S, GhostView gv,
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(256, GHB_GATHER_MINB) gather_nzval_kernel(int6
   constexpr int UNR = GHB_GATHER_UNR;
   const int gl = threadIdx.x % GL;
   const int64_t ngrp = ((int64_t)gridDim.x * blockDim.x) / GL;
-  int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GL;
+  int64_t j = j0 + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GL;     // columns [j0, nrows)
   if (j >= nrows) return;
   const unsigned long long M = n_b > 1 ? 0xffffffffffffffffull / (unsigned)n_b + 1ull : 0ull;
   const unsigned short* __restrict__ src16 = reinterpret_cast<const unsigned short*>(src);   // (a, b) byte pairs
@@ -299,11 +299,11 @@ __global__ void __launch_bounds__(256, GHB_GATHER_MINB) gather_nzval_kernel(int6
 
 // rhs gather with the Dirichlet lift g_K - S_K*vals_K (AttachDirichletMap)
 // (ghost contributions arrive already lifted by the sender, see pack_cut_plane_kernel)
-__global__ void gather_rhs_kernel(int64_t nrows, int n_b, const unsigned long long* __restrict__ occ,
+__global__ void gather_rhs_kernel(int64_t i0, int64_t nrows, int n_b, const unsigned long long* __restrict__ occ,
                                   const int64_t* __restrict__ ids, const uint8_t* __restrict__ celldir,
                                   const double* __restrict__ S, const double* __restrict__ g, GhostView gv,
                                   int ghost_ncols, const double* __restrict__ dvals, double* __restrict__ rhs) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;           // rows [i0, nrows)
   if (i >= nrows) return;
   double acc = 0.0;
   bool first = true;
@@ -391,6 +391,7 @@ int asm_symbolic(ghb_ctx* ctx, int64_t ncells_local, int64_t nghost, int ghost_n
   const int64_t nrows = ncols;   // owned columns (== rows of the local rhs)
   as.ncells = ncells; as.ncells_local = ncells_local; as.nghost = nghost; as.ghost_ncols = ghost_ncols;
   as.n_b = n_b; as.nrows = nrows; as.nrows_global = nrows_global; as.col0 = col0;
+  as.ready_chunk = 0; as.ready_J.clear(); as.ready_p.clear();
   const int64_t nent = ncells * n_b;
   const unsigned eb = (unsigned)((nent + 255) / 256), rb = (unsigned)((nrows + 255) / 256);
   int32_t* d_cnt = nullptr;
@@ -448,17 +449,79 @@ int asm_pack_cut_plane(ghb_ctx* ctx, int64_t ncut, int n_b, int ncols, const dou
   return GHB_OK;
 }
 
-int asm_numeric(ghb_ctx* ctx, const double* S, const double* g, const double* ghost, const double* dvals,
-                double* nzval, double* rhs) {
+// numeric assembly of the owned columns [j0, j1) (and the matching rhs entries)
+int asm_numeric_range(ghb_ctx* ctx, const double* S, const double* g, const double* ghost, const double* dvals,
+                      double* nzval, double* rhs, int64_t j0, int64_t j1) {
   const AsmState& as = ctx->as;
+  if (j1 <= j0) return GHB_OK;
   GhostView gv{as.ncells_local, ghost, (int64_t)as.n_b * as.ghost_ncols + as.ghost_ncols};
-  int64_t blocks = std::min<int64_t>((as.nrows + 15) / 16, (int64_t)ctx->sm_count * 16);
-  gather_nzval_kernel<16><<<(unsigned)blocks, 256, 0, ctx->stream>>>(as.nrows, as.n_b, as.d_colptr,
+  int64_t blocks = std::min<int64_t>((j1 - j0 + 15) / 16, (int64_t)ctx->sm_count * 16);
+  gather_nzval_kernel<16><<<(unsigned)blocks, 256, 0, ctx->stream>>>(j0, j1, as.n_b, as.d_colptr,
                                                                  (const unsigned long long*)as.d_occ, as.d_src, S, gv, nzval);
   GHB_LAUNCHED(ctx);
-  gather_rhs_kernel<<<(unsigned)((as.nrows + 255) / 256), 256, 0, ctx->stream>>>(
-      as.nrows, as.n_b, (const unsigned long long*)as.d_occ, as.d_ids, as.d_celldir, S, g, gv, as.ghost_ncols, dvals, rhs);
+  gather_rhs_kernel<<<(unsigned)((j1 - j0 + 255) / 256), 256, 0, ctx->stream>>>(
+      j0, j1, as.n_b, (const unsigned long long*)as.d_occ, as.d_ids, as.d_celldir, S, g, gv, as.ghost_ncols, dvals, rhs);
   GHB_LAUNCHED(ctx);
+  return GHB_OK;
+}
+
+int asm_numeric(ghb_ctx* ctx, const double* S, const double* g, const double* ghost, const double* dvals,
+                double* nzval, double* rhs) {
+  return asm_numeric_range(ctx, S, g, ghost, dvals, nzval, rhs, 0, ctx->as.nrows);
+}
+
+// ---- streaming support (ghb_condense_assemble_f64 with host records): when the cells [0, (k+1)*chunk) have been
+// condensed, the columns [0, J_k) are complete, J_k = first column with an occurrence in a later cell.  One kernel
+// finds, per chunk, the first column that needs it; a suffix minimum on the host turns that into J_k.
+__global__ void first_column_of_chunk_kernel(int64_t nrows, int n_b, int64_t chunk, int nchunks,
+                                             const unsigned long long* __restrict__ occ,
+                                             unsigned long long* __restrict__ first) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nrows) return;
+  const unsigned long long o1 = occ[2 * j + 1], o0 = occ[2 * j];
+  const unsigned long long o = o1 != ~0ull ? o1 : o0;          // occurrences are stored cell-ascending
+  if (o == ~0ull) return;                                      // dof without a cell: an empty column
+  const int64_t k = (int64_t)(o / (unsigned long long)n_b) / chunk;
+  if (k < nchunks) atomicMin(first + k, (unsigned long long)j);
+}
+
+__global__ void pick_colptr_kernel(int n, const int64_t* __restrict__ J, const int64_t* __restrict__ colptr,
+                                   int64_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = colptr[J[i]] - 1;
+}
+
+int asm_ready_columns(ghb_ctx* ctx, int64_t chunk, int nchunks) {
+  AsmState& as = ctx->as;
+  if (as.ready_chunk == chunk && (int)as.ready_J.size() == nchunks) return GHB_OK;
+  unsigned long long* d_first = nullptr;
+  GHB_CUDA(ctx, cudaMallocAsync((void**)&d_first, (size_t)nchunks * 8, ctx->stream));
+  GHB_CUDA(ctx, cudaMemsetAsync(d_first, 0xff, (size_t)nchunks * 8, ctx->stream));
+  first_column_of_chunk_kernel<<<(unsigned)((as.nrows + 255) / 256), 256, 0, ctx->stream>>>(
+      as.nrows, as.n_b, chunk, nchunks, (const unsigned long long*)as.d_occ, d_first);
+  GHB_LAUNCHED(ctx);
+  std::vector<unsigned long long> first(nchunks);
+  GHB_CUDA(ctx, cudaMemcpyAsync(first.data(), d_first, (size_t)nchunks * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  GHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  as.ready_J.assign(nchunks, as.nrows);
+  unsigned long long m = (unsigned long long)as.nrows;
+  for (int k = nchunks - 1; k >= 0; --k) {       // J_k = first column needing a chunk > k
+    as.ready_J[k] = (int64_t)m;
+    m = std::min(m, first[k]);
+  }
+  as.ready_J[nchunks - 1] = as.nrows;
+  // nzval offsets of the boundaries
+  int64_t *d_J = (int64_t*)d_first, *d_p = nullptr;
+  GHB_CUDA(ctx, cudaMallocAsync((void**)&d_p, (size_t)nchunks * 8, ctx->stream));
+  GHB_CUDA(ctx, cudaMemcpyAsync(d_J, as.ready_J.data(), (size_t)nchunks * 8, cudaMemcpyHostToDevice, ctx->stream));
+  pick_colptr_kernel<<<(nchunks + 127) / 128, 128, 0, ctx->stream>>>(nchunks, d_J, as.d_colptr, d_p);
+  GHB_LAUNCHED(ctx);
+  as.ready_p.assign(nchunks, 0);
+  GHB_CUDA(ctx, cudaMemcpyAsync(as.ready_p.data(), d_p, (size_t)nchunks * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  GHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFreeAsync(d_first, ctx->stream);
+  cudaFreeAsync(d_p, ctx->stream);
+  as.ready_chunk = chunk;
   return GHB_OK;
 }
 

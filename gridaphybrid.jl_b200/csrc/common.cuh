@@ -52,6 +52,10 @@ struct AsmState {
   int64_t* d_colptr = nullptr;   // [nrows+1] 1-based
   int64_t* d_rowval = nullptr;   // [nnz] 1-based
   uint8_t* d_src = nullptr;      // [nnz][2] local row index inside occurrence 0 / 1, 255 = none
+  // streaming (host records): columns complete after each chunk of cells, cached per chunk size
+  int64_t ready_chunk = 0;
+  std::vector<int64_t> ready_J;  // [nchunks] number of complete columns once chunks 0..k are condensed
+  std::vector<int64_t> ready_p;  // [nchunks] 0-based nzval offset of column ready_J[k]
 };
 
 struct Factors {
@@ -67,7 +71,8 @@ struct ghb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = true;
-  cudaStream_t copy_stream = nullptr;  // H2D/D2H staging of host-pointer calls
+  cudaStream_t copy_stream = nullptr;  // H2D staging of host-pointer calls
+  cudaStream_t d2h_stream = nullptr;   // results of the streaming path go back while records still come in
   int sm_count = 0;
   size_t smem_optin = 0;
   int64_t launches = 0;
@@ -170,6 +175,9 @@ int launch_backsub_factors(ghb_ctx* ctx, const Plan& p, int64_t ncells, const do
                            const double* lam_dir, const int64_t* ids, double* u);
 int asm_symbolic(ghb_ctx* ctx, int64_t ncells_local, int64_t nghost, int ghost_ncols, int n_b, const int64_t* d_ids,
                  int64_t nrows_global, int64_t col0, int64_t ncols);
+int asm_numeric_range(ghb_ctx* ctx, const double* S, const double* g, const double* ghost, const double* dvals,
+                      double* nzval, double* rhs, int64_t j0, int64_t j1);
+int asm_ready_columns(ghb_ctx* ctx, int64_t chunk, int nchunks);
 int asm_numeric(ghb_ctx* ctx, const double* S, const double* g, const double* ghost, const double* dvals,
                 double* nzval, double* rhs);
 int asm_pack_cut_plane(ghb_ctx* ctx, int64_t ncut, int n_b, int ncols, const double* S, const double* g,

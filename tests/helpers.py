@@ -6,6 +6,10 @@ import scipy.sparse.linalg as spla
 from oracle import hdg_darcy
 from oracle import oracle as o
 
+_HENCKY_TOUCHED = np.ones((8, 8), bool)
+for _i, _j in [(0, 1), (1, 0), (2, 4), (4, 2), (6, 7), (7, 6), (0, 7), (7, 0)]:
+    _HENCKY_TOUCHED[_i, _j] = False
+
 # named configurations of BASELINE.json / SURVEY section 8 (ndofs per field, touched, interior, boundary)
 CONFIGS = {
     "C1_hdg_k1_2d": dict(ndofs=[6, 1, 8], touched=np.ones((3, 3), bool), interior=[1, 2], boundary=[3]),
@@ -21,6 +25,12 @@ CONFIGS = {
                                                [0, 1, 0, 0, 0, 0], [1, 0, 0, 0, 0, 0], [0, 1, 0, 0, 0, 0]], bool),
                              interior=[1, 2, 3, 4], boundary=[5, 6]),
     "odd_shapes": dict(ndofs=[5, 3, 7], touched=np.ones((3, 3), bool), interior=[3, 1], boundary=[2]),
+    # BASELINE.json configs 4 and 5: elasticity HDG k=2 on 3-D hexes (sigma 6*10, u 3*20 ||
+    # u-hat 6*(3*6)) and Hencky HDG k=1 (six bulk fields || two skeleton fields); the Hencky mask leaves the
+    # skeleton-skeleton cross blocks and a few bulk pairs untouched to exercise the zero blocks at this size
+    "C4_elasticity_k2_3d": dict(ndofs=[60, 60, 108], touched=np.ones((3, 3), bool), interior=[1, 2], boundary=[3]),
+    "C5_hencky_k1_3d": dict(ndofs=[12, 12, 4, 24, 24, 30, 18, 54], touched=_HENCKY_TOUCHED,
+                            interior=[1, 2, 3, 4, 5, 6], boundary=[7, 8]),
 }
 
 

@@ -321,6 +321,21 @@ def test_fused_condense_assemble_host_streaming(ctx):
     nz = np.empty(A1.nnz); rhs = np.empty(assem.nrows); info = np.empty(n, dtype=np.int32)
     ctx.condense_assemble(plan, n, host.A, host.b, dv, nz, rhs, info)
     assert np.array_equal(nz, A1.nzval.cpu().numpy()) and np.array_equal(rhs, r1.cpu().numpy()) and not info.any()
+    # many small chunks: columns are assembled and copied back as soon as their cells are condensed
+    import os
+    for chunk_cells in (7, 31):
+        os.environ["GHB_STREAM_CHUNK_BYTES"] = str(chunk_cells * (plan.lenA + plan.lenb) * 8)
+        try:
+            nz2 = np.full(A1.nnz, np.nan); rhs2 = np.full(assem.nrows, np.nan)
+            ctx.condense_assemble(plan, n, host.A, host.b, dv, nz2, rhs2, info)
+            assert np.array_equal(nz2, nz) and np.array_equal(rhs2, rhs) and not info.any()
+            # device outputs with host records
+            nz3 = torch.full((A1.nnz,), float("nan"), dtype=torch.float64, device="cuda")
+            rhs3 = torch.full((assem.nrows,), float("nan"), dtype=torch.float64, device="cuda")
+            ctx.condense_assemble(plan, n, host.A, host.b, dv, nz3, rhs3, info)
+            assert np.array_equal(nz3.cpu().numpy(), nz) and np.array_equal(rhs3.cpu().numpy(), rhs)
+        finally:
+            del os.environ["GHB_STREAM_CHUNK_BYTES"]
 
 
 def test_full_size_properties_c3(ctx):

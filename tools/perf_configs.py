@@ -16,7 +16,11 @@ CONFIGS = {
     "C2 Darcy RT-H k=2 2-D (33,12)": ([24, 9, 12], np.array([[1, 1, 1], [1, 0, 0], [1, 0, 0]], bool), 1 << 20),
     "C2 Darcy RT-H k=3 2-D (56,16)": ([40, 16, 16], np.array([[1, 1, 1], [1, 0, 0], [1, 0, 0]], bool), 1 << 19),
     "C3 Darcy HDG k=2 3-D (34,36)": ([30, 4, 36], np.ones((3, 3), bool), 1 << 20),
+    "C4 Elasticity HDG k=2 3-D (120,108)": ([60, 60, 108], np.ones((3, 3), bool), 1 << 15),
 }
+INTERIOR = {"C4 Elasticity HDG k=2 3-D (120,108)": ([1, 2], [3])}
+if os.environ.get("GHB_PERF_ONLY"):
+    CONFIGS = {k: v for k, v in CONFIGS.items() if os.environ["GHB_PERF_ONLY"] in k}
 peak = 6545.9
 try:
     peak = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
