@@ -1,0 +1,40 @@
+"""Small driver for compute-sanitizer: every tuned kernel once on a few cells (memcheck / racecheck / synccheck)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import gridaphybrid_b200 as gh  # noqa: E402
+
+ctx = gh.Context(0)
+shapes = {"(7,8)": ([6, 1, 8], np.ones((3, 3), bool)), "(16,8)": ([12, 4, 8], np.array([[1, 1, 1], [1, 0, 0], [1, 0, 0]], bool)),
+          "(33,12)": ([24, 9, 12], np.array([[1, 1, 1], [1, 0, 0], [1, 0, 0]], bool)),
+          "(56,16)": ([40, 16, 16], np.array([[1, 1, 1], [1, 0, 0], [1, 0, 0]], bool)),
+          "(34,36)": ([30, 4, 36], np.ones((3, 3), bool)), "(5+7,3) generic": ([5, 3, 7], np.ones((3, 3), bool))}
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1500
+for name, (ndofs, touched) in shapes.items():
+    plan = ctx.plan_blocks(ndofs, touched, [1, 2] if "generic" not in name else [3, 1], [3] if "generic" not in name else [2])
+    A = torch.empty((n, plan.lenA), dtype=torch.float64, device="cuda"); b = torch.empty((n, plan.lenb), dtype=torch.float64, device="cuda")
+    ctx.synth_fill(plan, 0, n, A, b)
+    S = torch.empty((n, plan.n_b ** 2), dtype=torch.float64, device="cuda"); g = torch.empty((n, plan.n_b), dtype=torch.float64, device="cuda")
+    info = torch.empty(n, dtype=torch.int32, device="cuda")
+    ctx.condense(plan, n, A, b, S, g, info)
+    lam = torch.randn(n * plan.n_b, dtype=torch.float64, device="cuda")
+    ids = torch.arange(1, n * plan.n_b + 1, dtype=torch.int64, device="cuda")
+    u = torch.empty((n, plan.n_i), dtype=torch.float64, device="cuda")
+    ctx.backsub(plan, n, A, b, lam, None, ids, u, info)
+    torch.cuda.synchronize()
+    print(name, plan.kernel_name, "ok", float(S.abs().max()), float(u.abs().max()))
+# assembly on a small mesh
+sk = gh.CartesianSkeleton((6, 5, 4), ctx)
+M = gh.FacetFESpace(sk, 6, sk.facet_is_boundary())
+asm = gh.SparseMatrixAssembler(M)
+colptr, rowval, nnz = asm.symbolic()
+nc = asm.cell_ids.shape[0]
+S = torch.randn((nc, 36 * 36), dtype=torch.float64, device="cuda"); g = torch.randn((nc, 36), dtype=torch.float64, device="cuda")
+nz = torch.empty(nnz, dtype=torch.float64, device="cuda"); rhs = torch.empty(asm.nrows, dtype=torch.float64, device="cuda")
+ctx.assemble_numeric(S, g, M.dirichlet_values, nz, rhs)
+torch.cuda.synchronize()
+print("assembly ok", nnz)
