@@ -23,6 +23,7 @@ int launch_condense(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A
                     double* g, int32_t* info, double* X) {
   if (p.use_dmma && X == nullptr) return launch_condense_dmma(ctx, p, ncells, A, b, S, g, info);
   if (p.use_warp && X == nullptr) return launch_condense_warp(ctx, p, ncells, A, b, S, g, info);
+  if (p.use_large) return launch_condense_large(ctx, p, ncells, A, b, S, g, info, X);
   return launch_condense_generic(ctx, p, ncells, A, b, S, g, info, X);
 }
 
@@ -183,6 +184,11 @@ int ghb_plan_blocks(ghb_ctx* ctx, int nfields, const int32_t* ndofs, const uint8
   } else if (warp_kernel_name(*p) && !(force && force[0] == '1')) {
     p->use_warp = true;
     p->kernel_name = warp_kernel_name(*p);
+  } else if (large_supported(ctx, *p) && !(force && force[0] == '1')) {
+    int rc = dmma_prepare(ctx, *p);      // same re-layout tables
+    if (rc != GHB_OK) { cudaFree(p->d_emap); delete p; return rc; }
+    p->use_large = true;
+    p->kernel_name = "large_dmma";
   }
   ctx->plans.push_back(p);
   *plan_id = (int)ctx->plans.size() - 1;
@@ -473,6 +479,8 @@ int ghb_backsub_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A, 
     Arg<double> db(ctx, b, (size_t)ncells * p->lenb, true, false); GHB_TRY(db.rc);
     if (p->use_dmma && !getenv("GHB_FORCE_GENERIC"))
       GHB_TRY(launch_backsub_dmma(ctx, *p, ncells, dA.dev, db.dev, lambda_free, lambda_dirichlet, dids.dev, du.dev, di.dev));
+    else if (p->use_large)
+      GHB_TRY(launch_backsub_large(ctx, *p, ncells, dA.dev, db.dev, lambda_free, lambda_dirichlet, dids.dev, du.dev, di.dev));
     else if (p->use_warp)
       GHB_TRY(launch_backsub_warp(ctx, *p, ncells, dA.dev, db.dev, lambda_free, lambda_dirichlet, dids.dev, du.dev, di.dev));
     else

@@ -33,6 +33,7 @@ struct Plan {
   uint8_t* d_rowl = nullptr;
   bool use_dmma = false;
   bool use_warp = false;          // register-resident warp kernels for small cells (condense_warp.cu)
+  bool use_large = false;         // streamed large-cell kernel, 64 < n_i <= 128 (condense_large.cu)
   bool all_touched = false;
   const char* kernel_name = "generic";
   PlanDev dev() const { return PlanDev{n_i, n_b, n, lenA, lenb, d_emap}; }
@@ -162,6 +163,11 @@ int launch_backsub_dmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const doubl
 int launch_backsub_warp(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b,
                         const double* lam_free, const double* lam_dir, const int64_t* ids, double* u, int32_t* info);
 bool dmma_supported(const Plan& p);
+bool large_supported(const ghb_ctx* ctx, const Plan& p);
+int launch_condense_large(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
+                          double* g, int32_t* info, double* X);
+int launch_backsub_large(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b,
+                         const double* lam_free, const double* lam_dir, const int64_t* ids, double* u, int32_t* info);
 int dmma_prepare(ghb_ctx* ctx, Plan& p);
 int launch_condense_dmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
                          double* g, int32_t* info);

@@ -113,7 +113,7 @@ def test_persistent_grid_wraps(ctx, name):
 
 
 @pytest.mark.parametrize("name", ["C1_hdg_k1_2d", "C2_rth_k2_2d", "C2_rth_k3_2d", "C3_hdg_k2_3d", "multifield_2skel",
-                                  "odd_shapes"])
+                                  "odd_shapes", "C4_elasticity_k2_3d", "C5_hencky_k1_3d"])
 def test_backsub_parity_and_factor_reuse(ctx, name):
     plan, op = _dev_plan(ctx, name), oracle_plan(name)
     n = 33
