@@ -28,10 +28,19 @@ namespace ghb {
 
 namespace {
 
+// optional phase timing (-DGHB_LTRACE): thread 0 of CTA 0 prints clock64() deltas of its first cell
+#ifdef GHB_LTRACE
+__device__ long long g_ltrace[256];
+__device__ const char* g_lname[256];
+#define LTRACE(name) do { if (blockIdx.x == 0 && threadIdx.x == 0 && cell == 0 && t_n < 256) { g_ltrace[t_n] = clock64(); g_lname[t_n] = name; ++t_n; } } while (0)
+#else
+#define LTRACE(name) do { } while (0)
+#endif
+
 constexpr int kLT = 256;       // threads per CTA (8 warps), one CTA per SM
 constexpr int kWarps = kLT / 32;
 constexpr int kCT = 8;         // column tiles of [A12 | b1] per chunk: one per warp
-constexpr int kMaxSets = 4;    // the panel warp holds up to 4 rows per lane (n_i <= 128)
+// (the panel warp holds up to 4 rows per lane: n_i <= 128)
 
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -49,6 +58,20 @@ __device__ __forceinline__ double fast_rcp(double x) {
   r = fma(r, e, r);
   e = fma(-x, r, 1.0);
   return fma(r, e, r);
+}
+
+__device__ __forceinline__ void cp_async8_z(void* smem_dst, const void* gsrc, bool ok) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(gsrc), "r"(ok ? 8 : 0));
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+// one-instruction L2 prefetch of a contiguous global range (16-byte granules)
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, size_t bytes) {
+  const unsigned long long a0 = ((unsigned long long)gptr + 15ull) & ~15ull;
+  const unsigned long long a1 = ((unsigned long long)gptr + bytes) & ~15ull;
+  if (a1 > a0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((unsigned)(a1 - a0)) : "memory");
 }
 
 struct LCtl {
@@ -69,6 +92,7 @@ struct LargeTables {
 };
 
 // ---- panel factorisation by one warp: rows [c0, ni) of the 8 columns [c0, c0+8) -------------------
+template <int kMaxSets>
 __device__ __forceinline__ void panel_factor_l(double* __restrict__ Wa, const int ld, const int ni, const int c0,
                                                const int npiv, LCtl* ctl, int* __restrict__ info) {
   const int lane = threadIdx.x & 31;
@@ -264,30 +288,27 @@ __device__ __forceinline__ void tile_lower_step(double* __restrict__ T, const do
   __syncwarp();
   if (p + 1 < NT) {
     const double bf0 = -colg[c0 + tig], bf1 = -colg[c0 + 4 + tig];
-    int I = p + 1;
+    // four row tiles per step: independent accumulators, k-step outermost (a warp issues in order)
 #pragma unroll 1
-    for (; I + 1 < NT; I += 2) {
-      const int rA = 8 * I + gid, rB = rA + 8;
-      const bool vA = rA < ni, vB = rB < ni;
-      const double aA0 = vA ? Wa[rA + ld * (c0 + ka0)] : 0.0, aA1 = vA ? Wa[rA + ld * (c0 + ka1)] : 0.0;
-      const double aB0 = vB ? Wa[rB + ld * (c0 + ka0)] : 0.0, aB1 = vB ? Wa[rB + ld * (c0 + ka1)] : 0.0;
-      double dA0 = vA ? cc0[8 * I] : 0.0, dA1 = vA ? cc1[8 * I] : 0.0;
-      double dB0 = vB ? cc0[8 * I + 8] : 0.0, dB1 = vB ? cc1[8 * I + 8] : 0.0;
-      dmma(dA0, dA1, aA0, bf0);
-      dmma(dB0, dB1, aB0, bf0);
-      dmma(dA0, dA1, aA1, bf1);
-      dmma(dB0, dB1, aB1, bf1);
-      if (vA) { cc0[8 * I] = dA0; cc1[8 * I] = dA1; }
-      if (vB) { cc0[8 * I + 8] = dB0; cc1[8 * I + 8] = dB1; }
-    }
-    if (I < NT) {
-      const int r = 8 * I + gid;
-      const bool rv = r < ni;
-      const double a0 = rv ? Wa[r + ld * (c0 + ka0)] : 0.0, a1 = rv ? Wa[r + ld * (c0 + ka1)] : 0.0;
-      double d0 = rv ? cc0[8 * I] : 0.0, d1 = rv ? cc1[8 * I] : 0.0;
-      dmma(d0, d1, a0, bf0);
-      dmma(d0, d1, a1, bf1);
-      if (rv) { cc0[8 * I] = d0; cc1[8 * I] = d1; }
+    for (int I = p + 1; I < NT; I += 4) {
+      double a0[4], a1[4], d0[4], d1[4];
+      bool vv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = 8 * (I + q) + gid;
+        vv[q] = I + q < NT && r < ni;
+        a0[q] = vv[q] ? Wa[r + ld * (c0 + ka0)] : 0.0;
+        a1[q] = vv[q] ? Wa[r + ld * (c0 + ka1)] : 0.0;
+        d0[q] = vv[q] ? cc0[8 * (I + q)] : 0.0;
+        d1[q] = vv[q] ? cc1[8 * (I + q)] : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dmma(d0[q], d1[q], a0[q], bf0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dmma(d0[q], d1[q], a1[q], bf1);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (vv[q]) { cc0[8 * (I + q)] = d0[q]; cc1[8 * (I + q)] = d1[q]; }
     }
   }
   __syncwarp();
@@ -314,27 +335,25 @@ __device__ __forceinline__ void tile_upper_step(double* __restrict__ T, const do
   if (p > 0) {
     const double bf0 = c0 + tig < ni ? -colg[c0 + tig] : 0.0;
     const double bf1 = c0 + 4 + tig < ni ? -colg[c0 + 4 + tig] : 0.0;
-    int I = 0;
 #pragma unroll 1
-    for (; I + 1 < p; I += 2) {
-      const int rA = 8 * I + gid, rB = rA + 8;
-      const double aA0 = Wa[rA + ld * (c0 + ka0)], aA1 = Wa[rA + ld * (c0 + ka1)];
-      const double aB0 = Wa[rB + ld * (c0 + ka0)], aB1 = Wa[rB + ld * (c0 + ka1)];
-      double dA0 = cc0[8 * I], dA1 = cc1[8 * I], dB0 = cc0[8 * I + 8], dB1 = cc1[8 * I + 8];
-      dmma(dA0, dA1, aA0, bf0);
-      dmma(dB0, dB1, aB0, bf0);
-      dmma(dA0, dA1, aA1, bf1);
-      dmma(dB0, dB1, aB1, bf1);
-      cc0[8 * I] = dA0; cc1[8 * I] = dA1;
-      cc0[8 * I + 8] = dB0; cc1[8 * I + 8] = dB1;
-    }
-    if (I < p) {
-      const int r = 8 * I + gid;
-      const double a0 = Wa[r + ld * (c0 + ka0)], a1 = Wa[r + ld * (c0 + ka1)];
-      double d0 = cc0[8 * I], d1 = cc1[8 * I];
-      dmma(d0, d1, a0, bf0);
-      dmma(d0, d1, a1, bf1);
-      cc0[8 * I] = d0; cc1[8 * I] = d1;
+    for (int I = 0; I < p; I += 4) {
+      double a0[4], a1[4], d0[4], d1[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = 8 * (I + q) + gid;
+        const bool vq = I + q < p;
+        a0[q] = vq ? Wa[r + ld * (c0 + ka0)] : 0.0;
+        a1[q] = vq ? Wa[r + ld * (c0 + ka1)] : 0.0;
+        d0[q] = vq ? cc0[8 * (I + q)] : 0.0;
+        d1[q] = vq ? cc1[8 * (I + q)] : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dmma(d0[q], d1[q], a0[q], bf0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dmma(d0[q], d1[q], a1[q], bf1);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (I + q < p) { cc0[8 * (I + q)] = d0[q]; cc1[8 * (I + q)] = d1[q]; }
     }
   }
   __syncwarp();
@@ -366,18 +385,41 @@ condense_large_kernel(PlanDev pl, LargeTables tb, int ld, int64_t ncells, const 
   for (int i = tid; i < (n + 1) * nf; i += kLT) s_colbase[i] = tb.colbase[i];
   for (int i = tid; i < n; i += kLT) s_rowinfo[i] = (unsigned short)((tb.rowf[i] << 8) | tb.rowl[i]);
   for (int i = tid; i < NT * 8 * ld; i += kLT) Wa[i] = 0.0;
+  for (int i = tid; i < kCT * 8 * ld; i += kLT) Xc[i] = 0.0;
   __syncthreads();
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  const int ngrp = kLT / ni > 0 ? kLT / ni : 1;        // column groups of the A11 loader (n_i <= 128 < kLT)
+  const int ni4 = ni;
 
   for (int64_t cell = blockIdx.x; cell < ncells; cell += gridDim.x) {
     const double* Arec = A + cell * pl.lenA;
     const double* brec = b + cell * pl.lenb;
+#ifdef GHB_LTRACE
+    int t_n = 0;
+    LTRACE("start");
+#endif
     // ------------------------------------------------------------------ A11 -> shared memory
-    for (int idx = tid; idx < ni * ni; idx += kLT) {
-      const int c = idx / ni, r = idx - c * ni;
-      const int ri = s_rowinfo[r];
-      const int off = s_colbase[c * nf + (ri >> 8)];
-      Wa[r + ld * pc(c)] = off >= 0 ? Arec[off + (ri & 0xff)] : 0.0;
+    // the whole record is pulled into L2 now (one instruction per 64 kB piece): the chunk loads and the Schur phase,
+    // tens of microseconds later, then find it there instead of paying DRAM latency on dependent loads
+    if (tid == 32) {
+      const size_t bytes = (size_t)pl.lenA * 8;
+      for (size_t o = 0; o < bytes; o += 65536) l2_prefetch_bulk((const char*)Arec + o, bytes - o < 65536 ? bytes - o : 65536);
+    }
+    {
+      // thread = (row, column group): asynchronous 8-byte copies, all in flight at once
+      const int r = tid % ni4, grp = tid / ni4;       // ni4 = rows rounded so that kLT/ni4 groups exist
+      if (r < ni && grp < ngrp) {
+        const int ri = s_rowinfo[r];
+        const double* src = Arec + (ri & 0xff);
+        const int* cb = s_colbase + (ri >> 8);
+        double* dst = Wa + r;
+#pragma unroll 4
+        for (int c = grp; c < ni; c += ngrp) {
+          const int off = cb[c * nf];
+          cp_async8_z(dst + ld * pc(c), src + (off >= 0 ? off : 0), off >= 0);
+        }
+      }
+      cp_async_commit_wait_all();
     }
     if (tid == 0) *s_info = 0;
     if (MODE == 1) {
@@ -387,22 +429,34 @@ condense_large_kernel(PlanDev pl, LargeTables tb, int ld, int64_t ncells, const 
       }
     }
     __syncthreads();
+    LTRACE("load A11");
     // ------------------------------------------------------------------ LU of A11
-#pragma unroll 1
-    for (int p = 0; p < NT; ++p) {
+    // Bulk-synchronous: warp 0 factorises panel p and inverts its diagonal block, then all warps apply it to the column
+    // tiles to the right.  (A one-panel look-ahead -- warp 0 updating tile p+1 and factorising panel p+1 while warps
+    // 1-7 update the other tiles -- measured slower, 0.68 vs 0.71 M cells/s on (120,108): the panel chain slows down
+    // under the shared-memory traffic of the update warps by more than the hidden update time.)
+    auto factor_panel = [&](int p) {
       const int c0 = 8 * p;
       const int npiv = (ni - c0) < 8 ? (ni - c0) : 8;
       LCtl* ctl = ctlAll + p;
-      if (warp == 0) {
-        panel_factor_l(Wa, ld, ni, c0, npiv, ctl, s_info);
-        __syncwarp();
-        invert_unit_lower_l(Wa + c0 + ld * c0, ld, npiv, LinvAll + 64 * p);
-        invert_upper_l(Wa + c0 + ld * c0, ld, npiv, ctl->rinv, DinvAll + 64 * p);
-      }
+      const int nsets = (ni - c0 + 31) >> 5;              // rows still in play / 32
+      if (nsets >= 4) panel_factor_l<4>(Wa, ld, ni, c0, npiv, ctl, s_info);
+      else if (nsets == 3) panel_factor_l<3>(Wa, ld, ni, c0, npiv, ctl, s_info);
+      else if (nsets == 2) panel_factor_l<2>(Wa, ld, ni, c0, npiv, ctl, s_info);
+      else panel_factor_l<1>(Wa, ld, ni, c0, npiv, ctl, s_info);
+      __syncwarp();
+      invert_unit_lower_l(Wa + c0 + ld * c0, ld, npiv, LinvAll + 64 * p);
+      invert_upper_l(Wa + c0 + ld * c0, ld, npiv, ctl->rinv, DinvAll + 64 * p);
+    };
+#pragma unroll 1
+    for (int p = 0; p < NT; ++p) {
+      if (warp == 0) factor_panel(p);
       __syncthreads();
+      LTRACE("  panel + inverses");
       for (int J = p + 1 + warp; J < NT; J += kWarps)
-        tile_lower_step(Wa + ld * 8 * J, Wa, ld, ni, p, NT, ctl, LinvAll + 64 * p);
+        tile_lower_step(Wa + ld * 8 * J, Wa, ld, ni, p, NT, ctlAll + p, LinvAll + 64 * p);
       __syncthreads();
+      LTRACE("  column tiles");
     }
     const bool failed = *s_info != 0;
     // ------------------------------------------------------------------ [A12 | b1] in chunks of kCT column tiles
@@ -413,17 +467,20 @@ condense_large_kernel(PlanDev pl, LargeTables tb, int ld, int64_t ncells, const 
       const int nt = ntilesR - t0 < kCT ? ntilesR - t0 : kCT;    // tiles of this chunk
       // Xc[row][j] = record(interior row, column n_i + 8*t0 + j)
       if (MODE == 0) {
-        for (int idx = tid; idx < nt * 8 * ni; idx += kLT) {
-          const int j = idx / ni, pos = idx - j * ni;
-          const int c = 8 * t0 + j;                              // column of [A12 | b1]
-          double val = 0.0;
-          if (c <= nbd) {
-            const int ri = s_rowinfo[pos];
-            const int off = s_colbase[(ni + c) * nf + (ri >> 8)];
-            if (off >= 0) val = (c < nbd ? Arec : brec)[off + (ri & 0xff)];
+        const int r = tid % ni4, grp = tid / ni4;
+        if (r < ni && grp < ngrp) {
+          const int ri = s_rowinfo[r];
+          const int* cb = s_colbase + (ri >> 8);
+          double* dst = Xc + r;
+#pragma unroll 4
+          for (int j = grp; j < nt * 8; j += ngrp) {
+            const int c = 8 * t0 + j;                            // column of [A12 | b1]
+            const int off = c <= nbd ? cb[(ni + c) * nf] : -1;
+            const double* src = (c < nbd ? Arec : brec) + (ri & 0xff) + (off >= 0 ? off : 0);
+            cp_async8_z(dst + ld * (8 * (j >> 3) + pc(j & 7)), src, off >= 0);
           }
-          Xc[pos + ld * (8 * (j >> 3) + pc(j & 7))] = val;
         }
+        cp_async_commit_wait_all();
       } else {
         // r = b1 - A12 * lambda_K (gemv!('N', -1, A12, x, 1, b1), ascending columns); the other columns are zero
         for (int idx = tid; idx < 8 * ld; idx += kLT) Xc[idx] = 0.0;
@@ -440,13 +497,16 @@ condense_large_kernel(PlanDev pl, LargeTables tb, int ld, int64_t ncells, const 
         }
       }
       __syncthreads();
+      LTRACE("chunk load");
       if (warp < nt) {
         double* T = Xc + ld * 8 * warp;
         // forward solve L y = P c (the row moves of every panel replayed), then backward solve U x = y
 #pragma unroll 1
         for (int p = 0; p < NT; ++p) tile_lower_step(T, Wa, ld, ni, p, NT, ctlAll + p, LinvAll + 64 * p);
+        LTRACE("  forward solve (warp 0)");
 #pragma unroll 1
         for (int p = NT - 1; p >= 0; --p) tile_upper_step(T, Wa, ld, ni, p, DinvAll + 64 * p);
+        LTRACE("  backward solve (warp 0)");
         const int cbase = 8 * (t0 + warp);                       // first column of [A12 | b1] in this tile
         if (MODE == 0) {
           if (Xout) {      // keep_factors: X = A11^-1 [A12 | b1], n_i x (n_b + 1) column-major
@@ -456,73 +516,109 @@ condense_large_kernel(PlanDev pl, LargeTables tb, int ld, int64_t ncells, const 
               if (cbase + j <= nbd) Xg[i + (int64_t)ni * (cbase + j)] = failed ? qnan : T[i + ld * pc(j)];
             }
           }
-          // Schur update of this column tile: S(:, tile) = A22(:, tile) - A21 * X(:, tile), four row tiles at a time
-          const int NBT = (nbd + 7) / 8;
-          double* Sc = S + cell * (int64_t)nbd * nbd;
-          double* gc = g + cell * (int64_t)nbd;
-#pragma unroll 1
-          for (int I0 = 0; I0 < NBT; I0 += 4) {
-            double acc[4][2];
-            int roff[4];                                         // record offset pieces of this lane's row
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int r = 8 * (I0 + q) + gid;
-              const bool rv = I0 + q < NBT && r < nbd;
-              roff[q] = rv ? s_rowinfo[ni + r] : -1;
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int c = cbase + 2 * tig + e;
-                double val = 0.0;
-                if (rv && c <= nbd) {
-                  const int off = s_colbase[(ni + c) * nf + (roff[q] >> 8)];
-                  if (off >= 0) val = (c < nbd ? Arec : brec)[off + (roff[q] & 0xff)];
-                }
-                acc[q][e] = val;
-              }
-            }
-#pragma unroll 1
-            for (int k = 0; k < NT; ++k) {
-              const int kc0 = 8 * k + tig, kc1 = 8 * k + 4 + tig;        // A21 columns of this lane's A fragments
-              const double bf0 = kc0 < ni ? -T[kc0 + ld * nb] : 0.0;
-              const double bf1 = kc1 < ni ? -T[kc1 + ld * nb] : 0.0;
-              double a0[4], a1[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                a0[q] = 0.0; a1[q] = 0.0;
-                if (roff[q] >= 0) {
-                  const int f = roff[q] >> 8, lr = roff[q] & 0xff;
-                  if (kc0 < ni) { const int off = s_colbase[kc0 * nf + f]; if (off >= 0) a0[q] = Arec[off + lr]; }
-                  if (kc1 < ni) { const int off = s_colbase[kc1 * nf + f]; if (off >= 0) a1[q] = Arec[off + lr]; }
-                }
-              }
-#pragma unroll
-              for (int q = 0; q < 4; ++q) dmma(acc[q][0], acc[q][1], a0[q], bf0);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) dmma(acc[q][0], acc[q][1], a1[q], bf1);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int r = 8 * (I0 + q) + gid;
-              if (roff[q] >= 0) {
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                  const int c = cbase + 2 * tig + e;
-                  const double val = failed ? qnan : acc[q][e];
-                  if (c < nbd) Sc[r + (int64_t)nbd * c] = val;
-                  else if (c == nbd) gc[r] = val;
-                }
-              }
-            }
-          }
         } else if (warp == 0) {
           double* uc = uout + cell * (int64_t)ni;
           for (int i = lane; i < ni; i += 32) uc[i] = failed ? qnan : T[i + ld * pc(0)];
         }
       }
       __syncthreads();
+      LTRACE("solves done (all warps)");
+      if (MODE == 0) {
+        // Schur update of the chunk, S(:, chunk) = A22(:, chunk) - A21 * X: a warp owns row tiles of the boundary
+        // block (I = warp mod 8), reads its A21 row tile once from the record (A fragments: 8 consecutive rows x 4
+        // columns per load, 64-byte runs; the loads of the next k-tile are issued before the DMMAs of the current
+        // one) and sweeps the column tiles of the chunk with X as B fragments from shared memory.
+        const int NBT = (nbd + 7) / 8;
+        double* Sc = S + cell * (int64_t)nbd * nbd;
+        double* gc = g + cell * (int64_t)nbd;
+#pragma unroll 1
+        for (int I = warp; I < NBT; I += kWarps) {
+          const int r = 8 * I + gid;
+          const bool rv = r < nbd;
+          const int ri = rv ? s_rowinfo[ni + r] : 0;
+          const int f = ri >> 8;
+          const double* Arow = Arec + (ri & 0xff);
+          const double* brow = brec + (ri & 0xff);
+          double acc[kCT][2];
+#pragma unroll
+          for (int j = 0; j < kCT; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int c = 8 * (t0 + j) + 2 * tig + e;          // column of [A22 | b2]
+              double val = 0.0;
+              if (rv && j < nt && c <= nbd) {
+                const int off = s_colbase[(ni + c) * nf + f];
+                if (off >= 0) val = (c < nbd ? Arow : brow)[off];
+              }
+              acc[j][e] = val;
+            }
+          }
+          const int* cbf = s_colbase + f;
+          auto load_a = [&](int k, double& a0, double& a1) {
+            const int kc0 = 8 * k + tig, kc1 = kc0 + 4;
+            const int o0 = (rv && kc0 < ni) ? cbf[kc0 * nf] : -1;
+            const int o1 = (rv && kc1 < ni) ? cbf[kc1 * nf] : -1;
+            const double v0 = Arow[o0 >= 0 ? o0 : 0], v1 = Arow[o1 >= 0 ? o1 : 0];
+            a0 = o0 >= 0 ? v0 : 0.0;
+            a1 = o1 >= 0 ? v1 : 0.0;
+          };
+          // A fragments are fetched two k-tiles ahead into a ring of three register pairs; the k loop is unrolled by
+          // three so that the ring index is static (a register move of a pending load would wait for it)
+          double af0[3], af1[3];
+          load_a(0, af0[0], af1[0]);
+          if (NT > 1) load_a(1, af0[1], af1[1]);
+          const double* xb = Xc + ld * nb;
+          const int ld8 = 8 * ld;
+#pragma unroll 1
+          for (int k3 = 0; k3 < NT; k3 += 3) {
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+              const int k = k3 + u;
+              if (k < NT) {
+                if (k + 2 < NT) load_a(k + 2, af0[(u + 2) % 3], af1[(u + 2) % 3]);
+                const int kr0 = 8 * k + tig, kr1 = kr0 + 4;      // X rows of this lane's B fragments
+                // all B fragments first, then one DMMA per column tile and k-half: eight independent accumulators
+                // in flight (tiles beyond the chunk multiply zeros into accumulators that are never stored)
+                // (rows >= n_i of Xc are zero for the whole kernel and tiles >= nt hold finite leftovers, so the loads
+                // need no predicate)
+                double bf0[kCT], bf1[kCT];
+#pragma unroll
+                for (int j = 0; j < kCT; ++j) {
+                  bf0[j] = -xb[kr0 + ld8 * j];
+                  bf1[j] = -xb[kr1 + ld8 * j];
+                }
+#pragma unroll
+                for (int j = 0; j < kCT; ++j) dmma(acc[j][0], acc[j][1], af0[u], bf0[j]);
+#pragma unroll
+                for (int j = 0; j < kCT; ++j) dmma(acc[j][0], acc[j][1], af1[u], bf1[j]);
+              }
+            }
+          }
+          if (rv) {
+#pragma unroll
+            for (int j = 0; j < kCT; ++j) {
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int c = 8 * (t0 + j) + 2 * tig + e;
+                const double val = failed ? qnan : acc[j][e];
+                if (j < nt) {
+                  if (c < nbd) Sc[r + (int64_t)nbd * c] = val;
+                  else if (c == nbd) gc[r] = val;
+                }
+              }
+            }
+          }
+        }
+        __syncthreads();
+        LTRACE("Schur update");
+      }
     }
     if (info && tid == 0) info[cell] = *s_info;
     __syncthreads();
+#ifdef GHB_LTRACE
+    if (blockIdx.x == 0 && tid == 0 && cell == 0)
+      for (int i = 1; i < t_n; ++i) printf("%-28s %8lld\n", g_lname[i], g_ltrace[i] - g_ltrace[i - 1]);
+#endif
   }
 }
 

@@ -1,0 +1,16 @@
+"""ncu driver: the large-cell kernel on n cells of the (120,108) elasticity shape."""
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import gridaphybrid_b200 as gh
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+ctx = gh.Context(0)
+plan = ctx.plan_blocks([60, 60, 108], np.ones((3, 3), bool), [1, 2], [3])
+A = torch.empty((n, plan.lenA), dtype=torch.float64, device="cuda"); b = torch.empty((n, plan.lenb), dtype=torch.float64, device="cuda")
+ctx.synth_fill(plan, 0, n, A, b)
+S = torch.empty((n, plan.n_b ** 2), dtype=torch.float64, device="cuda"); g = torch.empty((n, plan.n_b), dtype=torch.float64, device="cuda")
+info = torch.empty(n, dtype=torch.int32, device="cuda")
+for _ in range(3):
+    ctx.condense(plan, n, A, b, S, g, info)
+torch.cuda.synchronize()
+print("done", plan.kernel_name)
