@@ -279,6 +279,29 @@ def run_ours(args):
     kernel_ms = float(np.mean([a.elapsed_time(bb) for a, bb in cond_ms]))
     value = ncells * world / (ms * 1e-3)
 
+    # ---- backward map on the same records (reported on its own; outside the timed region) ----
+    L = slab.layout
+    lam = torch.randn(L.nrows_global, dtype=torch.float64, device=dev)       # stands for the all-gathered lambda
+    u = torch.empty((ncells, plan.n_i), dtype=torch.float64, device=dev)
+    ids_local = slab.cell_ids[:ncells]
+    for _ in range(2):
+        ctx.backsub(plan, ncells, A, b, lam, None, ids_local, u, info)
+    barrier()
+    b0, b1 = ev(), ev()
+    b0.record()
+    for _ in range(3):
+        ctx.backsub(plan, ncells, A, b, lam, None, ids_local, u, info)
+    b1.record()
+    barrier()
+    back_ms = b0.elapsed_time(b1) / 3
+    if world > 1:
+        tms = torch.tensor([back_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        back_ms = float(tms.item())
+    backsub = {"value": ncells * world / (back_ms * 1e-3), "unit": "cells/s", "ms": back_ms,
+               "note": "BackwardStaticCondensationMap on the same records (LU recomputed, as the reference does)"}
+    del lam, u
+
     # ---- e2e: C-ABI with pinned host buffers, bounded sample, copies inside the timed region ----
     e2e = None
     cpu_base = None
@@ -332,7 +355,7 @@ def run_ours(args):
                              "kernel": "condense (" + plan.kernel_name + ")",
                              "kernel_ms": kernel_ms, "peak_source": how,
                              "fp64_tflops": flops_per_cell() * ncells / (kernel_ms * 1e-3) / 1e12},
-                "cpu_baseline": cpu_base}
+                "cpu_baseline": cpu_base, "backsub": backsub}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
