@@ -12,6 +12,11 @@
 
 #include "common.cuh"
 
+// The warp kernels are compiled for 8 resident blocks per SM for n <= 16 and 6 above (register caps 64 / 80): measured
+// best of 4 / 6 / 8 on a B200.  Staging the next record in shared memory with cp.async (double buffered per warp) was
+// measured too and did not pay (817 / 340 vs 932 / 364 M cells/s): these kernels are bound by the elimination chain,
+// not by the exposed load latency.
+
 namespace ghb {
 
 namespace {
@@ -37,7 +42,7 @@ __device__ __forceinline__ int pivot_lane(double v, bool cand, int lane, bool& z
 
 // One warp per cell.  Lane r < N holds row r of W = [A11 A12 b1; A21 A22 b2] (condensed order).
 template <int NI, int NB>
-__global__ void __launch_bounds__(128) condense_warp_kernel(PlanDev p, int64_t ncells, const double* __restrict__ A,
+__global__ void __launch_bounds__(128, (NI + NB <= 16 ? 8 : 6)) condense_warp_kernel(PlanDev p, int64_t ncells, const double* __restrict__ A,
                                                             const double* __restrict__ b, double* __restrict__ S,
                                                             double* __restrict__ g, int32_t* __restrict__ info) {
   constexpr int N = NI + NB;
@@ -92,7 +97,7 @@ __global__ void __launch_bounds__(128) condense_warp_kernel(PlanDev p, int64_t n
 // Backward map: lane r < NI holds row r of [A11 | b1 - A12*lambda_K]; Gauss-Jordan with partial pivoting, so the
 // lane whose row was chosen at step k ends up holding u[k].
 template <int NI, int NB>
-__global__ void __launch_bounds__(128) backsub_warp_kernel(PlanDev p, int64_t ncells, const double* __restrict__ A,
+__global__ void __launch_bounds__(128, (NI + NB <= 16 ? 8 : 6)) backsub_warp_kernel(PlanDev p, int64_t ncells, const double* __restrict__ A,
                                                            const double* __restrict__ b,
                                                            const double* __restrict__ lam_free,
                                                            const double* __restrict__ lam_dir,
@@ -154,7 +159,7 @@ __global__ void __launch_bounds__(128) backsub_warp_kernel(PlanDev p, int64_t nc
 template <int NI, int NB>
 int launch_cw(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S, double* g,
               int32_t* info) {
-  const int64_t blocks = std::min<int64_t>((ncells + 3) / 4, (int64_t)ctx->sm_count * 16);
+  const int64_t blocks = std::min<int64_t>((ncells + 3) / 4, (int64_t)ctx->sm_count * 32);
   condense_warp_kernel<NI, NB><<<(unsigned)blocks, 128, 0, ctx->stream>>>(p.dev(), ncells, A, b, S, g, info);
   GHB_LAUNCHED(ctx);
   return GHB_OK;
@@ -163,7 +168,7 @@ int launch_cw(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, cons
 template <int NI, int NB>
 int launch_bw(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, const double* lf,
               const double* ld, const int64_t* ids, double* u, int32_t* info) {
-  const int64_t blocks = std::min<int64_t>((ncells + 3) / 4, (int64_t)ctx->sm_count * 16);
+  const int64_t blocks = std::min<int64_t>((ncells + 3) / 4, (int64_t)ctx->sm_count * 32);
   backsub_warp_kernel<NI, NB><<<(unsigned)blocks, 128, 0, ctx->stream>>>(p.dev(), ncells, A, b, lf, ld, ids, u, info);
   GHB_LAUNCHED(ctx);
   return GHB_OK;
