@@ -450,6 +450,43 @@ def test_dmma_singular_cell_info(ctx):
     assert rel_err_cells(S[[0, 1, 2, 4, 5]], S0[[0, 1, 2, 4, 5]]) < TOL
 
 
+@pytest.mark.parametrize("name", ["C2_rth_k2_2d", "C2_rth_k3_2d", "C4_elasticity_k2_3d", "C5_hencky_k1_3d"])
+def test_tuned_kernels_singular_and_late_zero_pivot(ctx, name):
+    """every tuned kernel reports an exactly singular interior block like dgetrf: a zero record gives info = 1, a
+    zero interior column c gives info = c + 1 (LAPACK numbering); such cells come back as NaN, the others are exact.
+    The backward map reports the same info."""
+    plan, op = _dev_plan(ctx, name), oracle_plan(name)
+    assert plan.kernel_name != "generic"
+    n = 5
+    A0, b0 = o.synth_cell_records(op, 40, n)
+    A0[1, :] = 0.0
+    # zero the whole interior column `col` of cell 3 (all touched blocks holding it): dgetrf stops there
+    col = op.n_i - 3
+    f_of = np.repeat(np.arange(len(op.ndofs)), op.ndofs)
+    order = [f - 1 for f in op.interior]
+    cond_cols = np.concatenate([np.flatnonzero(f_of == f) for f in order])     # original dof of condensed column
+    dof = cond_cols[col]
+    fj = f_of[dof]; lj = dof - np.flatnonzero(f_of == fj)[0]
+    offs, _ = gh.PackedCells.layout(op.ndofs, op.touched)
+    for fi in order:
+        if op.touched[fi, fj]:
+            base = offs[fi][fj]
+            A0[3, base + lj * op.ndofs[fi]: base + (lj + 1) * op.ndofs[fi]] = 0.0
+    S = np.empty((n, plan.n_b ** 2)); g = np.empty((n, plan.n_b)); info = np.empty(n, dtype=np.int32)
+    ctx.condense(plan, n, A0, b0, S, g, info)
+    S0, g0, info0 = oc.condense(op, A0, b0)
+    assert info0.tolist() == [0, 1, 0, col + 1, 0]
+    assert info.tolist() == info0.tolist()
+    good = [0, 2, 4]
+    assert np.isnan(S[[1, 3]]).all() and np.isnan(g[[1, 3]]).all() and np.isfinite(S[good]).all()
+    assert rel_err_cells(S[good], S0[good]) < TOL
+    lam = np.linspace(-1, 1, plan.n_b * n)
+    ids = np.arange(1, plan.n_b * n + 1, dtype=np.int64).reshape(n, plan.n_b)
+    u = np.empty((n, plan.n_i)); info2 = np.empty(n, dtype=np.int32)
+    ctx.backsub(plan, n, A0, b0, torch.as_tensor(lam, device="cuda"), None, ids, u, info2)
+    assert info2.tolist() == info0.tolist() and np.isnan(u[[1, 3]]).all() and np.isfinite(u[good]).all()
+
+
 @pytest.mark.parametrize("shape", [(100, 4, 2, 4), (37, 6, 71), (5, 6, 4900)])
 def test_sum_facets_device(ctx, shape):
     """SumFacetsMap on the batch (test/SumFacetMapTests.jl:10-29: four equal facet blocks sum to 4a) and vs the oracle."""
