@@ -94,6 +94,73 @@ __global__ void __launch_bounds__(128, (NI + NB <= 16 ? 8 : 6)) condense_warp_ke
   }
 }
 
+// Two cells per warp for n <= 16 (Darcy HDG k=1 on quads): each half-warp holds one cell, one row per lane.  The
+// elimination is bound by the shuffle pipe (one 64-bit broadcast per remaining column and pivot); with two cells per
+// instruction every broadcast serves both, so the shuffle count per cell halves.  The pivot search is a butterfly
+// inside the half-warp (xor 8, 4, 2, 1 never leave it).
+template <int NI, int NB>
+__global__ void __launch_bounds__(128, 8) condense_warp2_kernel(PlanDev p, int64_t ncells, const double* __restrict__ A,
+                                                                 const double* __restrict__ b, double* __restrict__ S,
+                                                                 double* __restrict__ g, int32_t* __restrict__ info) {
+  constexpr int N = NI + NB;
+  static_assert(N <= 16, "one row per lane of a half-warp");
+  const int lane = threadIdx.x & 31, hl = lane & 15, hbase = lane & 16;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool rowok = hl < N;
+  const int32_t* em = p.emap + (rowok ? hl : 0);
+  for (int64_t pair = warp; 2 * pair < ncells; pair += nwarps) {
+    const int64_t cell = 2 * pair + (lane >> 4);
+    const bool cellok = cell < ncells;                 // odd cell count: the upper half idles on the last pair
+    const bool live = rowok && cellok;
+    const double* Arec = A + (cellok ? cell : 0) * p.lenA;
+    const double* brec = b + (cellok ? cell : 0) * p.lenb;
+    double a[N + 1];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const int o = live ? em[N * j] : -1;
+      a[j] = o >= 0 ? Arec[o] : 0.0;
+    }
+    a[N] = live ? brec[em[N * N]] : 0.0;
+    bool chosen = false;
+    int bad = 0;
+#pragma unroll
+    for (int k = 0; k < NI; ++k) {
+      const bool cand = hl < NI && !chosen;
+      const double rc = fast_rcp_w(a[k]);
+      // key = |a| (exponent + 16 mantissa bits) << 4 | (15 - row): largest magnitude, lowest row, per half-warp
+      const unsigned h = (unsigned)(__double_as_longlong(a[k]) >> 32) & 0x7fffffffu;
+      unsigned key = cand ? (((h >> 4) << 4) | (unsigned)(15 - hl)) : 0u;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        const unsigned other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other > key ? other : key;
+      }
+      const bool zero = (key >> 4) == 0u;              // every candidate below 2^-1018: reported as a zero pivot
+      bad = (bad == 0 && zero) ? k + 1 : bad;
+      const int q = hbase | (15 - (int)(key & 15u));   // pivot lane of this half
+      const double rinv = __shfl_sync(0xffffffffu, rc, q);
+      const bool me = lane == q;
+      const bool upd = rowok && !chosen && !me;
+      chosen = chosen || me;
+      const double nl = upd ? -(a[k] * rinv) : 0.0;
+#pragma unroll
+      for (int j = k + 1; j <= N; ++j) {
+        const double pj = __shfl_sync(0xffffffffu, a[j], q);
+        a[j] = fma(nl, pj, a[j]);
+      }
+    }
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    if (cellok && hl >= NI && hl < N) {
+      double* Sc = S + cell * (int64_t)NB * NB + (hl - NI);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) Sc[(int64_t)NB * j] = bad ? qnan : a[NI + j];
+      g[cell * (int64_t)NB + (hl - NI)] = bad ? qnan : a[N];
+    }
+    if (info && cellok && hl == 0) info[cell] = bad;
+  }
+}
+
 // Backward map: lane r < NI holds row r of [A11 | b1 - A12*lambda_K]; Gauss-Jordan with partial pivoting, so the
 // lane whose row was chosen at step k ends up holding u[k].
 template <int NI, int NB>
@@ -156,6 +223,78 @@ __global__ void __launch_bounds__(128, (NI + NB <= 16 ? 8 : 6)) backsub_warp_ker
   }
 }
 
+// Backward map, two cells per warp (n_i <= 16): see condense_warp2_kernel.
+template <int NI, int NB>
+__global__ void __launch_bounds__(128, 8) backsub_warp2_kernel(PlanDev p, int64_t ncells, const double* __restrict__ A,
+                                                                const double* __restrict__ b,
+                                                                const double* __restrict__ lam_free,
+                                                                const double* __restrict__ lam_dir,
+                                                                const int64_t* __restrict__ ids, double* __restrict__ u,
+                                                                int32_t* __restrict__ info) {
+  constexpr int N = NI + NB;
+  static_assert(NI <= 16, "one interior row per lane of a half-warp");
+  const int lane = threadIdx.x & 31, hl = lane & 15, hbase = lane & 16;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool rowok = hl < NI;
+  const int32_t* em = p.emap + (rowok ? hl : 0);
+  for (int64_t pair = warp; 2 * pair < ncells; pair += nwarps) {
+    const int64_t cell = 2 * pair + (lane >> 4);
+    const bool cellok = cell < ncells;
+    const bool live = rowok && cellok;
+    const int64_t cc = cellok ? cell : 0;
+    const double* Arec = A + cc * p.lenA;
+    const double* brec = b + cc * p.lenb;
+    double a[NI + 1];
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+      const int o = live ? em[N * j] : -1;
+      a[j] = o >= 0 ? Arec[o] : 0.0;
+    }
+    double r = live ? brec[em[N * N]] : 0.0;
+    // r -= A12 * lambda_K  (gemv!('N',-1,A12,x,1,b1), ascending columns); ids are uniform inside a half-warp
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int64_t id = ids[cc * NB + j];
+      const double lj = id > 0 ? lam_free[id - 1] : (id < 0 && lam_dir ? lam_dir[-id - 1] : 0.0);
+      const int o = live ? em[N * (NI + j)] : -1;
+      if (o >= 0) r = fma(-Arec[o], lj, r);
+    }
+    a[NI] = r;
+    bool chosen = false;
+    int step = -1, bad = 0;
+#pragma unroll
+    for (int k = 0; k < NI; ++k) {
+      const bool cand = rowok && !chosen;
+      const double rc = fast_rcp_w(a[k]);
+      const unsigned h = (unsigned)(__double_as_longlong(a[k]) >> 32) & 0x7fffffffu;
+      unsigned key = cand ? (((h >> 4) << 4) | (unsigned)(15 - hl)) : 0u;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        const unsigned other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other > key ? other : key;
+      }
+      const bool zero = (key >> 4) == 0u;
+      bad = (bad == 0 && zero) ? k + 1 : bad;
+      const int q = hbase | (15 - (int)(key & 15u));
+      const double rinv = __shfl_sync(0xffffffffu, rc, q);
+      const bool me = lane == q;
+      if (me) { chosen = true; step = k; }
+      // Gauss-Jordan: normalise the pivot row, eliminate column k from every other row
+      const double scale = me ? rinv : 1.0;
+      const double nl = (rowok && !me) ? -a[k] : 0.0;
+#pragma unroll
+      for (int j = k + 1; j <= NI; ++j) {
+        const double pj = __shfl_sync(0xffffffffu, a[j], q) * rinv;
+        a[j] = me ? a[j] * scale : fma(nl, pj, a[j]);
+      }
+    }
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    if (live && step >= 0) u[cell * (int64_t)NI + step] = bad ? qnan : a[NI];
+    if (info && cellok && hl == 0) info[cell] = bad;
+  }
+}
+
 template <int NI, int NB>
 int launch_cw(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S, double* g,
               int32_t* info) {
@@ -185,6 +324,12 @@ const char* warp_kernel_name(const Plan& p) {
 
 int launch_condense_warp(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
                          double* g, int32_t* info) {
+  if (p.n_i == 7 && p.n_b == 8 && !getenv("GHB_WARP_ONE_CELL")) {
+    const int64_t blocks = std::min<int64_t>((ncells + 7) / 8, (int64_t)ctx->sm_count * 32);
+    condense_warp2_kernel<7, 8><<<(unsigned)blocks, 128, 0, ctx->stream>>>(p.dev(), ncells, A, b, S, g, info);
+    GHB_LAUNCHED(ctx);
+    return GHB_OK;
+  }
   if (p.n_i == 7 && p.n_b == 8) return launch_cw<7, 8>(ctx, p, ncells, A, b, S, g, info);
   if (p.n_i == 16 && p.n_b == 8) return launch_cw<16, 8>(ctx, p, ncells, A, b, S, g, info);
   return fail(ctx, GHB_EUNSUPPORTED, "no warp kernel for this shape");
@@ -192,6 +337,12 @@ int launch_condense_warp(ghb_ctx* ctx, const Plan& p, int64_t ncells, const doub
 
 int launch_backsub_warp(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b,
                         const double* lam_free, const double* lam_dir, const int64_t* ids, double* u, int32_t* info) {
+  if (p.n_i == 7 && p.n_b == 8 && !getenv("GHB_WARP_ONE_CELL")) {
+    const int64_t blocks = std::min<int64_t>((ncells + 7) / 8, (int64_t)ctx->sm_count * 32);
+    backsub_warp2_kernel<7, 8><<<(unsigned)blocks, 128, 0, ctx->stream>>>(p.dev(), ncells, A, b, lam_free, lam_dir, ids, u, info);
+    GHB_LAUNCHED(ctx);
+    return GHB_OK;
+  }
   if (p.n_i == 7 && p.n_b == 8) return launch_bw<7, 8>(ctx, p, ncells, A, b, lam_free, lam_dir, ids, u, info);
   if (p.n_i == 16 && p.n_b == 8) return launch_bw<16, 8>(ctx, p, ncells, A, b, lam_free, lam_dir, ids, u, info);
   return fail(ctx, GHB_EUNSUPPORTED, "no warp kernel for this shape");
