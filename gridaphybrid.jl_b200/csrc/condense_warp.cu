@@ -94,68 +94,90 @@ __global__ void __launch_bounds__(128, (NI + NB <= 16 ? 8 : 6)) condense_warp_ke
   }
 }
 
-// Two cells per warp for n <= 16 (Darcy HDG k=1 on quads): each half-warp holds one cell, one row per lane.  The
-// elimination is bound by the shuffle pipe (one 64-bit broadcast per remaining column and pivot); with two cells per
-// instruction every broadcast serves both, so the shuffle count per cell halves.  The pivot search is a butterfly
-// inside the half-warp (xor 8, 4, 2, 1 never leave it).
-template <int NI, int NB>
-__global__ void __launch_bounds__(128, 8) condense_warp2_kernel(PlanDev p, int64_t ncells, const double* __restrict__ A,
-                                                                 const double* __restrict__ b, double* __restrict__ S,
-                                                                 double* __restrict__ g, int32_t* __restrict__ info) {
+// Two cells per warp: each half-warp holds one cell, R rows per lane (n <= 16 R).  The elimination is bound by the
+// shuffle pipe (one 64-bit broadcast per remaining column and pivot: 0.7 shuffles per cycle per SM in the one-cell
+// kernels); with two cells per instruction every broadcast serves both, so the shuffle count per cell halves.  The
+// pivot search is a butterfly inside the half-warp (xor 8, 4, 2, 1 never leave it).
+template <int NI, int NB, int R>
+__global__ void __launch_bounds__(128, (R == 1 ? 8 : 3))
+condense_warp2_kernel(PlanDev p, int64_t ncells, const double* __restrict__ A, const double* __restrict__ b,
+                      double* __restrict__ S, double* __restrict__ g, int32_t* __restrict__ info) {
   constexpr int N = NI + NB;
-  static_assert(N <= 16, "one row per lane of a half-warp");
+  static_assert(N <= 16 * R && R <= 2, "R rows per lane of a half-warp");
   const int lane = threadIdx.x & 31, hl = lane & 15, hbase = lane & 16;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const bool rowok = hl < N;
-  const int32_t* em = p.emap + (rowok ? hl : 0);
   for (int64_t pair = warp; 2 * pair < ncells; pair += nwarps) {
     const int64_t cell = 2 * pair + (lane >> 4);
     const bool cellok = cell < ncells;                 // odd cell count: the upper half idles on the last pair
-    const bool live = rowok && cellok;
     const double* Arec = A + (cellok ? cell : 0) * p.lenA;
     const double* brec = b + (cellok ? cell : 0) * p.lenb;
-    double a[N + 1];
+    double a[R][N + 1];
+    bool live[R], chosen[R];
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-      const int o = live ? em[N * j] : -1;
-      a[j] = o >= 0 ? Arec[o] : 0.0;
+    for (int r = 0; r < R; ++r) {
+      const int row = hl + 16 * r;
+      live[r] = row < N && cellok;
+      chosen[r] = false;
+      const int32_t* em = p.emap + (row < N ? row : 0);
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const int o = live[r] ? em[N * j] : -1;
+        a[r][j] = o >= 0 ? Arec[o] : 0.0;
+      }
+      a[r][N] = live[r] ? brec[em[N * N]] : 0.0;
     }
-    a[N] = live ? brec[em[N * N]] : 0.0;
-    bool chosen = false;
     int bad = 0;
 #pragma unroll
     for (int k = 0; k < NI; ++k) {
-      const bool cand = hl < NI && !chosen;
-      const double rc = fast_rcp_w(a[k]);
-      // key = |a| (exponent + 16 mantissa bits) << 4 | (15 - row): largest magnitude, lowest row, per half-warp
-      const unsigned h = (unsigned)(__double_as_longlong(a[k]) >> 32) & 0x7fffffffu;
-      unsigned key = cand ? (((h >> 4) << 4) | (unsigned)(15 - hl)) : 0u;
+      // key = |a| (exponent + 15 mantissa bits) << 5 | (31 - row): largest magnitude, lowest row, per half-warp
+      unsigned key = 0u;
+      double rc[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int row = hl + 16 * r;
+        const bool cand = row < NI && !chosen[r];
+        const unsigned h = (unsigned)(__double_as_longlong(a[r][k]) >> 32) & 0x7fffffffu;
+        const unsigned kr = cand ? (((h >> 5) << 5) | (unsigned)(31 - row)) : 0u;
+        key = kr > key ? kr : key;
+        rc[r] = fast_rcp_w(a[r][k]);                   // speculative: overlaps the search
+      }
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) {
         const unsigned other = __shfl_xor_sync(0xffffffffu, key, o);
         key = other > key ? other : key;
       }
-      const bool zero = (key >> 4) == 0u;              // every candidate below 2^-1018: reported as a zero pivot
+      const bool zero = (key >> 5) == 0u;              // every candidate below 2^-1017: reported as a zero pivot
       bad = (bad == 0 && zero) ? k + 1 : bad;
-      const int q = hbase | (15 - (int)(key & 15u));   // pivot lane of this half
-      const double rinv = __shfl_sync(0xffffffffu, rc, q);
-      const bool me = lane == q;
-      const bool upd = rowok && !chosen && !me;
-      chosen = chosen || me;
-      const double nl = upd ? -(a[k] * rinv) : 0.0;
+      const int prow = 31 - (int)(key & 31u);
+      const bool from2 = R > 1 && prow >= 16;          // which register set of the pivot lane (uniform per half)
+      const int q = hbase | (prow & 15);
+      const double rinv = __shfl_sync(0xffffffffu, from2 ? rc[R - 1] : rc[0], q);
+      double nl[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const bool me = lane == q && (r == 1) == from2;
+        const bool upd = live[r] && !chosen[r] && !me;
+        chosen[r] = chosen[r] || me;
+        nl[r] = upd ? -(a[r][k] * rinv) : 0.0;
+      }
 #pragma unroll
       for (int j = k + 1; j <= N; ++j) {
-        const double pj = __shfl_sync(0xffffffffu, a[j], q);
-        a[j] = fma(nl, pj, a[j]);
+        const double pj = __shfl_sync(0xffffffffu, from2 ? a[R - 1][j] : a[0][j], q);
+#pragma unroll
+        for (int r = 0; r < R; ++r) a[r][j] = fma(nl[r], pj, a[r][j]);
       }
     }
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-    if (cellok && hl >= NI && hl < N) {
-      double* Sc = S + cell * (int64_t)NB * NB + (hl - NI);
 #pragma unroll
-      for (int j = 0; j < NB; ++j) Sc[(int64_t)NB * j] = bad ? qnan : a[NI + j];
-      g[cell * (int64_t)NB + (hl - NI)] = bad ? qnan : a[N];
+    for (int r = 0; r < R; ++r) {
+      const int row = hl + 16 * r;
+      if (cellok && row >= NI && row < N) {
+        double* Sc = S + cell * (int64_t)NB * NB + (row - NI);
+#pragma unroll
+        for (int j = 0; j < NB; ++j) Sc[(int64_t)NB * j] = bad ? qnan : a[r][NI + j];
+        g[cell * (int64_t)NB + (row - NI)] = bad ? qnan : a[r][N];
+      }
     }
     if (info && cellok && hl == 0) info[cell] = bad;
   }
@@ -225,7 +247,7 @@ __global__ void __launch_bounds__(128, (NI + NB <= 16 ? 8 : 6)) backsub_warp_ker
 
 // Backward map, two cells per warp (n_i <= 16): see condense_warp2_kernel.
 template <int NI, int NB>
-__global__ void __launch_bounds__(128, 8) backsub_warp2_kernel(PlanDev p, int64_t ncells, const double* __restrict__ A,
+__global__ void __launch_bounds__(128, (NI <= 8 ? 8 : 5)) backsub_warp2_kernel(PlanDev p, int64_t ncells, const double* __restrict__ A,
                                                                 const double* __restrict__ b,
                                                                 const double* __restrict__ lam_free,
                                                                 const double* __restrict__ lam_dir,
@@ -324,9 +346,18 @@ const char* warp_kernel_name(const Plan& p) {
 
 int launch_condense_warp(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
                          double* g, int32_t* info) {
+  // (7,8): two cells per warp, 932 -> 1537 M cells/s.  (16,8) with two rows per lane (R = 2, 168 registers, 3 blocks
+  // per SM) measured 302 vs 364 M cells/s for the one-cell kernel, so it stays on the latter (GHB_WARP_TWO_ROWS=1 selects
+  // the R = 2 variant for experiments).
   if (p.n_i == 7 && p.n_b == 8 && !getenv("GHB_WARP_ONE_CELL")) {
     const int64_t blocks = std::min<int64_t>((ncells + 7) / 8, (int64_t)ctx->sm_count * 32);
-    condense_warp2_kernel<7, 8><<<(unsigned)blocks, 128, 0, ctx->stream>>>(p.dev(), ncells, A, b, S, g, info);
+    condense_warp2_kernel<7, 8, 1><<<(unsigned)blocks, 128, 0, ctx->stream>>>(p.dev(), ncells, A, b, S, g, info);
+    GHB_LAUNCHED(ctx);
+    return GHB_OK;
+  }
+  if (p.n_i == 16 && p.n_b == 8 && getenv("GHB_WARP_TWO_ROWS")) {
+    const int64_t blocks = std::min<int64_t>((ncells + 7) / 8, (int64_t)ctx->sm_count * 32);
+    condense_warp2_kernel<16, 8, 2><<<(unsigned)blocks, 128, 0, ctx->stream>>>(p.dev(), ncells, A, b, S, g, info);
     GHB_LAUNCHED(ctx);
     return GHB_OK;
   }
@@ -337,9 +368,12 @@ int launch_condense_warp(ghb_ctx* ctx, const Plan& p, int64_t ncells, const doub
 
 int launch_backsub_warp(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b,
                         const double* lam_free, const double* lam_dir, const int64_t* ids, double* u, int32_t* info) {
-  if (p.n_i == 7 && p.n_b == 8 && !getenv("GHB_WARP_ONE_CELL")) {
+  if (!getenv("GHB_WARP_ONE_CELL")) {
     const int64_t blocks = std::min<int64_t>((ncells + 7) / 8, (int64_t)ctx->sm_count * 32);
-    backsub_warp2_kernel<7, 8><<<(unsigned)blocks, 128, 0, ctx->stream>>>(p.dev(), ncells, A, b, lam_free, lam_dir, ids, u, info);
+    if (p.n_i == 7 && p.n_b == 8)
+      backsub_warp2_kernel<7, 8><<<(unsigned)blocks, 128, 0, ctx->stream>>>(p.dev(), ncells, A, b, lam_free, lam_dir, ids, u, info);
+    else
+      backsub_warp2_kernel<16, 8><<<(unsigned)blocks, 128, 0, ctx->stream>>>(p.dev(), ncells, A, b, lam_free, lam_dir, ids, u, info);
     GHB_LAUNCHED(ctx);
     return GHB_OK;
   }
