@@ -435,6 +435,9 @@ condense_large_kernel(PlanDev pl, LargeTables tb, int ld, int64_t ncells, const 
     // tiles to the right.  (A one-panel look-ahead -- warp 0 updating tile p+1 and factorising panel p+1 while warps
     // 1-7 update the other tiles -- measured slower, 0.68 vs 0.71 M cells/s on (120,108): the panel chain slows down
     // under the shared-memory traffic of the update warps by more than the hidden update time.)
+    // (A panel spread over one warp per 32 rows, keys and pivot row exchanged through shared memory with two named
+    // barriers per pivot, also measured slower: 6.7-7.0 k cycles per panel against 6.6 / 5.2 / 4.2 / 3.8 k for the
+    // single-warp panel on 4 / 3 / 2 / 1 register sets -- a barrier round trip costs more than the extra sets.)
     auto factor_panel = [&](int p) {
       const int c0 = 8 * p;
       const int npiv = (ni - c0) < 8 ? (ni - c0) : 8;
