@@ -19,7 +19,8 @@
 // getrf!, getrs!, gemm!, getrs!, gemv!) and evaluate!(cache, ::BackwardStaticCondensationMap, A, b, x)
 // (src/BackwardStaticCondensationMap.jl:61-102: gemv!, getrf!, getrs!) for these shapes; X = A11^-1 [A12 | b1] is a
 // by-product, so keep_factors costs only its store.  Pivot rule and info[] semantics as in condense_dmma.cu.
-// FP64-bound shapes (AI 12-14 flop/B): roofline = 37.1 TFLOP/s / F_cond.
+// FP64-bound shapes (AI 12-14 flop/B): roofline = 37.1 TFLOP/s / F_cond.  16 warps per CTA (128 registers): the column-tile
+// updates of the factorisation and the Schur phase use all of them (8 -> 16 warps: 1.06 -> 1.14 and 1.29 -> 1.47 M cells/s).
 #include <algorithm>
 
 #include "common.cuh"
@@ -37,9 +38,12 @@ __device__ const char* g_lname[256];
 #define LTRACE(name) do { } while (0)
 #endif
 
-constexpr int kLT = 256;       // threads per CTA (8 warps), one CTA per SM
+#ifndef GHB_LARGE_THREADS
+#define GHB_LARGE_THREADS 512
+#endif
+constexpr int kLT = GHB_LARGE_THREADS;       // threads per CTA, one CTA per SM
 constexpr int kWarps = kLT / 32;
-constexpr int kCT = 8;         // column tiles of [A12 | b1] per chunk: one per warp
+constexpr int kCT = 8;         // column tiles of [A12 | b1] per chunk: one per warp of the solve phase (the other warps join for the Schur phase)
 // (the panel warp holds up to 4 rows per lane: n_i <= 128)
 
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
