@@ -1,11 +1,12 @@
-// condense_dmma.cu -- tuned static condensation for mid-size cells (3-D HDG k=2: n_i=34, n_b=36) on
-// FP64 DMMA tensor cores (mma.sync.m8n8k4.f64; measured full-rate on B200: 37.1 TFLOP/s, see
-// profiles/r01_ubench_fp64.txt).
+// condense_dmma.cu -- tuned static condensation and backward static condensation for mid-size cells on FP64 DMMA
+// tensor cores (mma.sync.m8n8k4.f64; measured full-rate on B200: 37.1 TFLOP/s, see profiles/r01_ubench_fp64.txt).
+// Instantiated for 3-D HDG k=2 (n_i, n_b) = (34, 36) and RT-H k=2 / k=3 on quads (33, 12), (56, 16).
 //
-// One CTA (4 warps) per cell, 5 CTAs per SM.  Replaces evaluate!(cache, ::StaticCondensationMap, A, b)
-// (/root/reference/src/StaticCondensationMap.jl:152-196):
-//   * the packed record is re-laid out on the fly by 16-byte cp.async into two dense column-major
-//     images in shared memory: Wt = [A11 A12 b1] (n_i rows) and Bt = [A21 A22 b2] (n_b rows);
+// condense_dmma_kernel: one CTA (4 warps) per cell, 5 CTAs per SM for (34,36).  Replaces
+// evaluate!(cache, ::StaticCondensationMap, A, b) (/root/reference/src/StaticCondensationMap.jl:152-196):
+//   * the packed record is re-laid out on the fly by branch-free cp.async (16 bytes where the block heights allow it)
+//     into two dense column-major images in shared memory: Wt = [A11 A12 b1] (n_i rows) and Bt = [A21 A22 b2]
+//     (n_b rows; for (33,12) and (56,16) A22/b2 go straight into the S accumulators instead, Cfg::DIRECT_S);
 //   * top block (getrf! :179 + the L-solve half of getrs! :183,:189): blocked right-looking LU of Wt with
 //     partial pivoting, panel width 8, with look-ahead: warp 0 only factorises panels (one row per lane,
 //     pivot found with one REDUX.MAX on a packed magnitude|row key), warps 1-3 own the column tiles:
@@ -15,6 +16,8 @@
 //     S = A22 - (A21 U^-1)(L^-1 P A12)): warps 1-3 own row tiles of Bt; per panel
 //     L21 = X * inv(U_pp) and S -= L21 * U12 (DMMA, S accumulators in registers), overlapped with the
 //     factorisation of the following panels.
+// backsub_dmma_kernel: evaluate!(cache, ::BackwardStaticCondensationMap, A, b, x)
+// (src/BackwardStaticCondensationMap.jl:61-102) on the same panel warp / column-tile owners, image [A11 | b1 - A12 x].
 // Pivoting: the pivot of a column is an entry whose magnitude equals the column maximum to 2^-15 relative
 // (lowest row among those); S does not depend on the pivot order, only rounding does (parity bar 1e-11).
 #include <algorithm>
@@ -25,14 +28,8 @@
 #ifndef GHB_MINB34
 #define GHB_MINB34 5
 #endif
-#ifndef GHB_LTREGS
-#define GHB_LTREGS 0
-#endif
 #ifndef GHB_L2PREFETCH
 #define GHB_L2PREFETCH 1
-#endif
-#ifndef GHB_LTREGS34
-#define GHB_LTREGS34 0
 #endif
 #ifndef GHB_MINB33
 #define GHB_MINB33 7
@@ -335,11 +332,10 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
                      const double* __restrict__ b, double* __restrict__ S, double* __restrict__ g,
                      int32_t* __restrict__ info) {
   using C = Cfg<NI, NB>;
-  constexpr int N = C::N, NC = C::NC, LDW = C::LDW, LDB = C::LDB, RT = C::RT, BT = C::BT, CT = C::CT, NP = C::NP;
+  constexpr int N = C::N, LDW = C::LDW, LDB = C::LDB, RT = C::RT, BT = C::BT, CT = C::CT, NP = C::NP;
   constexpr int SJ0 = NI / 8;                   // first column tile holding S columns
   constexpr int NSJ = CT - SJ0;                 // S column tiles
   constexpr int MAXROWS = (BT + 2) / 3;         // bottom row tiles per update warp
-  constexpr bool LT_REGS = (NI != 33 && GHB_LTREGS34) || GHB_LTREGS;             // keep the panel's multipliers in registers across column tiles
   extern __shared__ __align__(16) double smem[];
   double* Wt = smem;
   double* Bt = Wt + C::WT_DOUBLES;
@@ -497,17 +493,6 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
         bar_sync<BAR_UW, 96>(p & 1);
         TRACE(5 + 6 * p);
         const double li0 = ctl->Linv[gid + 8 * tig], li1 = ctl->Linv[gid + 8 * (4 + tig)];
-        // A fragments of the panel's multipliers L[I][p], I > p, shared by all owned column tiles
-        double lt[LT_REGS ? RT : 1][2];
-        if (LT_REGS) {
-#pragma unroll
-          for (int I = 1; I < RT; ++I) {
-            const int r = 8 * I + gid;
-            const bool rv = I > p && r < NI;
-            lt[I][0] = rv ? Wt[r + LDW * (c0 + ka0)] : 0.0;
-            lt[I][1] = rv ? Wt[r + LDW * (c0 + ka1)] : 0.0;
-          }
-        }
         int Jfirst = p + 1 + (uw + 3 - (p + 1) % 3) % 3;   // first owned tile > p
 #pragma unroll 1
         for (int J = Jfirst; J < CT; J += 3) {
@@ -530,25 +515,10 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
             const double bf0 = neg(colg[c0 + tig]);
             const double bf1 = neg(colg[c0 + 4 + tig]);
             // two row tiles per step with independent accumulators, DMMAs interleaved (the asm statements keep
-            // their order): a single accumulator serialises the whole column tile on the 26-cycle DMMA latency
-            if (LT_REGS) {
-#pragma unroll
-              for (int I = 1; I < RT; I += 2) {
-                const bool two = I + 1 < RT;
-                if ((two ? I + 1 : I) > p) {
-                  const bool vA = I > p && 8 * I + gid < NI;
-                  const bool vB = two && 8 * (I + 1) + gid < NI;           // I + 1 > p holds here
-                  double dA0 = vA ? cc0[8 * I] : 0.0, dA1 = vA ? cc1[8 * I] : 0.0;
-                  double dB0 = vB ? cc0[8 * I + 8] : 0.0, dB1 = vB ? cc1[8 * I + 8] : 0.0;
-                  dmma(dA0, dA1, lt[I][0], bf0);
-                  if (two) dmma(dB0, dB1, lt[two ? I + 1 : I][0], bf0);
-                  dmma(dA0, dA1, lt[I][1], bf1);
-                  if (two) dmma(dB0, dB1, lt[two ? I + 1 : I][1], bf1);
-                  if (vA) { cc0[8 * I] = dA0; cc1[8 * I] = dA1; }
-                  if (vB) { cc0[8 * I + 8] = dB0; cc1[8 * I + 8] = dB1; }
-                }
-              }
-            } else {
+            // their order): a single accumulator serialises the whole column tile on the 26-cycle DMMA latency.
+            // The panel's multipliers (A fragments) are re-read per tile: holding them in registers across the
+            // tiles cost more in register pressure than the loads (36.4 vs 38.7 M cells/s).
+            {
               int I = p + 1;
 #pragma unroll 1
               for (; I + 1 < RT; I += 2) {
