@@ -73,6 +73,7 @@ void ghb_destroy(ghb_ctx* ctx) {
     if (p && p->d_emap) cudaFree(p->d_emap);
     if (p && p->d_colbase) cudaFree(p->d_colbase);
     if (p && p->d_rowf) cudaFree(p->d_rowf);
+    if (p && p->d_xoff) cudaFree(p->d_xoff);
     delete p;
   }
   asm_free(ctx);

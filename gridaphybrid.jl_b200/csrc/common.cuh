@@ -31,6 +31,7 @@ struct Plan {
   int32_t* d_colbase = nullptr;   // tables of the DMMA kernel's on-the-fly re-layout (condense_dmma.cu)
   uint8_t* d_rowf = nullptr;
   uint8_t* d_rowl = nullptr;
+  int32_t* d_xoff = nullptr;      // left-looking DMMA kernel: bottom-block record offsets in fragment order
   bool use_dmma = false;
   bool use_warp = false;          // register-resident warp kernels for small cells (condense_warp.cu)
   bool use_large = false;         // streamed large-cell kernel, 64 < n_i <= 128 (condense_large.cu)

@@ -102,6 +102,8 @@ struct DmmaTables {
   const uint8_t* rowf;     // [n]: field slot of condensed row r
   const uint8_t* rowl;     // [n]: row inside its field
   int nf;
+  const int32_t* xoff;     // left-looking kernel: [BT][CT][2][32] record offset of the accumulator-fragment element of
+                           // (row tile, column tile, e, lane); -1 = zero; <= -2: offset -2-v in the b record
 };
 
 // smallest leading dimension >= x with LD = 4 (mod 8): 2*LD = 8 or 24 (mod 32) words, the condition for
@@ -275,6 +277,153 @@ __device__ __forceinline__ void panel_factor(double* __restrict__ Wt, const int 
   }
   if (lane < 8) ctl->rinv[lane] = myrinv;
 }
+
+// ---- panel factorisation with look-ahead inside the panel warp (left-looking kernel) ---------------
+// panel_factor() plus: the panel warp itself applies panel p to column tile p+1 (the next panel), so that the chain
+// panel p -> panel p+1 never waits for an update warp; the update warps take the tiles J >= p+2.
+template <int NI, int LDW, bool TWO>
+__device__ __forceinline__ void panel_factor_la(double* __restrict__ Wt, const int c0, const int npiv, PanelCtl* ctl,
+                                                int* __restrict__ info, const int p, const bool next) {
+  const int lane = threadIdx.x & 31;
+  const int nrows = NI - c0;
+  const bool v1 = lane < nrows;
+  const bool v2 = TWO && (lane + 32 < nrows);
+  double a[8], a2[8];
+  int ch1 = -1, ch2 = -1;                       // step at which this lane's row became the pivot row
+  double myrinv = 0.0;                          // lane k keeps 1/pivot of step k
+  double* base = Wt + c0 + lane + LDW * c0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    a[j] = v1 ? base[LDW * pc(j)] : 0.0;
+    a2[j] = v2 ? base[32 + LDW * pc(j)] : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (k < npiv) {
+      // ---- pivot search: one REDUX.MAX over key = |a| (exponent + 15 mantissa bits) << 6 | (63 - row)
+      const bool c1 = v1 && ch1 < 0;
+      const bool c2 = v2 && ch2 < 0;
+      const unsigned h1 = (unsigned)(__double_as_longlong(a[k]) >> 32) & 0x7fffffffu;
+      const unsigned h2 = (unsigned)(__double_as_longlong(a2[k]) >> 32) & 0x7fffffffu;
+      unsigned key = c1 ? (((h1 >> 5) << 6) | (unsigned)(63 - lane)) : 0u;
+      if (TWO) {
+        const unsigned key2 = c2 ? (((h2 >> 5) << 6) | (unsigned)(31 - lane)) : 0u;
+        key = key > key2 ? key : key2;
+      }
+      const double rc1 = fast_rcp(a[k]);        // speculative reciprocal, overlaps the reduction
+      const double rc2 = TWO ? fast_rcp(a2[k]) : 0.0;
+      unsigned kmax = __reduce_max_sync(0xffffffffu, key);
+      if ((kmax >> 6) == 0u) {
+        // all candidates below 2^-1017: decide exactly (zero column => LAPACK info = k+1)
+        const unsigned long long e1 = c1 ? ((unsigned long long)__double_as_longlong(a[k]) & 0x7fffffffffffffffull) : 0ull;
+        const unsigned long long e2 = c2 ? ((unsigned long long)__double_as_longlong(a2[k]) & 0x7fffffffffffffffull) : 0ull;
+        const unsigned lo1 = __reduce_max_sync(0xffffffffu, (unsigned)(e1 >> 32) | (unsigned)(e2 >> 32));
+        const unsigned lo2 = __reduce_max_sync(0xffffffffu, (unsigned)e1 | (unsigned)e2);
+        if ((lo1 | lo2) == 0u) {
+          if (lane == 0 && *info == 0) *info = c0 + k + 1;
+        }
+        // keep going with the first candidate row (results of a failed cell are overwritten with NaN)
+        const unsigned bb1 = __ballot_sync(0xffffffffu, c1);
+        const unsigned bb2 = __ballot_sync(0xffffffffu, c2);
+        const int row = bb1 ? (__ffs(bb1) - 1) : (32 + __ffs(bb2) - 1);
+        kmax = (unsigned)(63 - row);
+      }
+      const int prow = 63 - (int)(kmax & 63u);  // row of the pivot inside the panel (0..63)
+      const bool from2 = TWO && prow >= 32;
+      const int q = prow & 31;
+      const double rinv = __shfl_sync(0xffffffffu, from2 ? rc2 : rc1, q);
+      if (lane == k) myrinv = rinv;
+      const bool me1 = !from2 && lane == q, me2 = from2 && lane == q;
+      if (me1) ch1 = k;
+      if (me2) ch2 = k;
+      // ---- multipliers and rank-1 update of the rows still in play
+      const bool u1 = c1 && !me1, u2 = TWO && c2 && !me2;
+      const double l1 = a[k] * rinv, l2 = a2[k] * rinv;   // dgetf2: scale by the reciprocal
+      a[k] = u1 ? l1 : a[k];
+      const double nl1 = u1 ? -l1 : 0.0;                  // rows out of play: a + 0*p = a
+      double nl2 = 0.0;
+      if (TWO) { a2[k] = u2 ? l2 : a2[k]; nl2 = u2 ? -l2 : 0.0; }
+#pragma unroll
+      for (int j = k + 1; j < 8; ++j) {
+        const double pj = __shfl_sync(0xffffffffu, from2 ? a2[j] : a[j], q);   // pivot row entry, to everyone
+        a[j] = fma(nl1, pj, a[j]);
+        if (TWO) a2[j] = fma(nl2, pj, a2[j]);
+      }
+    }
+  }
+  // ---- new positions: pivot rows first, displaced rows into the vacated slots
+  const bool disp = v1 && lane < npiv && ch1 < 0;          // rows of the diagonal block not chosen
+  const bool vc1 = v1 && lane >= npiv && ch1 >= 0;
+  const bool vc2 = v2 && ch2 >= 0;
+  const unsigned mdisp = __ballot_sync(0xffffffffu, disp);
+  const unsigned mv1 = __ballot_sync(0xffffffffu, vc1);
+  const unsigned mv2 = TWO ? __ballot_sync(0xffffffffu, vc2) : 0u;
+  const unsigned lt = (1u << lane) - 1u;
+  if (vc1) ctl->vac[__popc(mv1 & lt)] = c0 + lane;
+  if (vc2) ctl->vac[__popc(mv1) + __popc(mv2 & lt)] = c0 + 32 + lane;
+  __syncwarp();
+  int np1 = c0 + lane, np2 = c0 + 32 + lane;
+  if (ch1 >= 0) np1 = c0 + ch1;
+  else if (disp) np1 = ctl->vac[__popc(mdisp & lt)];
+  if (ch2 >= 0) np2 = c0 + ch2;
+  if (ch1 >= 0) ctl->psrc[ch1] = c0 + lane;
+  if (ch2 >= 0) ctl->psrc[ch2] = c0 + 32 + lane;
+  if (disp) {
+    const int t = __popc(mdisp & lt);
+    ctl->dsrc[t] = c0 + lane;
+    ctl->ddst[t] = np1;
+  }
+  if (lane == 0) ctl->ndisp = __popc(mdisp);
+  double* wb = Wt + LDW * c0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (v1) wb[np1 + LDW * pc(j)] = a[j];
+    if (v2) wb[np2 + LDW * pc(j)] = a2[j];
+  }
+  if (lane < 8) ctl->rinv[lane] = myrinv;
+  bar_arrive<BAR_PANEL, 128>(p & 1);            // panel p is published: the update warps start their stage
+  if (!next) return;
+  // ---- look-ahead: apply this panel to the next panel's column tile, rows still one per lane in the old order
+  // (multipliers are in a[], the pivot lane of step k is the one with ch == k), and write it back in the new order.
+  if (p > 0) bar_sync<BAR_COL, 64>((p + 1) & 1);   // tile p+1 carries every panel < p (first tile of stage p-1)
+  constexpr int XW = TWO ? 4 : 8;               // columns per pass (two passes keep the two-row case in registers)
+  const double* xb = Wt + c0 + lane + LDW * (c0 + 8);
+  double* wx = Wt + LDW * (c0 + 8);
+#pragma unroll
+  for (int h = 0; h < 8 / XW; ++h) {
+    double x[XW], x2[XW];
+#pragma unroll
+    for (int j = 0; j < XW; ++j) {
+      x[j] = v1 ? xb[LDW * pc(XW * h + j)] : 0.0;
+      x2[j] = v2 ? xb[32 + LDW * pc(XW * h + j)] : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (k < npiv) {
+        const unsigned b1 = __ballot_sync(0xffffffffu, ch1 == k);
+        const unsigned b2 = TWO ? __ballot_sync(0xffffffffu, ch2 == k) : 0u;
+        const bool from2 = TWO && b1 == 0u;
+        const int q = __ffs(from2 ? b2 : b1) - 1;
+        const double m1 = (v1 && (ch1 < 0 || ch1 > k)) ? -a[k] : 0.0;     // rows still in play after step k
+        const double m2 = (TWO && v2 && (ch2 < 0 || ch2 > k)) ? -a2[k] : 0.0;
+#pragma unroll
+        for (int j = 0; j < XW; ++j) {
+          const double pj = __shfl_sync(0xffffffffu, from2 ? x2[j] : x[j], q);
+          x[j] = fma(m1, pj, x[j]);
+          if (TWO) x2[j] = fma(m2, pj, x2[j]);
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < XW; ++j) {
+      if (v1) wx[np1 + LDW * pc(XW * h + j)] = x[j];
+      if (v2) wx[np2 + LDW * pc(XW * h + j)] = x2[j];
+    }
+  }
+  __syncwarp();
+}
+
 
 // ---- inverses of the 8x8 diagonal block of a factorised panel, by the (otherwise idle) update warps:
 // lanes 0-7 each own one column and run the same branch-free substitution; entries of L\U are uniform
@@ -704,6 +853,275 @@ condense_dmma_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const do
   }
 }
 
+// ---- condensation with a left-looking, register-resident bottom block -----------------------------
+// Same top block as condense_dmma_kernel (panel warp + column-tile owners, look-ahead), but only Wt = [A11 A12 b1]
+// lives in shared memory: 26.8 KB per cell for (34,36) instead of 45 KB, and no S accumulators are carried through
+// the top block (64 registers), so 8 cells are resident per SM instead of 5.  The bottom block [A21 A22 b2] never
+// touches shared memory: after the top block is final every warp takes row tiles of 8 boundary rows, reads them from
+// the record as accumulator fragments (64-byte runs of the packed columns; the record was pulled into L2 by the bulk
+// prefetch) and runs, panel by panel,
+//     Y_p = -X_p inv(U_pp),   X_J += Y_p U_pJ  (J > p)
+// entirely in registers (S = A22 - (A21 U^-1)(L^-1 P A12), the same re-association as above).  The accumulator
+// fragment of Y_p is fed back as the A operand without a shared-memory round trip: accumulator column n of a tile
+// stands for logical column sg(n), so that k-step s of lane tig is logical column sg(2 tig + s) and the B fragments of
+// U_pJ are read from rows c0 + sg(2 tig + s) -- with sg = (0,2,1,3,6,4,7,5) these loads are bank-conflict free for
+// leading dimensions = 4 (mod 8) under the pc() column permutation (tools/emulate_bottom.py checks indices and banks).
+__device__ __forceinline__ int sg8(int n) { return (int)((0x57463120u >> (4 * n)) & 7u); }
+
+template <int NI, int NB>
+struct LLCfg {
+  using C = Cfg<NI, NB>;
+  static size_t smem_bytes(int nf) {   // Wt + inv(U_pp) of every panel + 2 panel control blocks + info + tables
+    return (size_t)(C::WT_DOUBLES + C::NP * 64) * 8 + 2 * sizeof(PanelCtl) + 16 + (size_t)(C::N + 1) * nf * 4 +
+           2 * NI + 2 * NB + 16;
+  }
+};
+enum { BAR_UW_LL = 5 };   // + panel parity: ids 0..6 -> 7 barriers per CTA, 8 CTAs per SM
+
+template <int NI, int NB, int RPC, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+condense_dmma_ll_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const double* __restrict__ A,
+                        const double* __restrict__ b, double* __restrict__ S, double* __restrict__ g,
+                        int32_t* __restrict__ info) {
+  using C = Cfg<NI, NB>;
+  constexpr int N = C::N, LDW = C::LDW, RT = C::RT, BT = C::BT, CT = C::CT, NP = C::NP;
+  constexpr int SJ0 = NI / 8;                   // first column tile holding S columns
+  extern __shared__ __align__(16) double smem[];
+  double* Wt = smem;
+  double* s_dinv = Wt + C::WT_DOUBLES;                                  // [NP][64]: inv(U_pp), B operand k + 8 n
+  PanelCtl* ctl2 = reinterpret_cast<PanelCtl*>(s_dinv + NP * 64);      // [2]
+  int* s_info = reinterpret_cast<int*>(ctl2 + 2);
+  int* s_colbase = s_info + 4;                                         // [(N+1)*nf]
+  unsigned short* s_rowinfo = reinterpret_cast<unsigned short*>(s_colbase + (N + 1) * tb.nf);  // [NI/RPC] interior rows
+  unsigned short* s_rowinfo2 = s_rowinfo + NI;                                                 // [NB] boundary rows
+  static_assert(RPC == 1 || NI % 2 == 0, "16-byte cp.async needs an even interior height");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tig = lane & 3;    // fragment coordinates
+  const int ce0 = pc(2 * tig), ce1 = pc(2 * tig + 1);   // top block: C fragment
+  const int ka0 = tig, ka1 = pc(4 + tig);               // top block: A fragment (k-steps 0, 1)
+  const int nb = pc(gid);                               // top block: B fragment column
+
+  for (int i = tid; i < C::WT_DOUBLES; i += 128) Wt[i] = 0.0;   // padding never written by the loader
+  for (int i = tid; i < (N + 1) * tb.nf; i += 128) s_colbase[i] = tb.colbase[i];
+  constexpr int HP = NI / RPC;                  // copy units per column (interior rows only)
+  constexpr int LG = 128 / HP;                  // column groups
+  static_assert(LG >= 1, "cell too tall for the loader");
+  constexpr int LB = 6;                         // loader batch: look-ups in flight per thread
+  for (int i = tid; i < HP; i += 128) s_rowinfo[i] = (unsigned short)((tb.rowf[RPC * i] << 8) | tb.rowl[RPC * i]);
+  for (int i = tid; i < NB; i += 128) s_rowinfo2[i] = (unsigned short)((tb.rowf[NI + i] << 8) | tb.rowl[NI + i]);
+  __syncthreads();
+  const int l_grp = tid / HP, l_rp = tid - l_grp * HP;
+  const bool l_on = l_grp < LG;
+  const int l_ri = l_on ? s_rowinfo[l_rp] : 0;
+  const int l_f = l_ri >> 8, l_lr = l_ri & 0xff;
+  double* const l_dst0 = Wt + RPC * l_rp;
+
+  for (int64_t cell = blockIdx.x; cell < ncells; cell += gridDim.x) {
+    // ------------------------------------------------------------------ load + re-layout of the interior rows
+    if (l_on) {
+      const double* Arec = A + cell * lenA + l_lr;
+      const double* brec = b + cell * lenb + l_lr;
+      const int* cb = s_colbase + l_f;
+#pragma unroll 1
+      for (int cb0 = l_grp; cb0 < N; cb0 += LB * LG) {
+        int off[LB];
+#pragma unroll
+        for (int q = 0; q < LB; ++q) { const int c = cb0 + q * LG; off[q] = c < N ? cb[c * tb.nf] : -2; }
+#pragma unroll
+        for (int q = 0; q < LB; ++q) {
+          const int c = cb0 + q * LG;
+          double* dst = l_dst0 + LDW * pc(c);
+          const double* src = Arec + (off[q] >= 0 ? off[q] : 0);   // untouched block: zero fill, nothing read
+          if (off[q] != -2) { if (RPC == 2) cp_async16_z(dst, src, off[q] >= 0); else cp_async8_z(dst, src, off[q] >= 0); }
+        }
+      }
+      if (l_grp == N % LG) {                                                                         // rhs column
+        if (RPC == 2) cp_async16(l_dst0 + LDW * pc(N), brec + cb[N * tb.nf]);
+        else cp_async8(l_dst0 + LDW * pc(N), brec + cb[N * tb.nf]);
+      }
+    }
+    if (tid == 0) *s_info = 0;
+#if GHB_L2PREFETCH
+    // the boundary rows of this record are read (from L2) only after the top block, a whole cell latency from now: one
+    // bulk prefetch of the record.  (One cell *ahead*, as in the right-looking kernel, keeps 2 x 8 x 148 records in
+    // flight, more than L2 holds: measured 1.7x the algorithmic DRAM reads.)
+    if (tid == 32) l2_prefetch_bulk(A + cell * lenA, (unsigned)(lenA * 8));
+#endif
+    cp_async_commit_wait_all();
+    __syncthreads();
+
+    if (warp == 0) {
+      // ================================================================ panel warp
+#pragma unroll 1
+      for (int p = 0; p < NP; ++p) {
+        const int c0 = 8 * p;
+        const int npiv = (NI - c0) < 8 ? (NI - c0) : 8;
+        // column tile p is in this warp's hands since the look-ahead of panel p-1: no hand-off from the update warps
+        PanelCtl* ctl = ctl2 + (p & 1);
+        __syncwarp();
+        if ((NI - c0) > 32) panel_factor_la<NI, LDW, true>(Wt, c0, npiv, ctl, s_info, p, p + 1 < NP);
+        else panel_factor_la<NI, LDW, false>(Wt, c0, npiv, ctl, s_info, p, p + 1 < NP);
+      }
+    } else {
+      // ================================================================ update warps: column tiles J > p
+      const int uw = warp - 1;                    // 0..2
+#pragma unroll 1
+      for (int p = 0; p < NP; ++p) {
+        const int c0 = 8 * p;
+        const int npiv = (NI - c0) < 8 ? (NI - c0) : 8;
+        PanelCtl* ctl = ctl2 + (p & 1);
+        bar_sync<BAR_PANEL, 128>(p & 1);
+        // inverses of the diagonal block by the two update warps with the fewest tiles in this stage
+        if (uw == (p + 1) % 3) invert_unit_lower<LDW>(Wt + c0 + LDW * c0, npiv, ctl->Linv);
+        if (uw == p % 3) invert_upper<LDW>(Wt + c0 + LDW * c0, npiv, ctl->rinv, s_dinv + 64 * p);   // for the bottom block
+        const int nd = ctl->ndisp;
+        const int ps0 = tig < npiv ? ctl->psrc[tig] : -1;
+        const int ps1 = 4 + tig < npiv ? ctl->psrc[4 + tig] : -1;
+        const int dsr = gid < nd ? ctl->dsrc[gid] : -1;
+        const int dds = gid < nd ? ctl->ddst[gid] : -1;
+        bar_sync<BAR_UW_LL, 96>(p & 1);
+        const double li0 = ctl->Linv[gid + 8 * tig], li1 = ctl->Linv[gid + 8 * (4 + tig)];
+        const int Jlo = p + 1 < NP ? p + 2 : p + 1;          // tile p+1 (the next panel) is updated by the panel warp
+        const int Jfirst = Jlo + (uw + 3 - Jlo % 3) % 3;     // first owned tile (J mod 3 == uw)
+#pragma unroll 1
+        for (int J = Jfirst; J < CT; J += 3) {
+          double* colg = Wt + LDW * (8 * J + nb);      // B-fragment column of this lane
+          double* colt = Wt + LDW * (8 * J + tig);     // displaced rows: lane (t=gid) moves columns tig, tig+4
+          const double g0 = ps0 >= 0 ? colg[ps0] : 0.0;
+          const double g1 = ps1 >= 0 ? colg[ps1] : 0.0;
+          const double dv0 = dsr >= 0 ? colt[dsr] : 0.0;
+          const double dv1 = dsr >= 0 ? colt[dsr + 4 * LDW] : 0.0;
+          __syncwarp();
+          double u0 = 0.0, u1 = 0.0;              // U12 tile = inv(L_pp) * gathered rows
+          dmma(u0, u1, li0, g0);
+          dmma(u0, u1, li1, g1);
+          double* cc0 = Wt + gid + LDW * (8 * J + ce0);
+          double* cc1 = Wt + gid + LDW * (8 * J + ce1);
+          if (c0 + gid < NI) { cc0[c0] = u0; cc1[c0] = u1; }
+          if (dds >= 0) { colt[dds] = dv0; colt[dds + 4 * LDW] = dv1; }
+          __syncwarp();
+          if (p + 1 < RT) {
+            const double bf0 = neg(colg[c0 + tig]);
+            const double bf1 = neg(colg[c0 + 4 + tig]);
+            int I = p + 1;
+#pragma unroll 1
+            for (; I + 1 < RT; I += 2) {           // two row tiles per step: independent accumulators in flight
+              const int rA = 8 * I + gid, rB = rA + 8;
+              const bool vA = rA < NI, vB = rB < NI;
+              const double aA0 = vA ? Wt[rA + LDW * (c0 + ka0)] : 0.0, aA1 = vA ? Wt[rA + LDW * (c0 + ka1)] : 0.0;
+              const double aB0 = vB ? Wt[rB + LDW * (c0 + ka0)] : 0.0, aB1 = vB ? Wt[rB + LDW * (c0 + ka1)] : 0.0;
+              double dA0 = vA ? cc0[8 * I] : 0.0, dA1 = vA ? cc1[8 * I] : 0.0;
+              double dB0 = vB ? cc0[8 * I + 8] : 0.0, dB1 = vB ? cc1[8 * I + 8] : 0.0;
+              dmma(dA0, dA1, aA0, bf0);
+              dmma(dB0, dB1, aB0, bf0);
+              dmma(dA0, dA1, aA1, bf1);
+              dmma(dB0, dB1, aB1, bf1);
+              if (vA) { cc0[8 * I] = dA0; cc1[8 * I] = dA1; }
+              if (vB) { cc0[8 * I + 8] = dB0; cc1[8 * I + 8] = dB1; }
+            }
+            if (I < RT) {
+              const int r = 8 * I + gid;
+              const bool rv = r < NI;
+              const double a0 = rv ? Wt[r + LDW * (c0 + ka0)] : 0.0;
+              const double a1 = rv ? Wt[r + LDW * (c0 + ka1)] : 0.0;
+              double d0 = rv ? cc0[8 * I] : 0.0, d1 = rv ? cc1[8 * I] : 0.0;
+              dmma(d0, d1, a0, bf0);
+              dmma(d0, d1, a1, bf1);
+              if (rv) { cc0[8 * I] = d0; cc1[8 * I] = d1; }
+            }
+          }
+          if (J == p + 2 && p + 2 < NP) bar_arrive<BAR_COL, 64>((p + 2) & 1);   // look-ahead input of panel p+1
+        }
+      }
+    }
+    __syncthreads();                               // U, L^-1 P [A12 b1] and every inv(U_pp) are final
+
+    // ================================================================ bottom block: row tiles, registers only
+    {
+      const int r0s = sg8(2 * tig), r1s = sg8(2 * tig + 1);   // logical column of accumulator element e / row of k-step s
+      const int sgid = sg8(gid);                              // logical column of output column n = gid
+      const double* ubase = Wt + LDW * pc(sgid);              // B fragments of U_pJ: ubase[c0 + r_s + LDW*8*J]
+      const bool failed = *s_info != 0;
+      const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+      const double* Arec = A + cell * lenA;
+      const double* brec = b + cell * lenb;
+      double* Sc = S + cell * (int64_t)NB * NB;
+      double* gc = g + cell * (int64_t)NB;
+#pragma unroll 1
+      for (int I = warp; I < BT; I += 4) {
+        const int r = 8 * I + gid;
+        const bool rv = r < NB;
+        // accumulator fragments straight from the record: the offsets come from a per-plan table laid out per lane
+        // (one coalesced look-up per element, immediate offsets), all look-ups first
+        const int32_t* xo = tb.xoff + (size_t)I * (CT * 64) + lane;
+        int xoffs[CT][2];
+#pragma unroll
+        for (int J = 0; J < CT; ++J) {
+          xoffs[J][0] = __ldg(xo + J * 64);
+          xoffs[J][1] = __ldg(xo + J * 64 + 32);
+        }
+        double x[CT][2];
+#pragma unroll
+        for (int J = 0; J < CT; ++J) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int o = xoffs[J][e];
+            if (J == N / 8) x[J][e] = o >= 0 ? Arec[o] : (o < -1 ? brec[-2 - o] : 0.0);   // the tile of the rhs column
+            else x[J][e] = o >= 0 ? Arec[o] : 0.0;
+          }
+        }
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          const int c0 = 8 * p;
+          const int npiv = (NI - c0) < 8 ? (NI - c0) : 8;
+          const double* dv = s_dinv + 64 * p + 8 * sgid;      // zero padded beyond npiv
+          double y0 = 0.0, y1 = 0.0;                          // Y_p = -X_p inv(U_pp)
+          dmma(y0, y1, x[p][0], neg(dv[r0s]));
+          if (npiv > 2) dmma(y0, y1, x[p][1], neg(dv[r1s]));  // k-step 1 stands for rows 2..5
+          if (npiv < 8) {
+            // partial last panel: the rest of its own tile (columns >= npiv) is updated with U_pp rows < npiv
+            const double q0 = (r0s < npiv && sgid >= npiv) ? ubase[c0 + r0s + LDW * c0] : 0.0;
+            dmma(x[p][0], x[p][1], y0, q0);
+            if (npiv > 2) {
+              const double q1 = (r1s < npiv && sgid >= npiv) ? ubase[c0 + r1s + LDW * c0] : 0.0;
+              dmma(x[p][0], x[p][1], y1, q1);
+            }
+          }
+          // k-step outermost: consecutive DMMAs belong to independent accumulators
+#pragma unroll
+          for (int J = p + 1; J < CT; ++J) {
+            const double b0 = (npiv == 8 || r0s < npiv) ? ubase[c0 + r0s + LDW * 8 * J] : 0.0;
+            dmma(x[J][0], x[J][1], y0, b0);
+          }
+          if (npiv > 2) {
+#pragma unroll
+            for (int J = p + 1; J < CT; ++J) {
+              const double b1 = (npiv == 8 || r1s < npiv) ? ubase[c0 + r1s + LDW * 8 * J] : 0.0;
+              dmma(x[J][0], x[J][1], y1, b1);
+            }
+          }
+        }
+        if (rv) {
+#pragma unroll
+          for (int J = SJ0; J < CT; ++J) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int c = 8 * J + (e ? r1s : r0s);
+              const double v = failed ? qnan : x[J][e];
+              if (c >= NI) {
+                if (c < N) Sc[r + (int64_t)NB * (c - NI)] = v;
+                else if (c == N) gc[r] = v;
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (info && tid == 0) info[cell] = *s_info;
+  }
+}
+
 // ---- backward static condensation on the same machinery ------------------------------------------
 // u_K = A11^-1 (b1 - A12 lambda_K)   (/root/reference/src/BackwardStaticCondensationMap.jl:84-99; the LU is
 // recomputed from the record, as the reference does).  Image W = [A11 | r] (n_i rows, n_i+1 columns): the same
@@ -948,6 +1366,25 @@ int dmma_prepare(ghb_ctx* ctx, Plan& p) {
   GHB_CUDA(ctx, cudaMemcpy(p.d_colbase, colbase.data(), colbase.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   GHB_CUDA(ctx, cudaMemcpy(p.d_rowf, rowf.data(), n, cudaMemcpyHostToDevice));
   GHB_CUDA(ctx, cudaMemcpy(p.d_rowl, rowl.data(), n, cudaMemcpyHostToDevice));
+  {
+    // left-looking kernel: record offsets of the bottom block [A21 A22 b2] in accumulator-fragment order
+    const int ni = p.n_i, nbd = p.n_b, BT = (nbd + 7) / 8, CT = (n + 1 + 7) / 8;
+    static const int sg[8] = {0, 2, 1, 3, 6, 4, 7, 5};
+    std::vector<int32_t> xoff((size_t)BT * CT * 64, -1);
+    for (int I = 0; I < BT; ++I)
+      for (int J = 0; J < CT; ++J)
+        for (int e = 0; e < 2; ++e)
+          for (int lane = 0; lane < 32; ++lane) {
+            const int r = 8 * I + (lane >> 2), c = 8 * J + sg[2 * (lane & 3) + e];
+            if (r >= nbd || c > n) continue;
+            const int f = p.row_field[ni + r], lr = p.row_local[ni + r];
+            const int32_t base = colbase[(size_t)c * nf + f];
+            if (base < 0) continue;
+            xoff[((size_t)(I * CT + J) * 2 + e) * 32 + lane] = c < n ? base + lr : -2 - (base + lr);
+          }
+    GHB_CUDA(ctx, cudaMalloc((void**)&p.d_xoff, xoff.size() * sizeof(int32_t)));
+    GHB_CUDA(ctx, cudaMemcpy(p.d_xoff, xoff.data(), xoff.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
   p.kernel_name = p.n_i == 34 ? "dmma_34_36" : (p.n_i == 33 ? "dmma_33_12" : "dmma_56_16");
   return GHB_OK;
 }
@@ -965,11 +1402,48 @@ static int launch_dmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double
   if (per_sm < 1) return fail(ctx, GHB_ECUDA, "condense_dmma_kernel does not fit on an SM");
   if (const char* cap = getenv("GHB_MAX_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(cap)));   // profiling knob
   if (getenv("GHB_DEBUG")) fprintf(stderr, "condense_dmma<%d,%d>: %d CTAs/SM, %zu B smem\n", NI, NB, per_sm, smem);
-  DmmaTables tb{p.d_colbase, p.d_rowf, p.d_rowl, p.nfields};
+  DmmaTables tb{p.d_colbase, p.d_rowf, p.d_rowl, p.nfields, p.d_xoff};
   int64_t grid = std::min<int64_t>(ncells, (int64_t)ctx->sm_count * per_sm);
   kern<<<(unsigned)grid, 128, smem, ctx->stream>>>(tb, p.lenA, p.lenb, ncells, A, b, S, g, info);
   GHB_LAUNCHED(ctx);
   return GHB_OK;
+}
+
+// resident CTAs per SM the left-looking kernels are compiled for (64 / 72 / 80 / 96 registers at 8 / 7 / 6 / 5)
+#ifndef GHB_LL_MINB34
+#define GHB_LL_MINB34 8
+#endif
+#ifndef GHB_LL_MINB33
+#define GHB_LL_MINB33 8
+#endif
+#ifndef GHB_LL_MINB56
+#define GHB_LL_MINB56 5
+#endif
+
+template <int NI, int NB, int RPC, int MINB>
+static int launch_dmma_ll(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
+                          double* g, int32_t* info) {
+  auto kern = condense_dmma_ll_kernel<NI, NB, RPC, MINB>;
+  const size_t smem = LLCfg<NI, NB>::smem_bytes(p.nfields);
+  GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  int per_sm = 0;
+  GHB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
+  if (per_sm < 1) return fail(ctx, GHB_ECUDA, "condense_dmma_ll_kernel does not fit on an SM");
+  if (const char* cap = getenv("GHB_MAX_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(cap)));   // profiling knob
+  if (getenv("GHB_DEBUG")) fprintf(stderr, "condense_dmma_ll<%d,%d>: %d CTAs/SM, %zu B smem\n", NI, NB, per_sm, smem);
+  DmmaTables tb{p.d_colbase, p.d_rowf, p.d_rowl, p.nfields, p.d_xoff};
+  int64_t grid = std::min<int64_t>(ncells, (int64_t)ctx->sm_count * per_sm);
+  kern<<<(unsigned)grid, 128, smem, ctx->stream>>>(tb, p.lenA, p.lenb, ncells, A, b, S, g, info);
+  GHB_LAUNCHED(ctx);
+  return GHB_OK;
+}
+
+// kernel selection of the DMMA shapes: GHB_DMMA_LL=1 / 0 forces the left-looking / the right-looking bottom block
+static bool use_ll(const Plan& p) {
+  if (const char* e = getenv("GHB_DMMA_LL")) return e[0] == '1';
+  (void)p;
+  return false;
 }
 
 template <int NI, int NB, int RPC>
@@ -984,7 +1458,7 @@ static int launch_bdmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const doubl
   if (per_sm < 1) return fail(ctx, GHB_ECUDA, "backsub_dmma_kernel does not fit on an SM");
   if (const char* cap = getenv("GHB_MAX_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(cap)));   // profiling knob
   if (getenv("GHB_DEBUG")) fprintf(stderr, "backsub_dmma<%d,%d>: %d CTAs/SM, %zu B smem\n", NI, NB, per_sm, smem);
-  DmmaTables tb{p.d_colbase, p.d_rowf, p.d_rowl, p.nfields};
+  DmmaTables tb{p.d_colbase, p.d_rowf, p.d_rowl, p.nfields, p.d_xoff};
   int64_t grid = std::min<int64_t>(ncells, (int64_t)ctx->sm_count * per_sm);
   kern<<<(unsigned)grid, 128, smem, ctx->stream>>>(tb, p.lenA, p.lenb, ncells, A, b, lam_free, lam_dir, ids, u, info);
   GHB_LAUNCHED(ctx);
@@ -1000,6 +1474,17 @@ int launch_backsub_dmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const doubl
 
 int launch_condense_dmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
                          double* g, int32_t* info) {
+  if (use_ll(p)) {
+    if (p.n_i == 34) {
+      const char* e = getenv("GHB_LL_CTAS");           // tuning knob: register budget of the (34,36) instantiation
+      const int m = e ? atoi(e) : GHB_LL_MINB34;
+      if (m == 6) return launch_dmma_ll<34, 36, 2, 6>(ctx, p, ncells, A, b, S, g, info);
+      if (m == 7) return launch_dmma_ll<34, 36, 2, 7>(ctx, p, ncells, A, b, S, g, info);
+      return launch_dmma_ll<34, 36, 2, 8>(ctx, p, ncells, A, b, S, g, info);
+    }
+    if (p.n_i == 56) return launch_dmma_ll<56, 16, 2, GHB_LL_MINB56>(ctx, p, ncells, A, b, S, g, info);
+    return launch_dmma_ll<33, 12, 1, GHB_LL_MINB33>(ctx, p, ncells, A, b, S, g, info);
+  }
   if (p.n_i == 34) return launch_dmma<34, 36, 2>(ctx, p, ncells, A, b, S, g, info);
   if (p.n_i == 56) return launch_dmma<56, 16, 2>(ctx, p, ncells, A, b, S, g, info);
   return launch_dmma<33, 12, 1>(ctx, p, ncells, A, b, S, g, info);
