@@ -15,6 +15,8 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 _CSRC = os.path.join(_PKG, "csrc")
 SO_PATH = os.path.join(_PKG, "libgridaphybrid_b200.so")
+if os.environ.get("GHB_LIB_PATH"):      # A/B builds of the same sources with other -D knobs (tools/ab_variants.sh)
+    SO_PATH = os.path.abspath(os.environ["GHB_LIB_PATH"])
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

@@ -35,6 +35,25 @@
 #define GHB_MINB33 7
 #endif
 
+#ifndef GHB_LL_LOOKAHEAD
+#define GHB_LL_LOOKAHEAD 0  // 1: the panel warp applies panel p to tile p+1 itself (measured slower: 41.4 -> 31.8 M cells/s)
+#endif
+#ifndef GHB_LL_UNROLL_TRAIL
+#define GHB_LL_UNROLL_TRAIL 0  // 1: trailing update unrolled over the row-tile pairs (measured 40.3 vs 41.4 M cells/s rolled)
+#endif
+#ifndef GHB_LL_INVBOTH
+#define GHB_LL_INVBOTH 0    // 1: both inverses of the diagonal block by one 32-lane shuffle routine (measured slower)
+#endif
+#ifndef GHB_LL_INVU_UW
+#define GHB_LL_INVU_UW 0    // 1: inv(U_pp) by an update warp instead of the panel warp
+#endif
+#ifndef GHB_LL_EARLYX
+#define GHB_LL_EARLYX 1     // first row tile of the bottom block is loaded before the barrier that ends the top block
+#endif
+#ifndef GHB_LL_HOLD_A
+#define GHB_LL_HOLD_A 1     // update warps keep the panel's multipliers in registers across their column tiles
+#endif
+
 namespace ghb {
 
 namespace {
@@ -471,6 +490,35 @@ __device__ __forceinline__ void invert_upper(const double* __restrict__ D, const
 #pragma unroll
     for (int i = 0; i < 8; ++i) Dinv[i + 8 * n] = x[i];
   }
+}
+
+// Both inverses of the diagonal block by one warp, 32 lanes wide: element (i, n) of each inverse lives on lane
+// 4 i + n/2 (accumulator-fragment layout, two columns per lane).  Row operations on the identity -- L^-1: rows below k
+// minus L[i][k] x row k, k ascending; U^-1 = (D^-1 U)^-1 D^-1: rows above k minus U[i][k]/U[i][i] x row k, k descending --
+// one shuffle per column pair and step: 7 steps of (SHFL + DFMA) instead of two 28-term substitutions on 8 lanes.
+// Same padding rules as invert_unit_lower / invert_upper (rows/columns >= npiv: identity for L, zero for U^-1).
+template <int LDW>
+__device__ __forceinline__ void invert_both(const double* __restrict__ D, const int npiv, const double* __restrict__ rinv,
+                                            double* __restrict__ Linv, double* __restrict__ Dinv) {
+  const int lane = threadIdx.x & 31, i = lane >> 2, t = lane & 3;
+  double m[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) m[k] = D[i + LDW * pc(k)];
+  const double ri = i < npiv ? rinv[i] : 0.0;
+  double xl0 = (2 * t == i) ? 1.0 : 0.0, xl1 = (2 * t + 1 == i) ? 1.0 : 0.0;
+  double xu0 = (2 * t == i) ? ri : 0.0, xu1 = (2 * t + 1 == i) ? ri : 0.0;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const int kk = 7 - k;
+    const double pl0 = __shfl_sync(0xffffffffu, xl0, 4 * k + t), pl1 = __shfl_sync(0xffffffffu, xl1, 4 * k + t);
+    const double pu0 = __shfl_sync(0xffffffffu, xu0, 4 * kk + t), pu1 = __shfl_sync(0xffffffffu, xu1, 4 * kk + t);
+    const double cl = (i > k && i < npiv) ? -m[k] : 0.0;
+    const double cu = (i < kk && kk < npiv) ? -m[kk] * ri : 0.0;
+    xl0 = fma(cl, pl0, xl0); xl1 = fma(cl, pl1, xl1);
+    xu0 = fma(cu, pu0, xu0); xu1 = fma(cu, pu1, xu1);
+  }
+  Linv[i + 8 * (2 * t)] = xl0; Linv[i + 8 * (2 * t + 1)] = xl1;
+  Dinv[i + 8 * (2 * t)] = xu0; Dinv[i + 8 * (2 * t + 1)] = xu1;
 }
 
 // RPC = rows per cp.async: 2 (16 bytes) when every vertical pair of the condensed matrix is contiguous and aligned in
@@ -916,8 +964,10 @@ condense_dmma_ll_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const
   const int l_f = l_ri >> 8, l_lr = l_ri & 0xff;
   double* const l_dst0 = Wt + RPC * l_rp;
 
-  for (int64_t cell = blockIdx.x; cell < ncells; cell += gridDim.x) {
+  int trace_cell = 0; (void)trace_cell;
+  for (int64_t cell = blockIdx.x; cell < ncells; cell += gridDim.x, ++trace_cell) {
     // ------------------------------------------------------------------ load + re-layout of the interior rows
+    TRACE(0);
     if (l_on) {
       const double* Arec = A + cell * lenA + l_lr;
       const double* brec = b + cell * lenb + l_lr;
@@ -947,8 +997,10 @@ condense_dmma_ll_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const
     // flight, more than L2 holds: measured 1.7x the algorithmic DRAM reads.)
     if (tid == 32) l2_prefetch_bulk(A + cell * lenA, (unsigned)(lenA * 8));
 #endif
+    TRACE(1);
     cp_async_commit_wait_all();
     __syncthreads();
+    TRACE(2);
 
     if (warp == 0) {
       // ================================================================ panel warp
@@ -956,11 +1008,25 @@ condense_dmma_ll_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const
       for (int p = 0; p < NP; ++p) {
         const int c0 = 8 * p;
         const int npiv = (NI - c0) < 8 ? (NI - c0) : 8;
-        // column tile p is in this warp's hands since the look-ahead of panel p-1: no hand-off from the update warps
         PanelCtl* ctl = ctl2 + (p & 1);
+#if GHB_LL_LOOKAHEAD
+        // column tile p is in this warp's hands since the look-ahead of panel p-1: no hand-off from the update warps
         __syncwarp();
         if ((NI - c0) > 32) panel_factor_la<NI, LDW, true>(Wt, c0, npiv, ctl, s_info, p, p + 1 < NP);
         else panel_factor_la<NI, LDW, false>(Wt, c0, npiv, ctl, s_info, p, p + 1 < NP);
+#else
+        if (p > 0) bar_sync<BAR_COL, 64>(p & 1);             // column tile p is up to date
+        TRACE(4 + 6 * p);
+        if ((NI - c0) > 32) panel_factor<NI, LDW, true>(Wt, c0, npiv, ctl, s_info);
+        else panel_factor<NI, LDW, false>(Wt, c0, npiv, ctl, s_info);
+        bar_arrive<BAR_PANEL, 128>(p & 1);
+        TRACE(5 + 6 * p);
+#if !GHB_LL_INVBOTH && !GHB_LL_INVU_UW
+        __syncwarp();
+        invert_upper<LDW>(Wt + c0 + LDW * c0, npiv, ctl->rinv, s_dinv + 64 * p);   // read by the bottom block
+        TRACE(6 + 6 * p);
+#endif
+#endif
       }
     } else {
       // ================================================================ update warps: column tiles J > p
@@ -971,17 +1037,37 @@ condense_dmma_ll_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const
         const int npiv = (NI - c0) < 8 ? (NI - c0) : 8;
         PanelCtl* ctl = ctl2 + (p & 1);
         bar_sync<BAR_PANEL, 128>(p & 1);
-        // inverses of the diagonal block by the two update warps with the fewest tiles in this stage
+        TRACE(4 + 6 * p);
+        // both inverses of the diagonal block by the owner of the next panel's tile: inv(L_pp) for the column tiles of
+        // this stage (critical path), inv(U_pp) for the bottom block
+#if GHB_LL_INVBOTH
+        if (uw == (p + 1) % 3) invert_both<LDW>(Wt + c0 + LDW * c0, npiv, ctl->rinv, ctl->Linv, s_dinv + 64 * p);
+#else
         if (uw == (p + 1) % 3) invert_unit_lower<LDW>(Wt + c0 + LDW * c0, npiv, ctl->Linv);
-        if (uw == p % 3) invert_upper<LDW>(Wt + c0 + LDW * c0, npiv, ctl->rinv, s_dinv + 64 * p);   // for the bottom block
+#if GHB_LL_LOOKAHEAD || GHB_LL_INVU_UW
+        if (uw == p % 3) invert_upper<LDW>(Wt + c0 + LDW * c0, npiv, ctl->rinv, s_dinv + 64 * p);
+#endif
+#endif
         const int nd = ctl->ndisp;
         const int ps0 = tig < npiv ? ctl->psrc[tig] : -1;
         const int ps1 = 4 + tig < npiv ? ctl->psrc[4 + tig] : -1;
         const int dsr = gid < nd ? ctl->dsrc[gid] : -1;
         const int dds = gid < nd ? ctl->ddst[gid] : -1;
         bar_sync<BAR_UW_LL, 96>(p & 1);
+        TRACE(5 + 6 * p);
         const double li0 = ctl->Linv[gid + 8 * tig], li1 = ctl->Linv[gid + 8 * (4 + tig)];
-        const int Jlo = p + 1 < NP ? p + 2 : p + 1;          // tile p+1 (the next panel) is updated by the panel warp
+        // multipliers of panel p (A fragments) of the row tiles I > p
+#if GHB_LL_HOLD_A && GHB_LL_UNROLL_TRAIL
+        double am[RT][2];
+#pragma unroll
+        for (int I = 1; I < RT; ++I) {                     // held in registers across the column tiles of the stage
+          const bool rv = I > p && (I < RT - 1 || 8 * I + gid < NI);
+          am[I][0] = rv ? Wt[8 * I + gid + LDW * (c0 + ka0)] : 0.0;
+          am[I][1] = rv ? Wt[8 * I + gid + LDW * (c0 + ka1)] : 0.0;
+        }
+#endif
+        // with look-ahead, tile p+1 (the next panel) is updated by the panel warp; else it is this stage's first tile
+        const int Jlo = (GHB_LL_LOOKAHEAD && p + 1 < NP) ? p + 2 : p + 1;
         const int Jfirst = Jlo + (uw + 3 - Jlo % 3) % 3;     // first owned tile (J mod 3 == uw)
 #pragma unroll 1
         for (int J = Jfirst; J < CT; J += 3) {
@@ -1000,6 +1086,37 @@ condense_dmma_ll_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const
           if (c0 + gid < NI) { cc0[c0] = u0; cc1[c0] = u1; }
           if (dds >= 0) { colt[dds] = dv0; colt[dds + 4 * LDW] = dv1; }
           __syncwarp();
+#if GHB_LL_UNROLL_TRAIL
+          if (p + 1 < RT) {
+            // trailing update of the rows below, every row tile I > p in flight at once (independent accumulators:
+            // loads, then the DMMAs k-step outermost, then the stores); only the last row tile has a ragged edge
+            const double bf0 = neg(colg[c0 + tig]);
+            const double bf1 = neg(colg[c0 + 4 + tig]);
+#pragma unroll
+            for (int I0 = 1; I0 < RT; I0 += 2) {             // two row tiles per step: independent accumulators
+              if (I0 + 1 > p) {
+                const int I1 = I0 + 1;
+                const bool vA = I0 > p && (I0 < RT - 1 || 8 * I0 + gid < NI);
+                const bool vB = I1 < RT && (I1 < RT - 1 || 8 * I1 + gid < NI);
+                double dA0 = vA ? cc0[8 * I0] : 0.0, dA1 = vA ? cc1[8 * I0] : 0.0;
+                double dB0 = vB ? cc0[8 * I0 + 8] : 0.0, dB1 = vB ? cc1[8 * I0 + 8] : 0.0;
+#if GHB_LL_HOLD_A
+                const double aA0 = am[I0][0], aA1 = am[I0][1];
+                const double aB0 = I1 < RT ? am[I1 < RT ? I1 : I0][0] : 0.0, aB1 = I1 < RT ? am[I1 < RT ? I1 : I0][1] : 0.0;
+#else
+                const double aA0 = vA ? Wt[8 * I0 + gid + LDW * (c0 + ka0)] : 0.0, aA1 = vA ? Wt[8 * I0 + gid + LDW * (c0 + ka1)] : 0.0;
+                const double aB0 = vB ? Wt[8 * I1 + gid + LDW * (c0 + ka0)] : 0.0, aB1 = vB ? Wt[8 * I1 + gid + LDW * (c0 + ka1)] : 0.0;
+#endif
+                if (I0 > p) dmma(dA0, dA1, aA0, bf0);
+                if (I1 < RT) dmma(dB0, dB1, aB0, bf0);
+                if (I0 > p) dmma(dA0, dA1, aA1, bf1);
+                if (I1 < RT) dmma(dB0, dB1, aB1, bf1);
+                if (vA) { cc0[8 * I0] = dA0; cc1[8 * I0] = dA1; }
+                if (vB) { cc0[8 * I0 + 8] = dB0; cc1[8 * I0 + 8] = dB1; }
+              }
+            }
+          }
+#else
           if (p + 1 < RT) {
             const double bf0 = neg(colg[c0 + tig]);
             const double bf1 = neg(colg[c0 + 4 + tig]);
@@ -1030,18 +1147,29 @@ condense_dmma_ll_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const
               if (rv) { cc0[8 * I] = d0; cc1[8 * I] = d1; }
             }
           }
+#endif
+#if GHB_LL_LOOKAHEAD
           if (J == p + 2 && p + 2 < NP) bar_arrive<BAR_COL, 64>((p + 2) & 1);   // look-ahead input of panel p+1
+#else
+          if (J == p + 1 && p + 1 < NP) bar_arrive<BAR_COL, 64>((p + 1) & 1);   // hand the next panel's tile back
+#endif
+          if (J == Jfirst) TRACE(6 + 6 * p);
         }
+        TRACE(7 + 6 * p);
       }
     }
-    __syncthreads();                               // U, L^-1 P [A12 b1] and every inv(U_pp) are final
-
     // ================================================================ bottom block: row tiles, registers only
+    TRACE(40);
+#if GHB_LL_EARLYX
+    if (warp >= BT) __syncthreads();               // (no row tile for this warp; the others synchronise below)
+#else
+    __syncthreads();                               // U, L^-1 P [A12 b1] and every inv(U_pp) are final
+    TRACE(41);
+#endif
     {
       const int r0s = sg8(2 * tig), r1s = sg8(2 * tig + 1);   // logical column of accumulator element e / row of k-step s
       const int sgid = sg8(gid);                              // logical column of output column n = gid
       const double* ubase = Wt + LDW * pc(sgid);              // B fragments of U_pJ: ubase[c0 + r_s + LDW*8*J]
-      const bool failed = *s_info != 0;
       const double qnan = __longlong_as_double(0x7ff8000000000000LL);
       const double* Arec = A + cell * lenA;
       const double* brec = b + cell * lenb;
@@ -1052,7 +1180,8 @@ condense_dmma_ll_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const
         const int r = 8 * I + gid;
         const bool rv = r < NB;
         // accumulator fragments straight from the record: the offsets come from a per-plan table laid out per lane
-        // (one coalesced look-up per element, immediate offsets), all look-ups first
+        // (one coalesced look-up per element, immediate offsets), all look-ups first.  The loads of a warp's first row
+        // tile are issued before the barrier that ends the top block, so their latency overlaps the wait.
         const int32_t* xo = tb.xoff + (size_t)I * (CT * 64) + lane;
         int xoffs[CT][2];
 #pragma unroll
@@ -1060,6 +1189,7 @@ condense_dmma_ll_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const
           xoffs[J][0] = __ldg(xo + J * 64);
           xoffs[J][1] = __ldg(xo + J * 64 + 32);
         }
+        TRACE(I < 4 ? 42 : 46);
         double x[CT][2];
 #pragma unroll
         for (int J = 0; J < CT; ++J) {
@@ -1070,6 +1200,13 @@ condense_dmma_ll_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const
             else x[J][e] = o >= 0 ? Arec[o] : 0.0;
           }
         }
+#if GHB_LL_EARLYX
+        if (I < 4) {
+          __syncthreads();                           // U, L^-1 P [A12 b1] and every inv(U_pp) are final
+          TRACE(41);
+        }
+#endif
+        const bool failed = *s_info != 0;
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
           const int c0 = 8 * p;
@@ -1101,6 +1238,7 @@ condense_dmma_ll_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const
             }
           }
         }
+        TRACE(I < 4 ? 44 : 48);
         if (rv) {
 #pragma unroll
           for (int J = SJ0; J < CT; ++J) {
@@ -1117,7 +1255,9 @@ condense_dmma_ll_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const
         }
       }
     }
+    TRACE(50);
     __syncthreads();
+    TRACE(51);
     if (info && tid == 0) info[cell] = *s_info;
   }
 }

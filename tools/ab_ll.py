@@ -40,6 +40,33 @@ def run(plan, n, A, b, env):
     return n / (e0.elapsed_time(e1) / 5) / 1e3, S, g
 
 
+def dense_cell(ndofs, touched, Arec, brec):
+    """Packed record (touched blocks, block-column-major, each column-major) -> dense n x (n+1) [A | b]."""
+    off = np.concatenate(([0], np.cumsum(ndofs)))
+    n = off[-1]
+    M = np.zeros((n, n + 1), dtype=np.longdouble)
+    pos = 0
+    for j in range(len(ndofs)):
+        for i in range(len(ndofs)):
+            if touched[i, j]:
+                blk = Arec[pos:pos + ndofs[i] * ndofs[j]].reshape((ndofs[i], ndofs[j]), order="F")
+                M[off[i]:off[i + 1], off[j]:off[j + 1]] = blk
+                pos += ndofs[i] * ndofs[j]
+    M[:, n] = brec
+    return M
+
+
+def schur_longdouble(M, ni):
+    """[S | g] = [A22 b2] - A21 A11^-1 [A12 b1] in 80-bit arithmetic (partial pivoting); interior fields come first."""
+    M = M.copy()
+    for k in range(ni):
+        piv = k + int(np.argmax(np.abs(M[k:ni, k])))
+        M[[k, piv]] = M[[piv, k]]
+        l = M[k + 1:, k] / M[k, k]
+        M[k + 1:, k:] -= np.outer(l, M[k, k:])
+    return np.asarray(M[ni:, ni:])
+
+
 print("| shape | variant | M cells/s | max rel diff vs right-looking kernel |")
 print("|---|---|---|---|")
 for name, (ndofs, touched, n) in SHAPES.items():
@@ -60,6 +87,14 @@ for name, (ndofs, touched, n) in SHAPES.items():
         dS = float(((S1 - S0).abs() / sc).max())
         dg = float(((g1 - g0).abs() / g0.abs().amax(dim=1, keepdim=True)).max())
         print(f"| {name} | left-looking {env} | {r1:.2f} | S {dS:.2e}, g {dg:.2e} |", flush=True)
+        if dS > 1e-12:
+            # which of the two is off?  80-bit reference of the worst cell
+            c = int(((S1 - S0).abs() / sc).amax(dim=1).argmax())
+            ref = schur_longdouble(dense_cell(ndofs, touched, A[c].cpu().numpy(), b[c].cpu().numpy()), plan.n_i)
+            Sr = np.asarray(ref[:, :plan.n_b], dtype=np.float64).flatten(order="F")
+            e0 = np.abs(S0[c].cpu().numpy() - Sr).max() / np.abs(Sr).max()
+            e1 = np.abs(S1[c].cpu().numpy() - Sr).max() / np.abs(Sr).max()
+            print(f"|  | worst cell {c}: error vs 80-bit reference | right-looking {e0:.2e} | left-looking {e1:.2e} |", flush=True)
         del S1, g1
     del A, b, S0, g0
     torch.cuda.empty_cache()
