@@ -2,6 +2,10 @@
 // tensor cores (mma.sync.m8n8k4.f64; measured full-rate on B200: 37.1 TFLOP/s, see profiles/r01_ubench_fp64.txt).
 // Instantiated for 3-D HDG k=2 (n_i, n_b) = (34, 36) and RT-H k=2 / k=3 on quads (33, 12), (56, 16).
 //
+// Two condensation kernels share the top block; condense_dmma_ll_kernel (left-looking bottom block in registers, 8 cells
+// per SM, further down) is the one the library launches, condense_dmma_kernel (right-looking bottom block in shared
+// memory, 5 cells per SM) is kept for A/B runs (GHB_DMMA_LL=0).
+//
 // condense_dmma_kernel: one CTA (4 warps) per cell, 5 CTAs per SM for (34,36).  Replaces
 // evaluate!(cache, ::StaticCondensationMap, A, b) (/root/reference/src/StaticCondensationMap.jl:152-196):
 //   * the packed record is re-laid out on the fly by branch-free cp.async (16 bytes where the block heights allow it)
@@ -33,25 +37,6 @@
 #endif
 #ifndef GHB_MINB33
 #define GHB_MINB33 7
-#endif
-
-#ifndef GHB_LL_LOOKAHEAD
-#define GHB_LL_LOOKAHEAD 0  // 1: the panel warp applies panel p to tile p+1 itself (measured slower: 41.4 -> 31.8 M cells/s)
-#endif
-#ifndef GHB_LL_UNROLL_TRAIL
-#define GHB_LL_UNROLL_TRAIL 0  // 1: trailing update unrolled over the row-tile pairs (measured 40.3 vs 41.4 M cells/s rolled)
-#endif
-#ifndef GHB_LL_INVBOTH
-#define GHB_LL_INVBOTH 0    // 1: both inverses of the diagonal block by one 32-lane shuffle routine (measured slower)
-#endif
-#ifndef GHB_LL_INVU_UW
-#define GHB_LL_INVU_UW 0    // 1: inv(U_pp) by an update warp instead of the panel warp
-#endif
-#ifndef GHB_LL_EARLYX
-#define GHB_LL_EARLYX 1     // first row tile of the bottom block is loaded before the barrier that ends the top block
-#endif
-#ifndef GHB_LL_HOLD_A
-#define GHB_LL_HOLD_A 1     // update warps keep the panel's multipliers in registers across their column tiles
 #endif
 
 namespace ghb {
@@ -297,153 +282,6 @@ __device__ __forceinline__ void panel_factor(double* __restrict__ Wt, const int 
   if (lane < 8) ctl->rinv[lane] = myrinv;
 }
 
-// ---- panel factorisation with look-ahead inside the panel warp (left-looking kernel) ---------------
-// panel_factor() plus: the panel warp itself applies panel p to column tile p+1 (the next panel), so that the chain
-// panel p -> panel p+1 never waits for an update warp; the update warps take the tiles J >= p+2.
-template <int NI, int LDW, bool TWO>
-__device__ __forceinline__ void panel_factor_la(double* __restrict__ Wt, const int c0, const int npiv, PanelCtl* ctl,
-                                                int* __restrict__ info, const int p, const bool next) {
-  const int lane = threadIdx.x & 31;
-  const int nrows = NI - c0;
-  const bool v1 = lane < nrows;
-  const bool v2 = TWO && (lane + 32 < nrows);
-  double a[8], a2[8];
-  int ch1 = -1, ch2 = -1;                       // step at which this lane's row became the pivot row
-  double myrinv = 0.0;                          // lane k keeps 1/pivot of step k
-  double* base = Wt + c0 + lane + LDW * c0;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    a[j] = v1 ? base[LDW * pc(j)] : 0.0;
-    a2[j] = v2 ? base[32 + LDW * pc(j)] : 0.0;
-  }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    if (k < npiv) {
-      // ---- pivot search: one REDUX.MAX over key = |a| (exponent + 15 mantissa bits) << 6 | (63 - row)
-      const bool c1 = v1 && ch1 < 0;
-      const bool c2 = v2 && ch2 < 0;
-      const unsigned h1 = (unsigned)(__double_as_longlong(a[k]) >> 32) & 0x7fffffffu;
-      const unsigned h2 = (unsigned)(__double_as_longlong(a2[k]) >> 32) & 0x7fffffffu;
-      unsigned key = c1 ? (((h1 >> 5) << 6) | (unsigned)(63 - lane)) : 0u;
-      if (TWO) {
-        const unsigned key2 = c2 ? (((h2 >> 5) << 6) | (unsigned)(31 - lane)) : 0u;
-        key = key > key2 ? key : key2;
-      }
-      const double rc1 = fast_rcp(a[k]);        // speculative reciprocal, overlaps the reduction
-      const double rc2 = TWO ? fast_rcp(a2[k]) : 0.0;
-      unsigned kmax = __reduce_max_sync(0xffffffffu, key);
-      if ((kmax >> 6) == 0u) {
-        // all candidates below 2^-1017: decide exactly (zero column => LAPACK info = k+1)
-        const unsigned long long e1 = c1 ? ((unsigned long long)__double_as_longlong(a[k]) & 0x7fffffffffffffffull) : 0ull;
-        const unsigned long long e2 = c2 ? ((unsigned long long)__double_as_longlong(a2[k]) & 0x7fffffffffffffffull) : 0ull;
-        const unsigned lo1 = __reduce_max_sync(0xffffffffu, (unsigned)(e1 >> 32) | (unsigned)(e2 >> 32));
-        const unsigned lo2 = __reduce_max_sync(0xffffffffu, (unsigned)e1 | (unsigned)e2);
-        if ((lo1 | lo2) == 0u) {
-          if (lane == 0 && *info == 0) *info = c0 + k + 1;
-        }
-        // keep going with the first candidate row (results of a failed cell are overwritten with NaN)
-        const unsigned bb1 = __ballot_sync(0xffffffffu, c1);
-        const unsigned bb2 = __ballot_sync(0xffffffffu, c2);
-        const int row = bb1 ? (__ffs(bb1) - 1) : (32 + __ffs(bb2) - 1);
-        kmax = (unsigned)(63 - row);
-      }
-      const int prow = 63 - (int)(kmax & 63u);  // row of the pivot inside the panel (0..63)
-      const bool from2 = TWO && prow >= 32;
-      const int q = prow & 31;
-      const double rinv = __shfl_sync(0xffffffffu, from2 ? rc2 : rc1, q);
-      if (lane == k) myrinv = rinv;
-      const bool me1 = !from2 && lane == q, me2 = from2 && lane == q;
-      if (me1) ch1 = k;
-      if (me2) ch2 = k;
-      // ---- multipliers and rank-1 update of the rows still in play
-      const bool u1 = c1 && !me1, u2 = TWO && c2 && !me2;
-      const double l1 = a[k] * rinv, l2 = a2[k] * rinv;   // dgetf2: scale by the reciprocal
-      a[k] = u1 ? l1 : a[k];
-      const double nl1 = u1 ? -l1 : 0.0;                  // rows out of play: a + 0*p = a
-      double nl2 = 0.0;
-      if (TWO) { a2[k] = u2 ? l2 : a2[k]; nl2 = u2 ? -l2 : 0.0; }
-#pragma unroll
-      for (int j = k + 1; j < 8; ++j) {
-        const double pj = __shfl_sync(0xffffffffu, from2 ? a2[j] : a[j], q);   // pivot row entry, to everyone
-        a[j] = fma(nl1, pj, a[j]);
-        if (TWO) a2[j] = fma(nl2, pj, a2[j]);
-      }
-    }
-  }
-  // ---- new positions: pivot rows first, displaced rows into the vacated slots
-  const bool disp = v1 && lane < npiv && ch1 < 0;          // rows of the diagonal block not chosen
-  const bool vc1 = v1 && lane >= npiv && ch1 >= 0;
-  const bool vc2 = v2 && ch2 >= 0;
-  const unsigned mdisp = __ballot_sync(0xffffffffu, disp);
-  const unsigned mv1 = __ballot_sync(0xffffffffu, vc1);
-  const unsigned mv2 = TWO ? __ballot_sync(0xffffffffu, vc2) : 0u;
-  const unsigned lt = (1u << lane) - 1u;
-  if (vc1) ctl->vac[__popc(mv1 & lt)] = c0 + lane;
-  if (vc2) ctl->vac[__popc(mv1) + __popc(mv2 & lt)] = c0 + 32 + lane;
-  __syncwarp();
-  int np1 = c0 + lane, np2 = c0 + 32 + lane;
-  if (ch1 >= 0) np1 = c0 + ch1;
-  else if (disp) np1 = ctl->vac[__popc(mdisp & lt)];
-  if (ch2 >= 0) np2 = c0 + ch2;
-  if (ch1 >= 0) ctl->psrc[ch1] = c0 + lane;
-  if (ch2 >= 0) ctl->psrc[ch2] = c0 + 32 + lane;
-  if (disp) {
-    const int t = __popc(mdisp & lt);
-    ctl->dsrc[t] = c0 + lane;
-    ctl->ddst[t] = np1;
-  }
-  if (lane == 0) ctl->ndisp = __popc(mdisp);
-  double* wb = Wt + LDW * c0;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    if (v1) wb[np1 + LDW * pc(j)] = a[j];
-    if (v2) wb[np2 + LDW * pc(j)] = a2[j];
-  }
-  if (lane < 8) ctl->rinv[lane] = myrinv;
-  bar_arrive<BAR_PANEL, 128>(p & 1);            // panel p is published: the update warps start their stage
-  if (!next) return;
-  // ---- look-ahead: apply this panel to the next panel's column tile, rows still one per lane in the old order
-  // (multipliers are in a[], the pivot lane of step k is the one with ch == k), and write it back in the new order.
-  if (p > 0) bar_sync<BAR_COL, 64>((p + 1) & 1);   // tile p+1 carries every panel < p (first tile of stage p-1)
-  constexpr int XW = TWO ? 4 : 8;               // columns per pass (two passes keep the two-row case in registers)
-  const double* xb = Wt + c0 + lane + LDW * (c0 + 8);
-  double* wx = Wt + LDW * (c0 + 8);
-#pragma unroll
-  for (int h = 0; h < 8 / XW; ++h) {
-    double x[XW], x2[XW];
-#pragma unroll
-    for (int j = 0; j < XW; ++j) {
-      x[j] = v1 ? xb[LDW * pc(XW * h + j)] : 0.0;
-      x2[j] = v2 ? xb[32 + LDW * pc(XW * h + j)] : 0.0;
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (k < npiv) {
-        const unsigned b1 = __ballot_sync(0xffffffffu, ch1 == k);
-        const unsigned b2 = TWO ? __ballot_sync(0xffffffffu, ch2 == k) : 0u;
-        const bool from2 = TWO && b1 == 0u;
-        const int q = __ffs(from2 ? b2 : b1) - 1;
-        const double m1 = (v1 && (ch1 < 0 || ch1 > k)) ? -a[k] : 0.0;     // rows still in play after step k
-        const double m2 = (TWO && v2 && (ch2 < 0 || ch2 > k)) ? -a2[k] : 0.0;
-#pragma unroll
-        for (int j = 0; j < XW; ++j) {
-          const double pj = __shfl_sync(0xffffffffu, from2 ? x2[j] : x[j], q);
-          x[j] = fma(m1, pj, x[j]);
-          if (TWO) x2[j] = fma(m2, pj, x2[j]);
-        }
-      }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < XW; ++j) {
-      if (v1) wx[np1 + LDW * pc(XW * h + j)] = x[j];
-      if (v2) wx[np2 + LDW * pc(XW * h + j)] = x2[j];
-    }
-  }
-  __syncwarp();
-}
-
-
 // ---- inverses of the 8x8 diagonal block of a factorised panel, by the (otherwise idle) update warps:
 // lanes 0-7 each own one column and run the same branch-free substitution; entries of L\U are uniform
 // (broadcast) shared-memory loads.  Rows/columns >= npiv are treated as identity (L) / zero (U^-1).
@@ -490,35 +328,6 @@ __device__ __forceinline__ void invert_upper(const double* __restrict__ D, const
 #pragma unroll
     for (int i = 0; i < 8; ++i) Dinv[i + 8 * n] = x[i];
   }
-}
-
-// Both inverses of the diagonal block by one warp, 32 lanes wide: element (i, n) of each inverse lives on lane
-// 4 i + n/2 (accumulator-fragment layout, two columns per lane).  Row operations on the identity -- L^-1: rows below k
-// minus L[i][k] x row k, k ascending; U^-1 = (D^-1 U)^-1 D^-1: rows above k minus U[i][k]/U[i][i] x row k, k descending --
-// one shuffle per column pair and step: 7 steps of (SHFL + DFMA) instead of two 28-term substitutions on 8 lanes.
-// Same padding rules as invert_unit_lower / invert_upper (rows/columns >= npiv: identity for L, zero for U^-1).
-template <int LDW>
-__device__ __forceinline__ void invert_both(const double* __restrict__ D, const int npiv, const double* __restrict__ rinv,
-                                            double* __restrict__ Linv, double* __restrict__ Dinv) {
-  const int lane = threadIdx.x & 31, i = lane >> 2, t = lane & 3;
-  double m[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) m[k] = D[i + LDW * pc(k)];
-  const double ri = i < npiv ? rinv[i] : 0.0;
-  double xl0 = (2 * t == i) ? 1.0 : 0.0, xl1 = (2 * t + 1 == i) ? 1.0 : 0.0;
-  double xu0 = (2 * t == i) ? ri : 0.0, xu1 = (2 * t + 1 == i) ? ri : 0.0;
-#pragma unroll
-  for (int k = 0; k < 7; ++k) {
-    const int kk = 7 - k;
-    const double pl0 = __shfl_sync(0xffffffffu, xl0, 4 * k + t), pl1 = __shfl_sync(0xffffffffu, xl1, 4 * k + t);
-    const double pu0 = __shfl_sync(0xffffffffu, xu0, 4 * kk + t), pu1 = __shfl_sync(0xffffffffu, xu1, 4 * kk + t);
-    const double cl = (i > k && i < npiv) ? -m[k] : 0.0;
-    const double cu = (i < kk && kk < npiv) ? -m[kk] * ri : 0.0;
-    xl0 = fma(cl, pl0, xl0); xl1 = fma(cl, pl1, xl1);
-    xu0 = fma(cu, pu0, xu0); xu1 = fma(cu, pu1, xu1);
-  }
-  Linv[i + 8 * (2 * t)] = xl0; Linv[i + 8 * (2 * t + 1)] = xl1;
-  Dinv[i + 8 * (2 * t)] = xu0; Dinv[i + 8 * (2 * t + 1)] = xu1;
 }
 
 // RPC = rows per cp.async: 2 (16 bytes) when every vertical pair of the condensed matrix is contiguous and aligned in
@@ -1009,24 +818,15 @@ condense_dmma_ll_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const
         const int c0 = 8 * p;
         const int npiv = (NI - c0) < 8 ? (NI - c0) : 8;
         PanelCtl* ctl = ctl2 + (p & 1);
-#if GHB_LL_LOOKAHEAD
-        // column tile p is in this warp's hands since the look-ahead of panel p-1: no hand-off from the update warps
-        __syncwarp();
-        if ((NI - c0) > 32) panel_factor_la<NI, LDW, true>(Wt, c0, npiv, ctl, s_info, p, p + 1 < NP);
-        else panel_factor_la<NI, LDW, false>(Wt, c0, npiv, ctl, s_info, p, p + 1 < NP);
-#else
         if (p > 0) bar_sync<BAR_COL, 64>(p & 1);             // column tile p is up to date
         TRACE(4 + 6 * p);
         if ((NI - c0) > 32) panel_factor<NI, LDW, true>(Wt, c0, npiv, ctl, s_info);
         else panel_factor<NI, LDW, false>(Wt, c0, npiv, ctl, s_info);
         bar_arrive<BAR_PANEL, 128>(p & 1);
         TRACE(5 + 6 * p);
-#if !GHB_LL_INVBOTH && !GHB_LL_INVU_UW
         __syncwarp();
         invert_upper<LDW>(Wt + c0 + LDW * c0, npiv, ctl->rinv, s_dinv + 64 * p);   // read by the bottom block
         TRACE(6 + 6 * p);
-#endif
-#endif
       }
     } else {
       // ================================================================ update warps: column tiles J > p
@@ -1038,16 +838,8 @@ condense_dmma_ll_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const
         PanelCtl* ctl = ctl2 + (p & 1);
         bar_sync<BAR_PANEL, 128>(p & 1);
         TRACE(4 + 6 * p);
-        // both inverses of the diagonal block by the owner of the next panel's tile: inv(L_pp) for the column tiles of
-        // this stage (critical path), inv(U_pp) for the bottom block
-#if GHB_LL_INVBOTH
-        if (uw == (p + 1) % 3) invert_both<LDW>(Wt + c0 + LDW * c0, npiv, ctl->rinv, ctl->Linv, s_dinv + 64 * p);
-#else
+        // ---- the owner of the next panel's column tile inverts L_pp (on the critical path)
         if (uw == (p + 1) % 3) invert_unit_lower<LDW>(Wt + c0 + LDW * c0, npiv, ctl->Linv);
-#if GHB_LL_LOOKAHEAD || GHB_LL_INVU_UW
-        if (uw == p % 3) invert_upper<LDW>(Wt + c0 + LDW * c0, npiv, ctl->rinv, s_dinv + 64 * p);
-#endif
-#endif
         const int nd = ctl->ndisp;
         const int ps0 = tig < npiv ? ctl->psrc[tig] : -1;
         const int ps1 = 4 + tig < npiv ? ctl->psrc[4 + tig] : -1;
@@ -1056,19 +848,7 @@ condense_dmma_ll_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const
         bar_sync<BAR_UW_LL, 96>(p & 1);
         TRACE(5 + 6 * p);
         const double li0 = ctl->Linv[gid + 8 * tig], li1 = ctl->Linv[gid + 8 * (4 + tig)];
-        // multipliers of panel p (A fragments) of the row tiles I > p
-#if GHB_LL_HOLD_A && GHB_LL_UNROLL_TRAIL
-        double am[RT][2];
-#pragma unroll
-        for (int I = 1; I < RT; ++I) {                     // held in registers across the column tiles of the stage
-          const bool rv = I > p && (I < RT - 1 || 8 * I + gid < NI);
-          am[I][0] = rv ? Wt[8 * I + gid + LDW * (c0 + ka0)] : 0.0;
-          am[I][1] = rv ? Wt[8 * I + gid + LDW * (c0 + ka1)] : 0.0;
-        }
-#endif
-        // with look-ahead, tile p+1 (the next panel) is updated by the panel warp; else it is this stage's first tile
-        const int Jlo = (GHB_LL_LOOKAHEAD && p + 1 < NP) ? p + 2 : p + 1;
-        const int Jfirst = Jlo + (uw + 3 - Jlo % 3) % 3;     // first owned tile (J mod 3 == uw)
+        const int Jfirst = p + 1 + (uw + 3 - (p + 1) % 3) % 3;   // first owned tile > p (J mod 3 == uw)
 #pragma unroll 1
         for (int J = Jfirst; J < CT; J += 3) {
           double* colg = Wt + LDW * (8 * J + nb);      // B-fragment column of this lane
@@ -1086,37 +866,6 @@ condense_dmma_ll_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const
           if (c0 + gid < NI) { cc0[c0] = u0; cc1[c0] = u1; }
           if (dds >= 0) { colt[dds] = dv0; colt[dds + 4 * LDW] = dv1; }
           __syncwarp();
-#if GHB_LL_UNROLL_TRAIL
-          if (p + 1 < RT) {
-            // trailing update of the rows below, every row tile I > p in flight at once (independent accumulators:
-            // loads, then the DMMAs k-step outermost, then the stores); only the last row tile has a ragged edge
-            const double bf0 = neg(colg[c0 + tig]);
-            const double bf1 = neg(colg[c0 + 4 + tig]);
-#pragma unroll
-            for (int I0 = 1; I0 < RT; I0 += 2) {             // two row tiles per step: independent accumulators
-              if (I0 + 1 > p) {
-                const int I1 = I0 + 1;
-                const bool vA = I0 > p && (I0 < RT - 1 || 8 * I0 + gid < NI);
-                const bool vB = I1 < RT && (I1 < RT - 1 || 8 * I1 + gid < NI);
-                double dA0 = vA ? cc0[8 * I0] : 0.0, dA1 = vA ? cc1[8 * I0] : 0.0;
-                double dB0 = vB ? cc0[8 * I0 + 8] : 0.0, dB1 = vB ? cc1[8 * I0 + 8] : 0.0;
-#if GHB_LL_HOLD_A
-                const double aA0 = am[I0][0], aA1 = am[I0][1];
-                const double aB0 = I1 < RT ? am[I1 < RT ? I1 : I0][0] : 0.0, aB1 = I1 < RT ? am[I1 < RT ? I1 : I0][1] : 0.0;
-#else
-                const double aA0 = vA ? Wt[8 * I0 + gid + LDW * (c0 + ka0)] : 0.0, aA1 = vA ? Wt[8 * I0 + gid + LDW * (c0 + ka1)] : 0.0;
-                const double aB0 = vB ? Wt[8 * I1 + gid + LDW * (c0 + ka0)] : 0.0, aB1 = vB ? Wt[8 * I1 + gid + LDW * (c0 + ka1)] : 0.0;
-#endif
-                if (I0 > p) dmma(dA0, dA1, aA0, bf0);
-                if (I1 < RT) dmma(dB0, dB1, aB0, bf0);
-                if (I0 > p) dmma(dA0, dA1, aA1, bf1);
-                if (I1 < RT) dmma(dB0, dB1, aB1, bf1);
-                if (vA) { cc0[8 * I0] = dA0; cc1[8 * I0] = dA1; }
-                if (vB) { cc0[8 * I0 + 8] = dB0; cc1[8 * I0 + 8] = dB1; }
-              }
-            }
-          }
-#else
           if (p + 1 < RT) {
             const double bf0 = neg(colg[c0 + tig]);
             const double bf1 = neg(colg[c0 + 4 + tig]);
@@ -1147,12 +896,7 @@ condense_dmma_ll_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const
               if (rv) { cc0[8 * I] = d0; cc1[8 * I] = d1; }
             }
           }
-#endif
-#if GHB_LL_LOOKAHEAD
-          if (J == p + 2 && p + 2 < NP) bar_arrive<BAR_COL, 64>((p + 2) & 1);   // look-ahead input of panel p+1
-#else
           if (J == p + 1 && p + 1 < NP) bar_arrive<BAR_COL, 64>((p + 1) & 1);   // hand the next panel's tile back
-#endif
           if (J == Jfirst) TRACE(6 + 6 * p);
         }
         TRACE(7 + 6 * p);
@@ -1160,12 +904,8 @@ condense_dmma_ll_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const
     }
     // ================================================================ bottom block: row tiles, registers only
     TRACE(40);
-#if GHB_LL_EARLYX
-    if (warp >= BT) __syncthreads();               // (no row tile for this warp; the others synchronise below)
-#else
     __syncthreads();                               // U, L^-1 P [A12 b1] and every inv(U_pp) are final
     TRACE(41);
-#endif
     {
       const int r0s = sg8(2 * tig), r1s = sg8(2 * tig + 1);   // logical column of accumulator element e / row of k-step s
       const int sgid = sg8(gid);                              // logical column of output column n = gid
@@ -1180,8 +920,7 @@ condense_dmma_ll_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const
         const int r = 8 * I + gid;
         const bool rv = r < NB;
         // accumulator fragments straight from the record: the offsets come from a per-plan table laid out per lane
-        // (one coalesced look-up per element, immediate offsets), all look-ups first.  The loads of a warp's first row
-        // tile are issued before the barrier that ends the top block, so their latency overlaps the wait.
+        // (one coalesced look-up per element, immediate offsets), all look-ups first
         const int32_t* xo = tb.xoff + (size_t)I * (CT * 64) + lane;
         int xoffs[CT][2];
 #pragma unroll
@@ -1200,12 +939,6 @@ condense_dmma_ll_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const
             else x[J][e] = o >= 0 ? Arec[o] : 0.0;
           }
         }
-#if GHB_LL_EARLYX
-        if (I < 4) {
-          __syncthreads();                           // U, L^-1 P [A12 b1] and every inv(U_pp) are final
-          TRACE(41);
-        }
-#endif
         const bool failed = *s_info != 0;
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
@@ -1579,11 +1312,12 @@ static int launch_dmma_ll(ghb_ctx* ctx, const Plan& p, int64_t ncells, const dou
   return GHB_OK;
 }
 
-// kernel selection of the DMMA shapes: GHB_DMMA_LL=1 / 0 forces the left-looking / the right-looking bottom block
+// kernel selection of the DMMA shapes: the left-looking kernel is faster on all three (profiles/r01_condense_ll.md);
+// GHB_DMMA_LL=0 forces the right-looking kernel (A/B runs, tools/ab_ll.py)
 static bool use_ll(const Plan& p) {
   if (const char* e = getenv("GHB_DMMA_LL")) return e[0] == '1';
   (void)p;
-  return false;
+  return true;
 }
 
 template <int NI, int NB, int RPC>

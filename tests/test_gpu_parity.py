@@ -500,3 +500,28 @@ def test_sum_facets_device(ctx, shape):
     same = np.repeat(rng.random((shape[0], 1) + shape[2:]), 4, axis=1)
     out4 = gh.SumFacetsMap().evaluate(None, torch.as_tensor(same, device="cuda"))
     assert np.allclose(out4.cpu().numpy(), 4 * same[:, 0])
+
+
+@pytest.mark.parametrize("name", ["C2_rth_k2_2d", "C2_rth_k3_2d", "C3_hdg_k2_3d"])
+@pytest.mark.parametrize("left_looking", ["1", "0"])
+def test_both_dmma_condensation_kernels(ctx, name, left_looking, monkeypatch):
+    """the library launches the left-looking kernel (bottom block in registers); the right-looking one stays selectable
+    (GHB_DMMA_LL=0, read at every launch).  Both against the oracle: values, ragged cell counts around the resident-CTA
+    count (148 SMs x 8 / x 5), dgetrf info semantics and NaN outputs of a singular cell."""
+    monkeypatch.setenv("GHB_DMMA_LL", left_looking)
+    plan, op = _dev_plan(ctx, name), oracle_plan(name)
+    for n in (5, 1184, 1190, 3001):
+        A, b = _synth(ctx, plan, 4242, n)
+        bad = n // 2
+        A[bad].zero_()                               # exactly singular interior block
+        S = torch.empty((n, plan.n_b ** 2), dtype=torch.float64, device="cuda")
+        g = torch.empty((n, plan.n_b), dtype=torch.float64, device="cuda")
+        info = torch.empty(n, dtype=torch.int32, device="cuda")
+        ctx.condense(plan, n, A, b, S, g, info)
+        S0, g0, info0 = oc.condense(op, A.cpu().numpy(), b.cpu().numpy())
+        info_h = info.cpu().numpy()
+        assert info_h.tolist() == info0.tolist() and info_h[bad] == 1 and info_h.sum() == 1
+        ok = np.arange(n) != bad
+        Sh, gh_ = S.cpu().numpy(), g.cpu().numpy()
+        assert np.isnan(Sh[bad]).all() and np.isnan(gh_[bad]).all()
+        assert rel_err_cells(Sh[ok], S0[ok]) < TOL and rel_err_cells(gh_[ok], g0[ok]) < TOL
