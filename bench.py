@@ -35,9 +35,9 @@ N_I, N_B = 34, 36
 METRIC = "cells/s condensed+assembled (FP64, 3D HDG k=2)"
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of condense_dmma_kernel<34,36> from the committed `ncu --set full` capture,
-# per cell (5.3535 GB + 1.3818 GB for a 131 072-cell launch); algorithmic bytes are 50 416 B/cell
-NCU_DRAM_BYTES_PER_CELL = 51386
+# dram__bytes_read.sum + dram__bytes_write.sum of condense_dmma_ll_kernel<34,36> from the committed `ncu --set full`
+# capture, per cell (5.4339 GB + 1.3871 GB for a 131 072-cell launch); algorithmic bytes are 50 416 B/cell
+NCU_DRAM_BYTES_PER_CELL = 52040
 NCU_TRAFFIC_SOURCE = "profiles/r01_condense_dmma_summary.md (ncu --set full, 131072-cell launch, scaled per cell)"
 
 
@@ -358,7 +358,7 @@ def run_ours(args):
                 "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                              "traffic": NCU_DRAM_BYTES_PER_CELL * ncells, "traffic_source": NCU_TRAFFIC_SOURCE,
-                             "kernel": "condense (" + plan.kernel_name + ")",
+                             "kernel": "condense_dmma_ll_kernel<34,36> (" + plan.kernel_name + ")",
                              "kernel_ms": kernel_ms, "peak_source": how,
                              "fp64_tflops": flops_per_cell() * ncells / (kernel_ms * 1e-3) / 1e12},
                 "cpu_baseline": cpu_base, "backsub": backsub}

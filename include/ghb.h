@@ -58,7 +58,7 @@ int ghb_synchronize(ghb_ctx* ctx);
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 int64_t ghb_launch_count(const ghb_ctx* ctx);
 /* Name of the condensation kernel variant chosen for a plan: "dmma_34_36", "dmma_33_12", "dmma_56_16" (FP64 DMMA,
-   whole cell in shared memory), "large_dmma" (64 < n_i <= 128, streamed), "warp_7_8", "warp_16_8" (register-resident),
+   interior rows in shared memory, boundary rows in registers), "large_dmma" (64 < n_i <= 128, streamed), "warp_7_8", "warp_16_8" (register-resident),
    "generic" (any plan). */
 const char* ghb_plan_kernel_name(ghb_ctx* ctx, int plan_id);
 
