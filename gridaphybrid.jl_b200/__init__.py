@@ -11,7 +11,7 @@ from .blocks import ArrayBlock, CondensedCells, MatrixBlock, PackedCells, Vector
 from .maps import (BackwardStaticCondensationMap, RestrictArrayBlockMap, Scalar2ArrayBlockMap,  # noqa: F401
                    StaticCondensationMap, SumFacetsMap, default_context, lazy_map, set_default_context)
 from .skeleton import CartesianSkeleton, FacetFESpace, MultiFieldFacetFESpace  # noqa: F401
-from .assembly import (SparseMatrixAssembler, SparseMatrixCSC, assemble_matrix_and_vector,  # noqa: F401
-                       attach_dirichlet, condense_and_assemble)
+from .assembly import (SparseMatrixAssembler, SparseMatrixCSC, SparseMatrixCSR, assemble_matrix_and_vector,  # noqa: F401
+                       assemble_matrix_and_vector_csr, attach_dirichlet, condense_and_assemble)
 from .operators import (AffineFEOperator, HybridAffineFEOperator, HybridFEOperator,  # noqa: F401
                         hybrid_backslash_solve, solve_skeleton)

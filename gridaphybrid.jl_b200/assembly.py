@@ -74,6 +74,36 @@ def assemble_matrix_and_vector(assem: SparseMatrixAssembler, data, dirichlet_val
     return SparseMatrixCSC(assem.nrows, assem.nrows, colptr, rowval, nzval), rhs
 
 
+class SparseMatrixCSR:
+    """`SparseMatrixCSR{1,Float64,Int64}` (SparseMatricesCSR.jl, the reference's Manifest pins it) on the device:
+    1-based `rowptr` [m+1], `colval` [nnz] ascending within a row, `nzval`."""
+
+    def __init__(self, m, n, rowptr, colval, nzval):
+        self.m, self.n, self.rowptr, self.colval, self.nzval = int(m), int(n), rowptr, colval, nzval
+
+    @property
+    def nnz(self):
+        return int(self.nzval.numel())
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csr_matrix((self.nzval.cpu().numpy(), (self.colval - 1).cpu().numpy(), (self.rowptr - 1).cpu().numpy()),
+                             shape=(self.m, self.n))
+
+
+def assemble_matrix_and_vector_csr(assem: SparseMatrixAssembler, data, dirichlet_values=None):
+    """CSR hand-off of the same system: the pattern is structurally symmetric, so rowptr/colval are the
+    CSC pattern; the values are gathered from the transposed cell blocks.  `data.S` is transposed IN PLACE."""
+    assert isinstance(data, CondensedCells)
+    colptr, rowval, nnz = assem.symbolic()
+    dev = assem.cell_ids.device
+    nzval = torch.empty(nnz, dtype=torch.float64, device=dev)
+    rhs = torch.empty(assem.nrows, dtype=torch.float64, device=dev)
+    assem.ctx.use_torch_stream()
+    assem.ctx.assemble_numeric_csr(data.S, data.g, dirichlet_values, nzval, rhs)
+    return SparseMatrixCSR(assem.nrows, assem.nrows, colptr, rowval, nzval), rhs
+
+
 def condense_and_assemble(assem: SparseMatrixAssembler, plan, cells, dirichlet_values=None, nzval=None, rhs=None,
                           info=None):
     """Fused site: `lazy_map(StaticCondensationMap, t)` consumed directly by `assemble_matrix_and_vector`

@@ -153,6 +153,15 @@ class Context:
                                                      _ptr(nzval, np.float64, nnz, "nzval"),
                                                      _ptr(rhs, np.float64, nrows, "rhs")))
 
+    def assemble_numeric_csr(self, S, g, dirichlet_vals, nzval, rhs):
+        """CSR values of the skeleton matrix (pattern = the CSC pattern, structurally symmetric); transposes the
+        cell blocks of the device array `S` in place."""
+        nrows, nnz = self._asm_shape
+        self._check(self._L.ghb_assemble_numeric_csr_f64(self._h, _ptr(S, np.float64), _ptr(g, np.float64),
+                                                         _ptr(dirichlet_vals, np.float64),
+                                                         _ptr(nzval, np.float64, nnz, "nzval"),
+                                                         _ptr(rhs, np.float64, nrows, "rhs")))
+
     def assemble_symbolic_slab(self, ncells_local, nghost, ghost_ncols, n_b, cell_ids, nrows_global, col_begin,
                                col_end) -> int:
         nnz = ctypes.c_int64(0)

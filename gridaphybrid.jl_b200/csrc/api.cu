@@ -353,6 +353,28 @@ int ghb_assemble_numeric_f64(ghb_ctx* ctx, const double* S, const double* g, con
   return GHB_OK;
 }
 
+int ghb_assemble_numeric_csr_f64(ghb_ctx* ctx, double* S, const double* g, const double* dirichlet_vals,
+                                 double* nzval, double* rhs) {
+  if (!ctx) return GHB_EINVAL;
+  if (!ctx->as.valid) return fail(ctx, GHB_ESTATE, "ghb_assemble_numeric_csr_f64: call ghb_assemble_symbolic first");
+  if (ctx->as.nghost) return fail(ctx, GHB_EUNSUPPORTED, "ghb_assemble_numeric_csr_f64: slab patterns (ghost cells) are not supported");
+  if (!S || !g || !nzval || !rhs) return fail(ctx, GHB_EINVAL, "ghb_assemble_numeric_csr_f64: null array");
+  const AsmState& as = ctx->as;
+  if (!is_device_ptr(S)) return fail(ctx, GHB_EUNSUPPORTED, "ghb_assemble_numeric_csr_f64: S is transposed in place and must be a device pointer");
+  if (dirichlet_vals && !is_device_ptr(dirichlet_vals))
+    return fail(ctx, GHB_EUNSUPPORTED, "ghb_assemble_numeric_csr_f64: dirichlet_vals must be a device pointer (its length is not passed)");
+  cudaSetDevice(ctx->device);
+  Arg<double> dg(ctx, g, (size_t)as.ncells * as.n_b, true, false); GHB_TRY(dg.rc);
+  Arg<double> dz(ctx, nzval, (size_t)as.nnz, false, true); GHB_TRY(dz.rc);
+  Arg<double> dr(ctx, rhs, (size_t)as.nrows, false, true); GHB_TRY(dr.rc);
+  // the rhs (with the Dirichlet lift g_K - S_K vals_K) needs S_K itself, the row-major values its transpose
+  GHB_TRY(asm_numeric_range(ctx, S, dg.dev, nullptr, dirichlet_vals, dz.dev, dr.dev, 0, as.nrows, ASM_RHS));
+  GHB_TRY(launch_transpose_blocks(ctx, as.ncells, as.n_b, S));
+  GHB_TRY(asm_numeric_range(ctx, S, dg.dev, nullptr, dirichlet_vals, dz.dev, dr.dev, 0, as.nrows, ASM_MATRIX));
+  GHB_TRY(dz.finish()); GHB_TRY(dr.finish());
+  return GHB_OK;
+}
+
 int ghb_condense_assemble_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A, const double* b,
                               const double* dirichlet_vals, double* nzval, double* rhs, int32_t* info) {
   Plan* p = get_plan(ctx, plan_id);

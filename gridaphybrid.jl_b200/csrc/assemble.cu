@@ -451,17 +451,21 @@ int asm_pack_cut_plane(ghb_ctx* ctx, int64_t ncut, int n_b, int ncols, const dou
 
 // numeric assembly of the owned columns [j0, j1) (and the matching rhs entries)
 int asm_numeric_range(ghb_ctx* ctx, const double* S, const double* g, const double* ghost, const double* dvals,
-                      double* nzval, double* rhs, int64_t j0, int64_t j1) {
+                      double* nzval, double* rhs, int64_t j0, int64_t j1, int which) {
   const AsmState& as = ctx->as;
   if (j1 <= j0) return GHB_OK;
   GhostView gv{as.ncells_local, ghost, (int64_t)as.n_b * as.ghost_ncols + as.ghost_ncols};
-  int64_t blocks = std::min<int64_t>((j1 - j0 + 15) / 16, (int64_t)ctx->sm_count * 16);
-  gather_nzval_kernel<16><<<(unsigned)blocks, 256, 0, ctx->stream>>>(j0, j1, as.n_b, as.d_colptr,
-                                                                 (const unsigned long long*)as.d_occ, as.d_src, S, gv, nzval);
-  GHB_LAUNCHED(ctx);
-  gather_rhs_kernel<<<(unsigned)((j1 - j0 + 255) / 256), 256, 0, ctx->stream>>>(
-      j0, j1, as.n_b, (const unsigned long long*)as.d_occ, as.d_ids, as.d_celldir, S, g, gv, as.ghost_ncols, dvals, rhs);
-  GHB_LAUNCHED(ctx);
+  if (which & ASM_MATRIX) {
+    int64_t blocks = std::min<int64_t>((j1 - j0 + 15) / 16, (int64_t)ctx->sm_count * 16);
+    gather_nzval_kernel<16><<<(unsigned)blocks, 256, 0, ctx->stream>>>(j0, j1, as.n_b, as.d_colptr,
+                                                                   (const unsigned long long*)as.d_occ, as.d_src, S, gv, nzval);
+    GHB_LAUNCHED(ctx);
+  }
+  if (which & ASM_RHS) {
+    gather_rhs_kernel<<<(unsigned)((j1 - j0 + 255) / 256), 256, 0, ctx->stream>>>(
+        j0, j1, as.n_b, (const unsigned long long*)as.d_occ, as.d_ids, as.d_celldir, S, g, gv, as.ghost_ncols, dvals, rhs);
+    GHB_LAUNCHED(ctx);
+  }
   return GHB_OK;
 }
 

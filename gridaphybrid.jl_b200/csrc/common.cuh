@@ -182,8 +182,9 @@ int launch_backsub_factors(ghb_ctx* ctx, const Plan& p, int64_t ncells, const do
                            const double* lam_dir, const int64_t* ids, double* u);
 int asm_symbolic(ghb_ctx* ctx, int64_t ncells_local, int64_t nghost, int ghost_ncols, int n_b, const int64_t* d_ids,
                  int64_t nrows_global, int64_t col0, int64_t ncols);
+enum { ASM_MATRIX = 1, ASM_RHS = 2 };   // which: phases of the numeric assembly
 int asm_numeric_range(ghb_ctx* ctx, const double* S, const double* g, const double* ghost, const double* dvals,
-                      double* nzval, double* rhs, int64_t j0, int64_t j1);
+                      double* nzval, double* rhs, int64_t j0, int64_t j1, int which = ASM_MATRIX | ASM_RHS);
 int asm_ready_columns(ghb_ctx* ctx, int64_t chunk, int nchunks);
 int asm_numeric(ghb_ctx* ctx, const double* S, const double* g, const double* ghost, const double* dvals,
                 double* nzval, double* rhs);
@@ -193,6 +194,7 @@ void asm_free(ghb_ctx* ctx);
 int launch_restrict_facet_dofs(ghb_ctx* ctx, int64_t ncells, int nlf, int nf, const int64_t* cwf,
                                const int64_t* fdata, int64_t* out);
 int launch_sum_facets(ghb_ctx* ctx, int64_t ncells, int nlf, int64_t len, const double* in, double* out);
+int launch_transpose_blocks(ghb_ctx* ctx, int64_t ncells, int n, double* S);
 int launch_scatter_free(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* u, const double* lam,
                         int64_t nlam, double* x);
 int launch_synth_fill(ghb_ctx* ctx, const Plan& p, int64_t cell_start, int64_t ncells, uint64_t seed, double* A,

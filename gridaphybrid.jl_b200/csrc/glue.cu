@@ -178,6 +178,45 @@ int launch_sum_facets(ghb_ctx* ctx, int64_t ncells, int nlf, int64_t len, const 
   return GHB_OK;
 }
 
+// In-place transpose of every cell's n x n column-major block (CSR hand-off, see ghb_assemble_numeric_csr_f64): one
+// CTA per cell at a time, the block staged in shared memory (n x (n+1), conflict-free both ways), coalesced in and out.
+__global__ void transpose_blocks_kernel(int64_t ncells, int n, double* __restrict__ S) {
+  extern __shared__ double tile[];
+  const int nn = n * n;
+  for (int64_t c = blockIdx.x; c < ncells; c += gridDim.x) {
+    double* Sc = S + c * (int64_t)nn;
+    for (int e = threadIdx.x; e < nn; e += blockDim.x) { const int j = e / n, i = e - j * n; tile[i * (n + 1) + j] = Sc[e]; }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nn; e += blockDim.x) { const int j = e / n, i = e - j * n; Sc[e] = tile[j * (n + 1) + i]; }
+    __syncthreads();
+  }
+}
+// blocks too large for shared memory: swap the pairs directly (uncoalesced on one side)
+__global__ void transpose_blocks_swap_kernel(int64_t ncells, int n, double* __restrict__ S) {
+  const int64_t nn = (int64_t)n * n;
+  for (int64_t c = blockIdx.x; c < ncells; c += gridDim.x) {
+    double* Sc = S + c * nn;
+    for (int64_t e = threadIdx.x; e < nn; e += blockDim.x) {
+      const int j = (int)(e / n), i = (int)(e - (int64_t)j * n);
+      if (i < j) { const double a = Sc[e], b = Sc[j + (int64_t)i * n]; Sc[e] = b; Sc[j + (int64_t)i * n] = a; }
+    }
+  }
+}
+
+int launch_transpose_blocks(ghb_ctx* ctx, int64_t ncells, int n, double* S) {
+  if (ncells <= 0 || n <= 1) return GHB_OK;
+  const size_t smem = (size_t)n * (n + 1) * sizeof(double);
+  const int64_t grid = std::min<int64_t>(ncells, (int64_t)ctx->sm_count * 8);
+  if (smem <= ctx->smem_optin) {
+    GHB_CUDA(ctx, cudaFuncSetAttribute(transpose_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    transpose_blocks_kernel<<<(unsigned)grid, 256, smem, ctx->stream>>>(ncells, n, S);
+  } else {
+    transpose_blocks_swap_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(ncells, n, S);
+  }
+  GHB_LAUNCHED(ctx);
+  return GHB_OK;
+}
+
 int launch_scatter_free(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* u, const double* lam,
                         int64_t nlam, double* x) {
   const int nint = (int)p.interior.size();

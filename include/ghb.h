@@ -117,6 +117,17 @@ int ghb_assemble_pattern(ghb_ctx* ctx, int64_t* colptr, int64_t* rowval);
  * have a Dirichlet dof, vals_K[l] = dirichlet_vals[-id-1] for id<0, else 0. */
 int ghb_assemble_numeric_f64(ghb_ctx* ctx, const double* S, const double* g, const double* dirichlet_vals,
                              double* nzval, double* rhs);
+
+/* ---- (f-4) CSR hand-off (SparseMatricesCSR / device sparse solvers instead of the CSC round trip to UMFPACK,
+ * src/HybridAffineFEOperators.jl:74, src/HybridLinearSolvers.jl:45) ---------------------------
+ * Every cell contributes a full n_b x n_b block, so the pattern of the skeleton matrix is structurally symmetric:
+ * the CSR arrays rowptr / colval of A are the colptr / rowval that ghb_assemble_pattern returns (column indices
+ * ascending within a row), and the CSR values of A are the CSC values of A^T = sum of the transposed cell blocks.
+ * This call computes rhs from S (Dirichlet lift included), transposes every cell block of S IN PLACE (S is left
+ * transposed: call it with a scratch copy, or transpose back by a second call's side effect) and gathers nzval in
+ * CSR order.  S must be a device pointer; single-GPU patterns only (no ghost cells). */
+int ghb_assemble_numeric_csr_f64(ghb_ctx* ctx, double* S, const double* g, const double* dirichlet_vals,
+                                 double* nzval, double* rhs);
 /* ---- (e) multi-GPU slabs: cells are partitioned in contiguous slabs, one process per GPU --------
  * A slab owns the dofs of the facets first touched by its cells = a contiguous range of
  * global columns [col_begin, col_end) (1-based, end exclusive).  Its cell list is its own cells followed

@@ -525,3 +525,36 @@ def test_both_dmma_condensation_kernels(ctx, name, left_looking, monkeypatch):
         Sh, gh_ = S.cpu().numpy(), g.cpu().numpy()
         assert np.isnan(Sh[bad]).all() and np.isnan(gh_[bad]).all()
         assert rel_err_cells(Sh[ok], S0[ok]) < TOL and rel_err_cells(gh_[ok], g0[ok]) < TOL
+
+
+@pytest.mark.parametrize("dims,ndofs_f", [((6, 5), 3), ((3, 3, 3), 6), ((2, 2, 2), 18)])
+def test_csr_hand_off(ctx, dims, ndofs_f):
+    """CSR form of the skeleton system: rowptr/colval equal the CSC pattern (structurally symmetric),
+    values bit-equal to SciPy's CSR of the oracle's CSC matrix, rhs (with the Dirichlet lift) unchanged, cell blocks
+    transposed in place.  (2,2,2) with 18 dofs per facet is the elasticity boundary size n_b = 108."""
+    cwf = o.cartesian_cell_wise_facets(dims)
+    isb = o.facet_is_boundary(cwf)
+    fids, nfree, ndir = o.facet_dof_ids(isb, ndofs_f)
+    ids0 = o.restrict_facet_dofs_to_skeleton(cwf, fids)
+    sk = gh.CartesianSkeleton(dims, ctx)
+    sp_ = gh.FacetFESpace(sk, ndofs_f, sk.facet_is_boundary())
+    assem = gh.SparseMatrixAssembler(sp_)
+    nc, nb = ids0.shape
+    rng = np.random.default_rng(11)
+    S = rng.standard_normal((nc, nb * nb)); g = rng.standard_normal((nc, nb)); dv = rng.standard_normal(max(ndir, 1))
+    Sc = [S[c].reshape((nb, nb), order="F") for c in range(nc)]
+    gl = [o.attach_dirichlet(Sc[c], g[c], ids0[c], dv) for c in range(nc)]
+    colptr0, rowval0, nzval0, rhs0 = o.assemble_matrix_and_vector(Sc, gl, ids0, nfree)
+    import scipy.sparse as sp
+    ref = sp.csc_matrix((nzval0, rowval0 - 1, colptr0 - 1), shape=(nfree, nfree)).tocsr()
+    ref.sort_indices()
+    Sd = torch.as_tensor(S, device="cuda").clone()
+    cond = gh.CondensedCells(Sd, torch.as_tensor(g, device="cuda"), None, nb, None)
+    Acsr, rhs = gh.assemble_matrix_and_vector_csr(assem, cond, torch.as_tensor(dv, device="cuda"))
+    assert np.array_equal(Acsr.rowptr.cpu().numpy() - 1, ref.indptr)
+    assert np.array_equal(Acsr.colval.cpu().numpy() - 1, ref.indices)
+    assert np.array_equal(Acsr.nzval.cpu().numpy(), ref.data)
+    assert np.allclose(rhs.cpu().numpy(), rhs0, rtol=1e-13, atol=1e-13)
+    St = np.stack([Sc[c].T.flatten(order="F") for c in range(nc)])
+    assert np.array_equal(Sd.cpu().numpy(), St)                      # transposed in place
+    assert np.array_equal(Acsr.to_scipy().toarray(), ref.toarray())
