@@ -21,7 +21,7 @@ bool is_device_ptr(const void* p) {
 
 int launch_condense(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
                     double* g, int32_t* info, double* X) {
-  if (p.use_dmma && X == nullptr) return launch_condense_dmma(ctx, p, ncells, A, b, S, g, info);
+  if (p.use_dmma && !getenv("GHB_FACTORS_GENERIC")) return launch_condense_dmma(ctx, p, ncells, A, b, S, g, info, X);
   if (p.use_warp && X == nullptr) return launch_condense_warp(ctx, p, ncells, A, b, S, g, info);
   if (p.use_large) return launch_condense_large(ctx, p, ncells, A, b, S, g, info, X);
   return launch_condense_generic(ctx, p, ncells, A, b, S, g, info, X);

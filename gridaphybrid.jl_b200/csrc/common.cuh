@@ -171,7 +171,7 @@ int launch_backsub_large(ghb_ctx* ctx, const Plan& p, int64_t ncells, const doub
                          const double* lam_free, const double* lam_dir, const int64_t* ids, double* u, int32_t* info);
 int dmma_prepare(ghb_ctx* ctx, Plan& p);
 int launch_condense_dmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
-                         double* g, int32_t* info);
+                         double* g, int32_t* info, double* X = nullptr);
 // dispatch: tuned kernel when the plan has one and no factors are requested, else the generic kernel
 int launch_condense(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
                     double* g, int32_t* info, double* X);

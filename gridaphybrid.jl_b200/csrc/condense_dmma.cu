@@ -735,11 +735,11 @@ struct LLCfg {
 };
 enum { BAR_UW_LL = 5 };   // + panel parity: ids 0..6 -> 7 barriers per CTA, 8 CTAs per SM
 
-template <int NI, int NB, int RPC, int MINB>
+template <int NI, int NB, int RPC, int MINB, bool KEEPX>
 __global__ void __launch_bounds__(128, MINB)
 condense_dmma_ll_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const double* __restrict__ A,
                         const double* __restrict__ b, double* __restrict__ S, double* __restrict__ g,
-                        int32_t* __restrict__ info) {
+                        int32_t* __restrict__ info, double* __restrict__ X) {
   using C = Cfg<NI, NB>;
   constexpr int N = C::N, LDW = C::LDW, RT = C::RT, BT = C::BT, CT = C::CT, NP = C::NP;
   constexpr int SJ0 = NI / 8;                   // first column tile holding S columns
@@ -989,6 +989,61 @@ condense_dmma_ll_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const
       }
     }
     TRACE(50);
+    if (KEEPX) {
+      // ---- keep_factors: X = A11^-1 [A12 | b1] = U^-1 (L^-1 P [A12 b1]), in place in Wt.  The column tiles
+      // of the right-hand sides go over the warps; blocked back substitution from the last panel up:
+      // X_p = inv(U_pp) W_p, then W_I -= U_Ip X_p for the row tiles above.  Stores are masked to the right-hand-side
+      // columns (the tile that straddles column NI also holds columns of U).
+      __syncthreads();                             // the bottom block has read L^-1 P [A12 b1]
+#pragma unroll 1
+      for (int J = SJ0 + warp; J < CT; J += 4) {
+        double* colg = Wt + LDW * (8 * J + nb);
+        double* cc0 = Wt + gid + LDW * (8 * J + ce0);
+        double* cc1 = Wt + gid + LDW * (8 * J + ce1);
+        const bool w0 = 8 * J + 2 * tig >= NI, w1 = 8 * J + 2 * tig + 1 >= NI;
+#pragma unroll 1
+        for (int p = NP - 1; p >= 0; --p) {
+          const int c0 = 8 * p;
+          const int npiv = (NI - c0) < 8 ? (NI - c0) : 8;
+          const double* dv = s_dinv + 64 * p;
+          const double a0 = dv[gid + 8 * tig], a1 = dv[gid + 8 * (4 + tig)];     // A[i][k] = inv(U_pp)[i][k]
+          const double t0 = tig < npiv ? colg[c0 + tig] : 0.0;                    // B[k][n] = W[c0 + k][n]
+          const double t1 = 4 + tig < npiv ? colg[c0 + 4 + tig] : 0.0;
+          double x0 = 0.0, x1 = 0.0;
+          dmma(x0, x1, a0, t0);
+          dmma(x0, x1, a1, t1);
+          __syncwarp();
+          if (gid < npiv) {
+            if (w0) cc0[c0] = x0;
+            if (w1) cc1[c0] = x1;
+          }
+          __syncwarp();
+          if (p > 0) {
+            const double bf0 = tig < npiv ? neg(colg[c0 + tig]) : 0.0;            // -X_p as B fragments
+            const double bf1 = 4 + tig < npiv ? neg(colg[c0 + 4 + tig]) : 0.0;
+#pragma unroll 1
+            for (int I = 0; I < p; ++I) {
+              const int r = 8 * I + gid;
+              const double u0 = tig < npiv ? Wt[r + LDW * (c0 + ka0)] : 0.0;      // A[i][k] = U[r][c0 + k]
+              const double u1 = 4 + tig < npiv ? Wt[r + LDW * (c0 + ka1)] : 0.0;
+              double d0 = cc0[8 * I], d1 = cc1[8 * I];
+              dmma(d0, d1, u0, bf0);
+              dmma(d0, d1, u1, bf1);
+              if (w0) cc0[8 * I] = d0;
+              if (w1) cc1[8 * I] = d1;
+            }
+            __syncwarp();
+          }
+        }
+      }
+      __syncthreads();
+      const bool failedx = *s_info != 0;
+      double* Xc = X + cell * (int64_t)(NI * (NB + 1));
+      for (int e = tid; e < NI * (NB + 1); e += 128) {
+        const int c = e / NI, i = e - c * NI, lc = NI + c;
+        Xc[e] = failedx ? __longlong_as_double(0x7ff8000000000000LL) : Wt[i + LDW * (8 * (lc >> 3) + pc(lc & 7))];
+      }
+    }
     __syncthreads();
     TRACE(51);
     if (info && tid == 0) info[cell] = *s_info;
@@ -1293,10 +1348,10 @@ static int launch_dmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double
 #define GHB_LL_MINB56 5
 #endif
 
-template <int NI, int NB, int RPC, int MINB>
+template <int NI, int NB, int RPC, int MINB, bool KEEPX = false>
 static int launch_dmma_ll(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
-                          double* g, int32_t* info) {
-  auto kern = condense_dmma_ll_kernel<NI, NB, RPC, MINB>;
+                          double* g, int32_t* info, double* X = nullptr) {
+  auto kern = condense_dmma_ll_kernel<NI, NB, RPC, MINB, KEEPX>;
   const size_t smem = LLCfg<NI, NB>::smem_bytes(p.nfields);
   GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -1307,7 +1362,7 @@ static int launch_dmma_ll(ghb_ctx* ctx, const Plan& p, int64_t ncells, const dou
   if (getenv("GHB_DEBUG")) fprintf(stderr, "condense_dmma_ll<%d,%d>: %d CTAs/SM, %zu B smem\n", NI, NB, per_sm, smem);
   DmmaTables tb{p.d_colbase, p.d_rowf, p.d_rowl, p.nfields, p.d_xoff};
   int64_t grid = std::min<int64_t>(ncells, (int64_t)ctx->sm_count * per_sm);
-  kern<<<(unsigned)grid, 128, smem, ctx->stream>>>(tb, p.lenA, p.lenb, ncells, A, b, S, g, info);
+  kern<<<(unsigned)grid, 128, smem, ctx->stream>>>(tb, p.lenA, p.lenb, ncells, A, b, S, g, info, X);
   GHB_LAUNCHED(ctx);
   return GHB_OK;
 }
@@ -1347,7 +1402,12 @@ int launch_backsub_dmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const doubl
 }
 
 int launch_condense_dmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
-                         double* g, int32_t* info) {
+                         double* g, int32_t* info, double* X) {
+  if (X) {   // keep_factors: the left-looking kernel with the back substitution X = U^-1 (L^-1 P [A12 b1]) appended
+    if (p.n_i == 34) return launch_dmma_ll<34, 36, 2, GHB_LL_MINB34, true>(ctx, p, ncells, A, b, S, g, info, X);
+    if (p.n_i == 56) return launch_dmma_ll<56, 16, 2, GHB_LL_MINB56, true>(ctx, p, ncells, A, b, S, g, info, X);
+    return launch_dmma_ll<33, 12, 1, GHB_LL_MINB33, true>(ctx, p, ncells, A, b, S, g, info, X);
+  }
   if (use_ll(p)) {
     if (p.n_i == 34) {
       const char* e = getenv("GHB_LL_CTAS");           // tuning knob: register budget of the (34,36) instantiation

@@ -558,3 +558,38 @@ def test_csr_hand_off(ctx, dims, ndofs_f):
     St = np.stack([Sc[c].T.flatten(order="F") for c in range(nc)])
     assert np.array_equal(Sd.cpu().numpy(), St)                      # transposed in place
     assert np.array_equal(Acsr.to_scipy().toarray(), ref.toarray())
+
+
+@pytest.mark.parametrize("name", ["C2_rth_k2_2d", "C2_rth_k3_2d", "C3_hdg_k2_3d"])
+def test_dmma_keep_factors(ctx, name, monkeypatch):
+    """keep_factors on the DMMA shapes runs the left-looking kernel with the back substitution X = U^-1 (L^-1 P [A12 b1])
+    appended (SURVEY 8f-2): S, g unchanged, the stored factors reproduce the backward map, a singular cell gives NaN;
+    the generic kernel's factors (GHB_FACTORS_GENERIC=1) are the cross-check."""
+    plan, op = _dev_plan(ctx, name), oracle_plan(name)
+    n = 1500
+    A, b = _synth(ctx, plan, 99, n)
+    bad = 700
+    A[bad].zero_()
+    rng = np.random.default_rng(8)
+    nfree = 300
+    ids = rng.integers(1, nfree + 1, (n, plan.n_b))
+    lam = rng.standard_normal(nfree)
+    An, bn = A.cpu().numpy(), b.cpu().numpy()
+    S0, g0, info0 = oc.condense(op, An, bn)
+    u0, _ = oc.backsub(op, An, bn, o.cell_dof_values(lam, np.zeros(0), ids))
+    ok = np.arange(n) != bad
+    ids_d, lf = torch.as_tensor(ids, device="cuda"), torch.as_tensor(lam, device="cuda")
+    for generic in (False, True):
+        if generic:
+            monkeypatch.setenv("GHB_FACTORS_GENERIC", "1")
+        S = torch.empty((n, plan.n_b ** 2), dtype=torch.float64, device="cuda")
+        g = torch.empty((n, plan.n_b), dtype=torch.float64, device="cuda")
+        info = torch.empty(n, dtype=torch.int32, device="cuda")
+        ctx.condense(plan, n, A, b, S, g, info, keep_factors=True)
+        assert info.cpu().numpy().tolist() == info0.tolist()
+        assert rel_err_cells(S.cpu().numpy()[ok], S0[ok]) < TOL and rel_err_cells(g.cpu().numpy()[ok], g0[ok]) < TOL
+        u = torch.empty((n, plan.n_i), dtype=torch.float64, device="cuda")
+        ctx.backsub(plan, n, None, None, lf, None, ids_d, u, None)
+        uh = u.cpu().numpy()
+        assert rel_err_cells(uh[ok], u0[ok]) < TOL
+        assert np.isnan(uh[bad]).all()
