@@ -25,6 +25,12 @@ for name, (ndofs, touched) in shapes.items():
     ids = torch.arange(1, n * plan.n_b + 1, dtype=torch.int64, device="cuda")
     u = torch.empty((n, plan.n_i), dtype=torch.float64, device="cuda")
     ctx.backsub(plan, n, A, b, lam, None, ids, u, info)
+    ctx.condense(plan, n, A, b, S, g, info, keep_factors=True)      # DMMA shapes: left-looking kernel + back substitution
+    ctx.backsub(plan, n, None, None, lam, None, ids, u, None)        # backward map from the stored factors
+    if plan.kernel_name.startswith("dmma"):
+        os.environ["GHB_DMMA_LL"] = "0"                              # the right-looking kernel too
+        ctx.condense(plan, n, A, b, S, g, info)
+        del os.environ["GHB_DMMA_LL"]
     torch.cuda.synchronize()
     print(name, plan.kernel_name, "ok", float(S.abs().max()), float(u.abs().max()))
 # assembly on a small mesh
@@ -36,5 +42,6 @@ nc = asm.cell_ids.shape[0]
 S = torch.randn((nc, 36 * 36), dtype=torch.float64, device="cuda"); g = torch.randn((nc, 36), dtype=torch.float64, device="cuda")
 nz = torch.empty(nnz, dtype=torch.float64, device="cuda"); rhs = torch.empty(asm.nrows, dtype=torch.float64, device="cuda")
 ctx.assemble_numeric(S, g, M.dirichlet_values, nz, rhs)
+ctx.assemble_numeric_csr(S, g, M.dirichlet_values, nz, rhs)        # CSR hand-off: in-place block transpose + gather
 torch.cuda.synchronize()
 print("assembly ok", nnz)
