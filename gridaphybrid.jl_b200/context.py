@@ -133,6 +133,13 @@ class Context:
                                                _ptr(a, np.float64, ncells * nlfacets * length, "in"),
                                                _ptr(out, np.float64, ncells * length, "out")))
 
+    def expand_records(self, plan: BlockPlan, ncells, ntab, TA, Tb, coef, A, b):
+        """A_K = sum_t coef[K][t] TA[t], b_K likewise (records of an affine family, generated on the device)."""
+        self._check(self._L.ghb_expand_records_f64(
+            self._h, plan.id, int(ncells), int(ntab), _ptr(TA, np.float64, ntab * plan.lenA, "TA"),
+            _ptr(Tb, np.float64, ntab * plan.lenb, "Tb"), _ptr(coef, np.float64, ncells * ntab, "coef"),
+            _ptr(A, np.float64, ncells * plan.lenA, "A"), _ptr(b, np.float64, ncells * plan.lenb, "b")))
+
     def assemble_symbolic(self, ncells, n_b, cell_ids, nrows) -> int:
         nnz = ctypes.c_int64(0)
         self._check(self._L.ghb_assemble_symbolic(self._h, int(ncells), int(n_b),

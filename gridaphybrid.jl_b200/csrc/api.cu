@@ -259,6 +259,25 @@ int ghb_sum_facets_f64(ghb_ctx* ctx, int64_t ncells, int nlfacets, int64_t len, 
   return GHB_OK;
 }
 
+int ghb_expand_records_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, int ntab, const double* TA, const double* Tb,
+                           const double* coef, double* A, double* b) {
+  Plan* p = get_plan(ctx, plan_id);
+  if (!p) return fail(ctx, GHB_EINVAL, "ghb_expand_records_f64: bad plan id");
+  if (ncells < 0 || ntab < 1 || ntab > 16 || !TA || !Tb || !coef || !A || !b)
+    return fail(ctx, GHB_EINVAL, "ghb_expand_records_f64: bad argument (need 1 <= ntab <= 16, non-null arrays)");
+  if (ncells == 0) return GHB_OK;
+  cudaSetDevice(ctx->device);
+  Arg<double> dTA(ctx, TA, (size_t)ntab * p->lenA, true, false); GHB_TRY(dTA.rc);
+  Arg<double> dTb(ctx, Tb, (size_t)ntab * p->lenb, true, false); GHB_TRY(dTb.rc);
+  Arg<double> dc(ctx, coef, (size_t)ncells * ntab, true, false); GHB_TRY(dc.rc);
+  Arg<double> dA(ctx, A, (size_t)ncells * p->lenA, false, true); GHB_TRY(dA.rc);
+  Arg<double> db(ctx, b, (size_t)ncells * p->lenb, false, true); GHB_TRY(db.rc);
+  GHB_TRY(launch_expand_records(ctx, ncells, p->lenA, ntab, dTA.dev, dc.dev, dA.dev));
+  GHB_TRY(launch_expand_records(ctx, ncells, p->lenb, ntab, dTb.dev, dc.dev, db.dev));
+  GHB_TRY(dA.finish()); GHB_TRY(db.finish());
+  return GHB_OK;
+}
+
 int ghb_assemble_symbolic(ghb_ctx* ctx, int64_t ncells, int n_b, const int64_t* cell_ids, int64_t nrows,
                           int64_t* nnz_out) {
   if (!ctx) return GHB_EINVAL;

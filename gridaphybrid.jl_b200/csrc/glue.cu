@@ -178,6 +178,57 @@ int launch_sum_facets(ghb_ctx* ctx, int64_t ncells, int nlf, int64_t len, const 
   return GHB_OK;
 }
 
+// Records of an affine family: out[c][e] = sum_t coef[c][t] * T[t][e].  A thread owns one record element e,
+// keeps its ntab table values in registers and walks a slice of cells: per cell ntab FMAs (coefficients are uniform
+// loads) and one coalesced 8-byte store -- HBM-write bound (8 len bytes per cell, tables read once per block).
+template <int MAXT>
+__global__ void __launch_bounds__(256) expand_records_kernel(int64_t ncells, int len, int ntab, const double* __restrict__ T,
+                                                             const double* __restrict__ coef, double* __restrict__ out,
+                                                             int64_t cells_per_block) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= len) return;
+  double t[MAXT];
+#pragma unroll
+  for (int q = 0; q < MAXT; ++q) t[q] = q < ntab ? T[(size_t)q * len + e] : 0.0;
+  const int64_t c0 = (int64_t)blockIdx.y * cells_per_block;
+  const int64_t c1 = c0 + cells_per_block < ncells ? c0 + cells_per_block : ncells;
+  int64_t c = c0;
+  for (; c + 4 <= c1; c += 4) {                    // four cells per step: independent FMA chains, four stores in flight
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int q = 0; q < MAXT; ++q) {
+      if (q < ntab) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = fma(__ldg(coef + (c + u) * ntab + q), t[q], acc[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) __stcs(out + (c + u) * (int64_t)len + e, acc[u]);   // written once, read by another kernel
+  }
+  for (; c < c1; ++c) {
+    double acc = 0.0;
+#pragma unroll
+    for (int q = 0; q < MAXT; ++q)
+      if (q < ntab) acc = fma(__ldg(coef + c * ntab + q), t[q], acc);
+    __stcs(out + c * (int64_t)len + e, acc);
+  }
+}
+
+int launch_expand_records(ghb_ctx* ctx, int64_t ncells, int len, int ntab, const double* T, const double* coef,
+                          double* out) {
+  if (ncells <= 0 || len <= 0) return GHB_OK;
+  const unsigned gx = (unsigned)((len + 255) / 256);
+  // enough blocks to fill the machine, long enough cell slices to amortise the table loads
+  int64_t slices = std::max<int64_t>(1, std::min<int64_t>(ncells, ((int64_t)ctx->sm_count * 16 + gx - 1) / gx));
+  slices = std::min<int64_t>(slices, 65535);
+  const int64_t per = (ncells + slices - 1) / slices;
+  dim3 grid(gx, (unsigned)((ncells + per - 1) / per));
+  if (ntab <= 8) expand_records_kernel<8><<<grid, 256, 0, ctx->stream>>>(ncells, len, ntab, T, coef, out, per);
+  else expand_records_kernel<16><<<grid, 256, 0, ctx->stream>>>(ncells, len, ntab, T, coef, out, per);
+  GHB_LAUNCHED(ctx);
+  return GHB_OK;
+}
+
 // In-place transpose of every cell's n x n column-major block (CSR hand-off, see ghb_assemble_numeric_csr_f64): one
 // CTA per cell at a time, the block staged in shared memory (n x (n+1), conflict-free both ways), coalesced in and out.
 __global__ void transpose_blocks_kernel(int64_t ncells, int n, double* __restrict__ S) {

@@ -94,6 +94,19 @@ int ghb_condense_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A,
 int ghb_restrict_facet_dofs_i64(ghb_ctx* ctx, int64_t ncells, int nlfacets, int ndofs_f,
                                 const int64_t* cell_wise_facets, const int64_t* facet_data, int64_t* out);
 
+/* ---- (f-1) element records of an affine family, generated on the device -----------------------
+ * On Cartesian / affine meshes with cell-wise constant coefficients the element matrices the reference integrates
+ * cell by cell (lazy_map(::IntegrationMap, ...) + SumFacetsMap + Densify, src/GridapAPIExtensions.jl:442-451; weak form
+ * test/DarcyHDGTests.jl:125-135) are linear combinations of a few reference records:
+ *     A_K = sum_t coef[K][t] * TA[t],   b_K = sum_t coef[K][t] * Tb[t]      (t < ntab <= 16)
+ * e.g. Darcy HDG on a Cartesian mesh: TA[0] the interior cell, one table per axis for the owner-normal sign flip of a
+ * boundary low-side facet, one per axis for the x-dependence of the load, one for the permeability; the glue gets the
+ * tables from the reference's own integration on ntab representative cells (no FE code here) and the coefficients
+ * from the cell index.  TA [ntab][lenA], Tb [ntab][lenb], coef [ncells][ntab]; A, b: packed records as for
+ * ghb_condense_f64.  The records never cross PCIe; HBM-write bound. */
+int ghb_expand_records_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, int ntab, const double* TA, const double* Tb,
+                           const double* coef, double* A, double* b);
+
 /* ---- (a9) in-cell sum over local facets -------------------------------------------------------
  * replaces SumFacetsMap.evaluate! (src/SumFacetsMap.jl:19-30, wired in at src/GridapAPIExtensions.jl:442-451) on the
  * batch: in [ncells][nlfacets][len] = the dK contributions of every local facet already laid out on the cell record
