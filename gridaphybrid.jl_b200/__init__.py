@@ -9,7 +9,8 @@ from ._lib import GhbError, build, lib  # noqa: F401
 from .context import BlockPlan, Context  # noqa: F401
 from .blocks import ArrayBlock, CondensedCells, MatrixBlock, PackedCells, VectorBlock  # noqa: F401
 from .maps import (BackwardStaticCondensationMap, RestrictArrayBlockMap, Scalar2ArrayBlockMap,  # noqa: F401
-                   StaticCondensationMap, SumFacetsMap, default_context, lazy_map, set_default_context)
+                   StaticCondensationMap, SumFacetsMap, compute_bulk_to_skeleton_l2_projection_dofs, default_context,
+                   lazy_map, set_default_context)
 from .skeleton import CartesianSkeleton, FacetFESpace, MultiFieldFacetFESpace  # noqa: F401
 from .assembly import (SparseMatrixAssembler, SparseMatrixCSC, SparseMatrixCSR, assemble_matrix_and_vector,  # noqa: F401
                        assemble_matrix_and_vector_csr, attach_dirichlet, condense_and_assemble)

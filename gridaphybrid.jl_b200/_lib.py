@@ -25,7 +25,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 SYMBOLS = [
     "ghb_create", "ghb_destroy", "ghb_last_error", "ghb_set_stream", "ghb_synchronize", "ghb_launch_count",
     "ghb_plan_kernel_name", "ghb_plan_blocks", "ghb_plan_query", "ghb_condense_f64",
-    "ghb_restrict_facet_dofs_i64", "ghb_sum_facets_f64", "ghb_expand_records_f64", "ghb_assemble_symbolic", "ghb_assemble_pattern", "ghb_assemble_numeric_f64", "ghb_assemble_numeric_csr_f64",
+    "ghb_restrict_facet_dofs_i64", "ghb_sum_facets_f64", "ghb_expand_records_f64", "ghb_l2_projection_dofs_f64", "ghb_assemble_symbolic", "ghb_assemble_pattern", "ghb_assemble_numeric_f64", "ghb_assemble_numeric_csr_f64",
     "ghb_assemble_symbolic_slab", "ghb_pack_cut_plane_f64", "ghb_assemble_numeric_slab_f64",
     "ghb_condense_assemble_f64", "ghb_backsub_f64", "ghb_scatter_free_dof_values", "ghb_synth_fill_f64",
     "ghb_cartesian_cell_wise_facets",
@@ -96,6 +96,7 @@ def lib():
     L.ghb_condense_f64.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, i32]
     L.ghb_restrict_facet_dofs_i64.argtypes = [vp, i64, i32, i32, vp, vp, vp]
     L.ghb_sum_facets_f64.argtypes = [vp, i64, i32, i64, vp, vp]
+    L.ghb_l2_projection_dofs_f64.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp]
     L.ghb_expand_records_f64.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp, vp]
     L.ghb_assemble_symbolic.argtypes = [vp, i64, i32, vp, i64, ctypes.POINTER(i64)]
     L.ghb_assemble_pattern.argtypes = [vp, vp, vp]

@@ -133,6 +133,13 @@ class Context:
                                                _ptr(a, np.float64, ncells * nlfacets * length, "in"),
                                                _ptr(out, np.float64, ncells * length, "out")))
 
+    def l2_projection_dofs(self, nbatch, n, nrhs, A, B, X, info=None):
+        """X = A \\ B for a batch of n x n systems with nrhs right-hand sides (column-major per system)."""
+        self._check(self._L.ghb_l2_projection_dofs_f64(
+            self._h, int(nbatch), int(n), int(nrhs), _ptr(A, np.float64, nbatch * n * n, "A"),
+            _ptr(B, np.float64, nbatch * n * nrhs, "B"), _ptr(X, np.float64, nbatch * n * nrhs, "X"),
+            _ptr(info, np.int32, nbatch, "info")))
+
     def expand_records(self, plan: BlockPlan, ncells, ntab, TA, Tb, coef, A, b):
         """A_K = sum_t coef[K][t] TA[t], b_K likewise (records of an affine family, generated on the device)."""
         self._check(self._L.ghb_expand_records_f64(

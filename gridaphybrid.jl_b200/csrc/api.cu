@@ -259,6 +259,22 @@ int ghb_sum_facets_f64(ghb_ctx* ctx, int64_t ncells, int nlfacets, int64_t len, 
   return GHB_OK;
 }
 
+int ghb_l2_projection_dofs_f64(ghb_ctx* ctx, int64_t nbatch, int n, int nrhs, const double* A, const double* B, double* X,
+                               int32_t* info) {
+  if (!ctx) return GHB_EINVAL;
+  if (nbatch < 0 || n < 1 || nrhs < 1 || !A || !B || !X) return fail(ctx, GHB_EINVAL, "ghb_l2_projection_dofs_f64: bad argument");
+  if (n > 32) return fail(ctx, GHB_EUNSUPPORTED, "ghb_l2_projection_dofs_f64: n > 32 (one row per lane)");
+  if (nbatch == 0) return GHB_OK;
+  cudaSetDevice(ctx->device);
+  Arg<double> dA(ctx, A, (size_t)nbatch * n * n, true, false); GHB_TRY(dA.rc);
+  Arg<double> dB(ctx, B, (size_t)nbatch * n * nrhs, true, false); GHB_TRY(dB.rc);
+  Arg<double> dX(ctx, X, (size_t)nbatch * n * nrhs, false, true); GHB_TRY(dX.rc);
+  Arg<int32_t> di(ctx, info, info ? (size_t)nbatch : 0, false, true); GHB_TRY(di.rc);
+  GHB_TRY(launch_batched_solve(ctx, nbatch, n, nrhs, dA.dev, dB.dev, dX.dev, di.dev));
+  GHB_TRY(dX.finish()); GHB_TRY(di.finish());
+  return GHB_OK;
+}
+
 int ghb_expand_records_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, int ntab, const double* TA, const double* Tb,
                            const double* coef, double* A, double* b) {
   Plan* p = get_plan(ctx, plan_id);

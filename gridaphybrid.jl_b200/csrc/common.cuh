@@ -195,6 +195,8 @@ int launch_restrict_facet_dofs(ghb_ctx* ctx, int64_t ncells, int nlf, int nf, co
                                const int64_t* fdata, int64_t* out);
 int launch_sum_facets(ghb_ctx* ctx, int64_t ncells, int nlf, int64_t len, const double* in, double* out);
 int launch_transpose_blocks(ghb_ctx* ctx, int64_t ncells, int n, double* S);
+int launch_batched_solve(ghb_ctx* ctx, int64_t nbatch, int n, int m, const double* A, const double* B, double* X,
+                         int32_t* info);
 int launch_expand_records(ghb_ctx* ctx, int64_t ncells, int len, int ntab, const double* T, const double* coef,
                           double* out);
 int launch_scatter_free(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* u, const double* lam,

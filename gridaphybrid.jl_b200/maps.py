@@ -232,3 +232,24 @@ def lazy_map(k, t, *args, ctx: Context | None = None, keep_factors: bool = False
     if isinstance(k, RestrictArrayBlockMap):
         return [t[b - 1] for b in k.blocks]
     raise TypeError(f"lazy_map: unsupported map {type(k)}")
+
+
+def compute_bulk_to_skeleton_l2_projection_dofs(A, B, ctx: Context | None = None, info=None):
+    """`lazy_map(compute_bulk_to_skeleton_l2_projection_dofs, A_array, B_array)` of test/P_m.jl:4-23, evaluated on the
+    batch (src/GridapAPIExtensions.jl:453-500: `A\\B` per (cell, local facet)).  A [nbatch, n, n] facet mass matrices,
+    B [nbatch, n, m] bulk-basis moments or [nbatch, n] (FE function) -> X like B (device tensors)."""
+    ctx = ctx or default_context()
+    dev = torch.device("cuda", ctx.device)
+    A = torch.as_tensor(A, dtype=torch.float64).to(dev)
+    B = torch.as_tensor(B, dtype=torch.float64).to(dev)
+    vec = B.dim() == 2
+    nb, n = int(A.shape[0]), int(A.shape[1])
+    assert A.shape == (nb, n, n) and B.shape[:2] == (nb, n)
+    m = 1 if vec else int(B.shape[2])
+    Ac = A.transpose(1, 2).contiguous()                       # column-major per system
+    Bc = B.reshape(nb, n, m).transpose(1, 2).contiguous()
+    X = torch.empty_like(Bc)
+    ctx.use_torch_stream()
+    ctx.l2_projection_dofs(nb, n, m, Ac, Bc, X, info)
+    X = X.transpose(1, 2)
+    return X[:, :, 0].contiguous() if vec else X.contiguous()

@@ -107,6 +107,15 @@ int ghb_restrict_facet_dofs_i64(ghb_ctx* ctx, int64_t ncells, int nlfacets, int 
 int ghb_expand_records_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, int ntab, const double* TA, const double* Tb,
                            const double* coef, double* A, double* b);
 
+/* ---- (f-3) bulk -> skeleton L2 projection dofs --------------------------------------------------
+ * replaces compute_bulk_to_skeleton_l2_projection_dofs (src/GridapAPIExtensions.jl:453-500; called per (cell, local facet)
+ * by the elasticity / Hencky forms through test/P_m.jl:4-23): X = A \ B with A [nbatch][n*n] the facet mass matrices of
+ * the skeleton space (column-major) and B [nbatch][n*nrhs] the moments of the bulk basis (nrhs = 1: a FE function).
+ * Like Julia's `\` on a square dense matrix: LU-type elimination with partial pivoting; info[s] = k+1 if the k-th pivot
+ * column of system s is exactly zero (then X of that system is NaN); info may be NULL.  n <= 32. */
+int ghb_l2_projection_dofs_f64(ghb_ctx* ctx, int64_t nbatch, int n, int nrhs, const double* A, const double* B, double* X,
+                               int32_t* info);
+
 /* ---- (a9) in-cell sum over local facets -------------------------------------------------------
  * replaces SumFacetsMap.evaluate! (src/SumFacetsMap.jl:19-30, wired in at src/GridapAPIExtensions.jl:442-451) on the
  * batch: in [ncells][nlfacets][len] = the dK contributions of every local facet already laid out on the cell record

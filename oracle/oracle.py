@@ -660,3 +660,29 @@ def backsub_records(plan: BlockPlan, A, b, x_cells):
         blk, info[c] = backward_static_condensation(Ab, bb, x_cells[c], plan.interior, plan.boundary)
         u[c] = np.concatenate(blk.array[:len(plan.interior)]) if plan.n_i else np.zeros(0)
     return u, info
+
+
+# ---------------------------------------------------------------------------------------------------
+# bulk -> skeleton L2 projection dofs
+# ---------------------------------------------------------------------------------------------------
+
+def l2_projection_dofs(A, B):
+    """compute_bulk_to_skeleton_l2_projection_dofs (/root/reference/src/GridapAPIExtensions.jl:453-500): `A\\B` per
+    (cell, local facet).  Julia's `\\` on a square dense matrix that is neither triangular nor diagonal is `lu(A)\\B`,
+    i.e. dgetrf (partial pivoting) + dgetrs -- restated with the same LAPACK entry points through SciPy.
+    A [nbatch, n, n], B [nbatch, n, m] (or [nbatch, n]) -> X like B, info [nbatch] (dgetrf's)."""
+    from scipy.linalg import lapack
+    A = np.asarray(A, dtype=np.float64)
+    B = np.asarray(B, dtype=np.float64)
+    vec = B.ndim == 2
+    Bm = B[:, :, None] if vec else B
+    X = np.empty_like(Bm)
+    info = np.zeros(len(A), dtype=np.int32)
+    for s in range(len(A)):
+        lu, piv, inf = lapack.dgetrf(A[s])
+        info[s] = inf
+        if inf != 0:
+            X[s] = np.nan
+            continue
+        X[s], _ = lapack.dgetrs(lu, piv, Bm[s])
+    return (X[:, :, 0] if vec else X), info

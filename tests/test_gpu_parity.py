@@ -650,3 +650,29 @@ def test_affine_family_records_on_device(ctx, dims, order):
     assert np.abs(x - x0).max() < 1e-10
     err, err0 = p.l2_error_u(x[:nc * nu].reshape(nc, nu)), p.l2_error_u(x0[:nc * nu].reshape(nc, nu))
     assert err < (1e-12 if nc <= 16 else 1e-11) and err < 10 * max(err0, 1e-13)
+
+
+@pytest.mark.parametrize("n,m", [(3, 1), (6, 30), (6, 1), (18, 60), (18, 7), (32, 9), (25, 16)])
+def test_l2_projection_dofs(ctx, n, m):
+    """compute_bulk_to_skeleton_l2_projection_dofs (A\\B per (cell, local facet)) on the batch against the
+    LAPACK restatement; SPD facet mass matrices plus general matrices that need pivoting; singular system -> info, NaN."""
+    rng = np.random.default_rng(n * 100 + m)
+    nb = 700
+    Q = rng.standard_normal((nb, n, n))
+    A = Q @ np.transpose(Q, (0, 2, 1)) / n + 0.5 * np.eye(n)
+    A[nb // 2:] = rng.standard_normal((nb - nb // 2, n, n)) + np.roll(3.0 * np.eye(n), 1, axis=0)   # pivoting needed
+    A[11] = 0.0
+    A[12, :, 2 if n > 2 else 0] = 0.0                              # a later zero pivot column
+    B = rng.standard_normal((nb, n, m))
+    X0, info0 = o.l2_projection_dofs(A, B)
+    info = torch.empty(nb, dtype=torch.int32, device="cuda")
+    X = gh.compute_bulk_to_skeleton_l2_projection_dofs(A, B, ctx, info).cpu().numpy()
+    info = info.cpu().numpy()
+    assert (info != 0).tolist() == (info0 != 0).tolist() and info[11] == 1 and info[12] == info0[12]
+    ok = info0 == 0
+    assert np.isnan(X[~ok]).all()
+    assert rel_err_cells(X[ok], X0[ok]) < 1e-10          # general random matrices: conditioning, not the kernel
+    assert rel_err_cells(X[:11], X0[:11]) < TOL          # SPD mass-matrix-like systems: the 1e-11 bar
+    if m == 1:
+        x = gh.compute_bulk_to_skeleton_l2_projection_dofs(A[:5], B[:5, :, 0], ctx).cpu().numpy()
+        assert x.shape == (5, n) and np.array_equal(x, X[:5, :, 0])

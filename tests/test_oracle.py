@@ -151,3 +151,19 @@ def test_philox_known_answer():
     assert [int(x) for x in r] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     r = o.philox4x32(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0)
     assert [int(x) for x in r] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_l2_projection_dofs_oracle():
+    """A\\B restated with dgetrf/dgetrs: against numpy.linalg.solve, vector and matrix right-hand sides, singular info."""
+    rng = np.random.default_rng(5)
+    n, m, nb = 6, 10, 7
+    Q = rng.standard_normal((nb, n, n))
+    A = Q @ np.transpose(Q, (0, 2, 1)) + 0.5 * np.eye(n)          # SPD like a facet mass matrix
+    B = rng.standard_normal((nb, n, m))
+    X, info = o.l2_projection_dofs(A, B)
+    assert not info.any() and np.allclose(X, np.linalg.solve(A, B), rtol=1e-12, atol=1e-12)
+    x, _ = o.l2_projection_dofs(A, B[:, :, 0])
+    assert x.shape == (nb, n) and np.allclose(x, X[:, :, 0])
+    A[3] = 0.0
+    _, info = o.l2_projection_dofs(A, B)
+    assert info[3] == 1 and info.sum() == 1
