@@ -119,4 +119,38 @@ function backsub(k::BackwardStaticCondensationMap, p::PackedCells, lam_free, lam
   x                                                     # free dof values of the full space (:134-149)
 end
 
+# ---- next rows (SURVEY 8f) -----------------------------------------------------------------------------------
+# f-3: lazy_map(compute_bulk_to_skeleton_l2_projection_dofs, A_array, B_array) of test/P_m.jl:17 on the batch:
+# A [n, n, nbatch], B [n, m, nbatch] (Julia arrays are column-major per system already)
+function l2_projection_dofs(A::Array{Float64,3}, B::Array{Float64,3})
+  n, m, nb = size(B, 1), size(B, 2), size(B, 3)
+  X = similar(B); info = Vector{Int32}(undef, nb)
+  check(ccall((:ghb_l2_projection_dofs_f64, lib), Cint,
+              (Ptr{Cvoid}, Int64, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
+              ctx(), nb, n, m, A, B, X, info))
+  @assert all(==(0), info)                              # `A\B` would have thrown SingularException
+  X
+end
+
+# f-1: element records of an affine family (Cartesian mesh, cell-wise constant coefficients): evaluate the lazy cell
+# array `t` of _add_static_condensation's input on the `rep` representative cells only, solve for the tables, expand
+# on the device.  `coef_rep` [ntab, ntab] and `coef` [ntab, ncells] are the coefficient vectors (1, boundary flags of
+# the low-side facets, cell origin, material extras) of the representative / of all cells.
+function expand_records(k::StaticCondensationMap, t::AbstractArray, rep::Vector{Int}, coef_rep::Matrix{Float64},
+                        coef::Matrix{Float64})
+  pr = pack(t[rep]); id, q = plan(k, pr)
+  TA = (coef_rep' \ pr.A')'                             # [lenA, ntab]: records are columns on the Julia side
+  Tb = (coef_rep' \ pr.b')'
+  ncells = size(coef, 2); ntab = size(coef, 1)
+  A = Matrix{Float64}(undef, size(pr.A, 1), ncells); b = Matrix{Float64}(undef, size(pr.b, 1), ncells)
+  check(ccall((:ghb_expand_records_f64, lib), Cint,
+              (Ptr{Cvoid}, Cint, Int64, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+              ctx(), id, ncells, ntab, Matrix(TA), Matrix(Tb), coef, A, b))   # a production glue keeps A, b in CuArrays
+  PackedCells(A, b, pr.ndofs, pr.touched)
+end
+
+# f-4: CSR hand-off.  The pattern is structurally symmetric: rowptr/colval are the colptr/rowval of
+# ghb_assemble_pattern; ghb_assemble_numeric_csr_f64(ctx, S, g, dv, nzval, rhs) fills the values in row-major order
+# (S must be a device array; it is transposed in place) -> SparseMatrixCSR{1}(m, n, rowptr, colval, nzval).
+
 end # module
