@@ -730,7 +730,7 @@ struct LLCfg {
   using C = Cfg<NI, NB>;
   static size_t smem_bytes(int nf) {   // Wt + inv(U_pp) of every panel + 2 panel control blocks + info + tables
     return (size_t)(C::WT_DOUBLES + C::NP * 64) * 8 + 2 * sizeof(PanelCtl) + 16 + (size_t)(C::N + 1) * nf * 4 +
-           2 * NI + 2 * NB + 16;
+           2 * NI + 16;
   }
 };
 enum { BAR_UW_LL = 5 };   // + panel parity: ids 0..6 -> 7 barriers per CTA, 8 CTAs per SM
@@ -750,7 +750,6 @@ condense_dmma_ll_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const
   int* s_info = reinterpret_cast<int*>(ctl2 + 2);
   int* s_colbase = s_info + 4;                                         // [(N+1)*nf]
   unsigned short* s_rowinfo = reinterpret_cast<unsigned short*>(s_colbase + (N + 1) * tb.nf);  // [NI/RPC] interior rows
-  unsigned short* s_rowinfo2 = s_rowinfo + NI;                                                 // [NB] boundary rows
   static_assert(RPC == 1 || NI % 2 == 0, "16-byte cp.async needs an even interior height");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gid = lane >> 2, tig = lane & 3;    // fragment coordinates
@@ -765,7 +764,6 @@ condense_dmma_ll_kernel(DmmaTables tb, int lenA, int lenb, int64_t ncells, const
   static_assert(LG >= 1, "cell too tall for the loader");
   constexpr int LB = 6;                         // loader batch: look-ups in flight per thread
   for (int i = tid; i < HP; i += 128) s_rowinfo[i] = (unsigned short)((tb.rowf[RPC * i] << 8) | tb.rowl[RPC * i]);
-  for (int i = tid; i < NB; i += 128) s_rowinfo2[i] = (unsigned short)((tb.rowf[NI + i] << 8) | tb.rowl[NI + i]);
   __syncthreads();
   const int l_grp = tid / HP, l_rp = tid - l_grp * HP;
   const bool l_on = l_grp < LG;

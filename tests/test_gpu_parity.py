@@ -676,3 +676,30 @@ def test_l2_projection_dofs(ctx, n, m):
     if m == 1:
         x = gh.compute_bulk_to_skeleton_l2_projection_dofs(A[:5], B[:5, :, 0], ctx).cpu().numpy()
         assert x.shape == (5, n) and np.array_equal(x, X[:5, :, 0])
+
+
+def test_next_row_entry_points_edge_cases(ctx):
+    """empty batches and bad arguments of the SURVEY 8f entry points: expand, L2 projection, CSR hand-off."""
+    plan = _dev_plan(ctx, "C1_hdg_k1_2d")
+    TA = np.zeros((2, plan.lenA)); Tb = np.zeros((2, plan.lenb))
+    ctx.expand_records(plan, 0, 2, TA, Tb, np.zeros((0, 2)), np.zeros((0, plan.lenA)), np.zeros((0, plan.lenb)))   # empty
+    with pytest.raises(gh.GhbError):
+        ctx.expand_records(plan, 1, 17, np.zeros((17, plan.lenA)), np.zeros((17, plan.lenb)), np.zeros((1, 17)),
+                           np.zeros((1, plan.lenA)), np.zeros((1, plan.lenb)))                                      # ntab > 16
+    ctx.l2_projection_dofs(0, 4, 3, np.zeros(0), np.zeros(0), np.zeros(0))                                          # empty
+    with pytest.raises(gh.GhbError) as e:
+        ctx.l2_projection_dofs(1, 33, 1, np.zeros(33 * 33), np.zeros(33), np.zeros(33))                             # n > 32
+    assert e.value.code == gh._lib.GHB_EUNSUPPORTED
+    # identity systems through host pointers (staged by the library), ragged sizes
+    for n, m in [(1, 1), (2, 5), (5, 33)]:
+        A = np.tile(np.eye(n).flatten(order="F"), (3, 1)); B = np.arange(3 * n * m, dtype=np.float64).reshape(3, n * m)
+        X = np.empty_like(B); info = np.empty(3, dtype=np.int32)
+        ctx.l2_projection_dofs(3, n, m, A, B, X, info)
+        assert np.array_equal(X, B) and not info.any()
+    # CSR hand-off needs a device S and a pattern without ghost cells
+    sk = gh.CartesianSkeleton((2, 2), ctx)
+    assem = gh.SparseMatrixAssembler(gh.FacetFESpace(sk, 2, sk.facet_is_boundary()))
+    colptr, rowval, nnz = assem.symbolic()
+    with pytest.raises(gh.GhbError) as e:
+        ctx.assemble_numeric_csr(np.zeros((4, 64)), np.zeros((4, 8)), None, np.zeros(nnz), np.zeros(assem.nrows))
+    assert e.value.code == gh._lib.GHB_EUNSUPPORTED
