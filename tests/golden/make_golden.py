@@ -33,6 +33,20 @@ def main():
     np.savez_compressed(os.path.join(HERE, "darcy_hdg_3x2_k1.npz"), cell_wise_facets=prob.cwf, cell_ids=prob.cell_ids,
                         colptr=out["colptr"], rowval=out["rowval"], nzval=out["nzval"], rhs=out["rhs"], lam=out["lam"],
                         u=out["u"], S=out["S"], g=out["g"])
+    # bulk -> skeleton L2 projection dofs (src/GridapAPIExtensions.jl:453-500, A\B per (cell, local facet)): facet mass
+    # matrices of P2 on a hex face in the monomial basis (6 x 6, scaled per system) against 30 bulk moments, dgetrf/dgetrs
+    rng = np.random.default_rng(23)
+    xq, wq = np.polynomial.legendre.leggauss(4)
+    xq, wq = 0.5 * (xq + 1), 0.5 * wq
+    pts = np.array([(a, b_) for a in xq for b_ in xq]); w = np.array([wa * wb for wa in wq for wb in wq])
+    expo = [(0, 0), (0, 1), (1, 0), (0, 2), (1, 1), (2, 0)]
+    L = np.stack([pts[:, 0] ** e[0] * pts[:, 1] ** e[1] for e in expo], axis=1)
+    M = (L * w[:, None]).T @ L
+    areas = rng.uniform(0.01, 2.0, 9)
+    Am = M[None] * areas[:, None, None]
+    Bm = rng.standard_normal((9, 6, 30))
+    Xm, info = o.l2_projection_dofs(Am, Bm)
+    np.savez_compressed(os.path.join(HERE, "l2_projection_p2_facets.npz"), A=Am, B=Bm, X=Xm, info=info)
     print("golden fixtures written to", HERE)
 
 
