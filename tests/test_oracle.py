@@ -167,3 +167,31 @@ def test_l2_projection_dofs_oracle():
     A[3] = 0.0
     _, info = o.l2_projection_dofs(A, B)
     assert info[3] == 1 and info.sum() == 1
+
+
+def test_affine_family_tables_and_coefficients_cpu():
+    """host side of SURVEY 8f-1 (no GPU): tables from representative cells reproduce every cell record of the Darcy HDG
+    family as sum_t coef[K][t] T[t]; slab-wise coefficient vectors equal the slice of the global ones."""
+    import torch
+    import gridaphybrid_b200 as gh
+    from oracle import hdg_darcy
+    from tests.helpers import pack_blocks
+    dims, order = (4, 4), 1
+    D, n = len(dims), dims[0]
+    rep = hdg_darcy.DarcyHDG((3,) * D, order, length=3.0 / n)
+    Ar, br = pack_blocks(*rep.cell_blocks())
+    picks = [[1] * D] + [[0 if a == d else 1 for a in range(D)] for d in range(D)] + [[2 if a == d else 1 for a in range(D)] for d in range(D)]
+    cells = [int(sum(idx[a] * 3 ** a for a in range(D))) for idx in picks]
+    coefs = np.array([[1.0] + [float(idx[a] == 0) for a in range(D)] + [idx[a] * rep.h[a] for a in range(D)] for idx in picks])
+    fam = gh.AffineRecordFamily.from_representatives(coefs, Ar[cells], br[cells])
+    full = hdg_darcy.DarcyHDG(dims, order)
+    A, b = pack_blocks(*full.cell_blocks())
+    coef = gh.cartesian_coefficients(dims, full.h, "cpu").numpy()
+    assert coef.shape == (full.ncells, 1 + 2 * D)
+    assert np.abs(coef @ fam.TA - A).max() < 1e-13 * np.abs(A).max()
+    assert np.abs(coef @ fam.Tb - b).max() < 1e-13 * np.abs(b).max()
+    part = gh.cartesian_coefficients(dims, full.h, "cpu", cell_start=5, ncells=7).numpy()
+    assert np.array_equal(part, coef[5:12])
+    kappa = torch.arange(7, dtype=torch.float64)
+    ext = gh.cartesian_coefficients(dims, full.h, "cpu", cell_start=5, ncells=7, extra=kappa).numpy()
+    assert ext.shape == (7, 2 + 2 * D) and np.array_equal(ext[:, -1], kappa.numpy())
