@@ -189,7 +189,6 @@ __device__ __forceinline__ void panel_factor(double* __restrict__ Wt, const int 
   const bool v2 = TWO && (lane + 32 < nrows);
   double a[8], a2[8];
   int ch1 = -1, ch2 = -1;                       // step at which this lane's row became the pivot row
-  double myrinv = 0.0;                          // lane k keeps 1/pivot of step k
   double* base = Wt + c0 + lane + LDW * c0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -231,7 +230,7 @@ __device__ __forceinline__ void panel_factor(double* __restrict__ Wt, const int 
       const bool from2 = TWO && prow >= 32;
       const int q = prow & 31;
       const double rinv = __shfl_sync(0xffffffffu, from2 ? rc2 : rc1, q);
-      if (lane == k) myrinv = rinv;
+      if (lane == 0) ctl->rinv[k] = rinv;     // published with the rest of the control block
       const bool me1 = !from2 && lane == q, me2 = from2 && lane == q;
       if (me1) ch1 = k;
       if (me2) ch2 = k;
@@ -239,14 +238,14 @@ __device__ __forceinline__ void panel_factor(double* __restrict__ Wt, const int 
       const bool u1 = c1 && !me1, u2 = TWO && c2 && !me2;
       const double l1 = a[k] * rinv, l2 = a2[k] * rinv;   // dgetf2: scale by the reciprocal
       a[k] = u1 ? l1 : a[k];
-      const double nl1 = u1 ? -l1 : 0.0;                  // rows out of play: a + 0*p = a
-      double nl2 = 0.0;
-      if (TWO) { a2[k] = u2 ? l2 : a2[k]; nl2 = u2 ? -l2 : 0.0; }
+      const double m1 = u1 ? l1 : 0.0;                    // rows out of play: a - 0*p = a
+      double m2 = 0.0;
+      if (TWO) { a2[k] = u2 ? l2 : a2[k]; m2 = u2 ? l2 : 0.0; }
 #pragma unroll
       for (int j = k + 1; j < 8; ++j) {
         const double pj = __shfl_sync(0xffffffffu, from2 ? a2[j] : a[j], q);   // pivot row entry, to everyone
-        a[j] = fma(nl1, pj, a[j]);
-        if (TWO) a2[j] = fma(nl2, pj, a2[j]);
+        a[j] = fma(-m1, pj, a[j]);                        // (the negation is an operand modifier of DFMA)
+        if (TWO) a2[j] = fma(-m2, pj, a2[j]);
       }
     }
   }
@@ -279,7 +278,7 @@ __device__ __forceinline__ void panel_factor(double* __restrict__ Wt, const int 
     if (v1) wb[np1 + LDW * pc(j)] = a[j];
     if (v2) wb[np2 + LDW * pc(j)] = a2[j];
   }
-  if (lane < 8) ctl->rinv[lane] = myrinv;
+  if (lane >= npiv && lane < 8) ctl->rinv[lane] = 0.0;   // beyond a partial panel
 }
 
 // ---- inverses of the 8x8 diagonal block of a factorised panel, by the (otherwise idle) update warps:
