@@ -45,3 +45,18 @@ ctx.assemble_numeric(S, g, M.dirichlet_values, nz, rhs)
 ctx.assemble_numeric_csr(S, g, M.dirichlet_values, nz, rhs)        # CSR hand-off: in-place block transpose + gather
 torch.cuda.synchronize()
 print("assembly ok", nnz)
+# SURVEY 8f kernels: batched A\B (factors in shared memory, column per lane), affine-family record expansion
+for n_, m_ in [(6, 30), (18, 60), (18, 1), (32, 9)]:
+    nb = 300
+    Aq = torch.randn((nb, n_ * n_), dtype=torch.float64, device="cuda")
+    Aq.view(nb, n_, n_).diagonal(dim1=1, dim2=2).add_(2.0 * n_ ** 0.5)
+    Bq = torch.randn((nb, n_ * m_), dtype=torch.float64, device="cuda")
+    Xq = torch.empty_like(Bq); iq = torch.empty(nb, dtype=torch.int32, device="cuda")
+    ctx.l2_projection_dofs(nb, n_, m_, Aq, Bq, Xq, iq)
+    torch.cuda.synchronize()
+    print("l2 projection", n_, m_, "ok", int(iq.abs().sum()))
+plan = ctx.plan_blocks([30, 4, 36], np.ones((3, 3), bool), [1, 2], [3])
+fam = gh.AffineRecordFamily(np.random.default_rng(0).standard_normal((7, plan.lenA)), np.random.default_rng(1).standard_normal((7, plan.lenb)))
+cells = fam.expand(ctx, plan, gh.cartesian_coefficients((7, 6, 5), (0.1, 0.1, 0.1), "cuda"))
+torch.cuda.synchronize()
+print("expand ok", float(cells.A.abs().max()))
