@@ -127,6 +127,7 @@ def run(NI, NB, seed=0):
     err = np.abs(got - ref).max() / np.abs(ref).max()
     print(f"({NI},{NB}): max rel err {err:.2e}, worst B-fragment bank conflict degree {max(conflicts)}")
     assert err < 1e-12 and not np.isnan(got).any()
+    assert max(conflicts) == 1, "B-fragment loads must be bank-conflict free"
 
 
 if __name__ == "__main__":
