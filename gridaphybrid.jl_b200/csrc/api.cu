@@ -21,6 +21,7 @@ bool is_device_ptr(const void* p) {
 
 int launch_condense(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
                     double* g, int32_t* info, double* X) {
+  if (p.use_cw) return launch_condense_cw(ctx, p, ncells, A, b, S, g, info, X);
   if (p.use_dmma && !getenv("GHB_FACTORS_GENERIC")) return launch_condense_dmma(ctx, p, ncells, A, b, S, g, info, X);
   if (p.use_warp && X == nullptr) return launch_condense_warp(ctx, p, ncells, A, b, S, g, info);
   if (p.use_large) return launch_condense_large(ctx, p, ncells, A, b, S, g, info, X);
@@ -190,6 +191,15 @@ int ghb_plan_blocks(ghb_ctx* ctx, int nfields, const int32_t* ndofs, const uint8
     if (rc != GHB_OK) { cudaFree(p->d_emap); delete p; return rc; }
     p->use_large = true;
     p->kernel_name = "large_dmma";
+  }
+  // the one-warp-per-cell kernel takes the condensation of the shapes it is instantiated for (GHB_CW=0: A/B runs
+  // against the 4-warps-per-cell kernels, read once here)
+  const char* cwenv = getenv("GHB_CW");
+  if (cw_supported(*p) && !(force && force[0] == '1') && !(cwenv && cwenv[0] == '0')) {
+    int rc = cw_prepare(ctx, *p);
+    if (rc != GHB_OK) { cudaFree(p->d_emap); delete p; return rc; }
+    p->use_cw = true;
+    p->kernel_name = p->n_i == 34 ? "cw_34_36" : (p->n_i == 33 ? "cw_33_12" : (p->n_i == 40 ? "cw_40_36" : "cw_21_16"));
   }
   ctx->plans.push_back(p);
   *plan_id = (int)ctx->plans.size() - 1;

@@ -33,6 +33,8 @@ struct Plan {
   uint8_t* d_rowl = nullptr;
   int32_t* d_xoff = nullptr;      // left-looking DMMA kernel: bottom-block record offsets in fragment order
   bool use_dmma = false;
+  bool use_cw = false;            // one-warp-per-cell DMMA kernel (condense_cw.cu)
+  int cw_pf[6] = {0, 0, 0, 0, 0, 0};   // record ranges (offset, length) of A12 / A21 / A22 for its L2 prefetches
   bool use_warp = false;          // register-resident warp kernels for small cells (condense_warp.cu)
   bool use_large = false;         // streamed large-cell kernel, 64 < n_i <= 128 (condense_large.cu)
   bool all_touched = false;
@@ -170,6 +172,10 @@ int launch_condense_large(ghb_ctx* ctx, const Plan& p, int64_t ncells, const dou
 int launch_backsub_large(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b,
                          const double* lam_free, const double* lam_dir, const int64_t* ids, double* u, int32_t* info);
 int dmma_prepare(ghb_ctx* ctx, Plan& p);
+bool cw_supported(const Plan& p);
+int cw_prepare(ghb_ctx* ctx, Plan& p);
+int launch_condense_cw(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
+                       double* g, int32_t* info, double* X);
 int launch_condense_dmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
                          double* g, int32_t* info, double* X = nullptr);
 // dispatch: tuned kernel when the plan has one and no factors are requested, else the generic kernel

@@ -20,6 +20,10 @@ CONFIGS = {
     "C2_rth_k3_2d": dict(ndofs=[40, 16, 16], touched=np.array([[1, 1, 1], [1, 0, 0], [1, 0, 0]], bool),
                          interior=[1, 2], boundary=[3]),
     "C3_hdg_k2_3d": dict(ndofs=[30, 4, 36], touched=np.ones((3, 3), bool), interior=[1, 2], boundary=[3]),
+    # shapes the reference's own tests / SURVEY section 9 name besides the BASELINE configs: equal-order Darcy HDG k=2 on
+    # hexes (40,36) and elasticity HDG k=1 on quads (21,16) (test/LinearElasticityHDGTests.jl:86-94)
+    "hdg_equal_order_3d": dict(ndofs=[30, 10, 36], touched=np.ones((3, 3), bool), interior=[1, 2], boundary=[3]),
+    "elasticity_k1_2d": dict(ndofs=[9, 12, 16], touched=np.ones((3, 3), bool), interior=[1, 2], boundary=[3]),
     "multifield_2skel": dict(ndofs=[4, 4, 1, 1, 4, 4],
                              touched=np.array([[1, 0, 1, 0, 1, 0], [0, 1, 0, 1, 0, 1], [1, 0, 0, 0, 0, 0],
                                                [0, 1, 0, 0, 0, 0], [1, 0, 0, 0, 0, 0], [0, 1, 0, 0, 0, 0]], bool),
@@ -32,6 +36,35 @@ CONFIGS = {
     "C5_hencky_k1_3d": dict(ndofs=[12, 12, 4, 24, 24, 30, 18, 54], touched=_HENCKY_TOUCHED,
                             interior=[1, 2, 3, 4, 5, 6], boundary=[7, 8]),
 }
+
+
+def condensed_dofs(op):
+    """(field index 0-based, local dof) of every row of the condensed order: interior fields first, then boundary."""
+    return [(f - 1, l) for f in list(op.interior) + list(op.boundary) for l in range(op.ndofs[f - 1])]
+
+
+def dense_to_record(op, dense, bvec):
+    """dense [n, n] matrix and [n] vector in CONDENSED order -> packed record (touched blocks only)."""
+    dofs = condensed_dofs(op)
+    A = np.zeros(op.lenA)
+    b = np.zeros(op.lenb)
+    for r, (fr, lr) in enumerate(dofs):
+        b[op.field_offset[fr] + lr] = bvec[r]
+        for c, (fc, lc) in enumerate(dofs):
+            o_ = op.block_offset[fr, fc]
+            if o_ >= 0:
+                A[o_ + lr + lc * op.ndofs[fr]] = dense[r, c]
+    return A, b
+
+
+def zero_interior_column(op, Arec, col):
+    """zero interior column `col` (condensed numbering) of a packed record, rows of the interior fields only."""
+    dofs = condensed_dofs(op)
+    fc, lc = dofs[col]
+    for f in op.interior:
+        o_ = op.block_offset[f - 1, fc]
+        if o_ >= 0:
+            Arec[o_ + lc * op.ndofs[f - 1]: o_ + (lc + 1) * op.ndofs[f - 1]] = 0.0
 
 
 def oracle_plan(name):

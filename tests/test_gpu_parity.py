@@ -9,7 +9,8 @@ import torch
 import gridaphybrid_b200 as gh
 from oracle import oracle as o
 from oracle import oracle_c as oc
-from tests.helpers import CONFIGS, DarcyProblem, oracle_plan, rel_err_cells
+from tests.helpers import (CONFIGS, DarcyProblem, dense_to_record, oracle_plan, rel_err_cells,
+                           zero_interior_column)
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-11
@@ -438,7 +439,7 @@ def test_slab_assembly_matches_global(ctx, gdims, world):
 def test_dmma_singular_cell_info(ctx):
     """tuned kernel: an exactly singular interior block is reported like dgetrf (info = first zero pivot), NaN outputs."""
     plan, op = _dev_plan(ctx, "C3_hdg_k2_3d"), oracle_plan("C3_hdg_k2_3d")
-    assert plan.kernel_name.startswith("dmma")
+    assert plan.kernel_name.startswith(("dmma", "cw"))
     A0, b0 = o.synth_cell_records(op, 0, 6)
     A0[3, :] = 0.0                                  # zero matrix: first pivot column is zero
     S = np.empty((6, plan.n_b ** 2)); g = np.empty((6, plan.n_b)); info = np.empty(6, dtype=np.int32)
@@ -509,7 +510,9 @@ def test_both_dmma_condensation_kernels(ctx, name, left_looking, monkeypatch):
     (GHB_DMMA_LL=0, read at every launch).  Both against the oracle: values, ragged cell counts around the resident-CTA
     count (148 SMs x 8 / x 5), dgetrf info semantics and NaN outputs of a singular cell."""
     monkeypatch.setenv("GHB_DMMA_LL", left_looking)
+    monkeypatch.setenv("GHB_CW", "0")               # read at plan creation: the 4-warps-per-cell kernels
     plan, op = _dev_plan(ctx, name), oracle_plan(name)
+    assert plan.kernel_name.startswith("dmma")
     for n in (5, 1184, 1190, 3001):
         A, b = _synth(ctx, plan, 4242, n)
         bad = n // 2
@@ -703,3 +706,71 @@ def test_next_row_entry_points_edge_cases(ctx):
     with pytest.raises(gh.GhbError) as e:
         ctx.assemble_numeric_csr(np.zeros((4, 64)), np.zeros((4, 8)), None, np.zeros(nnz), np.zeros(assem.nrows))
     assert e.value.code == gh._lib.GHB_EUNSUPPORTED
+
+
+CW_NAMES = ["C3_hdg_k2_3d", "C2_rth_k2_2d", "hdg_equal_order_3d", "elasticity_k1_2d"]
+
+
+@pytest.mark.parametrize("name", CW_NAMES)
+def test_cellwarp_kernel(ctx, name):
+    """one-warp-per-cell kernel (csrc/condense_cw.cu): values against the oracle on ragged cell counts around the resident
+    warp count, dgetrf info semantics for a zero matrix and for a zero pivot that only appears late (column 20), NaN outputs
+    of failed cells, and the stored factors X = A11^-1 [A12 b1] through the backward map."""
+    plan, op = _dev_plan(ctx, name), oracle_plan(name)
+    assert plan.kernel_name.startswith("cw_"), plan.kernel_name
+    rng = np.random.default_rng(5)
+    for n in (1, 5, 1776, 1781, 4000):
+        A, b = _synth(ctx, plan, 777, n)
+        An, bn = A.cpu().numpy(), b.cpu().numpy()
+        bad = []
+        if n >= 5:
+            An[n // 2] = 0.0                         # zero matrix: info = 1
+            zero_interior_column(op, An[1], 20)      # a zero pivot that only appears late: info = 21
+            bad = [1, n // 2]
+        S = torch.empty((n, plan.n_b ** 2), dtype=torch.float64, device="cuda")
+        g = torch.empty((n, plan.n_b), dtype=torch.float64, device="cuda")
+        info = torch.empty(n, dtype=torch.int32, device="cuda")
+        Ad = torch.as_tensor(An, device="cuda")
+        ctx.condense(plan, n, Ad, b, S, g, info, keep_factors=True)
+        S0, g0, info0 = oc.condense(op, An, bn)
+        ih = info.cpu().numpy()
+        ok = np.ones(n, bool)
+        ok[bad] = False
+        assert (ih[ok] == 0).all() and (info0[ok] == 0).all()
+        if bad:
+            assert ih[n // 2] == 1 and info0[n // 2] == 1
+            assert ih[1] == 21 and info0[1] == 21, (ih[1], info0[1])
+            assert np.isnan(S.cpu().numpy()[bad]).all() and np.isnan(g.cpu().numpy()[bad]).all()
+        assert rel_err_cells(S.cpu().numpy()[ok], S0[ok]) < TOL and rel_err_cells(g.cpu().numpy()[ok], g0[ok]) < TOL
+        # factors through the backward map
+        nfree = 50
+        ids = rng.integers(1, nfree + 1, (n, plan.n_b))
+        lam = rng.standard_normal(nfree)
+        u0, _ = oc.backsub(op, An, bn, o.cell_dof_values(lam, np.zeros(0), ids))
+        u = torch.empty((n, plan.n_i), dtype=torch.float64, device="cuda")
+        ctx.backsub(plan, n, None, None, torch.as_tensor(lam, device="cuda"), None, torch.as_tensor(ids, device="cuda"), u, None)
+        assert rel_err_cells(u.cpu().numpy()[ok], u0[ok]) < TOL
+
+
+def test_cellwarp_pivot_ties_follow_lapack(ctx):
+    """columns whose maxima tie exactly (or to within 2^-15) must pivot like dgetf2's idamax (first exact maximum): cells
+    built from small integers make every elimination exact, so S agrees with the LAPACK oracle to rounding of the Schur
+    update only when the same rows were chosen -- and a cell that is singular only under the wrong tie-break stays regular."""
+    name = "C3_hdg_k2_3d"
+    plan, op = _dev_plan(ctx, name), oracle_plan(name)
+    rng = np.random.default_rng(11)
+    n = 64
+    An = np.empty((n, op.lenA)); bn = np.empty((n, op.lenb))
+    for c in range(n):
+        dense = rng.integers(-3, 4, (op.n, op.n)).astype(float)           # many exact ties in every column
+        dense[:op.n_i, :op.n_i] += np.diag(rng.choice([-4.0, 4.0], op.n_i))
+        if c % 2:                                                          # near ties: 1 + k 2^-20 relative perturbations
+            dense[:op.n_i, :op.n_i] *= 1.0 + rng.integers(0, 8, (op.n_i, op.n_i)) * 2.0 ** -20
+        An[c], bn[c] = dense_to_record(op, dense, rng.integers(-3, 4, op.n).astype(float))
+    S = np.empty((n, plan.n_b ** 2)); g = np.empty((n, plan.n_b)); info = np.empty(n, dtype=np.int32)
+    ctx.condense(plan, n, An, bn, S, g, info)
+    S0, g0, info0 = oc.condense(op, An, bn)
+    assert info.tolist() == info0.tolist()
+    ok = info0 == 0
+    assert ok.sum() > n // 2
+    assert rel_err_cells(S[ok], S0[ok]) < TOL and rel_err_cells(g[ok], g0[ok]) < TOL
