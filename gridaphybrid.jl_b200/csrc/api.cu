@@ -75,6 +75,7 @@ void ghb_destroy(ghb_ctx* ctx) {
     if (p && p->d_colbase) cudaFree(p->d_colbase);
     if (p && p->d_rowf) cudaFree(p->d_rowf);
     if (p && p->d_xoff) cudaFree(p->d_xoff);
+    if (p && p->d_cw) cudaFree(p->d_cw);
     delete p;
   }
   asm_free(ctx);
@@ -199,7 +200,7 @@ int ghb_plan_blocks(ghb_ctx* ctx, int nfields, const int32_t* ndofs, const uint8
     int rc = cw_prepare(ctx, *p);
     if (rc != GHB_OK) { cudaFree(p->d_emap); delete p; return rc; }
     p->use_cw = true;
-    p->kernel_name = p->n_i == 34 ? "cw_34_36" : (p->n_i == 33 ? "cw_33_12" : (p->n_i == 40 ? "cw_40_36" : "cw_21_16"));
+    p->kernel_name = cw_kernel_name(*p);
   }
   ctx->plans.push_back(p);
   *plan_id = (int)ctx->plans.size() - 1;
