@@ -161,7 +161,7 @@ static int launch_bs(ghb_ctx* ctx, int64_t nbatch, int n, int m, const double* A
   constexpr int WARPS = 8;
   const size_t smem = (size_t)WARPS * (NMAX * (NMAX + 1) + NMAX) * sizeof(double);
   auto kern = batched_solve_kernel<NMAX>;
-  GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GHB_SMEM_OPTIN(ctx, kern, smem);
   const int64_t blocks = std::min<int64_t>((nbatch + WARPS - 1) / WARPS, (int64_t)ctx->sm_count * 8);
   kern<<<(unsigned)blocks, 32 * WARPS, smem, ctx->stream>>>(nbatch, n, m, A, B, X, info);
   GHB_LAUNCHED(ctx);

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+#include <cstdio>
 #include <string>
 #include <vector>
 
@@ -19,7 +21,26 @@ struct PlanDev {
                         // offset; -1 = structural zero; column n maps into the b record
 };
 
+// Debugging / A-B knobs.  Read from the environment ONCE per context (ghb_create), changed by ghb_set_option, and
+// snapshotted into every plan when it is created: nothing on the launch path calls getenv.
+struct Options {
+  int force_generic = 0;      // GHB_FORCE_GENERIC   plans use the generic kernels only
+  int cw = 1;                 // GHB_CW              one-warp-per-cell DMMA kernel for the shapes it is instantiated for
+  int dmma_ll = 1;            // GHB_DMMA_LL         left-looking (1) or right-looking (0) 4-warps-per-cell DMMA kernel
+  int factors_generic = 0;    // GHB_FACTORS_GENERIC keep_factors through the generic kernel
+  int max_ctas_per_sm = 0;    // GHB_MAX_CTAS_PER_SM cap on resident CTAs (occupancy sweeps), 0 = none
+  int ll_ctas = 0;            // GHB_LL_CTAS         register budget of the (34,36) left-looking instantiation
+  int warp_one_cell = 0;      // GHB_WARP_ONE_CELL   small-cell kernels: one cell per warp
+  int warp_two_rows = 0;      // GHB_WARP_TWO_ROWS   (16,8): two rows per lane
+  int debug = 0;              // GHB_DEBUG           print launch geometry
+  int64_t stream_chunk_bytes = (int64_t)256 << 20;   // GHB_STREAM_CHUNK_BYTES: chunk of the host-record streaming path
+};
+
+// One-time (per kernel instantiation) shared-memory opt-in and occupancy query; `per_sm` < 0: not done yet.
+struct KernelSetup { int per_sm = -1; };
+
 struct Plan {
+  Options opt;                // snapshot of the context's knobs at plan creation
   int nfields = 0;
   std::vector<int32_t> ndofs, interior, boundary;
   std::vector<uint8_t> touched;        // col-major nfields x nfields
@@ -84,6 +105,7 @@ struct ghb_ctx {
   size_t smem_optin = 0;
   int64_t launches = 0;
   std::string err;
+  ghb::Options opt;
   std::vector<ghb::Plan*> plans;
   ghb::AsmState as;
   ghb::Factors fac;
@@ -119,6 +141,33 @@ int fail(ghb_ctx* ctx, int code, const std::string& msg);
   } while (0)
 
 bool is_device_ptr(const void* p);
+
+// raises the dynamic shared-memory limit of a kernel only when a launch needs more than any launch before it
+#define GHB_SMEM_OPTIN(ctx, kern, bytes)                                                                      \
+  do {                                                                                                        \
+    static size_t _cur = 0;                                                                                   \
+    if ((size_t)(bytes) > _cur) {                                                                             \
+      GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));   \
+      _cur = (size_t)(bytes);                                                                                 \
+    }                                                                                                         \
+  } while (0)
+
+// cudaFuncSetAttribute + occupancy once per kernel instantiation; returns the resident CTAs per SM to launch with
+template <typename K>
+int kernel_setup(ghb_ctx* ctx, const Options& opt, K kern, int threads, size_t smem, bool carveout, KernelSetup& ks,
+                 const char* name, int* per_sm_out) {
+  if (ks.per_sm < 0) {
+    GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (carveout) GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    int per_sm = 0;
+    GHB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+    if (per_sm < 1) return fail(ctx, GHB_ECUDA, std::string(name) + " does not fit on an SM");
+    if (opt.debug) fprintf(stderr, "%s: %d CTAs/SM x %d threads, %zu B smem\n", name, per_sm, threads, smem);
+    ks.per_sm = per_sm;
+  }
+  *per_sm_out = opt.max_ctas_per_sm > 0 ? std::max(1, std::min(ks.per_sm, opt.max_ctas_per_sm)) : ks.per_sm;
+  return GHB_OK;
+}
 
 // RAII device view of a caller array that may live on host or device.
 template <typename T>

@@ -39,13 +39,14 @@
 #define GHB_CW_WPC 4          // warps (= cells in flight) per CTA
 #endif
 #ifndef GHB_CW_MINB
-#define GHB_CW_MINB 3         // CTAs per SM the kernel is compiled for
+#define GHB_CW_MINB 4         // CTAs per SM the kernel is compiled for
 #endif
 #ifndef GHB_CW_EXACT
 #define GHB_CW_EXACT 1        // 1: LAPACK's pivot (first exact maximum in swapped order); 0: maximum to 2^-15 relative
 #endif
 #ifndef GHB_CW_PREFETCH
-#define GHB_CW_PREFETCH 2     // 0: none, 1: whole record at the head of the cell, 2: A12 at the head, A21/A22 after the LU
+#define GHB_CW_PREFETCH 2     // 0: none, 1: whole record at the head of the cell, 2: A12 at the head, A21/A22 after the LU,
+                              // 3: the warp's next record when the LU of this one is done
 #endif
 
 namespace ghb {
@@ -128,7 +129,6 @@ struct CwArgs {
 
 template <int NI, int NB>
 struct CwCfg {
-  static constexpr int N = NI + NB;
   static constexpr int NC = NB + 1;            // right-hand-side columns: A12 | b1
   static constexpr int RT = (NI + 7) / 8;      // tiles over the interior dofs (panels)
   static constexpr int CTB = (NC + 7) / 8;     // column tiles of [A12 b1]
@@ -139,8 +139,7 @@ struct CwCfg {
   static_assert(NI <= 64, "two register sets hold at most 64 rows");
   // per-warp shared memory (bytes)
   static constexpr unsigned OFF_INVL = (NI + 1) * ROWB;
-  static constexpr unsigned OFF_INVU = OFF_INVL + RT * 512;
-  static constexpr unsigned OFF_SCALEU = OFF_INVU + RT * 512;   // [8] -1/pivot, reversed (substitution of inv(U))
+  static constexpr unsigned OFF_SCALEU = OFF_INVL + RT * 512;   // [8] -1/pivot, reversed (substitution of inv(U))
   static constexpr unsigned OFF_PROW = OFF_SCALEU + 64;         // [8*RT] u32: image address info of the row at a position
   static constexpr unsigned OFF_INFO = OFF_PROW + 32 * RT;
   static constexpr unsigned WARP_BYTES = OFF_INFO + 16;
@@ -180,12 +179,15 @@ __device__ __noinline__ unsigned pivot_exact(double v1, double v2, bool c1, bool
 // ---- panel factorisation: one row per lane, implicit pivoting --------------------------------------
 // a[k]: logical columns c0..c0+7 of the lane's row (a2: second register set, rows 32.. while more than 32 rows are in
 // play).  act: the lane's row is still in play.  ch: step at which the row became the pivot row (-1 otherwise).  On return
-// rows still in play hold the NEGATED multipliers; pivot row k holds negated multipliers in columns < k and its U row in
-// columns >= k.  pos: position of the row in LAPACK's swapped order (tie-breaking only).
+// rows still in play hold the NEGATED multipliers.  The pivot row of step k is final when it is chosen (negated multipliers
+// in columns < k, its U row in columns >= k): its lane writes it to row mu(k) of the stage tile (the diagonal block in pivot
+// order, input of the inversion) together with -1/pivot, and every lane reads the entries it needs back from there -- one
+// 16-byte broadcast load per column pair instead of two shuffles and two register moves per column.
+// pos: position of the row in LAPACK's swapped order (tie-breaking only).
 template <bool TWO>
 __device__ __forceinline__ void panel_factor(double (&a)[8], double (&a2)[8], const bool act1, const bool act2, int& pos1,
                                              int& pos2, const int npiv, const int c0, int& ch1, int& ch2,
-                                             const unsigned scaleu_addr, const unsigned info_addr) {
+                                             const unsigned stage, const unsigned scaleu_addr, const unsigned info_addr) {
   const unsigned lane = threadIdx.x & 31;
   const unsigned pref = 31u - lane;
   ch1 = -1; ch2 = -1;
@@ -223,11 +225,23 @@ __device__ __forceinline__ void panel_factor(double (&a)[8], double (&a2)[8], co
         q = r & 31u;
         from2 = TWO && (r & 32u) != 0u;
       }
-      const double nrinv = __shfl_sync(0xffffffffu, from2 ? nr2 : nr1, q);
-      if (lane == 0) sts64(scaleu_addr + 8u * (unsigned)(7 - k), nrinv);   // -1/pivot, reversed order (inv(U) substitution)
       const bool me1 = !from2 && lane == q, me2 = from2 && lane == q;
-      if (me1) ch1 = k;
-      if (me2) ch2 = k;
+      const unsigned srow = stage + 64u * (unsigned)mu(k);
+      const unsigned sscl = scaleu_addr + 8u * (unsigned)(7 - k);   // -1/pivot, reversed order (inv(U) substitution)
+      if (me1) {
+        ch1 = k;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sts128(srow + 16u * c, a[c], a[4 + c]);
+        sts64(sscl, nr1);
+      }
+      if (TWO && me2) {
+        ch2 = k;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sts128(srow + 16u * c, a2[c], a2[4 + c]);
+        sts64(sscl, nr2);
+      }
+      __syncwarp();
+      const double nrinv = lds64(sscl);
       if (GHB_CW_EXACT) {
         // dlaswp: the row at position c0+k trades places with the pivot row
         const int pq = __shfl_sync(0xffffffffu, from2 ? pos2 : pos1, q);
@@ -238,11 +252,14 @@ __device__ __forceinline__ void panel_factor(double (&a)[8], double (&a2)[8], co
       double m1v = 0.0, m2v = 0.0;                  // negated multipliers (dgetf2 scales by the reciprocal of the pivot)
       if (u1) { m1v = a[k] * nrinv; a[k] = m1v; }
       if (TWO && u2) { m2v = a2[k] * nrinv; a2[k] = m2v; }
+      double pr[8];                                 // pivot row, logical columns > k
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c > k || 4 + c > k) lds128(srow + 16u * c, pr[c], pr[4 + c]);
 #pragma unroll
       for (int j = k + 1; j < 8; ++j) {
-        const double pj = __shfl_sync(0xffffffffu, from2 ? a2[j] : a[j], q);   // pivot row entry, to everyone
-        a[j] = fma(m1v, pj, a[j]);
-        if (TWO) a2[j] = fma(m2v, pj, a2[j]);
+        a[j] = fma(m1v, pr[j], a[j]);
+        if (TWO) a2[j] = fma(m2v, pr[j], a2[j]);
       }
     }
   }
@@ -259,7 +276,7 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
   const int g = lane >> 2, t = lane & 3;
   unsigned char* wsp = smem_raw + (size_t)warp * C::WARP_BYTES;
   const unsigned ws = (unsigned)__cvta_generic_to_shared(wsp);           // the warp's image (shared-window address)
-  const unsigned a_invL = ws + C::OFF_INVL, a_invU = ws + C::OFF_INVU, a_scaleU = ws + C::OFF_SCALEU;
+  const unsigned a_invL = ws + C::OFF_INVL, a_scaleU = ws + C::OFF_SCALEU;
   const unsigned a_prow = ws + C::OFF_PROW, a_info = ws + C::OFF_INFO;
   unsigned char* shp = smem_raw + (size_t)WPC * C::WARP_BYTES;           // CTA-shared tables
   const unsigned a_sh = (unsigned)__cvta_generic_to_shared(shp);
@@ -299,13 +316,26 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
     const double* Arec = ar.A + cell * lenA;
     const double* brec = ar.b + cell * lenb;
     // ------------------------------------------------------------------ load A11 (table-driven 8-byte cp.async)
+    // the table entries of a batch are fetched before its copies are issued (the registers are free at this point)
     {
       const char* Ab = reinterpret_cast<const char*>(Arec);
-#pragma unroll 4
-      for (int i = lane; i < ar.nld; i += 32) {
-        const uint2 e = __ldg(ar.ldtab + i);
-        const bool z = e.x == 0xffffffffu;
-        cp_async8_z(ws + e.y, Ab + (z ? 0u : e.x), z ? 0u : 8u);
+      constexpr int NLD = (NI * NI + 31) / 32, LB = 20;
+#pragma unroll
+      for (int i0 = 0; i0 < NLD; i0 += LB) {
+        uint2 e[LB];
+#pragma unroll
+        for (int i = 0; i < LB; ++i)
+          if (i0 + i < NLD) e[i] = __ldg(ar.ldtab + 32 * (i0 + i) + lane);
+#pragma unroll
+        for (int i = 0; i < LB; ++i)
+          if (i0 + i < NLD) {
+            if (SPARSE) {
+              const bool z = e[i].x == 0xffffffffu;
+              cp_async8_z(ws + e[i].y, Ab + (z ? 0u : e[i].x), z ? 0u : 8u);
+            } else {
+              cp_async8_z(ws + e[i].y, Ab + e[i].x, 8u);
+            }
+          }
       }
       if (GHB_CW_PREFETCH == 1) { if (lane == 0) l2_prefetch(Arec, (unsigned)lenA * 8u); }
       if (GHB_CW_PREFETCH == 2) { if (lane == 0) l2_prefetch(Arec + ar.pf12_off, (unsigned)ar.pf12_len * 8u); }
@@ -385,9 +415,9 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
 #pragma unroll
         for (int c = 0; c < 8; ++c) a2[c] = 0.0;
       }
+      const unsigned stL = a_invL + 512u * R;   // stage tile of this panel, then inv(L_pp)
       if (npiv < 8) {                         // partial last panel: unused stage rows, scales and positions are zero / dummy
-        sts128(a_invL + 512u * R + 16u * lane, 0.0, 0.0);
-        sts128(a_invU + 512u * R + 16u * lane, 0.0, 0.0);
+        sts128(stL + 16u * lane, 0.0, 0.0);
         if (lane < 8) {
           sts64(a_scaleU + 8u * lane, 0.0);
           sts_u32(a_prow + 32u * R + 4u * lane, C::enc(DUMMY));
@@ -395,38 +425,16 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
         __syncwarp();
       }
       int ch1, ch2;
-      if (HAS2 && two) panel_factor<true>(a, a2, act1, act2, pos1, pos2, npiv, c0, ch1, ch2, a_scaleU, a_info);
-      else panel_factor<false>(a, a2, act1, false, pos1, pos2, npiv, c0, ch1, ch2, a_scaleU, a_info);
-      // write back the rows still in play (negated multipliers); the pivot rows go to the stage tiles: the 8x8 diagonal
-      // block in pivot order, twice: natural (inv(L) lanes) and reversed in both directions (inv(U) lanes)
-      {
-        const unsigned stL = a_invL + 512u * R, stU = a_invU + 512u * R;
-        if (act1) {
-          if (ch1 < 0) {
+      if (HAS2 && two) panel_factor<true>(a, a2, act1, act2, pos1, pos2, npiv, c0, ch1, ch2, stL, a_scaleU, a_info);
+      else panel_factor<false>(a, a2, act1, false, pos1, pos2, npiv, c0, ch1, ch2, stL, a_scaleU, a_info);
+      // write back the rows still in play (negated multipliers); the pivot rows are in the stage tile
+      if (act1 && ch1 < 0) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) sts128(pa1 + (((unsigned)c ^ sw1) << 4), a[c], a[4 + c]);
-          } else {
-            const unsigned m = (unsigned)(2 * (ch1 & 3) + (ch1 >> 2));
+        for (int c = 0; c < 4; ++c) sts128(pa1 + (((unsigned)c ^ sw1) << 4), a[c], a[4 + c]);
+      }
+      if (HAS2 && act2 && ch2 < 0) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              sts128(stL + 64u * m + 16u * c, a[c], a[4 + c]);
-              sts128(stU + 64u * (7u - m) + 16u * (3 - c), a[4 + c], a[c]);
-            }
-          }
-        }
-        if (HAS2 && act2) {
-          if (ch2 < 0) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) sts128(pa2 + (((unsigned)c ^ sw2) << 4), a2[c], a2[4 + c]);
-          } else {
-            const unsigned m = (unsigned)(2 * (ch2 & 3) + (ch2 >> 2));
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              sts128(stL + 64u * m + 16u * c, a2[c], a2[4 + c]);
-              sts128(stU + 64u * (7u - m) + 16u * (3 - c), a2[4 + c], a2[c]);
-            }
-          }
-        }
+        for (int c = 0; c < 4; ++c) sts128(pa2 + (((unsigned)c ^ sw2) << 4), a2[c], a2[4 + c]);
       }
       // ---- positions: the pivots of this panel at mu(step), then the rows still in play (set 1 in lane order, then set 2)
       {
@@ -457,11 +465,14 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
         }
       }
       __syncwarp();
-      // ---- inverses of the diagonal block: lanes 0-7 columns of inv(L_pp), lanes 8-15 columns of inv(U_pp) (reversed:
-      //      step i of the U lanes is row 7 - i, register m is column 7 - m; mu(7 - k) = 7 - mu(k) makes the offsets equal)
+      // ---- inverses of the diagonal block: lanes 0-7 columns of inv(L_pp), lanes 8-15 columns of inv(U_pp).  The U lanes
+      //      run the same recurrence on the block reversed in both directions (step i is row 7 - i, register m is column
+      //      7 - m; mu(7 - k) = 7 - mu(k), so their stage offsets are 504 minus those of the L lanes).  inv(L_pp) replaces
+      //      the stage tile; inv(U_pp) goes to the (dead) diagonal block of the pivot rows in the image.
       {
         const int cidx = lane & 7, grp = (lane >> 3) & 1;
-        const unsigned st = (grp ? a_invU : a_invL) + 512u * R;
+        const unsigned sb = grp ? stL + 504u : stL;
+        const int sg = grp ? -1 : 1;
         const unsigned sc = grp ? a_scaleU : a_ones;
         const double sgn = grp ? -1.0 : 1.0;
         double z[8];
@@ -470,18 +481,27 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
           double d0 = (i == cidx) ? sgn : 0.0, d1 = 0.0;
 #pragma unroll
           for (int m = 0; m < i; ++m) {
-            const double v = lds64(st + 64u * mu(i) + 8u * mu(m));
+            unsigned ad;                                     // one IMAD (the compiler would emit an add and a predicated add)
+            asm volatile("mad.lo.s32 %0, %1, %2, %3;" : "=r"(ad) : "r"(sg), "r"(64 * mu(i) + 8 * mu(m)), "r"(sb));
+            const double v = lds64(ad);
             if (m & 1) d1 = fma(v, z[m], d1); else d0 = fma(v, z[m], d0);
           }
           z[i] = (d0 + d1) * lds64(sc + 8u * i);             // grp 0: 1; grp 1: -1/u_ss of the row of this step
         }
         __syncwarp();                                        // every lane has read its stage rows
-        if (lane < 16) {
-          const unsigned mc = 8u * (unsigned)(2 * (cidx & 3) + (cidx >> 2));
-          const unsigned ob = grp ? (st + 504u - mc) : (st + mc);
-          const int step = grp ? -64 : 64;
+        const unsigned mc = 8u * (unsigned)(2 * (cidx & 3) + (cidx >> 2));
+        if (lane < 8) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) sts64(ob + (unsigned)(step * mu(i)), z[i]);
+          for (int i = 0; i < 8; ++i) sts64(stL + 64u * mu(i) + mc, z[i]);
+        } else if (lane < 16) {
+          // logical (row 7 - i, column 7 - cidx): image row of pivot position mu(7 - i), physical column 7 - mu(cidx)
+          const unsigned colx = 56u - mc;
+          const unsigned wsc = ws + 64u * (unsigned)R;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const unsigned w = lds_u32(a_prow + 32u * R + 4u * (unsigned)(7 - mu(i)));
+            sts64(wsc + ((w & 0xffffu) ^ colx), z[i]);
+          }
         }
       }
       __syncwarp();
@@ -492,6 +512,8 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
       l2_prefetch(Arec + ar.pf21_off, (unsigned)ar.pf21_len * 8u);
       if (ar.pf22_len > 0) l2_prefetch(Arec + ar.pf22_off, (unsigned)ar.pf22_len * 8u);
     }
+    if (GHB_CW_PREFETCH == 3 && lane == 0 && cell + wstride < ar.ncells)   // the whole next record of this warp
+      l2_prefetch(Arec + wstride * lenA, (unsigned)lenA * 8u);
     const int failed = (int)lds_u32(a_info);
     // per position of this lane's tile rows (8j + 2t + e): record offset of A12(row, column g) and 8 x its column stride;
     // B-fragment rows of the L / U tiles
@@ -567,7 +589,7 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
 #pragma unroll
       for (int q = RT - 1; q >= 0; --q) {
         double b0, b1;
-        lds128(a_invU + 512u * q + 64u * g + T16, b0, b1);
+        lds128(rb[q] + 64u * q, b0, b1);                     // inv(U_qq) sits in the diagonal block of the image
         double x0 = 0.0, x1 = 0.0;
         dmma(x0, x1, T[q][0], b0);
         if (q < RT - 1 || NPL > 4) dmma(x0, x1, T[q][1], b1);
@@ -637,7 +659,8 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
 #pragma unroll
         for (int m = 0; m < BTM; ++m) {
           const int r = 8 * m + 2 * t;
-          const double v0 = failed ? qnan : acc[m][0], v1 = failed ? qnan : acc[m][1];
+          double v0 = acc[m][0], v1 = acc[m][1];
+          if (failed) { v0 = qnan; v1 = qnan; }
           if (al16) {
             if (NB % 8 == 0 || r < NB) *reinterpret_cast<double2*>(dst + r) = make_double2(v0, v1);
           } else {
@@ -699,7 +722,10 @@ static void cw_tables(const Plan& p, std::vector<uint2>& ld, std::vector<uint32_
       ld.push_back(make_uint2(src, dst));
     }
   std::stable_sort(ld.begin(), ld.end(), [](const uint2& x, const uint2& y) { return x.x < y.x; });
-  while (ld.size() % 32) ld.push_back(make_uint2(0xffffffffu, (uint32_t)C::DUMMY * C::ROWB));   // zeros into the dummy row
+  // padding of the last batch: zeros into the dummy row (plans with untouched blocks) or record element 0 into the scale
+  // array, which every panel rewrites before use (the copies of fully touched plans carry no zero-fill predicate)
+  while (ld.size() % 32)
+    ld.push_back(p.all_touched ? make_uint2(0u, C::OFF_SCALEU) : make_uint2(0xffffffffu, (uint32_t)C::DUMMY * C::ROWB));
   rowA12.assign(NI + 1, 0xffffffffu);
   rowb.assign(NI + 1, 0);
   for (int r = 0; r < NI; ++r) {
@@ -762,19 +788,11 @@ static int launch_cw(ghb_ctx* ctx, const Plan& p, CwArgs& ar) {
   constexpr int WPC = GHB_CW_WPC, MINB = GHB_CW_MINB;
   auto kern = condense_cw_kernel<NI, NB, WPC, MINB, KEEPX, SPARSE>;
   const size_t smem = CwCfg<NI, NB>::smem_bytes(WPC);
-  static int per_sm_cached = -1;          // per instantiation: attributes and occupancy are set once
-  if (per_sm_cached < 0) {
-    GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    int per_sm = 0;
-    GHB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * WPC, smem));
-    if (per_sm < 1) return fail(ctx, GHB_ECUDA, "condense_cw_kernel does not fit on an SM");
-    if (const char* cap = getenv("GHB_MAX_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(cap)));   // profiling knob
-    if (getenv("GHB_DEBUG")) fprintf(stderr, "condense_cw<%d,%d>: %d CTAs/SM x %d warps, %zu B smem\n", NI, NB, per_sm, WPC, smem);
-    per_sm_cached = per_sm;
-  }
+  static KernelSetup ks;
+  int per_sm = 0;
+  GHB_TRY(kernel_setup(ctx, p.opt, kern, 32 * WPC, smem, true, ks, "condense_cw_kernel", &per_sm));
   const int64_t want = (ar.ncells + WPC - 1) / WPC;
-  const int64_t grid = std::min<int64_t>(want, (int64_t)ctx->sm_count * per_sm_cached);
+  const int64_t grid = std::min<int64_t>(want, (int64_t)ctx->sm_count * per_sm);
   kern<<<(unsigned)grid, 32 * WPC, smem, ctx->stream>>>(ar);
   GHB_LAUNCHED(ctx);
   return GHB_OK;

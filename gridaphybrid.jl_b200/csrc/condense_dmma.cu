@@ -1320,13 +1320,9 @@ static int launch_dmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double
   using C = Cfg<NI, NB>;
   auto kern = condense_dmma_kernel<NI, NB, RPC>;
   const size_t smem = C::smem_bytes(p.nfields);
-  GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  static KernelSetup ks;
   int per_sm = 0;
-  GHB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
-  if (per_sm < 1) return fail(ctx, GHB_ECUDA, "condense_dmma_kernel does not fit on an SM");
-  if (const char* cap = getenv("GHB_MAX_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(cap)));   // profiling knob
-  if (getenv("GHB_DEBUG")) fprintf(stderr, "condense_dmma<%d,%d>: %d CTAs/SM, %zu B smem\n", NI, NB, per_sm, smem);
+  GHB_TRY(kernel_setup(ctx, p.opt, kern, 128, smem, true, ks, "condense_dmma_kernel", &per_sm));
   DmmaTables tb{p.d_colbase, p.d_rowf, p.d_rowl, p.nfields, p.d_xoff};
   int64_t grid = std::min<int64_t>(ncells, (int64_t)ctx->sm_count * per_sm);
   kern<<<(unsigned)grid, 128, smem, ctx->stream>>>(tb, p.lenA, p.lenb, ncells, A, b, S, g, info);
@@ -1350,13 +1346,9 @@ static int launch_dmma_ll(ghb_ctx* ctx, const Plan& p, int64_t ncells, const dou
                           double* g, int32_t* info, double* X = nullptr) {
   auto kern = condense_dmma_ll_kernel<NI, NB, RPC, MINB, KEEPX>;
   const size_t smem = LLCfg<NI, NB>::smem_bytes(p.nfields);
-  GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  static KernelSetup ks;
   int per_sm = 0;
-  GHB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
-  if (per_sm < 1) return fail(ctx, GHB_ECUDA, "condense_dmma_ll_kernel does not fit on an SM");
-  if (const char* cap = getenv("GHB_MAX_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(cap)));   // profiling knob
-  if (getenv("GHB_DEBUG")) fprintf(stderr, "condense_dmma_ll<%d,%d>: %d CTAs/SM, %zu B smem\n", NI, NB, per_sm, smem);
+  GHB_TRY(kernel_setup(ctx, p.opt, kern, 128, smem, true, ks, "condense_dmma_ll_kernel", &per_sm));
   DmmaTables tb{p.d_colbase, p.d_rowf, p.d_rowl, p.nfields, p.d_xoff};
   int64_t grid = std::min<int64_t>(ncells, (int64_t)ctx->sm_count * per_sm);
   kern<<<(unsigned)grid, 128, smem, ctx->stream>>>(tb, p.lenA, p.lenb, ncells, A, b, S, g, info, X);
@@ -1367,9 +1359,7 @@ static int launch_dmma_ll(ghb_ctx* ctx, const Plan& p, int64_t ncells, const dou
 // kernel selection of the DMMA shapes: the left-looking kernel is faster on all three (profiles/r01_condense_ll.md);
 // GHB_DMMA_LL=0 forces the right-looking kernel (A/B runs, tools/ab_ll.py)
 static bool use_ll(const Plan& p) {
-  if (const char* e = getenv("GHB_DMMA_LL")) return e[0] == '1';
-  (void)p;
-  return true;
+  return p.opt.dmma_ll != 0;
 }
 
 template <int NI, int NB, int RPC>
@@ -1377,13 +1367,9 @@ static int launch_bdmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const doubl
                         const double* lam_free, const double* lam_dir, const int64_t* ids, double* u, int32_t* info) {
   auto kern = backsub_dmma_kernel<NI, NB, RPC>;
   const size_t smem = BackCfg<NI, NB>::smem_bytes(p.nfields);
-  GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  static KernelSetup ks;
   int per_sm = 0;
-  GHB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
-  if (per_sm < 1) return fail(ctx, GHB_ECUDA, "backsub_dmma_kernel does not fit on an SM");
-  if (const char* cap = getenv("GHB_MAX_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(cap)));   // profiling knob
-  if (getenv("GHB_DEBUG")) fprintf(stderr, "backsub_dmma<%d,%d>: %d CTAs/SM, %zu B smem\n", NI, NB, per_sm, smem);
+  GHB_TRY(kernel_setup(ctx, p.opt, kern, 128, smem, true, ks, "backsub_dmma_kernel", &per_sm));
   DmmaTables tb{p.d_colbase, p.d_rowf, p.d_rowl, p.nfields, p.d_xoff};
   int64_t grid = std::min<int64_t>(ncells, (int64_t)ctx->sm_count * per_sm);
   kern<<<(unsigned)grid, 128, smem, ctx->stream>>>(tb, p.lenA, p.lenb, ncells, A, b, lam_free, lam_dir, ids, u, info);
@@ -1407,8 +1393,7 @@ int launch_condense_dmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const doub
   }
   if (use_ll(p)) {
     if (p.n_i == 34) {
-      const char* e = getenv("GHB_LL_CTAS");           // tuning knob: register budget of the (34,36) instantiation
-      const int m = e ? atoi(e) : GHB_LL_MINB34;
+      const int m = p.opt.ll_ctas > 0 ? p.opt.ll_ctas : GHB_LL_MINB34;   // tuning knob: register budget of this instantiation
       if (m == 6) return launch_dmma_ll<34, 36, 2, 6>(ctx, p, ncells, A, b, S, g, info);
       if (m == 7) return launch_dmma_ll<34, 36, 2, 7>(ctx, p, ncells, A, b, S, g, info);
       return launch_dmma_ll<34, 36, 2, 8>(ctx, p, ncells, A, b, S, g, info);

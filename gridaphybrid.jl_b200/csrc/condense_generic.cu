@@ -231,7 +231,7 @@ int launch_condense_generic(ghb_ctx* ctx, const Plan& p, int64_t ncells, const d
   int64_t grid = std::min<int64_t>(ncells, (int64_t)ctx->sm_count * per_sm);
   double* scratch = nullptr;
   if (smem) {
-    GHB_CUDA(ctx, cudaFuncSetAttribute(condense_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wbytes));
+    GHB_SMEM_OPTIN(ctx, condense_generic_kernel<true>, wbytes);
     condense_generic_kernel<true><<<(unsigned)grid, kThreads, wbytes, ctx->stream>>>(p.dev(), ncells, A, b, S, g, info, X, nullptr, ld);
   } else {
     GHB_CUDA(ctx, cudaMallocAsync((void**)&scratch, wbytes * grid, ctx->stream));
@@ -252,7 +252,7 @@ int launch_backsub_generic(ghb_ctx* ctx, const Plan& p, int64_t ncells, const do
   int64_t grid = std::min<int64_t>(ncells, (int64_t)ctx->sm_count * per_sm);
   double* scratch = nullptr;
   if (smem) {
-    GHB_CUDA(ctx, cudaFuncSetAttribute(backsub_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wbytes));
+    GHB_SMEM_OPTIN(ctx, backsub_generic_kernel<true>, wbytes);
     backsub_generic_kernel<true><<<(unsigned)grid, kThreads, wbytes, ctx->stream>>>(p.dev(), ncells, A, b, lam_free, lam_dir, ids, u, info, nullptr, ld);
   } else {
     GHB_CUDA(ctx, cudaMallocAsync((void**)&scratch, wbytes * grid, ctx->stream));

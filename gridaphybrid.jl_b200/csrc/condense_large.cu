@@ -652,7 +652,7 @@ static int launch_large(ghb_ctx* ctx, const Plan& p, int64_t ncells, const doubl
   const int ld = ld_for_l(p.n_i);
   const size_t smem = large_smem_bytes(p, ld);
   auto kern = condense_large_kernel<MODE>;
-  GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GHB_SMEM_OPTIN(ctx, kern, smem);
   LargeTables tb{p.d_colbase, p.d_rowf, p.d_rowl, p.nfields};
   const int64_t grid = std::min<int64_t>(ncells, ctx->sm_count);
   kern<<<(unsigned)grid, kLT, smem, ctx->stream>>>(p.dev(), tb, ld, ncells, A, b, S, g, info, X, lam_free, lam_dir, ids, u);

@@ -349,13 +349,13 @@ int launch_condense_warp(ghb_ctx* ctx, const Plan& p, int64_t ncells, const doub
   // (7,8): two cells per warp, 932 -> 1537 M cells/s.  (16,8) with two rows per lane (R = 2, 168 registers, 3 blocks
   // per SM) measured 302 vs 364 M cells/s for the one-cell kernel, so it stays on the latter (GHB_WARP_TWO_ROWS=1 selects
   // the R = 2 variant for experiments).
-  if (p.n_i == 7 && p.n_b == 8 && !getenv("GHB_WARP_ONE_CELL")) {
+  if (p.n_i == 7 && p.n_b == 8 && !p.opt.warp_one_cell) {
     const int64_t blocks = std::min<int64_t>((ncells + 7) / 8, (int64_t)ctx->sm_count * 32);
     condense_warp2_kernel<7, 8, 1><<<(unsigned)blocks, 128, 0, ctx->stream>>>(p.dev(), ncells, A, b, S, g, info);
     GHB_LAUNCHED(ctx);
     return GHB_OK;
   }
-  if (p.n_i == 16 && p.n_b == 8 && getenv("GHB_WARP_TWO_ROWS")) {
+  if (p.n_i == 16 && p.n_b == 8 && p.opt.warp_two_rows) {
     const int64_t blocks = std::min<int64_t>((ncells + 7) / 8, (int64_t)ctx->sm_count * 32);
     condense_warp2_kernel<16, 8, 2><<<(unsigned)blocks, 128, 0, ctx->stream>>>(p.dev(), ncells, A, b, S, g, info);
     GHB_LAUNCHED(ctx);
@@ -368,7 +368,7 @@ int launch_condense_warp(ghb_ctx* ctx, const Plan& p, int64_t ncells, const doub
 
 int launch_backsub_warp(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b,
                         const double* lam_free, const double* lam_dir, const int64_t* ids, double* u, int32_t* info) {
-  if (!getenv("GHB_WARP_ONE_CELL")) {
+  if (!p.opt.warp_one_cell) {
     const int64_t blocks = std::min<int64_t>((ncells + 7) / 8, (int64_t)ctx->sm_count * 32);
     if (p.n_i == 7 && p.n_b == 8)
       backsub_warp2_kernel<7, 8><<<(unsigned)blocks, 128, 0, ctx->stream>>>(p.dev(), ncells, A, b, lam_free, lam_dir, ids, u, info);

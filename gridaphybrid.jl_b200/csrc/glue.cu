@@ -259,7 +259,7 @@ int launch_transpose_blocks(ghb_ctx* ctx, int64_t ncells, int n, double* S) {
   const size_t smem = (size_t)n * (n + 1) * sizeof(double);
   const int64_t grid = std::min<int64_t>(ncells, (int64_t)ctx->sm_count * 8);
   if (smem <= ctx->smem_optin) {
-    GHB_CUDA(ctx, cudaFuncSetAttribute(transpose_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GHB_SMEM_OPTIN(ctx, transpose_blocks_kernel, smem);
     transpose_blocks_kernel<<<(unsigned)grid, 256, smem, ctx->stream>>>(ncells, n, S);
   } else {
     transpose_blocks_swap_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(ncells, n, S);
