@@ -19,11 +19,14 @@ if os.environ.get("GHB_LIB_PATH"):      # A/B builds of the same sources with ot
     SO_PATH = os.path.abspath(os.environ["GHB_LIB_PATH"])
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared", "-ldl"]
 
 # every symbol include/ghb.h declares (tests check the library exports each one)
 SYMBOLS = [
     "ghb_create", "ghb_destroy", "ghb_last_error", "ghb_set_stream", "ghb_synchronize", "ghb_launch_count",
+    "ghb_set_option", "ghb_device_alloc", "ghb_device_free", "ghb_copy", "ghb_factors_generation",
+    "ghb_assemble_current", "ghb_assemble_select", "ghb_assemble_release",
+    "ghb_comm_unique_id", "ghb_comm_init", "ghb_comm_destroy", "ghb_exchange_cut_plane_f64", "ghb_allgather_lambda_f64",
     "ghb_plan_kernel_name", "ghb_plan_blocks", "ghb_plan_query", "ghb_condense_f64",
     "ghb_restrict_facet_dofs_i64", "ghb_sum_facets_f64", "ghb_expand_records_f64", "ghb_l2_projection_dofs_f64", "ghb_assemble_symbolic", "ghb_assemble_pattern", "ghb_assemble_numeric_f64", "ghb_assemble_numeric_csr_f64",
     "ghb_assemble_symbolic_slab", "ghb_pack_cut_plane_f64", "ghb_assemble_numeric_slab_f64",
@@ -46,12 +49,26 @@ def sources():
     return sorted(glob.glob(os.path.join(_CSRC, "*.cu")))
 
 
+def _source_hash() -> str:
+    """content hash of every source the library is built from plus the build flags (mtimes do not survive a copy of
+    the tree to another box; the hash does)"""
+    import hashlib
+    h = hashlib.sha256((" ".join(NVCC_FLAGS) + "|" + os.environ.get("GHB_NVCC_EXTRA", "")).encode())
+    for d in sources() + sorted(glob.glob(os.path.join(_CSRC, "*.cuh"))) + [os.path.join(_ROOT, "include", "ghb.h")]:
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
+    """True if the library is missing or was built from other sources / flags (hash kept next to the .so)."""
     if not os.path.exists(SO_PATH):
         return True
-    t = os.path.getmtime(SO_PATH)
-    deps = sources() + glob.glob(os.path.join(_CSRC, "*.cuh")) + [os.path.join(_ROOT, "include", "ghb.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    try:
+        with open(SO_PATH + ".srchash") as f:
+            return f.read().strip() != _source_hash()
+    except OSError:
+        return True
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -66,6 +83,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
         if verbose:
             print(res.stderr)
+        with open(SO_PATH + ".srchash", "w") as f:
+            f.write(_source_hash())
     return SO_PATH
 
 
@@ -76,7 +95,7 @@ def lib():
     global _LIB
     if _LIB is not None:
         return _LIB
-    if not os.path.exists(SO_PATH):
+    if needs_build():     # missing, or edited sources: never run a stale library
         build()
     L = ctypes.CDLL(SO_PATH)
     vp, i32, i64, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint64
@@ -100,13 +119,27 @@ def lib():
     L.ghb_expand_records_f64.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp, vp]
     L.ghb_assemble_symbolic.argtypes = [vp, i64, i32, vp, i64, ctypes.POINTER(i64)]
     L.ghb_assemble_pattern.argtypes = [vp, vp, vp]
-    L.ghb_assemble_numeric_f64.argtypes = [vp, vp, vp, vp, vp, vp]
-    L.ghb_assemble_numeric_csr_f64.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.ghb_assemble_numeric_f64.argtypes = [vp, vp, vp, vp, i64, vp, vp]
+    L.ghb_assemble_numeric_csr_f64.argtypes = [vp, vp, vp, vp, i64, vp, vp]
+    L.ghb_set_option.argtypes = [vp, ctypes.c_char_p, i64]
+    L.ghb_device_alloc.argtypes = [vp, i64, ctypes.POINTER(vp)]
+    L.ghb_device_free.argtypes = [vp, vp]
+    L.ghb_copy.argtypes = [vp, vp, vp, i64]
+    L.ghb_factors_generation.argtypes = [vp]
+    L.ghb_factors_generation.restype = i64
+    L.ghb_assemble_current.argtypes = [vp]
+    L.ghb_assemble_select.argtypes = [vp, i32]
+    L.ghb_assemble_release.argtypes = [vp, i32]
+    L.ghb_comm_unique_id.argtypes = [vp, vp]
+    L.ghb_comm_init.argtypes = [vp, i32, i32, vp]
+    L.ghb_comm_destroy.argtypes = [vp]
+    L.ghb_exchange_cut_plane_f64.argtypes = [vp, vp, i64, vp, i64]
+    L.ghb_allgather_lambda_f64.argtypes = [vp, vp, vp, vp]
     L.ghb_assemble_symbolic_slab.argtypes = [vp, i64, i64, i32, i32, vp, i64, i64, i64, ctypes.POINTER(i64)]
     L.ghb_pack_cut_plane_f64.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp, vp]
     L.ghb_assemble_numeric_slab_f64.argtypes = [vp, vp, vp, vp, vp, vp, vp]
-    L.ghb_condense_assemble_f64.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, vp]
-    L.ghb_backsub_f64.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, vp, vp]
+    L.ghb_condense_assemble_f64.argtypes = [vp, i32, i64, vp, vp, vp, i64, vp, vp, vp]
+    L.ghb_backsub_f64.argtypes = [vp, i32, i64, vp, vp, vp, i64, vp, i64, vp, vp, vp]
     L.ghb_scatter_free_dof_values.argtypes = [vp, i32, i64, vp, vp, i64, vp]
     L.ghb_synth_fill_f64.argtypes = [vp, i32, i64, i64, u64, vp, vp]
     L.ghb_cartesian_cell_wise_facets.argtypes = [vp, i32, vp, i64, i64, vp]

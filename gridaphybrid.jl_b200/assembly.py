@@ -40,12 +40,19 @@ class SparseMatrixAssembler:
         self.cell_ids = trial.cell_dof_ids()
         self.nrows = trial.num_free_dofs
         self._pattern = None
+        self._pid = -1            # handle of this assembler's symbolic pattern inside the Context
+
+    def select(self):
+        """make this assembler's pattern the selected one of the Context (other assemblers may share it)"""
+        self.symbolic()
+        self.ctx.assemble_select(self._pid)
 
     def symbolic(self):
         if self._pattern is None:
             ncells, n_b = self.cell_ids.shape
             self.ctx.use_torch_stream()
             nnz = self.ctx.assemble_symbolic(ncells, n_b, self.cell_ids, self.nrows)
+            self._pid = self.ctx.assemble_current()
             dev = self.cell_ids.device
             colptr = torch.empty(self.nrows + 1, dtype=torch.int64, device=dev)
             rowval = torch.empty(nnz, dtype=torch.int64, device=dev)
@@ -70,6 +77,8 @@ def assemble_matrix_and_vector(assem: SparseMatrixAssembler, data, dirichlet_val
     nzval = torch.empty(nnz, dtype=torch.float64, device=dev)
     rhs = torch.empty(assem.nrows, dtype=torch.float64, device=dev)
     assem.ctx.use_torch_stream()
+    assem.select()
+    assert data.S.numel() == assem.cell_ids.shape[0] * assem.cell_ids.shape[1] ** 2, "S does not match the assembler's cells"
     assem.ctx.assemble_numeric(data.S, data.g, dirichlet_values, nzval, rhs)
     return SparseMatrixCSC(assem.nrows, assem.nrows, colptr, rowval, nzval), rhs
 
@@ -100,6 +109,8 @@ def assemble_matrix_and_vector_csr(assem: SparseMatrixAssembler, data, dirichlet
     nzval = torch.empty(nnz, dtype=torch.float64, device=dev)
     rhs = torch.empty(assem.nrows, dtype=torch.float64, device=dev)
     assem.ctx.use_torch_stream()
+    assem.select()
+    assert data.S.numel() == assem.cell_ids.shape[0] * assem.cell_ids.shape[1] ** 2, "S does not match the assembler's cells"
     assem.ctx.assemble_numeric_csr(data.S, data.g, dirichlet_values, nzval, rhs)
     return SparseMatrixCSR(assem.nrows, assem.nrows, colptr, rowval, nzval), rhs
 
@@ -115,5 +126,6 @@ def condense_and_assemble(assem: SparseMatrixAssembler, plan, cells, dirichlet_v
     if rhs is None:
         rhs = torch.empty(assem.nrows, dtype=torch.float64, device=dev)
     assem.ctx.use_torch_stream()
+    assem.select()
     assem.ctx.condense_assemble(plan, len(cells), cells.A, cells.b, dirichlet_values, nzval, rhs, info)
     return SparseMatrixCSC(assem.nrows, assem.nrows, colptr, rowval, nzval), rhs

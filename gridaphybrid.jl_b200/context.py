@@ -18,6 +18,10 @@ except Exception:  # pragma: no cover
     torch = None
 
 
+def _len(x):
+    return 0 if x is None else int(x.numel() if hasattr(x, "numel") else x.size)
+
+
 def _ptr(x, dtype=None, count=None, name="array"):
     if x is None:
         return None
@@ -68,6 +72,7 @@ class Context:
             raise GhbError(rc, "ghb_create failed")
         self._h = h
         self.device = int(device)
+        self._asm_shapes = {}
         if torch is not None and torch.cuda.is_available():
             self.use_torch_stream()   # stream-ordered with the caller's torch work from the start
 
@@ -98,6 +103,11 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self._L.ghb_launch_count(self._h))
+
+    def set_option(self, name: str, value: int):
+        """debugging / A-B knobs (ghb_set_option): "cw", "dmma_ll", "force_generic", "factors_generic",
+        "max_ctas_per_sm", "stream_chunk_bytes", ...; kernel-choice knobs act on plans created afterwards"""
+        self._check(self._L.ghb_set_option(self._h, name.encode(), int(value)))
 
     # ---- plans ----------------------------------------------------------------------------
     def plan_blocks(self, ndofs, touched, interior_fields, boundary_fields) -> BlockPlan:
@@ -153,7 +163,20 @@ class Context:
                                                   _ptr(cell_ids, np.int64, ncells * n_b, "cell_ids"), int(nrows),
                                                   ctypes.byref(nnz)))
         self._asm_shape = (int(nrows), int(nnz.value))
+        self._asm_shapes[self.assemble_current()] = self._asm_shape
         return int(nnz.value)
+
+    def assemble_current(self) -> int:
+        """handle of the selected symbolic pattern (every symbolic call creates and selects a new one)"""
+        return int(self._L.ghb_assemble_current(self._h))
+
+    def assemble_select(self, pattern_id: int):
+        self._check(self._L.ghb_assemble_select(self._h, int(pattern_id)))
+        self._asm_shape = self._asm_shapes[int(pattern_id)]
+
+    def assemble_release(self, pattern_id: int):
+        self._check(self._L.ghb_assemble_release(self._h, int(pattern_id)))
+        self._asm_shapes.pop(int(pattern_id), None)
 
     def assemble_pattern(self, colptr, rowval):
         nrows, nnz = self._asm_shape
@@ -163,7 +186,7 @@ class Context:
     def assemble_numeric(self, S, g, dirichlet_vals, nzval, rhs):
         nrows, nnz = self._asm_shape
         self._check(self._L.ghb_assemble_numeric_f64(self._h, _ptr(S, np.float64), _ptr(g, np.float64),
-                                                     _ptr(dirichlet_vals, np.float64),
+                                                     _ptr(dirichlet_vals, np.float64), _len(dirichlet_vals),
                                                      _ptr(nzval, np.float64, nnz, "nzval"),
                                                      _ptr(rhs, np.float64, nrows, "rhs")))
 
@@ -172,7 +195,7 @@ class Context:
         cell blocks of the device array `S` in place."""
         nrows, nnz = self._asm_shape
         self._check(self._L.ghb_assemble_numeric_csr_f64(self._h, _ptr(S, np.float64), _ptr(g, np.float64),
-                                                         _ptr(dirichlet_vals, np.float64),
+                                                         _ptr(dirichlet_vals, np.float64), _len(dirichlet_vals),
                                                          _ptr(nzval, np.float64, nnz, "nzval"),
                                                          _ptr(rhs, np.float64, nrows, "rhs")))
 
@@ -184,6 +207,7 @@ class Context:
             _ptr(cell_ids, np.int64, (ncells_local + nghost) * n_b, "cell_ids"), int(nrows_global), int(col_begin),
             int(col_end), ctypes.byref(nnz)))
         self._asm_shape = (int(col_end - col_begin), int(nnz.value))
+        self._asm_shapes[self.assemble_current()] = self._asm_shape
         return int(nnz.value)
 
     def pack_cut_plane(self, ncut, n_b, ncols, S, g, cell_ids, dirichlet_vals, out):
@@ -203,15 +227,16 @@ class Context:
         nrows, nnz = self._asm_shape
         self._check(self._L.ghb_condense_assemble_f64(
             self._h, plan.id, int(ncells), _ptr(A, np.float64, ncells * plan.lenA, "A"),
-            _ptr(b, np.float64, ncells * plan.lenb, "b"), _ptr(dirichlet_vals, np.float64),
+            _ptr(b, np.float64, ncells * plan.lenb, "b"), _ptr(dirichlet_vals, np.float64), _len(dirichlet_vals),
             _ptr(nzval, np.float64, nnz, "nzval"), _ptr(rhs, np.float64, nrows, "rhs"),
             _ptr(info, np.int32, ncells, "info")))
 
     def backsub(self, plan, ncells, A, b, lambda_free, lambda_dirichlet, cell_ids, u, info=None):
         self._check(self._L.ghb_backsub_f64(
             self._h, plan.id, int(ncells), _ptr(A, np.float64, ncells * plan.lenA, "A"),
-            _ptr(b, np.float64, ncells * plan.lenb, "b"), _ptr(lambda_free, np.float64),
-            _ptr(lambda_dirichlet, np.float64), _ptr(cell_ids, np.int64, ncells * plan.n_b, "cell_ids"),
+            _ptr(b, np.float64, ncells * plan.lenb, "b"), _ptr(lambda_free, np.float64), _len(lambda_free),
+            _ptr(lambda_dirichlet, np.float64), _len(lambda_dirichlet),
+            _ptr(cell_ids, np.int64, ncells * plan.n_b, "cell_ids"),
             _ptr(u, np.float64, ncells * plan.n_i, "u"), _ptr(info, np.int32, ncells, "info")))
 
     def scatter_free_dof_values(self, plan, ncells, u, lambda_free, x):
@@ -219,6 +244,41 @@ class Context:
         self._check(self._L.ghb_scatter_free_dof_values(
             self._h, plan.id, int(ncells), _ptr(u, np.float64, ncells * plan.n_i, "u"),
             _ptr(lambda_free, np.float64), int(nl), _ptr(x, np.float64, ncells * plan.n_i + nl, "x")))
+
+    @property
+    def factors_generation(self) -> int:
+        return int(self._L.ghb_factors_generation(self._h))
+
+    # ---- multi-GPU exchanges behind the C ABI (csrc/comm.cu) -------------------------------------
+    def comm_unique_id(self) -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        self._check(self._L.ghb_comm_unique_id(self._h, buf))
+        return buf.raw
+
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        assert len(unique_id) == 128
+        self._check(self._L.ghb_comm_init(self._h, int(nranks), int(rank), ctypes.create_string_buffer(unique_id, 128)))
+        self.comm_rank, self.comm_size = int(rank), int(nranks)
+
+    def comm_init_from_torch(self, group=None):
+        """ship rank 0's ncclUniqueId through torch.distributed (plumbing only) and create the communicator"""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [self.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        self.comm_init(world, rank, box[0])
+
+    def comm_destroy(self):
+        self._check(self._L.ghb_comm_destroy(self._h))
+
+    def exchange_cut_plane(self, send_down, recv_from_up):
+        self._check(self._L.ghb_exchange_cut_plane_f64(self._h, _ptr(send_down, np.float64), _len(send_down),
+                                                       _ptr(recv_from_up, np.float64), _len(recv_from_up)))
+
+    def allgather_lambda(self, owned, counts, out):
+        c = np.ascontiguousarray(counts, dtype=np.int64)
+        self._check(self._L.ghb_allgather_lambda_f64(self._h, _ptr(owned, np.float64), _ptr(c),
+                                                     _ptr(out, np.float64, int(c.sum()), "all")))
 
     # ---- synthetic workload -------------------------------------------------------------------
     def synth_fill(self, plan, cell_start, ncells, A, b, seed=20261017):

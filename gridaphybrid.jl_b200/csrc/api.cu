@@ -2,6 +2,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
 
 #include "common.cuh"
 
@@ -19,13 +20,67 @@ bool is_device_ptr(const void* p) {
   return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
+// true for cudaHostAlloc'ed / cudaHostRegister'ed memory; false for pageable host memory
+static bool is_pinned_host_ptr(const void* p) {
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
+// pageable -> pinned staging copy on a few host threads (one memcpy stream does not reach the PCIe rate)
+static void host_copy_parallel(void* dst, const void* src, size_t bytes) {
+  unsigned nt = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+  if (bytes < ((size_t)8 << 20)) nt = 1;
+  if (nt == 1) { memcpy(dst, src, bytes); return; }
+  std::vector<std::thread> th;
+  const size_t per = ((bytes / nt) + 4095) & ~(size_t)4095;
+  for (unsigned i = 0; i < nt; ++i) {
+    const size_t o = std::min(bytes, (size_t)i * per), n = std::min(per, bytes - o);
+    if (n) th.emplace_back([=] { memcpy(static_cast<char*>(dst) + o, static_cast<const char*>(src) + o, n); });
+  }
+  for (auto& t : th) t.join();
+}
+
 int launch_condense(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
                     double* g, int32_t* info, double* X) {
+  if (X && ctx->opt.factors_generic) return launch_condense_generic(ctx, p, ncells, A, b, S, g, info, X);   // A/B knob
   if (p.use_cw) return launch_condense_cw(ctx, p, ncells, A, b, S, g, info, X);
-  if (p.use_dmma && !getenv("GHB_FACTORS_GENERIC")) return launch_condense_dmma(ctx, p, ncells, A, b, S, g, info, X);
+  if (p.use_dmma) return launch_condense_dmma(ctx, p, ncells, A, b, S, g, info, X);
   if (p.use_warp && X == nullptr) return launch_condense_warp(ctx, p, ncells, A, b, S, g, info);
   if (p.use_large) return launch_condense_large(ctx, p, ncells, A, b, S, g, info, X);
   return launch_condense_generic(ctx, p, ncells, A, b, S, g, info, X);
+}
+
+static int64_t env_i64(const char* name, int64_t dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoll(e) : dflt;
+}
+
+// the only place the environment is read: once per context
+static void options_from_env(Options& o) {
+  o.force_generic = (int)env_i64("GHB_FORCE_GENERIC", o.force_generic);
+  o.cw = (int)env_i64("GHB_CW", o.cw);
+  o.dmma_ll = (int)env_i64("GHB_DMMA_LL", o.dmma_ll);
+  o.factors_generic = (int)env_i64("GHB_FACTORS_GENERIC", o.factors_generic);
+  o.max_ctas_per_sm = (int)env_i64("GHB_MAX_CTAS_PER_SM", o.max_ctas_per_sm);
+  o.ll_ctas = (int)env_i64("GHB_LL_CTAS", o.ll_ctas);
+  o.warp_one_cell = (int)env_i64("GHB_WARP_ONE_CELL", o.warp_one_cell);
+  o.warp_two_rows = (int)env_i64("GHB_WARP_TWO_ROWS", o.warp_two_rows);
+  o.debug = (int)env_i64("GHB_DEBUG", o.debug);
+  o.stream_chunk_bytes = std::max<int64_t>(1, env_i64("GHB_STREAM_CHUNK_BYTES", o.stream_chunk_bytes));
+}
+
+// ---- symbolic patterns are handles: ctx->as is the SELECTED pattern, the others wait in ctx->as_store -------------------
+static void asm_stash(ghb_ctx* ctx) {
+  if (ctx->as_id >= 0) { ctx->as_store[ctx->as_id] = ctx->as; ctx->as = AsmState(); ctx->as_id = -1; }
+}
+static int asm_new(ghb_ctx* ctx) {
+  asm_stash(ctx);
+  ctx->as_store.emplace_back();
+  ctx->as_id = (int)ctx->as_store.size() - 1;
+  ctx->as = AsmState();
+  return ctx->as_id;
 }
 
 static Plan* get_plan(ghb_ctx* ctx, int id) {
@@ -52,6 +107,7 @@ int ghb_create(int device_id, ghb_ctx** out) {
   if (cudaSetDevice(device_id) != cudaSuccess) { delete ctx; return GHB_ECUDA; }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) { delete ctx; return GHB_ECUDA; }
+  options_from_env(ctx->opt);
   ctx->sm_count = prop.multiProcessorCount;
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return GHB_ECUDA; }
@@ -79,9 +135,11 @@ void ghb_destroy(ghb_ctx* ctx) {
     delete p;
   }
   asm_free(ctx);
+  for (AsmState& st : ctx->as_store) { ctx->as = st; asm_free(ctx); }
   if (ctx->fac.d_X) cudaFree(ctx->fac.d_X);
   for (int i = 0; i < 2; ++i)
     if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
+  if (ctx->comm) comm_free(ctx);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
@@ -90,6 +148,26 @@ void ghb_destroy(ghb_ctx* ctx) {
 
 const char* ghb_last_error(const ghb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 
+int ghb_set_option(ghb_ctx* ctx, const char* name, int64_t value) {
+  if (!ctx || !name) return GHB_EINVAL;
+  Options& o = ctx->opt;
+  const std::string n(name);
+  if (n == "force_generic") o.force_generic = (int)value;
+  else if (n == "cw") o.cw = (int)value;
+  else if (n == "dmma_ll") o.dmma_ll = (int)value;
+  else if (n == "factors_generic") o.factors_generic = (int)value;
+  else if (n == "max_ctas_per_sm") o.max_ctas_per_sm = (int)value;
+  else if (n == "ll_ctas") o.ll_ctas = (int)value;
+  else if (n == "warp_one_cell") o.warp_one_cell = (int)value;
+  else if (n == "warp_two_rows") o.warp_two_rows = (int)value;
+  else if (n == "debug") o.debug = (int)value;
+  else if (n == "stream_chunk_bytes") o.stream_chunk_bytes = std::max<int64_t>(1, value);
+  else return fail(ctx, GHB_EINVAL, "ghb_set_option: unknown option " + n);
+  for (Plan* p : ctx->plans)          // launch-time knobs follow; the kernel choice of existing plans does not change
+    if (p) { p->opt.max_ctas_per_sm = o.max_ctas_per_sm; p->opt.debug = o.debug; p->opt.dmma_ll = o.dmma_ll; p->opt.ll_ctas = o.ll_ctas; }
+  return GHB_OK;
+}
+
 int ghb_set_stream(ghb_ctx* ctx, void* s) {
   if (!ctx) return GHB_EINVAL;
   cudaSetDevice(ctx->device);
@@ -97,6 +175,35 @@ int ghb_set_stream(ghb_ctx* ctx, void* s) {
   // NULL is a valid handle: the legacy default stream (what torch uses unless told otherwise)
   ctx->stream = (cudaStream_t)s;
   ctx->own_stream = false;
+  return GHB_OK;
+}
+
+/* device buffers for hosts without a CUDA array library of their own (the Julia glue keeps S_K, g_K and the CSC values
+   on the device between the call sites instead of round-tripping them through host memory) */
+int ghb_device_alloc(ghb_ctx* ctx, int64_t bytes, void** out) {
+  if (!ctx || !out || bytes < 0) return GHB_EINVAL;
+  *out = nullptr;
+  if (bytes == 0) return GHB_OK;
+  cudaSetDevice(ctx->device);
+  if (cudaMalloc(out, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); return fail(ctx, GHB_ENOMEM, "ghb_device_alloc"); }
+  return GHB_OK;
+}
+
+int ghb_device_free(ghb_ctx* ctx, void* ptr) {
+  if (!ctx) return GHB_EINVAL;
+  if (!ptr) return GHB_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  GHB_CUDA(ctx, cudaFree(ptr));
+  return GHB_OK;
+}
+
+int ghb_copy(ghb_ctx* ctx, void* dst, const void* src, int64_t bytes) {
+  if (!ctx || bytes < 0 || (bytes > 0 && (!dst || !src))) return GHB_EINVAL;
+  if (bytes == 0) return GHB_OK;
+  cudaSetDevice(ctx->device);
+  GHB_CUDA(ctx, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, ctx->stream));
+  GHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return GHB_OK;
 }
 
@@ -179,24 +286,24 @@ int ghb_plan_blocks(ghb_ctx* ctx, int nfields, const int32_t* ndofs, const uint8
   cudaSetDevice(ctx->device);
   if (cudaMalloc((void**)&p->d_emap, emap.size() * sizeof(int32_t)) != cudaSuccess) { delete p; return fail(ctx, GHB_ENOMEM, "emap alloc"); }
   cudaMemcpy(p->d_emap, emap.data(), emap.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
-  const char* force = getenv("GHB_FORCE_GENERIC");
-  if (dmma_supported(*p) && !(force && force[0] == '1')) {
+  p->opt = ctx->opt;
+  const bool force = ctx->opt.force_generic != 0;
+  if (dmma_supported(*p) && !force) {
     int rc = dmma_prepare(ctx, *p);
     if (rc != GHB_OK) { cudaFree(p->d_emap); delete p; return rc; }
     p->use_dmma = true;
-  } else if (warp_kernel_name(*p) && !(force && force[0] == '1')) {
+  } else if (warp_kernel_name(*p) && !force) {
     p->use_warp = true;
     p->kernel_name = warp_kernel_name(*p);
-  } else if (large_supported(ctx, *p) && !(force && force[0] == '1')) {
+  } else if (large_supported(ctx, *p) && !force) {
     int rc = dmma_prepare(ctx, *p);      // same re-layout tables
     if (rc != GHB_OK) { cudaFree(p->d_emap); delete p; return rc; }
     p->use_large = true;
     p->kernel_name = "large_dmma";
   }
-  // the one-warp-per-cell kernel takes the condensation of the shapes it is instantiated for (GHB_CW=0: A/B runs
-  // against the 4-warps-per-cell kernels, read once here)
-  const char* cwenv = getenv("GHB_CW");
-  if (cw_supported(*p) && !(force && force[0] == '1') && !(cwenv && cwenv[0] == '0')) {
+  // the one-warp-per-cell kernel takes the condensation of the shapes it is instantiated for (option cw = 0: A/B runs
+  // against the 4-warps-per-cell kernels)
+  if (cw_supported(*p) && !force && ctx->opt.cw) {
     int rc = cw_prepare(ctx, *p);
     if (rc != GHB_OK) { cudaFree(p->d_emap); delete p; return rc; }
     p->use_cw = true;
@@ -223,16 +330,21 @@ int ghb_condense_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A,
   if (!A || !b || !S || !g) return fail(ctx, GHB_EINVAL, "ghb_condense_f64: null array");
   cudaSetDevice(ctx->device);
   double* X = nullptr;
+  int32_t* finfo = nullptr;
   if (keep_factors) {
-    size_t need = (size_t)ncells * p->n_i * (p->n_b + 1) * sizeof(double);
+    // factor storage X = A11^-1 [A12 | b1] plus the info[] of this condensation (ghb_backsub_f64 with A = b = NULL reports
+    // it: a singular cell has NaN factors); `generation` lets a caller check that the factors are still its own
+    size_t need = (size_t)ncells * p->n_i * (p->n_b + 1) * sizeof(double) + (size_t)ncells * sizeof(int32_t);
     if (ctx->fac.bytes < need) {
       if (ctx->fac.d_X) cudaFree(ctx->fac.d_X);
       ctx->fac.d_X = nullptr; ctx->fac.bytes = 0;
       if (cudaMalloc((void**)&ctx->fac.d_X, need) != cudaSuccess) { cudaGetLastError(); return fail(ctx, GHB_ENOMEM, "factor storage"); }
       ctx->fac.bytes = need;
     }
-    ctx->fac.plan_id = plan_id; ctx->fac.ncells = ncells;
+    ctx->fac.plan_id = plan_id; ctx->fac.ncells = ncells; ctx->fac.generation++;
+    ctx->fac.d_info = reinterpret_cast<int32_t*>(ctx->fac.d_X + (size_t)ncells * p->n_i * (p->n_b + 1));
     X = ctx->fac.d_X;
+    finfo = ctx->fac.d_info;
   } else {
     ctx->fac.plan_id = -1;
   }
@@ -241,10 +353,14 @@ int ghb_condense_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A,
   Arg<double> dS(ctx, S, (size_t)ncells * p->n_b * p->n_b, false, true); GHB_TRY(dS.rc);
   Arg<double> dg(ctx, g, (size_t)ncells * p->n_b, false, true); GHB_TRY(dg.rc);
   Arg<int32_t> di(ctx, info, info ? (size_t)ncells : 0, false, true); GHB_TRY(di.rc);
-  GHB_TRY(launch_condense(ctx, *p, ncells, dA.dev, db.dev, dS.dev, dg.dev, di.dev, X));
+  GHB_TRY(launch_condense(ctx, *p, ncells, dA.dev, db.dev, dS.dev, dg.dev, finfo ? finfo : di.dev, X));
+  if (finfo && di.dev)
+    GHB_CUDA(ctx, cudaMemcpyAsync(di.dev, finfo, (size_t)ncells * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
   GHB_TRY(dS.finish()); GHB_TRY(dg.finish()); GHB_TRY(di.finish());
   return GHB_OK;
 }
+
+int64_t ghb_factors_generation(const ghb_ctx* ctx) { return (ctx && ctx->fac.plan_id >= 0) ? (int64_t)ctx->fac.generation : -1; }
 
 int ghb_restrict_facet_dofs_i64(ghb_ctx* ctx, int64_t ncells, int nlfacets, int ndofs_f,
                                 const int64_t* cell_wise_facets, const int64_t* facet_data, int64_t* out) {
@@ -311,7 +427,7 @@ int ghb_assemble_symbolic(ghb_ctx* ctx, int64_t ncells, int n_b, const int64_t* 
   if (ncells <= 0 || n_b <= 0 || n_b > 255 || !cell_ids || nrows <= 0)
     return fail(ctx, GHB_EINVAL, "ghb_assemble_symbolic: bad argument (need ncells>0, 0<n_b<=255, nrows>0)");
   cudaSetDevice(ctx->device);
-  asm_free(ctx);
+  asm_new(ctx);
   size_t cnt = (size_t)ncells * n_b;
   GHB_CUDA(ctx, cudaMalloc((void**)&ctx->as.d_ids, cnt * sizeof(int64_t)));
   GHB_CUDA(ctx, cudaMemcpyAsync(ctx->as.d_ids, cell_ids, cnt * sizeof(int64_t),
@@ -331,7 +447,7 @@ int ghb_assemble_symbolic_slab(ghb_ctx* ctx, int64_t ncells_local, int64_t nghos
     return fail(ctx, GHB_EINVAL, "ghb_assemble_symbolic_slab: bad argument");
   if (col_end == col_begin) return fail(ctx, GHB_EINVAL, "ghb_assemble_symbolic_slab: empty owned column range");
   cudaSetDevice(ctx->device);
-  asm_free(ctx);
+  asm_new(ctx);
   size_t cnt = (size_t)(ncells_local + nghost) * n_b;
   GHB_CUDA(ctx, cudaMalloc((void**)&ctx->as.d_ids, cnt * sizeof(int64_t)));
   GHB_CUDA(ctx, cudaMemcpyAsync(ctx->as.d_ids, cell_ids, cnt * sizeof(int64_t),
@@ -368,6 +484,34 @@ int ghb_assemble_numeric_slab_f64(ghb_ctx* ctx, const double* S, const double* g
   return asm_numeric(ctx, S, g, ghost, dirichlet_vals, nzval, rhs);
 }
 
+int ghb_assemble_current(const ghb_ctx* ctx) { return ctx ? ctx->as_id : -1; }
+
+int ghb_assemble_select(ghb_ctx* ctx, int pattern_id) {
+  if (!ctx) return GHB_EINVAL;
+  if (pattern_id < 0 || pattern_id >= (int)ctx->as_store.size()) return fail(ctx, GHB_EINVAL, "ghb_assemble_select: bad pattern id");
+  if (pattern_id == ctx->as_id) return GHB_OK;
+  if (!ctx->as_store[pattern_id].valid) return fail(ctx, GHB_ESTATE, "ghb_assemble_select: the pattern was released or its symbolic phase failed");
+  asm_stash(ctx);
+  ctx->as = ctx->as_store[pattern_id];
+  ctx->as_store[pattern_id] = AsmState();
+  ctx->as_id = pattern_id;
+  return GHB_OK;
+}
+
+int ghb_assemble_release(ghb_ctx* ctx, int pattern_id) {
+  if (!ctx) return GHB_EINVAL;
+  if (pattern_id < 0 || pattern_id >= (int)ctx->as_store.size()) return fail(ctx, GHB_EINVAL, "ghb_assemble_release: bad pattern id");
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (pattern_id == ctx->as_id) { asm_free(ctx); ctx->as_id = -1; return GHB_OK; }
+  AsmState keep = ctx->as;
+  ctx->as = ctx->as_store[pattern_id];
+  asm_free(ctx);
+  ctx->as_store[pattern_id] = AsmState();
+  ctx->as = keep;
+  return GHB_OK;
+}
+
 int ghb_assemble_pattern(ghb_ctx* ctx, int64_t* colptr, int64_t* rowval) {
   if (!ctx) return GHB_EINVAL;
   if (!ctx->as.valid) return fail(ctx, GHB_ESTATE, "ghb_assemble_pattern: no symbolic phase cached");
@@ -381,48 +525,49 @@ int ghb_assemble_pattern(ghb_ctx* ctx, int64_t* colptr, int64_t* rowval) {
 }
 
 int ghb_assemble_numeric_f64(ghb_ctx* ctx, const double* S, const double* g, const double* dirichlet_vals,
-                             double* nzval, double* rhs) {
+                             int64_t ndirichlet, double* nzval, double* rhs) {
   if (!ctx) return GHB_EINVAL;
   if (!ctx->as.valid) return fail(ctx, GHB_ESTATE, "ghb_assemble_numeric_f64: call ghb_assemble_symbolic first");
   if (ctx->as.nghost) return fail(ctx, GHB_ESTATE, "ghb_assemble_numeric_f64: the cached pattern has ghost cells; use ghb_assemble_numeric_slab_f64");
   if (!S || !g || !nzval || !rhs) return fail(ctx, GHB_EINVAL, "ghb_assemble_numeric_f64: null array");
   cudaSetDevice(ctx->device);
   const AsmState& as = ctx->as;
-  if (dirichlet_vals && !is_device_ptr(dirichlet_vals))
-    return fail(ctx, GHB_EUNSUPPORTED, "ghb_assemble_numeric_f64: dirichlet_vals must be a device pointer (its length is not passed)");
+  if (ndirichlet < 0) return fail(ctx, GHB_EINVAL, "ghb_assemble_numeric_f64: ndirichlet < 0");
+  Arg<double> dd(ctx, dirichlet_vals, dirichlet_vals ? (size_t)ndirichlet : 0, true, false); GHB_TRY(dd.rc);
   Arg<double> dS(ctx, S, (size_t)as.ncells * as.n_b * as.n_b, true, false); GHB_TRY(dS.rc);
   Arg<double> dg(ctx, g, (size_t)as.ncells * as.n_b, true, false); GHB_TRY(dg.rc);
   Arg<double> dz(ctx, nzval, (size_t)as.nnz, false, true); GHB_TRY(dz.rc);
   Arg<double> dr(ctx, rhs, (size_t)as.nrows, false, true); GHB_TRY(dr.rc);
-  GHB_TRY(asm_numeric(ctx, dS.dev, dg.dev, nullptr, dirichlet_vals, dz.dev, dr.dev));
+  GHB_TRY(asm_numeric(ctx, dS.dev, dg.dev, nullptr, dd.dev, dz.dev, dr.dev));
   GHB_TRY(dz.finish()); GHB_TRY(dr.finish());
   return GHB_OK;
 }
 
 int ghb_assemble_numeric_csr_f64(ghb_ctx* ctx, double* S, const double* g, const double* dirichlet_vals,
-                                 double* nzval, double* rhs) {
+                                 int64_t ndirichlet, double* nzval, double* rhs) {
   if (!ctx) return GHB_EINVAL;
   if (!ctx->as.valid) return fail(ctx, GHB_ESTATE, "ghb_assemble_numeric_csr_f64: call ghb_assemble_symbolic first");
   if (ctx->as.nghost) return fail(ctx, GHB_EUNSUPPORTED, "ghb_assemble_numeric_csr_f64: slab patterns (ghost cells) are not supported");
   if (!S || !g || !nzval || !rhs) return fail(ctx, GHB_EINVAL, "ghb_assemble_numeric_csr_f64: null array");
   const AsmState& as = ctx->as;
   if (!is_device_ptr(S)) return fail(ctx, GHB_EUNSUPPORTED, "ghb_assemble_numeric_csr_f64: S is transposed in place and must be a device pointer");
-  if (dirichlet_vals && !is_device_ptr(dirichlet_vals))
-    return fail(ctx, GHB_EUNSUPPORTED, "ghb_assemble_numeric_csr_f64: dirichlet_vals must be a device pointer (its length is not passed)");
+  if (ndirichlet < 0) return fail(ctx, GHB_EINVAL, "ghb_assemble_numeric_csr_f64: ndirichlet < 0");
   cudaSetDevice(ctx->device);
+  Arg<double> dd(ctx, dirichlet_vals, dirichlet_vals ? (size_t)ndirichlet : 0, true, false); GHB_TRY(dd.rc);
   Arg<double> dg(ctx, g, (size_t)as.ncells * as.n_b, true, false); GHB_TRY(dg.rc);
   Arg<double> dz(ctx, nzval, (size_t)as.nnz, false, true); GHB_TRY(dz.rc);
   Arg<double> dr(ctx, rhs, (size_t)as.nrows, false, true); GHB_TRY(dr.rc);
   // the rhs (with the Dirichlet lift g_K - S_K vals_K) needs S_K itself, the row-major values its transpose
-  GHB_TRY(asm_numeric_range(ctx, S, dg.dev, nullptr, dirichlet_vals, dz.dev, dr.dev, 0, as.nrows, ASM_RHS));
+  GHB_TRY(asm_numeric_range(ctx, S, dg.dev, nullptr, dd.dev, dz.dev, dr.dev, 0, as.nrows, ASM_RHS));
   GHB_TRY(launch_transpose_blocks(ctx, as.ncells, as.n_b, S));
-  GHB_TRY(asm_numeric_range(ctx, S, dg.dev, nullptr, dirichlet_vals, dz.dev, dr.dev, 0, as.nrows, ASM_MATRIX));
+  GHB_TRY(asm_numeric_range(ctx, S, dg.dev, nullptr, dd.dev, dz.dev, dr.dev, 0, as.nrows, ASM_MATRIX));
   GHB_TRY(dz.finish()); GHB_TRY(dr.finish());
   return GHB_OK;
 }
 
 int ghb_condense_assemble_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A, const double* b,
-                              const double* dirichlet_vals, double* nzval, double* rhs, int32_t* info) {
+                              const double* dirichlet_vals_in, int64_t ndirichlet, double* nzval, double* rhs,
+                              int32_t* info) {
   Plan* p = get_plan(ctx, plan_id);
   if (!p) return fail(ctx, GHB_EINVAL, "ghb_condense_assemble_f64: bad plan id");
   if (!ctx->as.valid) return fail(ctx, GHB_ESTATE, "ghb_condense_assemble_f64: call ghb_assemble_symbolic first");
@@ -431,9 +576,10 @@ int ghb_condense_assemble_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const d
   if (ncells != as.ncells || p->n_b != as.n_b)
     return fail(ctx, GHB_EINVAL, "ghb_condense_assemble_f64: ncells / n_b differ from the symbolic phase");
   if (!A || !b || !nzval || !rhs) return fail(ctx, GHB_EINVAL, "ghb_condense_assemble_f64: null array");
-  if (dirichlet_vals && !is_device_ptr(dirichlet_vals))
-    return fail(ctx, GHB_EUNSUPPORTED, "ghb_condense_assemble_f64: dirichlet_vals must be a device pointer");
+  if (ndirichlet < 0) return fail(ctx, GHB_EINVAL, "ghb_condense_assemble_f64: ndirichlet < 0");
   cudaSetDevice(ctx->device);
+  Arg<double> dd(ctx, dirichlet_vals_in, dirichlet_vals_in ? (size_t)ndirichlet : 0, true, false); GHB_TRY(dd.rc);
+  const double* dirichlet_vals = dd.dev;
   const bool hostA = !is_device_ptr(A), hostb = !is_device_ptr(b);
   if (hostA != hostb) return fail(ctx, GHB_EINVAL, "ghb_condense_assemble_f64: A and b must both be host or both device");
   double *dS = nullptr, *dg = nullptr;
@@ -454,8 +600,7 @@ int ghb_condense_assemble_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const d
     // Host records are streamed through two device chunk buffers: the H2D copy of chunk k+1 overlaps the
     // condensation of chunk k.  After chunk k the columns whose cells have all been condensed are assembled and, if
     // nzval/rhs are host arrays, copied back on a third stream, so that the D2H traffic overlaps the H2D traffic.
-    int64_t chunk_bytes = (int64_t)(256u << 20);
-    if (const char* e = getenv("GHB_STREAM_CHUNK_BYTES")) chunk_bytes = std::max<int64_t>(1, atoll(e));   // tests: force many chunks
+    const int64_t chunk_bytes = ctx->opt.stream_chunk_bytes;   // option stream_chunk_bytes (tests force many chunks)
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(ncells, chunk_bytes / ((p->lenA + p->lenb) * 8)));
     const int nchunks = (int)((ncells + chunk - 1) / chunk);
     rc = asm_ready_columns(ctx, chunk, nchunks);
@@ -467,6 +612,24 @@ int ghb_condense_assemble_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const d
     double* dA[2] = {nullptr, nullptr};
     double* db[2] = {nullptr, nullptr};
     cudaEvent_t h2d_done[2] = {nullptr, nullptr}, k_done[2] = {nullptr, nullptr}, g_done = nullptr;
+    // Pageable caller memory (a Julia Array, a numpy array) would make every cudaMemcpyAsync a synchronous staged copy:
+    // such records go through two pinned staging buffers owned by the context, filled by host threads while the
+    // previous chunk is on its way to the device.
+    const bool pageable = !is_pinned_host_ptr(A) || !is_pinned_host_ptr(b);
+    const size_t stage_bytes = (size_t)chunk * (p->lenA + p->lenb) * 8;
+    if (rc == GHB_OK && pageable && ctx->pinned_bytes < stage_bytes) {
+      for (int i = 0; i < 2; ++i) {
+        if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
+        ctx->pinned[i] = nullptr;
+      }
+      ctx->pinned_bytes = 0;
+      for (int i = 0; i < 2 && rc == GHB_OK; ++i)
+        if (cudaHostAlloc(&ctx->pinned[i], stage_bytes, cudaHostAllocDefault) != cudaSuccess) {
+          cudaGetLastError();
+          rc = fail(ctx, GHB_ENOMEM, "ghb_condense_assemble_f64: pinned staging buffers");
+        }
+      if (rc == GHB_OK) ctx->pinned_bytes = stage_bytes;
+    }
     if (rc == GHB_OK) {
       for (int i = 0; i < 2; ++i) {
         GHB_CUDA(ctx, cudaMallocAsync((void**)&dA[i], (size_t)chunk * p->lenA * 8, ctx->stream));
@@ -483,8 +646,18 @@ int ghb_condense_assemble_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const d
       int s = it & 1;
       int64_t nc = std::min(chunk, ncells - c0);
       GHB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, k_done[s], 0));
-      GHB_CUDA(ctx, cudaMemcpyAsync(dA[s], A + c0 * p->lenA, (size_t)nc * p->lenA * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
-      GHB_CUDA(ctx, cudaMemcpyAsync(db[s], b + c0 * p->lenb, (size_t)nc * p->lenb * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+      const double* srcA = A + c0 * p->lenA;
+      const double* srcb = b + c0 * p->lenb;
+      if (pageable) {
+        GHB_CUDA(ctx, cudaEventSynchronize(h2d_done[s]));   // the copy that last read this staging buffer is done
+        double* stA = static_cast<double*>(ctx->pinned[s]);
+        double* stb = stA + (size_t)chunk * p->lenA;
+        host_copy_parallel(stA, srcA, (size_t)nc * p->lenA * 8);
+        host_copy_parallel(stb, srcb, (size_t)nc * p->lenb * 8);
+        srcA = stA; srcb = stb;
+      }
+      GHB_CUDA(ctx, cudaMemcpyAsync(dA[s], srcA, (size_t)nc * p->lenA * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+      GHB_CUDA(ctx, cudaMemcpyAsync(db[s], srcb, (size_t)nc * p->lenb * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
       GHB_CUDA(ctx, cudaEventRecord(h2d_done[s], ctx->copy_stream));
       GHB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, h2d_done[s], 0));
       rc = launch_condense(ctx, *p, nc, dA[s], db[s], dS + c0 * p->n_b * p->n_b, dg + c0 * p->n_b,
@@ -524,16 +697,19 @@ int ghb_condense_assemble_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const d
 }
 
 int ghb_backsub_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A, const double* b,
-                    const double* lambda_free, const double* lambda_dirichlet, const int64_t* cell_ids,
-                    double* u, int32_t* info) {
+                    const double* lambda_free_in, int64_t nlambda_free, const double* lambda_dirichlet_in,
+                    int64_t nlambda_dirichlet, const int64_t* cell_ids, double* u, int32_t* info) {
   Plan* p = get_plan(ctx, plan_id);
   if (!p) return fail(ctx, GHB_EINVAL, "ghb_backsub_f64: bad plan id");
   if (ncells < 0) return fail(ctx, GHB_EINVAL, "ghb_backsub_f64: ncells < 0");
   if (ncells == 0) return GHB_OK;
-  if (!cell_ids || !u || !lambda_free) return fail(ctx, GHB_EINVAL, "ghb_backsub_f64: null array");
+  if (!cell_ids || !u || !lambda_free_in) return fail(ctx, GHB_EINVAL, "ghb_backsub_f64: null array");
+  if (nlambda_free < 0 || nlambda_dirichlet < 0) return fail(ctx, GHB_EINVAL, "ghb_backsub_f64: negative length");
   cudaSetDevice(ctx->device);
-  if (!is_device_ptr(lambda_free) || (lambda_dirichlet && !is_device_ptr(lambda_dirichlet)))
-    return fail(ctx, GHB_EUNSUPPORTED, "ghb_backsub_f64: lambda vectors must be device pointers (their lengths are not passed)");
+  Arg<double> dlf(ctx, lambda_free_in, (size_t)nlambda_free, true, false); GHB_TRY(dlf.rc);
+  Arg<double> dld(ctx, lambda_dirichlet_in, lambda_dirichlet_in ? (size_t)nlambda_dirichlet : 0, true, false); GHB_TRY(dld.rc);
+  const double* lambda_free = dlf.dev;
+  const double* lambda_dirichlet = dld.dev;
   Arg<int64_t> dids(ctx, cell_ids, (size_t)ncells * p->n_b, true, false); GHB_TRY(dids.rc);
   Arg<double> du(ctx, u, (size_t)ncells * p->n_i, false, true); GHB_TRY(du.rc);
   Arg<int32_t> di(ctx, info, info ? (size_t)ncells : 0, false, true); GHB_TRY(di.rc);
@@ -541,12 +717,13 @@ int ghb_backsub_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A, 
     if (ctx->fac.plan_id != plan_id || ctx->fac.ncells != ncells)
       return fail(ctx, GHB_ESTATE, "ghb_backsub_f64: A,b are NULL but no matching keep_factors condensation is stored");
     GHB_TRY(launch_backsub_factors(ctx, *p, ncells, ctx->fac.d_X, lambda_free, lambda_dirichlet, dids.dev, du.dev));
-    if (di.dev) GHB_CUDA(ctx, cudaMemsetAsync(di.dev, 0, ncells * sizeof(int32_t), ctx->stream));
+    if (di.dev)   // the info of the condensation that produced the factors (a singular cell has NaN factors)
+      GHB_CUDA(ctx, cudaMemcpyAsync(di.dev, ctx->fac.d_info, ncells * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
   } else {
     if (!A || !b) return fail(ctx, GHB_EINVAL, "ghb_backsub_f64: A and b must both be given or both NULL");
     Arg<double> dA(ctx, A, (size_t)ncells * p->lenA, true, false); GHB_TRY(dA.rc);
     Arg<double> db(ctx, b, (size_t)ncells * p->lenb, true, false); GHB_TRY(db.rc);
-    if (p->use_dmma && !getenv("GHB_FORCE_GENERIC"))
+    if (p->use_dmma)
       GHB_TRY(launch_backsub_dmma(ctx, *p, ncells, dA.dev, db.dev, lambda_free, lambda_dirichlet, dids.dev, du.dev, di.dev));
     else if (p->use_large)
       GHB_TRY(launch_backsub_large(ctx, *p, ncells, dA.dev, db.dev, lambda_free, lambda_dirichlet, dids.dev, du.dev, di.dev));
@@ -567,6 +744,11 @@ int ghb_scatter_free_dof_values(ghb_ctx* ctx, int plan_id, int64_t ncells, const
   if (!p) return fail(ctx, GHB_EINVAL, "ghb_scatter_free_dof_values: bad plan id");
   if (ncells < 0 || nlambda < 0 || !u || !x || (nlambda > 0 && !lambda_free))
     return fail(ctx, GHB_EINVAL, "ghb_scatter_free_dof_values: bad argument");
+  // the layout below is the reference's MultiFieldFESpace order (trial field order) only when the bulk fields come
+  // first and ascending -- what every reference test uses (I = 1:nI); anything else would be silently permuted
+  for (size_t k = 0; k < p->interior.size(); ++k)
+    if (p->interior[k] != (int)k + 1)
+      return fail(ctx, GHB_EUNSUPPORTED, "ghb_scatter_free_dof_values: interior fields must be 1..nI in ascending order");
   cudaSetDevice(ctx->device);
   Arg<double> du(ctx, u, (size_t)ncells * p->n_i, true, false); GHB_TRY(du.rc);
   Arg<double> dl(ctx, lambda_free, (size_t)nlambda, true, false); GHB_TRY(dl.rc);

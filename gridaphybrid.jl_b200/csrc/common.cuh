@@ -90,6 +90,8 @@ struct Factors {
   int plan_id = -1;
   int64_t ncells = 0;
   double* d_X = nullptr;  // [ncells][n_i*(n_b+1)] col-major n_i x (n_b+1): A11^-1 [A12 | b1]
+  int32_t* d_info = nullptr;   // [ncells] info[] of the condensation that produced X (inside the same allocation)
+  uint64_t generation = 0;     // bumped by every keep_factors condensation
   size_t bytes = 0;
 };
 
@@ -107,11 +109,16 @@ struct ghb_ctx {
   std::string err;
   ghb::Options opt;
   std::vector<ghb::Plan*> plans;
-  ghb::AsmState as;
+  ghb::AsmState as;                     // the selected symbolic pattern (ghb_assemble_select)
+  int as_id = -1;                       // its handle, -1: none
+  std::vector<ghb::AsmState> as_store;  // the other patterns, indexed by handle
   ghb::Factors fac;
-  // pinned staging for host-pointer streaming
+  // pinned double buffer of the host-record streaming path (pageable caller memory is staged through it)
   void* pinned[2] = {nullptr, nullptr};
   size_t pinned_bytes = 0;
+  // NCCL communicator of the multi-GPU exchanges (comm.cu; ncclComm_t, loaded at run time)
+  void* comm = nullptr;
+  int comm_rank = 0, comm_size = 1;
 };
 
 namespace ghb {
@@ -250,6 +257,7 @@ int asm_numeric(ghb_ctx* ctx, const double* S, const double* g, const double* gh
 int asm_pack_cut_plane(ghb_ctx* ctx, int64_t ncut, int n_b, int ncols, const double* S, const double* g,
                        const int64_t* ids, const double* dvals, double* out);
 void asm_free(ghb_ctx* ctx);
+void comm_free(ghb_ctx* ctx);
 int launch_restrict_facet_dofs(ghb_ctx* ctx, int64_t ncells, int nlf, int nf, const int64_t* cwf,
                                const int64_t* fdata, int64_t* out);
 int launch_sum_facets(ghb_ctx* ctx, int64_t ncells, int nlf, int64_t len, const double* in, double* out);

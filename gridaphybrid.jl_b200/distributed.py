@@ -166,6 +166,7 @@ class SlabAssembler:
         ctx.use_torch_stream()
         self.nnz = ctx.assemble_symbolic_slab(L.ncells, L.nghost, L.ndofs_f, L.n_b, self.cell_ids, L.nrows_global,
                                               L.col_begin, L.col_end)
+        self._pid = ctx.assemble_current()
         self.nrows_local = L.nrows_local
         stride = L.n_b * L.ndofs_f + L.ndofs_f
         self.send_buf = torch.empty((L.layer, stride), dtype=torch.float64, device=dev) if rank > 0 else None
@@ -175,6 +176,7 @@ class SlabAssembler:
         dev = self.cell_ids.device
         colptr = torch.empty(self.nrows_local + 1, dtype=torch.int64, device=dev)
         rowval = torch.empty(self.nnz, dtype=torch.int64, device=dev)
+        self.ctx.assemble_select(self._pid)
         self.ctx.assemble_pattern(colptr, rowval)
         return colptr, rowval
 
@@ -187,7 +189,24 @@ class SlabAssembler:
         """numeric phase for the owned columns: pack -> cut-plane exchange -> owner-computes gather."""
         L = self.layout
         self.ctx.use_torch_stream()
+        self.ctx.assemble_select(self._pid)
         if L.world > 1:
             self.pack(S, g)
-            (exchange or exchange_cut_plane)(self.send_buf, self.ghost, L.rank, L.world, self.group)
+            if exchange is not None:
+                exchange(self.send_buf, self.ghost, L.rank, L.world, self.group)
+            elif getattr(self.ctx, "comm_size", 1) == L.world:
+                self.ctx.exchange_cut_plane(self.send_buf, self.ghost)      # NCCL behind the C ABI (ghb_comm_init)
+            else:
+                exchange_cut_plane(self.send_buf, self.ghost, L.rank, L.world, self.group)
         self.ctx.assemble_numeric_slab(S, g, self.ghost, self.dirichlet_values, nzval, rhs)
+
+    def allgather_lambda(self, lam_owned):
+        """collective 2 through the C ABI (grouped ncclBroadcast, no object gather): the global free-dof vector"""
+        L = self.layout
+        if L.world == 1:
+            return lam_owned
+        counts = [SlabLayout(L.gdims, L.ndofs_f, r, L.world).nrows_local for r in range(L.world)]
+        out = torch.empty(sum(counts), dtype=torch.float64, device=lam_owned.device)
+        self.ctx.use_torch_stream()
+        self.ctx.allgather_lambda(lam_owned, counts, out)
+        return out

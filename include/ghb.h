@@ -57,9 +57,20 @@ int ghb_set_stream(ghb_ctx* ctx, void* cuda_stream);
 int ghb_synchronize(ghb_ctx* ctx);
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 int64_t ghb_launch_count(const ghb_ctx* ctx);
+/* Debugging / A-B knobs.  ghb_create reads them ONCE from the environment (GHB_FORCE_GENERIC, GHB_CW, GHB_DMMA_LL,
+ * GHB_FACTORS_GENERIC, GHB_MAX_CTAS_PER_SM, GHB_LL_CTAS, GHB_WARP_ONE_CELL, GHB_WARP_TWO_ROWS, GHB_DEBUG,
+ * GHB_STREAM_CHUNK_BYTES); this call changes one by its lower-case name without the prefix ("cw", "stream_chunk_bytes",
+ * ...).  Kernel-choice knobs act on plans created afterwards; nothing on the launch path reads the environment. */
+int ghb_set_option(ghb_ctx* ctx, const char* name, int64_t value);
+/* Device buffers for hosts without a CUDA array library of their own: the Julia glue keeps S_K, g_K between the
+ * condensation site and the assembly site on the device instead of round-tripping them through host memory.
+ * ghb_copy moves bytes between any two of host / device (cudaMemcpyDefault) and is complete on return. */
+int ghb_device_alloc(ghb_ctx* ctx, int64_t bytes, void** out);
+int ghb_device_free(ghb_ctx* ctx, void* ptr);
+int ghb_copy(ghb_ctx* ctx, void* dst, const void* src, int64_t bytes);
 /* Name of the condensation kernel variant chosen for a plan: "dmma_34_36", "dmma_33_12", "dmma_56_16" (FP64 DMMA,
    interior rows in shared memory, boundary rows in registers), "large_dmma" (64 < n_i <= 128, streamed), "warp_7_8", "warp_16_8" (register-resident),
-   "generic" (any plan). */
+   "cw_34_36", "cw_33_12", "cw_40_36", "cw_21_16" (one warp per cell, FP64 DMMA, csrc/condense_cw.cu), "generic" (any plan). */
 const char* ghb_plan_kernel_name(ghb_ctx* ctx, int plan_id);
 
 /* ---- block plan: mirrors StaticCondensationMap{IFT,BFT} + the touched mask ------------------
@@ -86,6 +97,9 @@ int ghb_plan_query(ghb_ctx* ctx, int plan_id, int64_t out[4]);
  */
 int ghb_condense_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A, const double* b, double* S,
                      double* g, int32_t* info, int keep_factors);
+/* Generation of the stored factors (bumped by every keep_factors condensation; -1: none stored): a caller that holds
+ * several condensed batches checks it before ghb_backsub_f64(A = b = NULL) to know the factors are still its own. */
+int64_t ghb_factors_generation(const ghb_ctx* ctx);
 
 /* ---- (a6) id glue: facet dofs -> cell boundary ids ------------------------------------------
  * replaces RestrictFacetDoFsToSkeleton / restrict_facet_dof_ids_to_cell_boundary
@@ -132,13 +146,20 @@ int ghb_sum_facets_f64(ghb_ctx* ctx, int64_t ncells, int nlfacets, int64_t len, 
  */
 int ghb_assemble_symbolic(ghb_ctx* ctx, int64_t ncells, int n_b, const int64_t* cell_ids, int64_t nrows,
                           int64_t* nnz_out);
+/* Symbolic patterns are handles.  Every ghb_assemble_symbolic / ghb_assemble_symbolic_slab creates a new pattern and
+ * selects it; ghb_assemble_current returns its handle (>= 0).  An assembler that shares the ctx with others (two
+ * operators or meshes, a slab assembler next to a global one, a Newton loop) selects its own pattern before
+ * ghb_assemble_pattern / ghb_assemble_numeric* / ghb_condense_assemble_f64; ghb_assemble_release frees one. */
+int ghb_assemble_current(const ghb_ctx* ctx);
+int ghb_assemble_select(ghb_ctx* ctx, int pattern_id);
+int ghb_assemble_release(ghb_ctx* ctx, int pattern_id);
 /* Copies the cached pattern out: colptr [nrows+1], rowval [nnz]; 1-based Int64 (Julia CSC). */
 int ghb_assemble_pattern(ghb_ctx* ctx, int64_t* colptr, int64_t* rowval);
-/* Numeric: nzval [nnz], rhs [nrows].  dirichlet_vals (may be NULL) applies the lift of
+/* Numeric: nzval [nnz], rhs [nrows].  dirichlet_vals [ndirichlet] (may be NULL) applies the lift of
  * _attach_dirichlet (src/HybridAffineFEOperators.jl:41-42): g_K <- g_K - S_K * vals_K on cells that
- * have a Dirichlet dof, vals_K[l] = dirichlet_vals[-id-1] for id<0, else 0. */
+ * have a Dirichlet dof, vals_K[l] = dirichlet_vals[-id-1] for id<0, else 0.  Host or device pointer. */
 int ghb_assemble_numeric_f64(ghb_ctx* ctx, const double* S, const double* g, const double* dirichlet_vals,
-                             double* nzval, double* rhs);
+                             int64_t ndirichlet, double* nzval, double* rhs);
 
 /* ---- (f-4) CSR hand-off (SparseMatricesCSR / device sparse solvers instead of the CSC round trip to UMFPACK,
  * src/HybridAffineFEOperators.jl:74, src/HybridLinearSolvers.jl:45) ---------------------------
@@ -149,7 +170,7 @@ int ghb_assemble_numeric_f64(ghb_ctx* ctx, const double* S, const double* g, con
  * transposed: call it with a scratch copy, or transpose back by a second call's side effect) and gathers nzval in
  * CSR order.  S must be a device pointer; single-GPU patterns only (no ghost cells). */
 int ghb_assemble_numeric_csr_f64(ghb_ctx* ctx, double* S, const double* g, const double* dirichlet_vals,
-                                 double* nzval, double* rhs);
+                                 int64_t ndirichlet, double* nzval, double* rhs);
 /* ---- (e) multi-GPU slabs: cells are partitioned in contiguous slabs, one process per GPU --------
  * A slab owns the dofs of the facets first touched by its cells = a contiguous range of
  * global columns [col_begin, col_end) (1-based, end exclusive).  Its cell list is its own cells followed
@@ -168,25 +189,48 @@ int ghb_pack_cut_plane_f64(ghb_ctx* ctx, int64_t ncut, int n_b, int ncols, const
 int ghb_assemble_numeric_slab_f64(ghb_ctx* ctx, const double* S, const double* g, const double* ghost,
                                   const double* dirichlet_vals, double* nzval, double* rhs);
 
-/* Fused condensation + numeric assembly (S_K, g_K never stored by the caller). Host pointers are
- * streamed through pinned staging in chunks (H2D, kernels and the final D2H overlap). */
+/* Condensation + numeric assembly in one call (S_K, g_K never seen by the caller; they live in a device scratch
+ * buffer between the two kernels).  Host records are streamed in chunks (option stream_chunk_bytes, 256 MB): the H2D
+ * copy of chunk k+1 overlaps the condensation of chunk k, and the columns whose cells are all condensed are assembled
+ * and copied back while later records are still arriving.  Pinned caller memory is copied from directly; PAGEABLE
+ * caller memory (a Julia Array, a numpy array) is staged through two pinned buffers owned by the ctx, filled by host
+ * threads, so that the copies stay asynchronous. */
 int ghb_condense_assemble_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A, const double* b,
-                              const double* dirichlet_vals, double* nzval, double* rhs, int32_t* info);
+                              const double* dirichlet_vals, int64_t ndirichlet, double* nzval, double* rhs,
+                              int32_t* info);
 
 /* ---- (a11)+(a12) backward static condensation -----------------------------------------------
  * replaces evaluate!(cache, ::BackwardStaticCondensationMap, A, b, x)
  * (src/BackwardStaticCondensationMap.jl:61-102) fed by get_cell_dof_values(lh, dK)
  * (src/HybridAffineFEOperators.jl:113): lambda_K[l] = lambda_free[id-1] (id>0) or lambda_dirichlet[-id-1].
  * u [ncells][n_i] = interior fields concatenated in `interior` order.  If the last condense call used
- * keep_factors on the same cells, A and b may be NULL and the stored X, y are used.
+ * keep_factors on the same cells, A and b may be NULL and the stored X, y are used (info[] then repeats the info of
+ * that condensation).  lambda_free [nlambda_free] and lambda_dirichlet [nlambda_dirichlet] (may be NULL) are host or
+ * device pointers.
  */
 int ghb_backsub_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A, const double* b,
-                    const double* lambda_free, const double* lambda_dirichlet, const int64_t* cell_ids,
-                    double* u, int32_t* info);
+                    const double* lambda_free, int64_t nlambda_free, const double* lambda_dirichlet,
+                    int64_t nlambda_dirichlet, const int64_t* cell_ids, double* u, int32_t* info);
 /* (a12) full-space free-dof vector (src/HybridAffineFEOperators.jl:134-149):
  * x = [bulk field 1 cell-major | bulk field 2 | ... | lambda_free].  x has sum(n_i)*ncells + nlambda entries. */
 int ghb_scatter_free_dof_values(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* u,
                                 const double* lambda_free, int64_t nlambda, double* x);
+
+/* ---- (e) the two NCCL exchanges behind the C ABI (a rank-per-GPU host in any language; csrc/comm.cu) ---------------
+ * NCCL is loaded at run time (libnccl.so.2); without it these return GHB_EUNSUPPORTED and everything else works.
+ * ghb_comm_unique_id: rank 0 fills id128 (128 bytes = ncclUniqueId) and ships it to the other ranks with whatever
+ * the host has (MPI, a store, a file); ghb_comm_init: every rank, on its ctx's device (ncclCommInitRank).
+ * ghb_exchange_cut_plane_f64: collective 1 -- rank r > 0 sends `nsend` doubles (its ghb_pack_cut_plane_f64 buffer) to
+ * r-1, rank r < P-1 receives `nrecv` doubles from r+1 (its ghost buffer); one grouped ncclSend/ncclRecv on the ctx's
+ * stream.  ghb_allgather_lambda_f64: collective 2 before the backward step (src/HybridAffineFEOperators.jl:113-118) --
+ * counts[r] = owned lambda entries of rank r (host array [P]); `all` [sum counts] receives the global vector, `owned`
+ * = this rank's range (NULL: already in place inside `all`). */
+int ghb_comm_unique_id(ghb_ctx* ctx, void* id128);
+int ghb_comm_init(ghb_ctx* ctx, int nranks, int rank, const void* id128);
+int ghb_comm_destroy(ghb_ctx* ctx);
+int ghb_exchange_cut_plane_f64(ghb_ctx* ctx, const double* send_down, int64_t nsend, double* recv_from_up,
+                               int64_t nrecv);
+int ghb_allgather_lambda_f64(ghb_ctx* ctx, const double* owned, const int64_t* counts, double* all);
 
 /* ---- synthetic workload (bench / tests): counter-based Philox4x32-10, bit-identical to oracle ---
  * Fills records of cells [cell_start, cell_start+ncells) (oracle.synth_cell_records). */

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-11
 
 
-def _dev_plan(ctx, name):
+def _dev_plan(ctx, name, fresh=False):
     c = CONFIGS[name]
     return ctx.plan_blocks(c["ndofs"], c["touched"], c["interior"], c["boundary"])
 
@@ -144,6 +144,13 @@ def test_backsub_parity_and_factor_reuse(ctx, name):
     assert rel_err_cells(u2.cpu().numpy(), u0) < TOL
     # full-space scatter
     x = torch.empty(n * plan.n_i + nfree, dtype=torch.float64, device="cuda")
+    if list(op.interior) != list(range(1, len(op.interior) + 1)):
+        # the layout is the reference's trial-field order only for bulk fields 1..nI (every reference test); anything
+        # else would come out silently permuted, so the library refuses it
+        with pytest.raises(gh.GhbError) as e:
+            ctx.scatter_free_dof_values(plan, n, u, lf, x)
+        assert e.value.code == gh._lib.GHB_EUNSUPPORTED
+        return
     ctx.scatter_free_dof_values(plan, n, u, lf, x)
     ibrs = [op.ndofs[f - 1] for f in op.interior]
     assert np.array_equal(x.cpu().numpy(), o.hybridizable_free_dof_values(u.cpu().numpy(), ibrs, lam_f))
@@ -323,9 +330,8 @@ def test_fused_condense_assemble_host_streaming(ctx):
     ctx.condense_assemble(plan, n, host.A, host.b, dv, nz, rhs, info)
     assert np.array_equal(nz, A1.nzval.cpu().numpy()) and np.array_equal(rhs, r1.cpu().numpy()) and not info.any()
     # many small chunks: columns are assembled and copied back as soon as their cells are condensed
-    import os
     for chunk_cells in (7, 31):
-        os.environ["GHB_STREAM_CHUNK_BYTES"] = str(chunk_cells * (plan.lenA + plan.lenb) * 8)
+        ctx.set_option("stream_chunk_bytes", chunk_cells * (plan.lenA + plan.lenb) * 8)
         try:
             nz2 = np.full(A1.nnz, np.nan); rhs2 = np.full(assem.nrows, np.nan)
             ctx.condense_assemble(plan, n, host.A, host.b, dv, nz2, rhs2, info)
@@ -336,7 +342,7 @@ def test_fused_condense_assemble_host_streaming(ctx):
             ctx.condense_assemble(plan, n, host.A, host.b, dv, nz3, rhs3, info)
             assert np.array_equal(nz3.cpu().numpy(), nz) and np.array_equal(rhs3.cpu().numpy(), rhs)
         finally:
-            del os.environ["GHB_STREAM_CHUNK_BYTES"]
+            ctx.set_option("stream_chunk_bytes", 256 << 20)
 
 
 def test_full_size_properties_c3(ctx):
@@ -505,13 +511,16 @@ def test_sum_facets_device(ctx, shape):
 
 @pytest.mark.parametrize("name", ["C2_rth_k2_2d", "C2_rth_k3_2d", "C3_hdg_k2_3d"])
 @pytest.mark.parametrize("left_looking", ["1", "0"])
-def test_both_dmma_condensation_kernels(ctx, name, left_looking, monkeypatch):
-    """the library launches the left-looking kernel (bottom block in registers); the right-looking one stays selectable
-    (GHB_DMMA_LL=0, read at every launch).  Both against the oracle: values, ragged cell counts around the resident-CTA
-    count (148 SMs x 8 / x 5), dgetrf info semantics and NaN outputs of a singular cell."""
-    monkeypatch.setenv("GHB_DMMA_LL", left_looking)
-    monkeypatch.setenv("GHB_CW", "0")               # read at plan creation: the 4-warps-per-cell kernels
-    plan, op = _dev_plan(ctx, name), oracle_plan(name)
+def test_both_dmma_condensation_kernels(ctx, name, left_looking):
+    """the 4-warps-per-cell kernels (option cw = 0): left-looking (bottom block in registers) and right-looking (option
+    dmma_ll = 0).  Both against the oracle: values, ragged cell counts around the resident-CTA count (148 SMs x 8 / x 5),
+    dgetrf info semantics and NaN outputs of a singular cell."""
+    ctx.set_option("cw", 0)
+    try:
+        plan, op = _dev_plan(ctx, name, fresh=True), oracle_plan(name)
+    finally:
+        ctx.set_option("cw", 1)
+    ctx.set_option("dmma_ll", int(left_looking))
     assert plan.kernel_name.startswith("dmma")
     for n in (5, 1184, 1190, 3001):
         A, b = _synth(ctx, plan, 4242, n)
@@ -564,11 +573,17 @@ def test_csr_hand_off(ctx, dims, ndofs_f):
 
 
 @pytest.mark.parametrize("name", ["C2_rth_k2_2d", "C2_rth_k3_2d", "C3_hdg_k2_3d"])
-def test_dmma_keep_factors(ctx, name, monkeypatch):
-    """keep_factors on the DMMA shapes runs the left-looking kernel with the back substitution X = U^-1 (L^-1 P [A12 b1])
-    appended (SURVEY 8f-2): S, g unchanged, the stored factors reproduce the backward map, a singular cell gives NaN;
-    the generic kernel's factors (GHB_FACTORS_GENERIC=1) are the cross-check."""
-    plan, op = _dev_plan(ctx, name), oracle_plan(name)
+def test_dmma_keep_factors(ctx, name):
+    """keep_factors on the DMMA shapes (option cw = 0) runs the left-looking kernel with the back substitution
+    X = U^-1 (L^-1 P [A12 b1]) appended: S, g unchanged, the stored factors reproduce the backward map, a
+    singular cell gives NaN and keeps its info through the factors path; the generic kernel's factors (option
+    factors_generic = 1) are the cross-check."""
+    ctx.set_option("cw", 0)
+    try:
+        plan, op = _dev_plan(ctx, name), oracle_plan(name)
+    finally:
+        ctx.set_option("cw", 1)
+    assert plan.kernel_name.startswith("dmma")
     n = 1500
     A, b = _synth(ctx, plan, 99, n)
     bad = 700
@@ -583,8 +598,7 @@ def test_dmma_keep_factors(ctx, name, monkeypatch):
     ok = np.arange(n) != bad
     ids_d, lf = torch.as_tensor(ids, device="cuda"), torch.as_tensor(lam, device="cuda")
     for generic in (False, True):
-        if generic:
-            monkeypatch.setenv("GHB_FACTORS_GENERIC", "1")
+        ctx.set_option("factors_generic", int(generic))
         S = torch.empty((n, plan.n_b ** 2), dtype=torch.float64, device="cuda")
         g = torch.empty((n, plan.n_b), dtype=torch.float64, device="cuda")
         info = torch.empty(n, dtype=torch.int32, device="cuda")
@@ -592,10 +606,13 @@ def test_dmma_keep_factors(ctx, name, monkeypatch):
         assert info.cpu().numpy().tolist() == info0.tolist()
         assert rel_err_cells(S.cpu().numpy()[ok], S0[ok]) < TOL and rel_err_cells(g.cpu().numpy()[ok], g0[ok]) < TOL
         u = torch.empty((n, plan.n_i), dtype=torch.float64, device="cuda")
-        ctx.backsub(plan, n, None, None, lf, None, ids_d, u, None)
+        binfo = torch.empty(n, dtype=torch.int32, device="cuda")
+        ctx.backsub(plan, n, None, None, lf, None, ids_d, u, binfo)
         uh = u.cpu().numpy()
         assert rel_err_cells(uh[ok], u0[ok]) < TOL
         assert np.isnan(uh[bad]).all()
+        assert binfo.cpu().numpy().tolist() == info0.tolist()      # the factors path reports the condensation's info
+    ctx.set_option("factors_generic", 0)
 
 
 def _darcy_family(dims, order):
@@ -774,3 +791,127 @@ def test_cellwarp_pivot_ties_follow_lapack(ctx):
     ok = info0 == 0
     assert ok.sum() > n // 2
     assert rel_err_cells(S[ok], S0[ok]) < TOL and rel_err_cells(g[ok], g0[ok]) < TOL
+
+
+def test_julia_glue_call_sequence():
+    """replays gridaphybrid.jl_b200/julia/GridapHybridB200.jl call for call through ctypes, with PAGEABLE numpy arrays
+    in the roles of the Julia Arrays (records, cell ids, dirichlet_values, lam_free, lam_dirichlet are all host
+    vectors): plan -> symbolic / current / pattern -> select -> condense_assemble (site 2, lazy site 1) -> indexing a
+    cell (materialize! into ghb_device_alloc buffers, ghb_copy) -> assemble_numeric from the device cells ->
+    backsub + scatter (site 3).  Everything against the oracle; indices bit-exact."""
+    import ctypes as C
+    from gridaphybrid_b200 import _lib
+    L = _lib.lib()
+    vp = C.c_void_p
+    P = lambda a: vp(a.ctypes.data)
+    h = vp()
+    assert L.ghb_create(0, C.byref(h)) == 0
+    def check(rc):
+        assert rc == 0, L.ghb_last_error(h).decode()
+    try:
+        cfg = CONFIGS["C3_hdg_k2_3d"]
+        op = oracle_plan("C3_hdg_k2_3d")
+        dims = (4, 3, 3)
+        cwf = o.cartesian_cell_wise_facets(dims)
+        isb = o.facet_is_boundary(cwf)
+        fids, nfree, ndir = o.facet_dof_ids(isb, 6)
+        cell_ids = np.ascontiguousarray(o.restrict_facet_dofs_to_skeleton(cwf, fids), dtype=np.int64)   # Julia: n_b x ncells
+        n = cell_ids.shape[0]
+        rng = np.random.default_rng(3)
+        A = rng.standard_normal((n, op.lenA)); b = rng.standard_normal((n, op.lenb))
+        for c in range(n):                                   # a well-conditioned interior block
+            dense = np.zeros((op.n, op.n)); dense[:op.n_i, :op.n_i] = 12.0 * np.eye(op.n_i)
+            dA, _ = dense_to_record(op, dense, np.zeros(op.n))
+            A[c] += dA
+        dirichlet_values = rng.standard_normal(ndir)
+        # plan(k, p)
+        ndofs = np.array(cfg["ndofs"], dtype=np.int32)
+        touched = np.ascontiguousarray(np.array(cfg["touched"], dtype=np.uint8).T)
+        interior = np.array(cfg["interior"], dtype=np.int32); boundary = np.array(cfg["boundary"], dtype=np.int32)
+        pid = C.c_int(-1)
+        check(L.ghb_plan_blocks(h, len(ndofs), P(ndofs), P(touched), len(interior), P(interior), len(boundary), P(boundary), C.byref(pid)))
+        q = (C.c_int64 * 4)()
+        check(L.ghb_plan_query(h, pid.value, q))
+        ni, nb = int(q[0]), int(q[1])
+        # symbolic(cell_ids, nfree)
+        nnz = C.c_int64(0)
+        check(L.ghb_assemble_symbolic(h, n, nb, P(cell_ids), nfree, C.byref(nnz)))
+        pat = L.ghb_assemble_current(h)
+        assert pat >= 0
+        colptr = np.empty(nfree + 1, dtype=np.int64); rowval = np.empty(nnz.value, dtype=np.int64)
+        check(L.ghb_assemble_pattern(h, P(colptr), P(rowval)))
+        # a second assembler on the same context must not disturb the first (pattern handles)
+        other_ids = np.ascontiguousarray(cell_ids[:2])
+        nnz2 = C.c_int64(0)
+        check(L.ghb_assemble_symbolic(h, 2, nb, P(other_ids), nfree, C.byref(nnz2)))
+        assert L.ghb_assemble_current(h) == pat + 1
+        # assemble_condensed: select, then the streamed condense + assemble with a HOST dirichlet vector
+        check(L.ghb_assemble_select(h, pat))
+        nzval = np.empty(nnz.value); rhs = np.empty(nfree); info = np.empty(n, dtype=np.int32)
+        check(L.ghb_condense_assemble_f64(h, pid.value, n, P(A), P(b), P(dirichlet_values), ndir, P(nzval), P(rhs), P(info)))
+        assert not info.any()
+        S0, g0, info0 = oc.condense(op, A, b)
+        Sc = [S0[c].reshape((nb, nb), order="F") for c in range(n)]
+        gl = [o.attach_dirichlet(Sc[c], g0[c], cell_ids[c], dirichlet_values) for c in range(n)]
+        colptr0, rowval0, nzval0, rhs0 = o.assemble_matrix_and_vector(Sc, gl, cell_ids, nfree)
+        assert np.array_equal(colptr, colptr0) and np.array_equal(rowval, rowval0)
+        assert np.abs(nzval - nzval0).max() < TOL * np.abs(nzval0).max() and np.abs(rhs - rhs0).max() < TOL * np.abs(rhs0).max()
+        # getindex: materialize! into device buffers, copy one cell back
+        dS, dg = vp(), vp()
+        check(L.ghb_device_alloc(h, 8 * nb * nb * n, C.byref(dS)))
+        check(L.ghb_device_alloc(h, 8 * nb * n, C.byref(dg)))
+        check(L.ghb_condense_f64(h, pid.value, n, P(A), P(b), dS, dg, P(info), 0))
+        c = n - 2
+        Sk = np.empty(nb * nb); gk = np.empty(nb)
+        check(L.ghb_copy(h, P(Sk), vp(dS.value + 8 * nb * nb * c), 8 * nb * nb))
+        check(L.ghb_copy(h, P(gk), vp(dg.value + 8 * nb * c), 8 * nb))
+        assert rel_err_cells(Sk[None], S0[c][None]) < TOL and rel_err_cells(gk[None], g0[c][None]) < TOL
+        # ... and the assembly from the device cells gives the same system
+        nz2 = np.empty(nnz.value); rhs2 = np.empty(nfree)
+        check(L.ghb_assemble_numeric_f64(h, dS, dg, P(dirichlet_values), ndir, P(nz2), P(rhs2)))
+        assert np.array_equal(nz2, nzval) and np.array_equal(rhs2, rhs)
+        check(L.ghb_device_free(h, dS)); check(L.ghb_device_free(h, dg))
+        # backsub with host lambda vectors + scatter
+        lam_free = rng.standard_normal(nfree)
+        u = np.empty((n, ni)); binfo = np.empty(n, dtype=np.int32)
+        check(L.ghb_backsub_f64(h, pid.value, n, P(A), P(b), P(lam_free), nfree, P(dirichlet_values), ndir, P(cell_ids), P(u), P(binfo)))
+        assert not binfo.any()
+        u0, _ = oc.backsub(op, A, b, o.cell_dof_values(lam_free, dirichlet_values, cell_ids))
+        assert rel_err_cells(u, u0) < TOL
+        x = np.empty(ni * n + nfree)
+        check(L.ghb_scatter_free_dof_values(h, pid.value, n, P(u), P(lam_free), nfree, P(x)))
+        x0 = o.hybridizable_free_dof_values(u0, [30, 4], lam_free)
+        assert np.abs(x - x0).max() < TOL * np.abs(x0).max()
+        check(L.ghb_assemble_release(h, pat + 1))
+        assert L.ghb_assemble_select(h, pat + 1) != 0
+    finally:
+        L.ghb_destroy(h)
+
+
+def test_pageable_and_pinned_host_records_agree(ctx):
+    """ghb_condense_assemble_f64 stages PAGEABLE records through its pinned double buffer (host threads) and copies
+    pinned ones directly: identical results, several chunks."""
+    dims = (6, 5, 4)
+    c = CONFIGS["C3_hdg_k2_3d"]
+    plan = ctx.plan_blocks(c["ndofs"], c["touched"], c["interior"], c["boundary"])
+    sk = gh.CartesianSkeleton(dims, ctx)
+    M = gh.FacetFESpace(sk, 6, sk.facet_is_boundary())
+    assem = gh.SparseMatrixAssembler(M)
+    colptr, rowval, nnz = assem.symbolic()
+    n = sk.ncells
+    A, b = _synth(ctx, plan, 0, n)
+    Ap, bp = A.cpu().pin_memory(), b.cpu().pin_memory()
+    An, bn = A.cpu().numpy().copy(), b.cpu().numpy().copy()       # pageable
+    dv = np.linspace(-1, 1, max(M.num_dirichlet_dofs, 1))          # host Dirichlet values
+    ctx.set_option("stream_chunk_bytes", 17 * (plan.lenA + plan.lenb) * 8)
+    try:
+        assem.select()
+        out = []
+        for Ah, bh in ((Ap, bp), (An, bn)):
+            nz = np.full(nnz, np.nan); rhs = np.full(assem.nrows, np.nan); info = np.empty(n, dtype=np.int32)
+            ctx.condense_assemble(plan, n, Ah, bh, dv, nz, rhs, info)
+            assert not info.any() and not np.isnan(nz).any()
+            out.append((nz, rhs))
+        assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    finally:
+        ctx.set_option("stream_chunk_bytes", 256 << 20)

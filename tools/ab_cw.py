@@ -1,5 +1,5 @@
 """A/B of the one-warp-per-cell condensation kernel (condense_cw.cu) against the 4-warps-per-cell left-looking kernel
-(GHB_CW=0) : throughput with CUDA events on inputs larger than L2, difference of the results, keep_factors timing.
+(option cw = 0) : throughput with CUDA events on inputs larger than L2, difference of the results, keep_factors timing.
 usage: [GHB_LIB_PATH=tools/_bin/libghb_x.so] python tools/ab_cw.py [ncells_log2=20] [shapes=34,36;33,12]"""
 import os
 import sys
@@ -40,9 +40,9 @@ def timeit(plan, n, A, b, keep=False, reps=5):
 for name in which:
     ndofs, touched = SHAPES[name]
     n = 1 << lg
-    os.environ["GHB_CW"] = "0"
+    ctx.set_option("cw", 0)
     p_old = ctx.plan_blocks(ndofs, touched, [1, 2], [3])
-    os.environ.pop("GHB_CW")
+    ctx.set_option("cw", 1)
     p_new = ctx.plan_blocks(ndofs, touched, [1, 2], [3])
     A = torch.empty((n, p_new.lenA), dtype=torch.float64, device="cuda")
     b = torch.empty((n, p_new.lenb), dtype=torch.float64, device="cuda")

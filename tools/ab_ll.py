@@ -18,13 +18,13 @@ SHAPES = {
 }
 only = os.environ.get("GHB_AB_ONLY")
 ctx = gh.Context(0)
+ctx.set_option("cw", 0)      # these experiments are about the 4-warps-per-cell kernels
 ev = lambda: torch.cuda.Event(enable_timing=True)
 
 
 def run(plan, n, A, b, env):
-    for k in ("GHB_DMMA_LL", "GHB_LL_CTAS"):
-        os.environ.pop(k, None)
-    os.environ.update(env)
+    ctx.set_option("dmma_ll", int(env.get("GHB_DMMA_LL", "1")))
+    ctx.set_option("ll_ctas", int(env.get("GHB_LL_CTAS", "0")))
     S = torch.empty((n, plan.n_b ** 2), dtype=torch.float64, device="cuda")
     g = torch.empty((n, plan.n_b), dtype=torch.float64, device="cuda")
     info = torch.empty(n, dtype=torch.int32, device="cuda")

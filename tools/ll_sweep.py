@@ -10,6 +10,7 @@ import gridaphybrid_b200 as gh  # noqa: E402
 
 os.environ["GHB_DMMA_LL"] = os.environ.get("GHB_DMMA_LL", "1")
 ctx = gh.Context(0)
+ctx.set_option("cw", 0)      # these experiments are about the 4-warps-per-cell kernels
 n = 1 << 19
 plan = ctx.plan_blocks([30, 4, 36], np.ones((3, 3), bool), [1, 2], [3])
 A = torch.empty((n, plan.lenA), dtype=torch.float64, device="cuda"); b = torch.empty((n, plan.lenb), dtype=torch.float64, device="cuda")
@@ -31,6 +32,6 @@ def timed(f, reps=3):
 print("| CTAs/SM | condense M cells/s | cycles per cell latency (1.965 GHz) |")
 print("|---|---|---|")
 for k in range(1, 9):
-    os.environ["GHB_MAX_CTAS_PER_SM"] = str(k)
+    ctx.set_option("max_ctas_per_sm", k)
     mc = timed(lambda: ctx.condense(plan, n, A, b, S, g, info))
     print(f"| {k} | {n / mc / 1e3:.1f} | {mc * 1e-3 * 1.965e9 * 148 * k / n:.0f} |", flush=True)

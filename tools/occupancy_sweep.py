@@ -10,6 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import gridaphybrid_b200 as gh  # noqa: E402
 
 ctx = gh.Context(0)
+ctx.set_option("cw", 0)      # these experiments are about the 4-warps-per-cell kernels
 n = 1 << 18
 plan = ctx.plan_blocks([30, 4, 36], np.ones((3, 3), bool), [1, 2], [3])
 A = torch.empty((n, plan.lenA), dtype=torch.float64, device="cuda"); b = torch.empty((n, plan.lenb), dtype=torch.float64, device="cuda")
@@ -34,7 +35,7 @@ def timed(f, reps=3):
 print("| CTAs/SM | condense M cells/s | cycles per cell (1.965 GHz) | backsub M cells/s | cycles per cell |")
 print("|---|---|---|---|---|")
 for k in range(1, 9):
-    os.environ["GHB_MAX_CTAS_PER_SM"] = str(k)
+    ctx.set_option("max_ctas_per_sm", k)
     mc = timed(lambda: ctx.condense(plan, n, A, b, S, g, info))
     mb = timed(lambda: ctx.backsub(plan, n, A, b, lam, None, ids, u, info))
     kc, kb = min(k, 5), k

@@ -36,9 +36,9 @@ for name, (ndofs, touched, n) in SHAPES.items():
     ids = torch.arange(1, n * plan.n_b + 1, dtype=torch.int64, device="cuda")
     u = torch.empty((n, plan.n_i), dtype=torch.float64, device="cuda")
     f0 = timed(lambda: ctx.condense(plan, n, A, b, S, g, None))
-    os.environ["GHB_FACTORS_GENERIC"] = "1"
+    ctx.set_option("factors_generic", 1)
     f2 = timed(lambda: ctx.condense(plan, n, A, b, S, g, None, keep_factors=True), reps=1)
-    del os.environ["GHB_FACTORS_GENERIC"]
+    ctx.set_option("factors_generic", 0)
     f1 = timed(lambda: ctx.condense(plan, n, A, b, S, g, None, keep_factors=True))
     b1 = timed(lambda: ctx.backsub(plan, n, None, None, lam, None, ids, u, None))
     b0 = timed(lambda: ctx.backsub(plan, n, A, b, lam, None, ids, u, None))

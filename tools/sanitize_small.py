@@ -28,9 +28,9 @@ for name, (ndofs, touched) in shapes.items():
     ctx.condense(plan, n, A, b, S, g, info, keep_factors=True)      # DMMA shapes: left-looking kernel + back substitution
     ctx.backsub(plan, n, None, None, lam, None, ids, u, None)        # backward map from the stored factors
     if plan.kernel_name.startswith("dmma"):
-        os.environ["GHB_DMMA_LL"] = "0"                              # the right-looking kernel too
+        ctx.set_option("dmma_ll", 0)                              # the right-looking kernel too
         ctx.condense(plan, n, A, b, S, g, info)
-        del os.environ["GHB_DMMA_LL"]
+        ctx.set_option("dmma_ll", 1)
     torch.cuda.synchronize()
     print(name, plan.kernel_name, "ok", float(S.abs().max()), float(u.abs().max()))
 # assembly on a small mesh
