@@ -1,5 +1,5 @@
 """Multi-GPU check of the slab path with real NCCL (launch with torchrun, one rank per GPU):
-condense on every rank -> cut-plane exchange (NCCL send/recv) -> owner-computes assembly of the owned columns,
+condense on every rank -> cut-plane exchange (NCCL send/recv behind the C ABI) -> owner-computes assembly of the owned columns,
 gathered on rank 0 and compared bit-for-bit with the single-GPU global assembly; then the lambda all-gather and
 the backward step against the oracle.  Used by tests/test_gpu_multi.py and by hand:
   python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/nccl_slab_check.py 6 5 8
@@ -14,7 +14,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import gridaphybrid_b200 as gh  # noqa: E402
-from gridaphybrid_b200.distributed import SlabAssembler, SlabLayout, halo_lambda  # noqa: E402
+from gridaphybrid_b200.distributed import SlabAssembler, SlabLayout  # noqa: E402
 
 
 def main():
@@ -23,6 +23,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = gh.Context(local)
+    ctx.comm_init_from_torch()                       # the library's own NCCL communicator (ghb_comm_init); torch ships the id
     ndofs, touched = [30, 4, 36], np.ones((3, 3), bool)
     plan = ctx.plan_blocks(ndofs, touched, [1, 2], [3])
     L = SlabLayout(gdims, 6, rank, world)
@@ -42,7 +43,7 @@ def main():
     asm = SlabAssembler(ctx, gdims, 6, rank, world, dirichlet_values=dv)
     nz = torch.empty(asm.nnz, dtype=torch.float64, device=dev)
     rhs = torch.empty(asm.nrows_local, dtype=torch.float64, device=dev)
-    asm.assemble(S, g, nz, rhs)                      # NCCL cut-plane exchange inside
+    asm.assemble(S, g, nz, rhs)                      # cut-plane exchange through the C ABI (ghb_exchange_cut_plane_f64)
     colptr, rowval = asm.pattern()
     torch.cuda.synchronize()
     parts = [None] * world
@@ -50,7 +51,7 @@ def main():
                                        rhs=rhs.cpu().numpy(), S=S.cpu().numpy(), g=g.cpu().numpy()))
     # collective 2 + backward step
     lam_own = torch.arange(L.col_begin, L.col_end, dtype=torch.float64, device=dev) * 1e-3
-    lam = halo_lambda(lam_own, L)
+    lam = asm.allgather_lambda(lam_own)              # ghb_allgather_lambda_f64: grouped ncclBroadcast, unequal ranges
     u = torch.empty((n, plan.n_i), dtype=torch.float64, device=dev)
     ctx.backsub(plan, n, A, b, lam, dv, asm.cell_ids[:n].contiguous(), u, info)
     ok = True
@@ -82,6 +83,7 @@ def main():
         print(f"NCCL_SLAB_CHECK world={world} gdims={gdims} nnz={nnz} ok={bool(ok)} backsub_err={err.max():.2e}")
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
+    ctx.comm_destroy()
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)
 
