@@ -72,17 +72,46 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu under csrc/ for sm_100a into one in-tree shared library."""
+    """Compile every .cu under csrc/ for sm_100a into one in-tree shared library.  The translation units are compiled in
+    parallel and their objects cached by content hash (sources + headers + flags) under csrc/_obj/, so an A/B build
+    that changes one knob of one kernel recompiles one file."""
     if force or needs_build():
+        import hashlib
+        from concurrent.futures import ThreadPoolExecutor
         nvcc = os.environ.get("NVCC", "nvcc")
-        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("GHB_NVCC_EXTRA", "").split() + ["-o", SO_PATH] + sources()
-        if verbose:
-            cmd += ["-Xptxas", "-v"]
-        res = subprocess.run(cmd, capture_output=True, text=True)
+        extra = os.environ.get("GHB_NVCC_EXTRA", "").split()
+        cflags = [f for f in NVCC_FLAGS if f not in ("-shared", "-ldl")] + extra
+        hdr = hashlib.sha256()
+        for d in sorted(glob.glob(os.path.join(_CSRC, "*.cuh"))) + [os.path.join(_ROOT, "include", "ghb.h")]:
+            with open(d, "rb") as f:
+                hdr.update(f.read())
+        objdir = os.path.join(_CSRC, "_obj")
+        os.makedirs(objdir, exist_ok=True)
+
+        def compile_one(src):
+            with open(src, "rb") as f:
+                h = hashlib.sha256(hdr.digest() + f.read() + " ".join(cflags).encode()).hexdigest()[:24]
+            obj = os.path.join(objdir, os.path.basename(src)[:-3] + "." + h + ".o")
+            if not os.path.exists(obj):
+                cmd = [nvcc] + cflags + ["-c", "-o", obj + ".tmp", src] + (["-Xptxas", "-v"] if verbose else [])
+                res = subprocess.run(cmd, capture_output=True, text=True)
+                if res.returncode != 0:
+                    raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+                os.replace(obj + ".tmp", obj)
+                if verbose:
+                    print(res.stderr)
+            return obj
+
+        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+            objs = list(ex.map(compile_one, sources()))
+        res = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO_PATH] + objs + ["-ldl"],
+                             capture_output=True, text=True)
         if res.returncode != 0:
-            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-        if verbose:
-            print(res.stderr)
+            raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
+        keep = set(objs)                                   # drop objects of older versions of the same files
+        for o in glob.glob(os.path.join(objdir, "*.o")):
+            if o not in keep and os.path.getmtime(o) < __import__("time").time() - 86400:
+                os.remove(o)
         with open(SO_PATH + ".srchash", "w") as f:
             f.write(_source_hash())
     return SO_PATH
@@ -95,7 +124,8 @@ def lib():
     global _LIB
     if _LIB is not None:
         return _LIB
-    if needs_build():     # missing, or edited sources: never run a stale library
+    # missing, or edited sources: never run a stale library (an explicit A/B artifact, GHB_LIB_PATH, is used as it is)
+    if not os.path.exists(SO_PATH) or (not os.environ.get("GHB_LIB_PATH") and needs_build()):
         build()
     L = ctypes.CDLL(SO_PATH)
     vp, i32, i64, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint64

@@ -161,11 +161,11 @@ bool is_device_ptr(const void* p);
 
 // cudaFuncSetAttribute + occupancy once per kernel instantiation; returns the resident CTAs per SM to launch with
 template <typename K>
-int kernel_setup(ghb_ctx* ctx, const Options& opt, K kern, int threads, size_t smem, bool carveout, KernelSetup& ks,
+int kernel_setup(ghb_ctx* ctx, const Options& opt, K kern, int threads, size_t smem, int carveout, KernelSetup& ks,
                  const char* name, int* per_sm_out) {
   if (ks.per_sm < 0) {
     GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (carveout) GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    if (carveout) GHB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout == 1 ? 100 : carveout));
     int per_sm = 0;
     GHB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) return fail(ctx, GHB_ECUDA, std::string(name) + " does not fit on an SM");

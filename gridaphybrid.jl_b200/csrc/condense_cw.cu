@@ -32,6 +32,7 @@
 //            Z = L^-1 P A12_J (record -> registers), X = U^-1 Z, S_J = A22_J - A21 X; X is A11^-1 [A12 b1], so
 //            keep_factors is one extra store.
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -40,6 +41,12 @@
 #endif
 #ifndef GHB_CW_MINB
 #define GHB_CW_MINB 4         // CTAs per SM the kernel is compiled for
+#endif
+#ifndef GHB_CW_NJ
+#define GHB_CW_NJ 1           // column tiles of [A12 b1] per pass of phase B (2: B fragments shared by two DMMA chains)
+#endif
+#ifndef GHB_CW_CARVEOUT
+#define GHB_CW_CARVEOUT 100   // preferred shared-memory carve-out (%): below 100 leaves L1 for the A21 / A12 reads
 #endif
 #ifndef GHB_CW_EXACT
 #define GHB_CW_EXACT 1        // 1: LAPACK's pivot (first exact maximum in swapped order); 0: maximum to 2^-15 relative
@@ -538,13 +545,17 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
     double* Sc = ar.S + cell * (int64_t)NB * NB;
     double* gc = ar.g + cell * (int64_t)NB;
 
-#pragma unroll 1
-    for (int J = 0; J < CTB; ++J) {
-      const int col = 8 * J + g;                             // column of [A12 b1] held by this lane's fragments
-      const bool cA = col < NB;                              // A12 column (else: the right-hand side, or padding)
+    // One pass handles NJ column tiles at a time: every B fragment (L / U tiles from shared memory, A21 from L2) is loaded
+    // once and used for NJ independent DMMA chains.
+    auto pass = [&](auto njc, const int J0) {
+      constexpr int NJ = decltype(njc)::value;
+      int col[NJ];                                           // column of [A12 b1] held by this lane's fragments, per tile
+      bool cA[NJ];                                           // A12 column (else: the right-hand side, or padding)
+#pragma unroll
+      for (int jj = 0; jj < NJ; ++jj) { col[jj] = 8 * (J0 + jj) + g; cA[jj] = col[jj] < NB; }
       const double* tbase = Arec;
-      if (J == CTB - 1 && !cA) {
-        // the right-hand side b1 (padding columns repeat it; they are never stored)
+      if (NJ == 1 && J0 == CTB - 1 && !cA[0]) {
+        // the right-hand side b1 (padding columns repeat it; they are never stored); the last tile is always a single pass
         tbase = brec;
 #pragma unroll
         for (int j = 0; j < RT; ++j) {
@@ -558,31 +569,43 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
         }
       }
       // ---- T = (P A12_J)^T straight from the record
-      double T[RT][2];
+      double T[NJ][RT][2];
+#pragma unroll
+      for (int jj = 0; jj < NJ; ++jj)
+#pragma unroll
+        for (int j = 0; j < RT; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            if (j == RT - 1 && 4 * e >= NPL) { T[jj][j][e] = 0.0; continue; }
+            const int of = o[j][e] + jj * st8[j][e];
+            if (SPARSE || j == RT - 1) T[jj][j][e] = o[j][e] >= 0 ? __ldg(tbase + of) : 0.0;
+            else T[jj][j][e] = __ldg(tbase + of);
+          }
 #pragma unroll
       for (int j = 0; j < RT; ++j)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          if (j == RT - 1 && 4 * e >= NPL) { T[j][e] = 0.0; continue; }
-          if (SPARSE || j == RT - 1) T[j][e] = o[j][e] >= 0 ? __ldg(tbase + o[j][e]) : 0.0;
-          else T[j][e] = __ldg(tbase + o[j][e]);
-          o[j][e] += st8[j][e];
-        }
+        for (int e = 0; e < 2; ++e) o[j][e] += NJ * st8[j][e];
       // ---- Z = L^-1 P A12_J
 #pragma unroll
       for (int q = 0; q < RT; ++q) {
         double b0, b1;
         lds128(a_invL + 512u * q + 64u * g + T16, b0, b1);
-        double z0 = 0.0, z1 = 0.0;
-        dmma(z0, z1, T[q][0], b0);
-        if (q < RT - 1 || NPL > 4) dmma(z0, z1, T[q][1], b1);
-        T[q][0] = z0; T[q][1] = z1;
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) {
+          double z0 = 0.0, z1 = 0.0;
+          dmma(z0, z1, T[jj][q][0], b0);
+          if (q < RT - 1 || NPL > 4) dmma(z0, z1, T[jj][q][1], b1);
+          T[jj][q][0] = z0; T[jj][q][1] = z1;
+        }
 #pragma unroll
         for (int i = q + 1; i < RT; ++i) {
           double l0, l1;
           lds128(rb[i] + 64u * q, l0, l1);
-          dmma(T[i][0], T[i][1], z0, l0);
-          dmma(T[i][0], T[i][1], z1, l1);
+#pragma unroll
+          for (int jj = 0; jj < NJ; ++jj) {
+            dmma(T[jj][i][0], T[jj][i][1], T[jj][q][0], l0);
+            dmma(T[jj][i][0], T[jj][i][1], T[jj][q][1], l1);
+          }
         }
       }
       // ---- X = U^-1 Z
@@ -590,44 +613,55 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
       for (int q = RT - 1; q >= 0; --q) {
         double b0, b1;
         lds128(rb[q] + 64u * q, b0, b1);                     // inv(U_qq) sits in the diagonal block of the image
-        double x0 = 0.0, x1 = 0.0;
-        dmma(x0, x1, T[q][0], b0);
-        if (q < RT - 1 || NPL > 4) dmma(x0, x1, T[q][1], b1);
-        T[q][0] = x0; T[q][1] = x1;
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) {
+          double x0 = 0.0, x1 = 0.0;
+          dmma(x0, x1, T[jj][q][0], b0);
+          if (q < RT - 1 || NPL > 4) dmma(x0, x1, T[jj][q][1], b1);
+          T[jj][q][0] = x0; T[jj][q][1] = x1;
+        }
 #pragma unroll
         for (int p = q - 1; p >= 0; --p) {                   // off-diagonal U tiles are stored negated
           double u0, u1;
           lds128(rb[p] + 64u * q, u0, u1);
-          dmma(T[p][0], T[p][1], x0, u0);
-          if (q < RT - 1 || NPL > 4) dmma(T[p][0], T[p][1], x1, u1);
+#pragma unroll
+          for (int jj = 0; jj < NJ; ++jj) {
+            dmma(T[jj][p][0], T[jj][p][1], T[jj][q][0], u0);
+            if (q < RT - 1 || NPL > 4) dmma(T[jj][p][0], T[jj][p][1], T[jj][q][1], u1);
+          }
         }
       }
       if (KEEPX) {
         // X = A11^-1 [A12 | b1], col-major n_i x (n_b+1) per cell
-        if (col < NC) {
-          double* Xc = ar.X + cell * (int64_t)(NI * NC) + (int64_t)col * NI;
 #pragma unroll
-          for (int p = 0; p < RT; ++p)
+        for (int jj = 0; jj < NJ; ++jj)
+          if (col[jj] < NC) {
+            double* Xc = ar.X + cell * (int64_t)(NI * NC) + (int64_t)col[jj] * NI;
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int k = 8 * p + 4 * e + t;
-              if (8 * p + 4 * e < NI && (p < RT - 1 || (e ? vl1 : vl0))) Xc[k] = failed ? qnan : T[p][e];
-            }
-        }
+            for (int p = 0; p < RT; ++p)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int k = 8 * p + 4 * e + t;
+                if (8 * p + 4 * e < NI && (p < RT - 1 || (e ? vl1 : vl0))) Xc[k] = failed ? qnan : T[jj][p][e];
+              }
+          }
       }
       // ---- S_J = A22_J - A21 X_J  (transposed tiles: acc[m][e] = S[8m + 2t + e][col])
-      double acc[BTM][2];
-      const double* ini = cA ? ((SPARSE && ar.a22base < 0) ? nullptr : Arec + ar.a22base + col * NB) : brec + ar.b2base;
+      double acc[NJ][BTM][2];
 #pragma unroll
-      for (int m = 0; m < BTM; ++m) {
-        const int r = 8 * m + 2 * t;
-        acc[m][0] = 0.0; acc[m][1] = 0.0;
-        if (!SPARSE || ini != nullptr) {
-          if (al16) {
-            if (NB % 8 == 0 || r < NB) { const double2 v = __ldg(reinterpret_cast<const double2*>(ini + r)); acc[m][0] = v.x; acc[m][1] = v.y; }
-          } else {
-            if (NB % 8 == 0 || r < NB) acc[m][0] = __ldg(ini + r);
-            if (NB % 8 == 0 || r + 1 < NB) acc[m][1] = __ldg(ini + r + 1);
+      for (int jj = 0; jj < NJ; ++jj) {
+        const double* ini = cA[jj] ? ((SPARSE && ar.a22base < 0) ? nullptr : Arec + ar.a22base + col[jj] * NB) : brec + ar.b2base;
+#pragma unroll
+        for (int m = 0; m < BTM; ++m) {
+          const int r = 8 * m + 2 * t;
+          acc[jj][m][0] = 0.0; acc[jj][m][1] = 0.0;
+          if (!SPARSE || ini != nullptr) {
+            if (al16) {
+              if (NB % 8 == 0 || r < NB) { const double2 v = __ldg(reinterpret_cast<const double2*>(ini + r)); acc[jj][m][0] = v.x; acc[jj][m][1] = v.y; }
+            } else {
+              if (NB % 8 == 0 || r < NB) acc[jj][m][0] = __ldg(ini + r);
+              if (NB % 8 == 0 || r + 1 < NB) acc[jj][m][1] = __ldg(ini + r + 1);
+            }
           }
         }
       }
@@ -636,10 +670,9 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           if (8 * p + 4 * e < NI) {                          // k-step with at least one real column
-            const double xa = flip(T[p][e]);
-            const int ofs = cbk[p][e];
-            const bool okc = (!SPARSE || ofs >= 0) && (p < RT - 1 || (e ? vl1 : vl0));
-            const double* src = Arec + (okc ? ofs : 0);
+            const int of = cbk[p][e];
+            const bool okc = (!SPARSE || of >= 0) && (p < RT - 1 || (e ? vl1 : vl0));
+            const double* src = Arec + (okc ? of : 0);
             double bf[BTM];
 #pragma unroll
             for (int m = 0; m < BTM; ++m) {
@@ -649,26 +682,41 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
                 bf[m] = __ldg(src + 8 * m);
             }
 #pragma unroll
-            for (int m = 0; m < BTM; ++m) dmma(acc[m][0], acc[m][1], xa, bf[m]);
+            for (int jj = 0; jj < NJ; ++jj) {
+              const double xa = flip(T[jj][p][e]);
+#pragma unroll
+              for (int m = 0; m < BTM; ++m) dmma(acc[jj][m][0], acc[jj][m][1], xa, bf[m]);
+            }
           }
         }
       }
       // ---- store
-      if (col < NC) {
-        double* dst = cA ? Sc + (int64_t)col * NB : gc;
 #pragma unroll
-        for (int m = 0; m < BTM; ++m) {
-          const int r = 8 * m + 2 * t;
-          double v0 = acc[m][0], v1 = acc[m][1];
-          if (failed) { v0 = qnan; v1 = qnan; }
-          if (al16) {
-            if (NB % 8 == 0 || r < NB) *reinterpret_cast<double2*>(dst + r) = make_double2(v0, v1);
-          } else {
-            if (NB % 8 == 0 || r < NB) dst[r] = v0;
-            if (NB % 8 == 0 || r + 1 < NB) dst[r + 1] = v1;
+      for (int jj = 0; jj < NJ; ++jj)
+        if (col[jj] < NC) {
+          double* dst = cA[jj] ? Sc + (int64_t)col[jj] * NB : gc;
+#pragma unroll
+          for (int m = 0; m < BTM; ++m) {
+            const int r = 8 * m + 2 * t;
+            double v0 = acc[jj][m][0], v1 = acc[jj][m][1];
+            if (failed) { v0 = qnan; v1 = qnan; }
+            if (al16) {
+              if (NB % 8 == 0 || r < NB) *reinterpret_cast<double2*>(dst + r) = make_double2(v0, v1);
+            } else {
+              if (NB % 8 == 0 || r < NB) dst[r] = v0;
+              if (NB % 8 == 0 || r + 1 < NB) dst[r + 1] = v1;
+            }
           }
         }
+    };
+    {
+      int J = 0;
+      if (GHB_CW_NJ == 2) {
+#pragma unroll 1
+        for (; J + 2 < CTB; J += 2) pass(std::integral_constant<int, 2>{}, J);   // the last tile is a single pass
       }
+#pragma unroll 1
+      for (; J < CTB; ++J) pass(std::integral_constant<int, 1>{}, J);
     }
     if (ar.info && lane == 0) ar.info[cell] = failed;
     if (failed) {
@@ -685,7 +733,11 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
 // ---- host side ----------------------------------------------------------------------------------------
 // Shapes the kernel is instantiated for: one boundary field, n_i <= 64, interior fields first in the condensed order
 // (always true: Plan orders interior rows first).
+#ifdef GHB_CW_MORE_SHAPES   // experiments: shapes that have other tuned kernels
+#define GHB_CW_SHAPES(X) X(34, 36) X(33, 12) X(40, 36) X(21, 16) X(56, 16) X(16, 8)
+#else
 #define GHB_CW_SHAPES(X) X(34, 36) X(33, 12) X(40, 36) X(21, 16)
+#endif
 
 static bool cw_shape(int ni, int nb) {
 #define X(a, b) if (ni == a && nb == b) return true;
@@ -790,7 +842,7 @@ static int launch_cw(ghb_ctx* ctx, const Plan& p, CwArgs& ar) {
   const size_t smem = CwCfg<NI, NB>::smem_bytes(WPC);
   static KernelSetup ks;
   int per_sm = 0;
-  GHB_TRY(kernel_setup(ctx, p.opt, kern, 32 * WPC, smem, true, ks, "condense_cw_kernel", &per_sm));
+  GHB_TRY(kernel_setup(ctx, p.opt, kern, 32 * WPC, smem, GHB_CW_CARVEOUT, ks, "condense_cw_kernel", &per_sm));
   const int64_t want = (ar.ncells + WPC - 1) / WPC;
   const int64_t grid = std::min<int64_t>(want, (int64_t)ctx->sm_count * per_sm);
   kern<<<(unsigned)grid, 32 * WPC, smem, ctx->stream>>>(ar);
