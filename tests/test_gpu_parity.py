@@ -915,3 +915,70 @@ def test_pageable_and_pinned_host_records_agree(ctx):
         assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
     finally:
         ctx.set_option("stream_chunk_bytes", 256 << 20)
+
+
+@pytest.mark.parametrize("dims,order", [((2, 2), 1), ((4, 3), 1), ((2, 2, 2), 2)])
+def test_newton_path_hybrid_fe_operator(ctx, dims, order):
+    """test/DarcyHDGTests.jl:157-165: the same (linear) problem through HybridFEOperator + Newton from x0 = 0.  Every
+    Newton step is hybrid_backslash_solve (src/HybridLinearSolvers.jl:15-59): condensation of (J_K, -R_K), assembly
+    WITHOUT the Dirichlet lift (:37-41), A\\b, back-substitution with a zero Dirichlet correction (:47-57).  One step must
+    land on the exact solution (||u - u_h||_L2 < 1e-12, the reference's criterion) and on the affine operator's solution;
+    the second step's correction must vanish (same cached pattern, another assembler sharing the context in between)."""
+    prob = DarcyProblem(dims, order)
+    p = prob.prob
+    nc, nu, npp, nl = p.ncells, p.D * p.Nu, p.Np, prob.plan.n_b
+    sk = gh.CartesianSkeleton(dims, ctx)
+    dv = torch.as_tensor(prob.dir_vals, device="cuda")
+    M = gh.FacetFESpace(sk, p.Nl, sk.facet_is_boundary(), dv)
+    trial = [p.ndofs[0], p.ndofs[1], M]
+    mats_t = [[torch.as_tensor(m) for m in row] for row in prob.mats]
+
+    def jacobian_and_residual(xu, xp, lam_free):
+        """cell-wise block system of the Newton step at the iterate (u, p, lambda): A_K = J_K (the problem is linear),
+        b_K = -R_K = b_K - A_K x_K with the Dirichlet values of lambda inside x_K"""
+        lamK = o.cell_dof_values(lam_free, prob.dir_vals, prob.cell_ids)
+        xs = [xu, xp, lamK]
+        vecs = []
+        for i in range(3):
+            r = prob.vecs[i].copy()
+            for j in range(3):
+                if prob.touched[i, j]:
+                    r -= np.einsum("cij,cj->ci", prob.mats[i][j], xs[j])
+            vecs.append(torch.as_tensor(r))
+        return gh.PackedCells.from_blocks(mats_t, vecs, prob.touched, device="cuda")
+
+    op = gh.HybridFEOperator(jacobian_and_residual, trial, trial, [1, 2], [3])
+    x_u, x_p, x_l = np.zeros((nc, nu)), np.zeros((nc, npp)), np.zeros(prob.nfree)
+    affine = gh.HybridAffineFEOperator(
+        lambda: gh.PackedCells.from_blocks(mats_t, [torch.as_tensor(v) for v in prob.vecs], prob.touched, device="cuda"),
+        trial, trial, [1, 2], [3])                     # a second assembler on the same context (pattern handles)
+    x_aff = affine.solve().cpu().numpy()
+    for it in range(2):
+        dx = gh.hybrid_backslash_solve(op, op.jacobian_and_residual(x_u, x_p, x_l)).cpu().numpy()
+        if it == 1:
+            assert np.abs(dx).max() < 1e-10            # converged after one step: the correction vanishes
+        x_u = x_u + dx[:nc * nu].reshape(nc, nu)
+        x_p = x_p + dx[nc * nu:nc * (nu + npp)].reshape(nc, npp)
+        x_l = x_l + dx[nc * (nu + npp):]
+        assert p.l2_error_u(x_u) < 1e-12
+    x1 = np.concatenate([x_u.ravel(), x_p.ravel(), x_l])
+    assert np.abs(x1 - x_aff).max() < 1e-10 * max(1.0, np.abs(x_aff).max())
+    assert np.allclose(x_l.reshape(-1, p.Nl)[:, 0], -3.14, atol=1e-10)
+
+
+@pytest.mark.parametrize("name", ["C3_hdg_k2_3d", "C2_rth_k2_2d"])
+def test_ill_conditioned_cells_follow_kappa_eps(ctx, name):
+    """physically ill-conditioned interior blocks (prescribed cond(A11) up to 1e8, tools/illcond_sweep.py): the tuned
+    kernel stays within a modest multiple of kappa * eps of the LAPACK oracle -- the distance two backward-stable LU
+    codes have from each other -- so the 1e-11 bar holds up to cond ~ 1e3-1e4 and degrades proportionally beyond, not
+    faster (profiles/r02_illcond.md has the measured table)."""
+    import importlib.util, os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "illcond_sweep.py")
+    spec = importlib.util.spec_from_file_location("illcond_sweep", path)
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    eps = np.finfo(float).eps
+    kn, rows = mod.sweep(ctx, name, 96, [1e2, 1e4, 1e6, 1e8])
+    assert kn.startswith("cw_")
+    for kappa, eS, eg in rows:
+        assert max(eS, eg) < 256 * kappa * eps, (kappa, eS, eg)
+    assert max(rows[0][1], rows[0][2]) < TOL
