@@ -308,6 +308,13 @@ int ghb_plan_blocks(ghb_ctx* ctx, int nfields, const int32_t* ndofs, const uint8
     if (rc != GHB_OK) { cudaFree(p->d_emap); delete p; return rc; }
     p->use_cw = true;
     p->kernel_name = cw_kernel_name(*p);
+  } else if (!p->use_dmma && !p->use_warp && !p->use_large && cw_pad_supported(*p) && !force && ctx->opt.cw) {
+    // no tuned kernel for this shape: the shape-generic instantiation of the same kernel (padded n_i class, any fields)
+    p->cw_pad = cw_pad_class_of(*p);
+    int rc = cw_prepare(ctx, *p);
+    if (rc != GHB_OK) { cudaFree(p->d_emap); delete p; return rc; }
+    p->use_cw = true;
+    p->kernel_name = cw_kernel_name(*p);
   }
   ctx->plans.push_back(p);
   *plan_id = (int)ctx->plans.size() - 1;

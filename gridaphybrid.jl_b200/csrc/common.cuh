@@ -58,7 +58,8 @@ struct Plan {
   int cw_pf[6] = {0, 0, 0, 0, 0, 0};   // record ranges (offset, length) of A12 / A21 / A22 for its L2 prefetches
   unsigned char* d_cw = nullptr;  // its tables in one block: loader | rowA12 | colA21 | rowb (byte offsets cw_off)
   int cw_nld = 0;
-  size_t cw_off[3] = {0, 0, 0};
+  size_t cw_off[5] = {0, 0, 0, 0, 0};
+  int cw_pad = 0;                 // 0: tuned instantiation of the exact shape; else the padded n_i class of the generic one
   bool use_warp = false;          // register-resident warp kernels for small cells (condense_warp.cu)
   bool use_large = false;         // streamed large-cell kernel, 64 < n_i <= 128 (condense_large.cu)
   bool all_touched = false;
@@ -232,6 +233,8 @@ int launch_backsub_large(ghb_ctx* ctx, const Plan& p, int64_t ncells, const doub
                          const double* lam_free, const double* lam_dir, const int64_t* ids, double* u, int32_t* info);
 int dmma_prepare(ghb_ctx* ctx, Plan& p);
 bool cw_supported(const Plan& p);
+bool cw_pad_supported(const Plan& p);
+int cw_pad_class_of(const Plan& p);
 const char* cw_kernel_name(const Plan& p);
 int cw_prepare(ghb_ctx* ctx, Plan& p);
 int launch_condense_cw(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,

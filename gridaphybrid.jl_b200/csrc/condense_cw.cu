@@ -118,6 +118,10 @@ struct CwArgs {
   const uint32_t* rowA12;   // [n_i + 1] per interior row: record offset of A12(row, 0) | stride << 16; 0xffffffff: zero row
   const uint16_t* rowb;     // [n_i + 1] per interior row: offset in the b record
   const int32_t* colA21;    // [8 RT] per interior column: record offset of A21(0, col) or -1
+  const int32_t* colbase;   // PAD kernels: [(n+1)*nf] record offset of (first row of field f, condensed column c) or -1;
+                            // c == n: offsets in the b record
+  const uint16_t* rowinfo;  // PAD kernels: [n] field << 8 | local row of condensed row r
+  int n_i, n_b, nf;         // PAD kernels: the plan's real sizes (<= the padded NI, NB of the instantiation)
   int nld;
   int a22base, b2base;      // record offsets of A22(0,0) (-1: untouched) and of b2 in the b record
   int al16;                 // pairs of boundary rows are 16-byte aligned in A22, b2, S and g
@@ -154,7 +158,11 @@ struct CwCfg {
   static constexpr unsigned SH_ROWA12 = 64;
   static constexpr unsigned SH_ROWB = SH_ROWA12 + 4 * ((NI + 1 + 3) & ~3);
   static constexpr unsigned SH_BYTES = SH_ROWB + 2 * ((NI + 1 + 7) & ~7);
-  static size_t smem_bytes(int wpc) { return (size_t)wpc * WARP_BYTES + SH_BYTES; }
+  // PAD kernels add: colbase[(NI+NB+1) * 8 fields] (i32), rowinfo[NI+NB] (u16)
+  static constexpr unsigned SH_COLBASE = SH_BYTES;
+  static constexpr unsigned SH_ROWINFO = SH_COLBASE + 4 * (NI + NB + 1) * 8;
+  static constexpr unsigned SH_BYTES_PAD = SH_ROWINFO + 2 * ((NI + NB + 7) & ~7);
+  static size_t smem_bytes(int wpc, bool pad = false) { return (size_t)wpc * WARP_BYTES + (pad ? SH_BYTES_PAD : SH_BYTES); }
   // position-table entry of image row r: byte offset of the row | swizzle bits (4,5) | r << 16
   __host__ __device__ static constexpr unsigned enc(unsigned r) { return r * ROWB | ((r & 6u) << 3) | (r << 16); }
 };
@@ -272,10 +280,21 @@ __device__ __forceinline__ void panel_factor(double (&a)[8], double (&a2)[8], co
   }
 }
 
-template <int NI, int NB, int WPC, int MINB, bool KEEPX, bool SPARSE>
+// PAD: the shape-generic mode.  The instantiation is for a PADDED shape (NI a multiple of 8, NB = 40); the plan's real
+// n_i <= NI, n_b <= NB arrive at run time.  The image is completed with an identity on the pad diagonal (pad rows are
+// never pivots of real columns, pad columns have their own row as the only candidate: LAPACK's choices on the real part
+// are unchanged), everything outside the real blocks reads as zero, and all record offsets come from the plan's
+// (column, field) table -- any number of interior and skeleton fields, any touched mask.
+template <int NI, int NB, int WPC, int MINB, bool KEEPX, bool SPARSE, bool PAD>
 __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArgs ar) {
   using C = CwCfg<NI, NB>;
-  constexpr int NC = C::NC, RT = C::RT, CTB = C::CTB, BTM = C::BTM, NPL = C::NPL, DUMMY = C::DUMMY;
+  constexpr int RT = C::RT, NPL = C::NPL, DUMMY = C::DUMMY;
+  constexpr int BTM = C::BTM;
+  static_assert(!PAD || (SPARSE && NI % 8 == 0), "PAD kernels are instantiated for padded shapes");
+  const int nir = PAD ? ar.n_i : NI, nbr = PAD ? ar.n_b : NB;       // real sizes
+  const int NC = nbr + 1;                                           // right-hand-side columns: A12 | b1
+  const int CTB = PAD ? (NC + 7) / 8 : C::CTB;
+  const int btm = PAD ? (nbr + 7) / 8 : BTM;
   constexpr unsigned ROWB = C::ROWB;
   constexpr bool HAS2 = NI > 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -296,13 +315,33 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
     reinterpret_cast<uint32_t*>(shp + C::SH_ROWA12)[i] = ar.rowA12[i];
     reinterpret_cast<uint16_t*>(shp + C::SH_ROWB)[i] = ar.rowb[i];
   }
+  const int nf = ar.nf, ntot = nir + nbr;
+  const unsigned a_colbase = a_sh + C::SH_COLBASE, a_rowinfo = a_sh + C::SH_ROWINFO;
+  if (PAD) {
+    for (int i = threadIdx.x; i < (ntot + 1) * nf; i += 32 * WPC) reinterpret_cast<int32_t*>(shp + C::SH_COLBASE)[i] = ar.colbase[i];
+    for (int i = threadIdx.x; i < ntot; i += 32 * WPC) reinterpret_cast<uint16_t*>(shp + C::SH_ROWINFO)[i] = ar.rowinfo[i];
+  }
   __syncthreads();
 
   // lane constants
   const unsigned G8 = 8u * (unsigned)mu(g);                  // image column offset of logical column g of a tile
   const unsigned T16 = 16u * (unsigned)t;
   const bool vl0 = t < NPL, vl1 = 4 + t < NPL;               // logical indices t, 4+t exist in the last panel
-  const bool vb = (NB % 8 == 0) || (8 * (BTM - 1) + g < NB);   // boundary row 8(BTM-1)+g exists
+  const bool vb = !PAD && ((NB % 8 == 0) || (8 * (BTM - 1) + g < NB));   // boundary row 8(BTM-1)+g exists
+  // PAD: field << 8 | local of this lane's boundary rows (8m + g: A21 fragments; 8m + 2t + e: A22 / b2), 0xffff: no such row
+  unsigned rinfo21[PAD ? BTM : 1], rinfo22[PAD ? BTM : 1][2];
+  if (PAD) {
+#pragma unroll
+    for (int m = 0; m < BTM; ++m) {
+      const int r = 8 * m + g;
+      rinfo21[m] = r < nbr ? reinterpret_cast<uint16_t*>(shp + C::SH_ROWINFO)[nir + r] : 0xffffu;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int r2 = 8 * m + 2 * t + e;
+        rinfo22[m][e] = r2 < nbr ? reinterpret_cast<uint16_t*>(shp + C::SH_ROWINFO)[nir + r2] : 0xffffu;
+      }
+    }
+  }
   const unsigned encA = C::enc(lane < NI ? lane : DUMMY);
   const unsigned encB = C::enc((HAS2 && lane + 32 < NI) ? lane + 32 : DUMMY);
   // A21 fragments: record offset of element (boundary row 8m + g, interior column 8p + 4e + t) = cbk[p][e] + 8m
@@ -311,8 +350,9 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
   for (int p = 0; p < RT; ++p)
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const int v = ar.colA21[8 * p + 4 * e + t];
-      cbk[p][e] = v >= 0 ? v + g : -1;
+      const int k = 8 * p + 4 * e + t;
+      const int v = PAD ? (k < nir ? k * nf : -1) : ar.colA21[k];      // PAD: row of the (column, field) table
+      cbk[p][e] = PAD ? v : (v >= 0 ? v + g : -1);
     }
   const int lenA = ar.lenA, lenb = ar.lenb;
   const bool al16 = ar.al16 != 0;
@@ -352,6 +392,10 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
     if (lane + 32 < 8 * RT) sts_u32(a_prow + 4u * (lane + 32), encB);
     if (lane == 0) sts_u32(a_info, 0u);
     cp_async_wait_all();
+    if (PAD && nir + lane < NI) {                            // identity on the pad diagonal
+      const unsigned r = (unsigned)(nir + lane);
+      sts64(ws + r * ROWB + ((8u * (8u * (r >> 3) + (unsigned)mu(r & 7))) ^ ((r & 6u) << 3)), 1.0);
+    }
     __syncwarp();
 
     // ------------------------------------------------------------------ LU of A11, left-looking by column tiles
@@ -534,6 +578,14 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const unsigned w = e ? w1 : w0;
+        if (PAD) {                                           // field << 8 | local of the row at this position, -1: pad row
+          const unsigned row = w >> 16;
+          unsigned short si = 0xffffu;
+          if (row < (unsigned)nir) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(si) : "r"(a_rowinfo + (row << 1)));
+          o[j][e] = si == 0xffffu ? -1 : (int)si;
+          st8[j][e] = 0;
+          continue;
+        }
         const unsigned ra = lds_u32(a_rowA12 + ((w >> 16) << 2));
         const bool ok = !(SPARSE && ra == 0xffffffffu) && !(j == RT - 1 && !(e ? vl1 : vl0));
         const int strd = (int)(ra >> 16);
@@ -542,8 +594,8 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
       }
       rb[j] = ws + ((lds_u32(a_prow + 32u * j + 4u * (unsigned)g) & 0xffffu) ^ T16);
     }
-    double* Sc = ar.S + cell * (int64_t)NB * NB;
-    double* gc = ar.g + cell * (int64_t)NB;
+    double* Sc = ar.S + cell * (int64_t)nbr * nbr;
+    double* gc = ar.g + cell * (int64_t)nbr;
 
     // One pass handles NJ column tiles at a time: every B fragment (L / U tiles from shared memory, A21 from L2) is loaded
     // once and used for NJ independent DMMA chains.
@@ -552,9 +604,11 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
       int col[NJ];                                           // column of [A12 b1] held by this lane's fragments, per tile
       bool cA[NJ];                                           // A12 column (else: the right-hand side, or padding)
 #pragma unroll
-      for (int jj = 0; jj < NJ; ++jj) { col[jj] = 8 * (J0 + jj) + g; cA[jj] = col[jj] < NB; }
+      for (int jj = 0; jj < NJ; ++jj) { col[jj] = 8 * (J0 + jj) + g; cA[jj] = col[jj] < nbr; }
       const double* tbase = Arec;
-      if (NJ == 1 && J0 == CTB - 1 && !cA[0]) {
+      if (PAD) {
+        if (!cA[0]) tbase = brec;
+      } else if (NJ == 1 && J0 == CTB - 1 && !cA[0]) {
         // the right-hand side b1 (padding columns repeat it; they are never stored); the last tile is always a single pass
         tbase = brec;
 #pragma unroll
@@ -577,6 +631,16 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             if (j == RT - 1 && 4 * e >= NPL) { T[jj][j][e] = 0.0; continue; }
+            if (PAD) {
+              // (column, field) table: condensed column n_i + col of A12, or the right-hand side (column n)
+              T[jj][j][e] = 0.0;
+              if (o[j][e] >= 0 && col[jj] <= nbr) {
+                const int ccol = cA[jj] ? nir + col[jj] : ntot;
+                const int base = (int)lds_u32(a_colbase + 4u * (unsigned)(ccol * nf + (o[j][e] >> 8)));
+                if (base >= 0) T[jj][j][e] = __ldg(tbase + base + (o[j][e] & 0xff));
+              }
+              continue;
+            }
             const int of = o[j][e] + jj * st8[j][e];
             if (SPARSE || j == RT - 1) T[jj][j][e] = o[j][e] >= 0 ? __ldg(tbase + of) : 0.0;
             else T[jj][j][e] = __ldg(tbase + of);
@@ -636,13 +700,13 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
 #pragma unroll
         for (int jj = 0; jj < NJ; ++jj)
           if (col[jj] < NC) {
-            double* Xc = ar.X + cell * (int64_t)(NI * NC) + (int64_t)col[jj] * NI;
+            double* Xc = ar.X + cell * (int64_t)(nir * NC) + (int64_t)col[jj] * nir;
 #pragma unroll
             for (int p = 0; p < RT; ++p)
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
                 const int k = 8 * p + 4 * e + t;
-                if (8 * p + 4 * e < NI && (p < RT - 1 || (e ? vl1 : vl0))) Xc[k] = failed ? qnan : T[jj][p][e];
+                if (8 * p + 4 * e < NI && k < nir && (p < RT - 1 || (e ? vl1 : vl0))) Xc[k] = failed ? qnan : T[jj][p][e];
               }
           }
       }
@@ -655,6 +719,20 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
         for (int m = 0; m < BTM; ++m) {
           const int r = 8 * m + 2 * t;
           acc[jj][m][0] = 0.0; acc[jj][m][1] = 0.0;
+          if (PAD) {
+            if (m < btm && col[jj] <= nbr) {
+              const int ccol = cA[jj] ? nir + col[jj] : ntot;
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const unsigned ri = rinfo22[m][e];
+                if (ri != 0xffffu) {
+                  const int base = (int)lds_u32(a_colbase + 4u * (unsigned)(ccol * nf + (int)(ri >> 8)));
+                  if (base >= 0) acc[jj][m][e] = __ldg(tbase + base + (int)(ri & 0xffu));
+                }
+              }
+            }
+            continue;
+          }
           if (!SPARSE || ini != nullptr) {
             if (al16) {
               if (NB % 8 == 0 || r < NB) { const double2 v = __ldg(reinterpret_cast<const double2*>(ini + r)); acc[jj][m][0] = v.x; acc[jj][m][1] = v.y; }
@@ -676,6 +754,14 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
             double bf[BTM];
 #pragma unroll
             for (int m = 0; m < BTM; ++m) {
+              if (PAD) {
+                bf[m] = 0.0;
+                if (of >= 0 && rinfo21[m] != 0xffffu) {
+                  const int base = (int)lds_u32(a_colbase + 4u * (unsigned)(of + (int)(rinfo21[m] >> 8)));
+                  if (base >= 0) bf[m] = __ldg(Arec + base + (int)(rinfo21[m] & 0xffu));
+                }
+                continue;
+              }
               if (SPARSE || p == RT - 1 || (m == BTM - 1 && NB % 8 != 0))
                 bf[m] = (okc && (m < BTM - 1 || vb)) ? __ldg(src + 8 * m) : 0.0;
               else
@@ -685,7 +771,8 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
             for (int jj = 0; jj < NJ; ++jj) {
               const double xa = flip(T[jj][p][e]);
 #pragma unroll
-              for (int m = 0; m < BTM; ++m) dmma(acc[jj][m][0], acc[jj][m][1], xa, bf[m]);
+              for (int m = 0; m < BTM; ++m)
+                if (!PAD || m < btm) dmma(acc[jj][m][0], acc[jj][m][1], xa, bf[m]);
             }
           }
         }
@@ -694,12 +781,17 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
 #pragma unroll
       for (int jj = 0; jj < NJ; ++jj)
         if (col[jj] < NC) {
-          double* dst = cA[jj] ? Sc + (int64_t)col[jj] * NB : gc;
+          double* dst = cA[jj] ? Sc + (int64_t)col[jj] * nbr : gc;
 #pragma unroll
           for (int m = 0; m < BTM; ++m) {
             const int r = 8 * m + 2 * t;
             double v0 = acc[jj][m][0], v1 = acc[jj][m][1];
             if (failed) { v0 = qnan; v1 = qnan; }
+            if (PAD) {
+              if (r < nbr) dst[r] = v0;
+              if (r + 1 < nbr) dst[r + 1] = v1;
+              continue;
+            }
             if (al16) {
               if (NB % 8 == 0 || r < NB) *reinterpret_cast<double2*>(dst + r) = make_double2(v0, v1);
             } else {
@@ -711,7 +803,7 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
     };
     {
       int J = 0;
-      if (GHB_CW_NJ == 2) {
+      if (GHB_CW_NJ == 2 && !PAD) {
 #pragma unroll 1
         for (; J + 2 < CTB; J += 2) pass(std::integral_constant<int, 2>{}, J);   // the last tile is a single pass
       }
@@ -746,15 +838,41 @@ static bool cw_shape(int ni, int nb) {
   return false;
 }
 
+// padded classes of the shape-generic (PAD) kernels: n_i <= NI, n_b <= 40
+#define GHB_CW_PAD_NB 40
+#define GHB_CW_PAD_CLASSES(X) X(16) X(24) X(32) X(40) X(48) X(56) X(64)
+
+static int cw_pad_class(int ni) {
+#define X(a) if (ni <= a) return a;
+  GHB_CW_PAD_CLASSES(X)
+#undef X
+  return 0;
+}
+
+// tuned instantiation: exact shape, one skeleton field
 bool cw_supported(const Plan& p) {
   if (p.boundary.size() != 1 || p.lenA >= 65536 || p.lenb >= 65536) return false;
   for (int f = 0; f < p.nfields; ++f) if (p.ndofs[f] > 255) return false;
   return cw_shape(p.n_i, p.n_b);
 }
 
+// shape-generic instantiation: any fields / touched mask with n_i <= 64, n_b <= 40
+int cw_pad_class_of(const Plan& p) { return cw_pad_class(p.n_i); }
+
+bool cw_pad_supported(const Plan& p) {
+  if (p.nfields > 8 || p.n_b > GHB_CW_PAD_NB || cw_pad_class(p.n_i) == 0 || p.lenb >= 65536) return false;
+  for (int f = 0; f < p.nfields; ++f) if (p.ndofs[f] > 255) return false;
+  return true;
+}
+
 const char* cw_kernel_name(const Plan& p) {
+  if (!p.cw_pad) {
 #define X(a, b) if (p.n_i == a && p.n_b == b) return "cw_" #a "_" #b;
-  GHB_CW_SHAPES(X)
+    GHB_CW_SHAPES(X)
+#undef X
+  }
+#define X(a) if (p.cw_pad == a) return "cw_pad_" #a;
+  GHB_CW_PAD_CLASSES(X)
 #undef X
   return "cw";
 }
@@ -767,7 +885,8 @@ static void cw_tables(const Plan& p, std::vector<uint2>& ld, std::vector<uint32_
   // loader: interior element (r, c) -> image row r, tile c / 8, physical column mu(c % 8), chunk-swizzled
   for (int c = 0; c < NI; ++c)
     for (int r = 0; r < NI; ++r) {
-      const int64_t bo = p.block_offset[p.row_field[r] + nf * p.row_field[c]];
+      const bool real = r < p.n_i && c < p.n_i;              // PAD classes: everything outside the real block is zero
+      const int64_t bo = real ? p.block_offset[p.row_field[r] + nf * p.row_field[c]] : -1;
       const uint32_t src = bo < 0 ? 0xffffffffu : (uint32_t)(8 * (bo + (int64_t)p.row_local[c] * p.ndofs[p.row_field[r]] + p.row_local[r]));
       const uint32_t colb = 8u * (uint32_t)(8 * (c / 8) + mu(c % 8));
       const uint32_t dst = (uint32_t)r * C::ROWB + (colb ^ (((uint32_t)r & 6u) << 3));
@@ -780,14 +899,14 @@ static void cw_tables(const Plan& p, std::vector<uint2>& ld, std::vector<uint32_
     ld.push_back(p.all_touched ? make_uint2(0u, C::OFF_SCALEU) : make_uint2(0xffffffffu, (uint32_t)C::DUMMY * C::ROWB));
   rowA12.assign(NI + 1, 0xffffffffu);
   rowb.assign(NI + 1, 0);
-  for (int r = 0; r < NI; ++r) {
+  for (int r = 0; r < NI && r < p.n_i; ++r) {
     const int fr = p.row_field[r];
     const int64_t bo = p.block_offset[fr + nf * fb];
-    if (bo >= 0) rowA12[r] = (uint32_t)(bo + p.row_local[r]) | ((uint32_t)p.ndofs[fr] << 16);
+    if (bo >= 0 && !p.cw_pad) rowA12[r] = (uint32_t)(bo + p.row_local[r]) | ((uint32_t)p.ndofs[fr] << 16);
     rowb[r] = (uint16_t)(p.field_offset_b[fr] + p.row_local[r]);
   }
   colA21.assign(8 * C::RT, -1);
-  for (int c = 0; c < NI; ++c) {
+  for (int c = 0; c < NI && c < p.n_i && !p.cw_pad; ++c) {
     const int64_t bo = p.block_offset[fb + nf * p.row_field[c]];
     if (bo >= 0) colA21[c] = (int32_t)(bo + (int64_t)p.row_local[c] * NB);
   }
@@ -799,18 +918,42 @@ int cw_prepare(ghb_ctx* ctx, Plan& p) {
     std::vector<uint32_t> rowA12;
     std::vector<uint16_t> rowb;
     std::vector<int32_t> colA21;
+    if (!p.cw_pad) {
 #define X(a, b) if (p.n_i == a && p.n_b == b) cw_tables<a, b>(p, ld, rowA12, rowb, colA21);
-    GHB_CW_SHAPES(X)
+      GHB_CW_SHAPES(X)
 #undef X
-    // one device block: ldtab | rowA12 | colA21 | rowb
-    const size_t b0 = ld.size() * sizeof(uint2), b1 = rowA12.size() * 4, b2 = colA21.size() * 4, b3 = rowb.size() * 2;
-    GHB_CUDA(ctx, cudaMalloc((void**)&p.d_cw, b0 + b1 + b2 + b3));
+    } else {
+#define X(a) if (p.cw_pad == a) cw_tables<a, GHB_CW_PAD_NB>(p, ld, rowA12, rowb, colA21);
+      GHB_CW_PAD_CLASSES(X)
+#undef X
+    }
+    // PAD kernels: (condensed column, field) -> record offset of the field's first row in that column, and the
+    // (field, local row) of every condensed row
+    const int n = p.n, nf = p.nfields;
+    std::vector<int32_t> colbase((size_t)(n + 1) * nf, -1);
+    std::vector<uint16_t> rowinfo((size_t)n + 1, 0);
+    for (int c = 0; c < n; ++c) {
+      const int fc = p.row_field[c], lc = p.row_local[c];
+      for (int f = 0; f < nf; ++f) {
+        const int64_t bo = p.block_offset[f + nf * fc];
+        if (bo >= 0) colbase[(size_t)c * nf + f] = (int32_t)(bo + (int64_t)lc * p.ndofs[f]);
+      }
+      rowinfo[c] = (uint16_t)((p.row_field[c] << 8) | p.row_local[c]);
+    }
+    for (int f = 0; f < nf; ++f) colbase[(size_t)n * nf + f] = p.field_offset_b[f];
+    // one device block: ldtab | rowA12 | colA21 | colbase | rowb | rowinfo
+    const size_t b0 = ld.size() * sizeof(uint2), b1 = rowA12.size() * 4, b2 = colA21.size() * 4, b3 = colbase.size() * 4,
+                 b4 = ((rowb.size() * 2 + 3) & ~(size_t)3), b5 = rowinfo.size() * 2;
+    GHB_CUDA(ctx, cudaMalloc((void**)&p.d_cw, b0 + b1 + b2 + b3 + b4 + b5));
     GHB_CUDA(ctx, cudaMemcpy(p.d_cw, ld.data(), b0, cudaMemcpyHostToDevice));
     GHB_CUDA(ctx, cudaMemcpy(p.d_cw + b0, rowA12.data(), b1, cudaMemcpyHostToDevice));
     GHB_CUDA(ctx, cudaMemcpy(p.d_cw + b0 + b1, colA21.data(), b2, cudaMemcpyHostToDevice));
-    GHB_CUDA(ctx, cudaMemcpy(p.d_cw + b0 + b1 + b2, rowb.data(), b3, cudaMemcpyHostToDevice));
+    GHB_CUDA(ctx, cudaMemcpy(p.d_cw + b0 + b1 + b2, colbase.data(), b3, cudaMemcpyHostToDevice));
+    GHB_CUDA(ctx, cudaMemcpy(p.d_cw + b0 + b1 + b2 + b3, rowb.data(), rowb.size() * 2, cudaMemcpyHostToDevice));
+    GHB_CUDA(ctx, cudaMemcpy(p.d_cw + b0 + b1 + b2 + b3 + b4, rowinfo.data(), b5, cudaMemcpyHostToDevice));
     p.cw_nld = (int)ld.size();
-    p.cw_off[0] = b0; p.cw_off[1] = b0 + b1; p.cw_off[2] = b0 + b1 + b2;
+    p.cw_off[0] = b0; p.cw_off[1] = b0 + b1; p.cw_off[2] = b0 + b1 + b2; p.cw_off[3] = b0 + b1 + b2 + b3;
+    p.cw_off[4] = b0 + b1 + b2 + b3 + b4;
   }
   // bounding record ranges of the A12 / A21 / A22 blocks (L2 prefetches)
   const int nf = p.nfields;
@@ -835,11 +978,14 @@ int cw_prepare(ghb_ctx* ctx, Plan& p) {
   return GHB_OK;
 }
 
-template <int NI, int NB, bool KEEPX, bool SPARSE>
+template <int NI, int NB, bool KEEPX, bool SPARSE, bool PAD = false>
 static int launch_cw(ghb_ctx* ctx, const Plan& p, CwArgs& ar) {
-  constexpr int WPC = GHB_CW_WPC, MINB = GHB_CW_MINB;
-  auto kern = condense_cw_kernel<NI, NB, WPC, MINB, KEEPX, SPARSE>;
-  const size_t smem = CwCfg<NI, NB>::smem_bytes(WPC);
+  constexpr int WPC = GHB_CW_WPC;
+  // PAD classes: as many CTAs per SM as their shared memory allows (the register cap follows)
+  constexpr int fit = (int)(233472u / (WPC * CwCfg<NI, NB>::WARP_BYTES + CwCfg<NI, NB>::SH_BYTES_PAD + 1024u));
+  constexpr int MINB = PAD ? (fit < 1 ? 1 : (fit > 4 ? 4 : fit)) : GHB_CW_MINB;
+  auto kern = condense_cw_kernel<NI, NB, WPC, MINB, KEEPX, SPARSE, PAD>;
+  const size_t smem = CwCfg<NI, NB>::smem_bytes(WPC, PAD);
   static KernelSetup ks;
   int per_sm = 0;
   GHB_TRY(kernel_setup(ctx, p.opt, kern, 32 * WPC, smem, GHB_CW_CARVEOUT, ks, "condense_cw_kernel", &per_sm));
@@ -860,6 +1006,12 @@ static int launch_cw_shape(ghb_ctx* ctx, const Plan& p, CwArgs& ar) {
   return launch_cw<NI, NB, false, true>(ctx, p, ar);
 }
 
+template <int NI>
+static int launch_cw_pad(ghb_ctx* ctx, const Plan& p, CwArgs& ar) {
+  if (ar.X) return launch_cw<NI, GHB_CW_PAD_NB, true, true, true>(ctx, p, ar);
+  return launch_cw<NI, GHB_CW_PAD_NB, false, true, true>(ctx, p, ar);
+}
+
 int launch_condense_cw(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
                        double* g, int32_t* info, double* X) {
   const int nf = p.nfields, fb = p.boundary[0] - 1;
@@ -867,7 +1019,10 @@ int launch_condense_cw(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double
   ar.ldtab = reinterpret_cast<const uint2*>(p.d_cw);
   ar.rowA12 = reinterpret_cast<const uint32_t*>(p.d_cw + p.cw_off[0]);
   ar.colA21 = reinterpret_cast<const int32_t*>(p.d_cw + p.cw_off[1]);
-  ar.rowb = reinterpret_cast<const uint16_t*>(p.d_cw + p.cw_off[2]);
+  ar.colbase = reinterpret_cast<const int32_t*>(p.d_cw + p.cw_off[2]);
+  ar.rowb = reinterpret_cast<const uint16_t*>(p.d_cw + p.cw_off[3]);
+  ar.rowinfo = reinterpret_cast<const uint16_t*>(p.d_cw + p.cw_off[4]);
+  ar.n_i = p.n_i; ar.n_b = p.n_b; ar.nf = nf;
   ar.nld = p.cw_nld;
   ar.a22base = (int)p.block_offset[fb + nf * fb];
   ar.b2base = p.field_offset_b[fb];
@@ -878,9 +1033,15 @@ int launch_condense_cw(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double
   ar.pf22_off = p.cw_pf[4]; ar.pf22_len = p.cw_pf[5];
   ar.lenA = p.lenA; ar.lenb = p.lenb; ar.ncells = ncells;
   ar.A = A; ar.b = b; ar.S = S; ar.g = g; ar.info = info; ar.X = X;
-#define X(a, b) if (p.n_i == a && p.n_b == b) return launch_cw_shape<a, b>(ctx, p, ar);
-  GHB_CW_SHAPES(X)
+  if (p.cw_pad) {
+#define X(a) if (p.cw_pad == a) return launch_cw_pad<a>(ctx, p, ar);
+    GHB_CW_PAD_CLASSES(X)
 #undef X
+  } else {
+#define X(a, b) if (p.n_i == a && p.n_b == b) return launch_cw_shape<a, b>(ctx, p, ar);
+    GHB_CW_SHAPES(X)
+#undef X
+  }
   return fail(ctx, GHB_EUNSUPPORTED, "condense_cw: shape not instantiated");
 }
 

@@ -28,6 +28,12 @@ CONFIGS = {
                              touched=np.array([[1, 0, 1, 0, 1, 0], [0, 1, 0, 1, 0, 1], [1, 0, 0, 0, 0, 0],
                                                [0, 1, 0, 0, 0, 0], [1, 0, 0, 0, 0, 0], [0, 1, 0, 0, 0, 0]], bool),
                              interior=[1, 2, 3, 4], boundary=[5, 6]),
+    # 2-D shapes of the reference's own tests that only the shape-generic kernel covers: Hencky HDG k=1 on quads (45,24)
+    # with two skeleton fields (test/StressAssistedHenckyHDGTests.jl:134-157) and RT-H k=0 (5,4) (test/DarcyRTHTests.jl:80)
+    "hencky_k1_2d": dict(ndofs=[6, 6, 3, 9, 9, 12, 8, 16], touched=_HENCKY_TOUCHED, interior=[1, 2, 3, 4, 5, 6],
+                         boundary=[7, 8]),
+    "rth_k0_2d": dict(ndofs=[4, 1, 4], touched=np.array([[1, 1, 1], [1, 0, 0], [1, 0, 0]], bool), interior=[1, 2],
+                      boundary=[3]),
     "odd_shapes": dict(ndofs=[5, 3, 7], touched=np.ones((3, 3), bool), interior=[3, 1], boundary=[2]),
     # BASELINE.json configs 4 and 5: elasticity HDG k=2 on 3-D hexes (sigma 6*10, u 3*20 ||
     # u-hat 6*(3*6)) and Hencky HDG k=1 (six bulk fields || two skeleton fields); the Hencky mask leaves the

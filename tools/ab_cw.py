@@ -38,12 +38,18 @@ def timeit(plan, n, A, b, keep=False, reps=5):
 
 
 for name in which:
-    ndofs, touched = SHAPES[name]
+    if name in SHAPES:
+        ndofs, touched = SHAPES[name]
+        interior, boundary = [1, 2], [3]
+    else:                                   # a named configuration of tests/helpers.py (any fields)
+        from tests.helpers import CONFIGS
+        c = CONFIGS[name]
+        ndofs, touched, interior, boundary = c["ndofs"], c["touched"], c["interior"], c["boundary"]
     n = 1 << lg
     ctx.set_option("cw", 0)
-    p_old = ctx.plan_blocks(ndofs, touched, [1, 2], [3])
+    p_old = ctx.plan_blocks(ndofs, touched, interior, boundary)
     ctx.set_option("cw", 1)
-    p_new = ctx.plan_blocks(ndofs, touched, [1, 2], [3])
+    p_new = ctx.plan_blocks(ndofs, touched, interior, boundary)
     A = torch.empty((n, p_new.lenA), dtype=torch.float64, device="cuda")
     b = torch.empty((n, p_new.lenb), dtype=torch.float64, device="cuda")
     ctx.synth_fill(p_new, 0, n, A, b)
