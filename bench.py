@@ -362,15 +362,23 @@ def run_ours(args):
     ev = lambda: torch.cuda.Event(enable_timing=True)
     cond_ms, step_ms = [], []
 
+    fused = bool(args.fused) and plan.kernel_name.startswith("cw")
+
     def one_pass(timed):
-        e0, e1, e2 = ev(), ev(), ev()
-        e0.record()
-        ctx.condense(plan, ncells, A, b, S, g, info)
-        e1.record()
-        slab.assemble(S, g, nzval, rhs)
+        e0, e1, e2, ea = ev(), ev(), ev(), ev()
+        ea.record()
+        if fused:
+            # one kernel condenses and scatters S_K into the zeroed nzval (no S round trip, no gather kernel); the events
+            # e0..e1 bracket that kernel alone, ea..e2 the whole pass (memset of nzval, pack + exchange, ghosts, rhs)
+            slab.condense_assemble(plan, A, b, S, g, info, nzval, rhs, events=(e0, e1))
+        else:
+            e0.record()
+            ctx.condense(plan, ncells, A, b, S, g, info)
+            e1.record()
+            slab.assemble(S, g, nzval, rhs)
         e2.record()
         if timed:
-            cond_ms.append((e0, e1)); step_ms.append((e0, e2))
+            cond_ms.append((e0, e1)); step_ms.append((ea, e2))
 
     def step(timed):
         for k in range(nchunk):
@@ -413,10 +421,37 @@ def run_ours(args):
     value = total_cells / (ms * 1e-3)
     launches -= (nchunk if nchunk > 1 else 0) * args.steps           # synth_fill launches are not the path
 
+    # ---- the other assembly variant, measured next to the headline (same records, same pattern) ----
+    other = None
+    if plan.kernel_name.startswith("cw") and nchunk == 1:
+        def other_pass():
+            if fused:
+                ctx.condense(plan, ncells, A, b, S, g, info)
+                slab.assemble(S, g, nzval, rhs)
+            else:
+                slab.condense_assemble(plan, A, b, S, g, info, nzval, rhs)
+        for _ in range(2):
+            other_pass()
+        barrier()
+        o0, o1 = ev(), ev()
+        o0.record()
+        for _ in range(max(2, args.steps // 2)):
+            other_pass()
+        o1.record()
+        barrier()
+        oms = max_over_ranks(o0.elapsed_time(o1) / max(2, args.steps // 2))
+        other = {"value": total_cells / (oms * 1e-3), "unit": "cells/s", "ms_per_step": oms,
+                 "variant": "condense, then gather_nzval (two kernels)" if fused else
+                            "one kernel: the condensation scatters S_K into the zeroed nzval with FP64 atomics (<= 2 contributions "
+                            "per entry: bit-equal to the gather, tests/test_gpu_parity.py::test_fused_scatter_assembly_bit_equal_to_gather)"}
+        if not fused:
+            ctx.condense(plan, ncells, A, b, S, g, info)      # leave all of S_K behind for the legs below
+
     # ---- N > 1: the assembled system against a local property of the condensed cells (no second copy of the mesh needed):
     # sum(nzval) over all ranks == sum over all cells of the free-free entries of S_K (cut-plane contributions included)
     check = None
     if world > 1:
+        ctx.condense(plan, ncells, A, b, S, g, info)          # all of S_K (the fused step keeps only what it needs)
         ids = slab.cell_ids[:ncells]
         tot = torch.zeros((), dtype=torch.float64, device=dev)
         for c0 in range(0, ncells, 32768):
@@ -516,8 +551,11 @@ def run_ours(args):
 
         def gen_step():
             fam.expand(ctx, plan, coef, A, b)
-            ctx.condense(plan, ncells, A, b, S, g, info)
-            slab.assemble(S, g, nzval, rhs)
+            if fused:
+                slab.condense_assemble(plan, A, b, S, g, info, nzval, rhs)
+            else:
+                ctx.condense(plan, ncells, A, b, S, g, info)
+                slab.assemble(S, g, nzval, rhs)
 
         gen_step()
         barrier()
@@ -563,10 +601,11 @@ def run_ours(args):
                            "cells_per_gpu": ncells_rank, "sequential_sub_slabs": nchunk,
                            "sub_slab": "x".join(map(str, cdims)), "l2": "inputs larger than L2 (no flush needed)"
                            if ncells * (lenA + lenb) * 8 > 256e6 else "inputs smaller than L2 (launch-bound configuration)",
-                           "kernel": plan.kernel_name, "nnz_per_gpu": int(slab.nnz) * nchunk},
+                           "kernel": plan.kernel_name + (" + fused scatter into nzval" if fused else ", then gather_nzval"),
+                           "nnz_per_gpu": int(slab.nnz) * nchunk},
                 "clocks": clk.summary(), "e2e": e2e, "e2e_pageable": e2e_pageable, "gpu_launches": int(launches),
                 "roofline": roof, "cpu_baseline": cpu_base, "backsub": backsub, "device_generated_records": devgen,
-                "multi_gpu_check": check}
+                "multi_gpu_check": check, ("two_kernel_step" if fused else "fused_assembly"): other}
         print(json.dumps(line))
     if world > 1:
         ctx.comm_destroy()
@@ -588,6 +627,10 @@ def main():
     ap.add_argument("--dims", type=int, nargs="+", default=None)
     ap.add_argument("--e2e-dims", type=int, nargs="+", default=None)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--fused", type=int, default=0,
+                    help="1: the condensation kernel scatters S_K into nzval itself (no gather pass); 0: condense, then gather. "
+                         "The default line is the two-kernel step (its dominant kernel is the one the roofline describes); the "
+                         "fused step is measured next to it and reported under fused_assembly")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -223,6 +223,21 @@ class Context:
                                                           _ptr(nzval, np.float64, nnz, "nzval"),
                                                           _ptr(rhs, np.float64, nrows, "rhs")))
 
+    def condense_scatter_slab(self, plan, ncells, A, b, S, g, info, nzval, keep_cut, zero_nzval=True):
+        """fused condensation + scatter of the local cells of a slab (device arrays); S only where it is needed later"""
+        nrows, nnz = self._asm_shape
+        self._check(self._L.ghb_condense_scatter_slab_f64(
+            self._h, plan.id, int(ncells), _ptr(A, np.float64, ncells * plan.lenA, "A"), _ptr(b, np.float64, ncells * plan.lenb, "b"),
+            _ptr(S, np.float64, ncells * plan.n_b ** 2, "S"), _ptr(g, np.float64, ncells * plan.n_b, "g"),
+            _ptr(info, np.int32, ncells, "info"), _ptr(nzval, np.float64, nnz, "nzval"), int(keep_cut), int(bool(zero_nzval))))
+
+    def assemble_finish_slab(self, S, g, ghost, dirichlet_vals, nzval, rhs):
+        nrows, nnz = self._asm_shape
+        self._check(self._L.ghb_assemble_finish_slab_f64(self._h, _ptr(S, np.float64), _ptr(g, np.float64),
+                                                         _ptr(ghost, np.float64), _ptr(dirichlet_vals, np.float64),
+                                                         _ptr(nzval, np.float64, nnz, "nzval"),
+                                                         _ptr(rhs, np.float64, nrows, "rhs")))
+
     def condense_assemble(self, plan, ncells, A, b, dirichlet_vals, nzval, rhs, info=None):
         nrows, nnz = self._asm_shape
         self._check(self._L.ghb_condense_assemble_f64(

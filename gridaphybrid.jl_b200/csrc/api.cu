@@ -68,6 +68,7 @@ static void options_from_env(Options& o) {
   o.warp_one_cell = (int)env_i64("GHB_WARP_ONE_CELL", o.warp_one_cell);
   o.warp_two_rows = (int)env_i64("GHB_WARP_TWO_ROWS", o.warp_two_rows);
   o.debug = (int)env_i64("GHB_DEBUG", o.debug);
+  o.fused_assembly = (int)env_i64("GHB_FUSED_ASSEMBLY", o.fused_assembly);
   o.stream_chunk_bytes = std::max<int64_t>(1, env_i64("GHB_STREAM_CHUNK_BYTES", o.stream_chunk_bytes));
 }
 
@@ -161,6 +162,7 @@ int ghb_set_option(ghb_ctx* ctx, const char* name, int64_t value) {
   else if (n == "warp_one_cell") o.warp_one_cell = (int)value;
   else if (n == "warp_two_rows") o.warp_two_rows = (int)value;
   else if (n == "debug") o.debug = (int)value;
+  else if (n == "fused_assembly") o.fused_assembly = (int)value;
   else if (n == "stream_chunk_bytes") o.stream_chunk_bytes = std::max<int64_t>(1, value);
   else return fail(ctx, GHB_EINVAL, "ghb_set_option: unknown option " + n);
   for (Plan* p : ctx->plans)          // launch-time knobs follow; the kernel choice of existing plans does not change
@@ -519,6 +521,43 @@ int ghb_assemble_release(ghb_ctx* ctx, int pattern_id) {
   return GHB_OK;
 }
 
+/* fused condensation + assembly of a slab (device pointers): condenses the local cells and scatters S_K into the zeroed
+   nzval; S_K is stored for the cells with a Dirichlet dof and for the first keep_cut cells (the layer whose cut-plane
+   columns ghb_pack_cut_plane_f64 sends down), g_K for all. */
+int ghb_condense_scatter_slab_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A, const double* b, double* S,
+                                  double* g, int32_t* info, double* nzval, int64_t keep_cut, int zero_nzval) {
+  Plan* p = get_plan(ctx, plan_id);
+  if (!p) return fail(ctx, GHB_EINVAL, "ghb_condense_scatter_slab_f64: bad plan id");
+  if (!ctx->as.valid) return fail(ctx, GHB_ESTATE, "ghb_condense_scatter_slab_f64: call ghb_assemble_symbolic_slab first");
+  const AsmState& as = ctx->as;
+  if (ncells != as.ncells_local || p->n_b != as.n_b || keep_cut < 0)
+    return fail(ctx, GHB_EINVAL, "ghb_condense_scatter_slab_f64: ncells / n_b differ from the symbolic phase");
+  if (!p->use_cw) return fail(ctx, GHB_EUNSUPPORTED, "ghb_condense_scatter_slab_f64: the plan has no cell-warp kernel");
+  if (!A || !b || !S || !g || !nzval) return fail(ctx, GHB_EINVAL, "ghb_condense_scatter_slab_f64: null array");
+  cudaSetDevice(ctx->device);
+  if (!is_device_ptr(A) || !is_device_ptr(b) || !is_device_ptr(S) || !is_device_ptr(g) || !is_device_ptr(nzval) ||
+      (info && !is_device_ptr(info)))
+    return fail(ctx, GHB_EUNSUPPORTED, "ghb_condense_scatter_slab_f64: device pointers required");
+  GHB_TRY(asm_scatter_prepare(ctx, keep_cut));
+  if (zero_nzval) GHB_CUDA(ctx, cudaMemsetAsync(nzval, 0, (size_t)as.nnz * sizeof(double), ctx->stream));
+  ScatterArgs sc{nzval, as.d_colpos, as.d_rowrank, as.d_keepS};
+  return launch_condense_cw_scatter(ctx, *p, ncells, A, b, S, g, info, sc);
+}
+
+/* second half: contributions of the ghost cells (the packed buffer received from the slab above) and the rhs gather */
+int ghb_assemble_finish_slab_f64(ghb_ctx* ctx, const double* S, const double* g, const double* ghost,
+                                 const double* dirichlet_vals, double* nzval, double* rhs) {
+  if (!ctx) return GHB_EINVAL;
+  if (!ctx->as.valid || !ctx->as.d_colpos) return fail(ctx, GHB_ESTATE, "ghb_assemble_finish_slab_f64: call ghb_condense_scatter_slab_f64 first");
+  if (!S || !g || !nzval || !rhs || (ctx->as.nghost > 0 && !ghost)) return fail(ctx, GHB_EINVAL, "ghb_assemble_finish_slab_f64: null array");
+  cudaSetDevice(ctx->device);
+  if (!is_device_ptr(S) || !is_device_ptr(g) || !is_device_ptr(nzval) || !is_device_ptr(rhs) ||
+      (ghost && !is_device_ptr(ghost)) || (dirichlet_vals && !is_device_ptr(dirichlet_vals)))
+    return fail(ctx, GHB_EUNSUPPORTED, "ghb_assemble_finish_slab_f64: device pointers required");
+  GHB_TRY(asm_scatter_ghosts(ctx, ghost, nzval));
+  return asm_numeric_range(ctx, S, g, ghost, dirichlet_vals, nzval, rhs, 0, ctx->as.nrows, ASM_RHS);
+}
+
 int ghb_assemble_pattern(ghb_ctx* ctx, int64_t* colptr, int64_t* rowval) {
   if (!ctx) return GHB_EINVAL;
   if (!ctx->as.valid) return fail(ctx, GHB_ESTATE, "ghb_assemble_pattern: no symbolic phase cached");
@@ -594,7 +633,22 @@ int ghb_condense_assemble_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const d
   GHB_CUDA(ctx, cudaMallocAsync((void**)&dg, (size_t)ncells * p->n_b * sizeof(double), ctx->stream));
   Arg<int32_t> di(ctx, info, info ? (size_t)ncells : 0, false, true); GHB_TRY(di.rc);
   int rc = GHB_OK;
-  if (!hostA) {
+  if (!hostA && p->use_cw && ctx->opt.fused_assembly) {
+    // fused: the condensation kernel adds S_K into the zeroed nzval itself (scatter map of the pattern, built on first
+    // use); S_K is stored only for the cells with a Dirichlet dof (the lift of the rhs needs it)
+    Arg<double> dz(ctx, nzval, (size_t)as.nnz, false, true); rc = dz.rc;
+    Arg<double> dr(ctx, rhs, (size_t)as.nrows, false, true); if (rc == GHB_OK) rc = dr.rc;
+    if (rc == GHB_OK) rc = asm_scatter_prepare(ctx, 0);
+    if (rc == GHB_OK && cudaMemsetAsync(dz.dev, 0, (size_t)as.nnz * sizeof(double), ctx->stream) != cudaSuccess)
+      rc = fail(ctx, GHB_ECUDA, "ghb_condense_assemble_f64: memset of nzval");
+    if (rc == GHB_OK) {
+      ScatterArgs sc{dz.dev, as.d_colpos, as.d_rowrank, dirichlet_vals ? as.d_keepS : nullptr};
+      rc = launch_condense_cw_scatter(ctx, *p, ncells, A, b, dS, dg, di.dev, sc);
+    }
+    if (rc == GHB_OK) rc = asm_numeric_range(ctx, dS, dg, nullptr, dirichlet_vals, dz.dev, dr.dev, 0, as.nrows, ASM_RHS);
+    if (rc == GHB_OK) rc = dz.finish();
+    if (rc == GHB_OK) rc = dr.finish();
+  } else if (!hostA) {
     rc = launch_condense(ctx, *p, ncells, A, b, dS, dg, di.dev, nullptr);
     if (rc == GHB_OK) {
       Arg<double> dz(ctx, nzval, (size_t)as.nnz, false, true); rc = dz.rc;

@@ -381,6 +381,7 @@ void asm_free(ghb_ctx* ctx) {
   AsmState& as = ctx->as;
   cudaFree(as.d_ids); cudaFree(as.d_occ); cudaFree(as.d_sorted); cudaFree(as.d_npos); cudaFree(as.d_celldir);
   cudaFree(as.d_colptr); cudaFree(as.d_rowval); cudaFree(as.d_src);
+  cudaFree(as.d_colpos); cudaFree(as.d_rowrank); cudaFree(as.d_keepS);
   as = AsmState();
 }
 
@@ -437,6 +438,106 @@ int asm_symbolic(ghb_ctx* ctx, int64_t ncells_local, int64_t nghost, int ghost_n
   cudaFreeAsync(d_cnt, ctx->stream); cudaFreeAsync(d_err, ctx->stream);
   GHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   as.valid = true;
+  return GHB_OK;
+}
+
+// ---- fused condensation + assembly: scatter map ---------------------------------------------------------------
+// Every stored entry of the skeleton matrix has at most TWO contributions (a facet has two cells), so adding them with
+// floating-point atomics into a zeroed nzval is bit-reproducible and equal to the reference's COO sum: 0 + a + b and
+// 0 + b + a are the same number.  The condensation kernel therefore scatters S_K straight from its accumulators
+// (red.global.add.f64) instead of storing it for a second kernel to gather.  One thread per (cell, local column): the same
+// two-pointer merge of the two cells' sorted ids as column_merge_kernel, recording where THIS cell's rows land.
+__global__ void scatter_map_kernel(int64_t ncells, int n_b, const int64_t* __restrict__ ids,
+                                   const unsigned long long* __restrict__ occ, const uint8_t* __restrict__ sorted,
+                                   const uint8_t* __restrict__ npos, const int64_t* __restrict__ colptr, int64_t col0,
+                                   int64_t ncols, int64_t* __restrict__ colpos, uint8_t* __restrict__ rowrank) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ncells * n_b) return;
+  const int64_t c = t / n_b;
+  uint8_t* rr = rowrank + t * n_b;
+  for (int l = 0; l < n_b; ++l) rr[l] = 255;
+  const int64_t j = ids[t] - col0 - 1;                     // owned column index (0-based) or outside
+  if (ids[t] <= 0 || j < 0 || j >= ncols) { colpos[t] = -1; return; }
+  colpos[t] = colptr[j] - 1;
+  const unsigned long long o0 = occ[2 * j], o1 = occ[2 * j + 1];
+  const int64_t c0 = (int64_t)(o0 / n_b);
+  const int64_t* id0 = ids + c0 * n_b;
+  const uint8_t* s0 = sorted + c0 * n_b;
+  const int n0 = npos[c0];
+  if (o1 == ~0ull) {
+    for (int a = 0; a < n0; ++a) rr[s0[a]] = (uint8_t)a;     // c0 == c: the only occurrence, plain stores
+    return;
+  }
+  const int64_t c1 = (int64_t)(o1 / n_b);
+  const int64_t* id1 = ids + c1 * n_b;
+  const uint8_t* s1 = sorted + c1 * n_b;
+  const int n1 = npos[c1];
+  int a = 0, bq = 0, pos = 0;
+  while (a < n0 || bq < n1) {
+    const int64_t va = a < n0 ? id0[s0[a]] : INT64_MAX;
+    const int64_t vb = bq < n1 ? id1[s1[bq]] : INT64_MAX;
+    const int64_t v = va < vb ? va : vb;
+    // bit 7: both cells have this row (the facet block they share): the only entries that need an atomic add; every
+    // other entry of the column has ONE contribution and is stored
+    const unsigned sh = (va == v && vb == v) ? 0x80u : 0u;
+    if (va == v) { if (c0 == c) rr[s0[a]] = (uint8_t)(pos | sh); ++a; }
+    if (vb == v) { if (c1 == c) rr[s1[bq]] = (uint8_t)(pos | sh); ++bq; }
+    ++pos;
+  }
+}
+
+__global__ void keep_flags_kernel(int64_t ncells_local, int64_t keep_cut, const uint8_t* __restrict__ celldir,
+                                  uint8_t* __restrict__ keep) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < ncells_local) keep[c] = (uint8_t)((celldir[c] != 0) || c < keep_cut);
+}
+
+// contributions of the ghost cells (the packed cut-plane columns received from the slab above): one thread per entry
+__global__ void scatter_ghost_kernel(int64_t nghost, int64_t ncells_local, int n_b, int ncols, const double* __restrict__ G,
+                                     int64_t stride, const int64_t* __restrict__ colpos, const uint8_t* __restrict__ rowrank,
+                                     double* __restrict__ nzval) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per = (int64_t)n_b * ncols;
+  if (t >= nghost * per) return;
+  const int64_t gc = t / per;
+  const int e = (int)(t - gc * per);
+  const int lj = e / n_b, li = e - lj * n_b;
+  const int64_t c = ncells_local + gc;
+  const int64_t cp = colpos[c * n_b + lj];
+  const uint8_t rk = rowrank[(c * n_b + lj) * n_b + li];
+  if (cp >= 0 && rk != 255) atomicAdd(nzval + cp + (rk & 0x7f), G[gc * stride + e]);
+}
+
+int asm_scatter_prepare(ghb_ctx* ctx, int64_t keep_cut) {
+  AsmState& as = ctx->as;
+  if (as.n_b > 63) return fail(ctx, GHB_EUNSUPPORTED, "fused assembly: n_b > 63 (ranks are 7 bits)");
+  if (!as.d_colpos) {
+    const int64_t nent = as.ncells * as.n_b;
+    GHB_CUDA(ctx, cudaMalloc((void**)&as.d_colpos, nent * sizeof(int64_t)));
+    GHB_CUDA(ctx, cudaMalloc((void**)&as.d_rowrank, nent * as.n_b));
+    GHB_CUDA(ctx, cudaMalloc((void**)&as.d_keepS, std::max<int64_t>(as.ncells_local, 1)));
+    scatter_map_kernel<<<(unsigned)((nent + 127) / 128), 128, 0, ctx->stream>>>(
+        as.ncells, as.n_b, as.d_ids, (const unsigned long long*)as.d_occ, as.d_sorted, as.d_npos, as.d_colptr, as.col0, as.nrows,
+        as.d_colpos, as.d_rowrank);
+    GHB_LAUNCHED(ctx);
+    as.keep_cut = -1;
+  }
+  if (as.keep_cut != keep_cut) {
+    keep_flags_kernel<<<(unsigned)((as.ncells_local + 255) / 256), 256, 0, ctx->stream>>>(as.ncells_local, keep_cut, as.d_celldir, as.d_keepS);
+    GHB_LAUNCHED(ctx);
+    as.keep_cut = keep_cut;
+  }
+  return GHB_OK;
+}
+
+int asm_scatter_ghosts(ghb_ctx* ctx, const double* ghost, double* nzval) {
+  const AsmState& as = ctx->as;
+  if (as.nghost == 0 || as.ghost_ncols == 0) return GHB_OK;
+  const int64_t tot = as.nghost * (int64_t)as.n_b * as.ghost_ncols;
+  scatter_ghost_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(
+      as.nghost, as.ncells_local, as.n_b, as.ghost_ncols, ghost, (int64_t)as.n_b * as.ghost_ncols + as.ghost_ncols, as.d_colpos,
+      as.d_rowrank, nzval);
+  GHB_LAUNCHED(ctx);
   return GHB_OK;
 }
 

@@ -33,6 +33,7 @@ struct Options {
   int warp_one_cell = 0;      // GHB_WARP_ONE_CELL   small-cell kernels: one cell per warp
   int warp_two_rows = 0;      // GHB_WARP_TWO_ROWS   (16,8): two rows per lane
   int debug = 0;              // GHB_DEBUG           print launch geometry
+  int fused_assembly = 1;     // GHB_FUSED_ASSEMBLY  condensation kernels scatter S_K into nzval themselves (cell-warp plans)
   int64_t stream_chunk_bytes = (int64_t)256 << 20;   // GHB_STREAM_CHUNK_BYTES: chunk of the host-record streaming path
 };
 
@@ -81,6 +82,11 @@ struct AsmState {
   int64_t* d_colptr = nullptr;   // [nrows+1] 1-based
   int64_t* d_rowval = nullptr;   // [nnz] 1-based
   uint8_t* d_src = nullptr;      // [nnz][2] local row index inside occurrence 0 / 1, 255 = none
+  // scatter map of the fused condensation + assembly (built on first use, asm_scatter_prepare)
+  int64_t* d_colpos = nullptr;   // [ncells][n_b] 0-based nzval offset of the column of local dof lj, -1: not an owned column
+  uint8_t* d_rowrank = nullptr;  // [ncells][n_b (lj)][n_b (li)] rank of row ids[li] inside that column, 255: not assembled
+  uint8_t* d_keepS = nullptr;    // [ncells_local] 1: the fused kernel must also store S_K (Dirichlet lift / cut-plane pack)
+  int64_t keep_cut = -1;         // leading cells whose S_K is kept for ghb_pack_cut_plane_f64 (d_keepS was built for it)
   // streaming (host records): columns complete after each chunk of cells, cached per chunk size
   int64_t ready_chunk = 0;
   std::vector<int64_t> ready_J;  // [nchunks] number of complete columns once chunks 0..k are condensed
@@ -255,6 +261,17 @@ enum { ASM_MATRIX = 1, ASM_RHS = 2 };   // which: phases of the numeric assembly
 int asm_numeric_range(ghb_ctx* ctx, const double* S, const double* g, const double* ghost, const double* dvals,
                       double* nzval, double* rhs, int64_t j0, int64_t j1, int which = ASM_MATRIX | ASM_RHS);
 int asm_ready_columns(ghb_ctx* ctx, int64_t chunk, int nchunks);
+// fused path: scatter map of the selected pattern (lazily), flags of the cells whose S_K must be kept; ghost scatter
+int asm_scatter_prepare(ghb_ctx* ctx, int64_t keep_cut);
+int asm_scatter_ghosts(ghb_ctx* ctx, const double* ghost, double* nzval);
+struct ScatterArgs {             // epilogue of the condensation kernel in fused mode
+  double* nzval;
+  const int64_t* colpos;
+  const uint8_t* rowrank;
+  const uint8_t* keepS;
+};
+int launch_condense_cw_scatter(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
+                               double* g, int32_t* info, const ScatterArgs& sc);
 int asm_numeric(ghb_ctx* ctx, const double* S, const double* g, const double* ghost, const double* dvals,
                 double* nzval, double* rhs);
 int asm_pack_cut_plane(ghb_ctx* ctx, int64_t ncut, int n_b, int ncols, const double* S, const double* g,

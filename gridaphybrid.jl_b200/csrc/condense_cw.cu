@@ -136,6 +136,11 @@ struct CwArgs {
   double* g;
   int32_t* info;
   double* X;
+  // fused assembly (SCAT kernels): S_K is added into the zeroed nzval through the scatter map of the selected pattern
+  double* nzval;
+  const int64_t* colpos;    // [ncells][n_b] 0-based nzval offset of the column of local dof lj, -1: not assembled here
+  const uint8_t* rowrank;   // [ncells][n_b][n_b] rank of row li inside the column of lj, 255: not assembled
+  const uint8_t* keepS;     // [ncells] 1: also store S_K (Dirichlet lift, cut-plane pack); NULL: never
 };
 
 template <int NI, int NB>
@@ -285,7 +290,7 @@ __device__ __forceinline__ void panel_factor(double (&a)[8], double (&a2)[8], co
 // never pivots of real columns, pad columns have their own row as the only candidate: LAPACK's choices on the real part
 // are unchanged), everything outside the real blocks reads as zero, and all record offsets come from the plan's
 // (column, field) table -- any number of interior and skeleton fields, any touched mask.
-template <int NI, int NB, int WPC, int MINB, bool KEEPX, bool SPARSE, bool PAD>
+template <int NI, int NB, int WPC, int MINB, bool KEEPX, bool SPARSE, bool PAD, bool SCAT>
 __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArgs ar) {
   using C = CwCfg<NI, NB>;
   constexpr int RT = C::RT, NPL = C::NPL, DUMMY = C::DUMMY;
@@ -596,6 +601,7 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
     }
     double* Sc = ar.S + cell * (int64_t)nbr * nbr;
     double* gc = ar.g + cell * (int64_t)nbr;
+    const bool keepS = !SCAT || (ar.keepS != nullptr && ar.keepS[cell] != 0);   // fused mode: S_K only where it is needed
 
     // One pass handles NJ column tiles at a time: every B fragment (L / U tiles from shared memory, A21 from L2) is loaded
     // once and used for NJ independent DMMA chains.
@@ -777,10 +783,38 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
           }
         }
       }
+      // ---- fused assembly: add this column of S_K to its place in the CSC values (at most two cells contribute to an
+      //      entry of a zeroed nzval, so the floating-point atomics are order-independent and bit-reproducible)
+      if (SCAT) {
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj)
+          if (cA[jj]) {
+            const int64_t ce = cell * nbr + col[jj];
+            const int64_t cpos = __ldg(ar.colpos + ce);
+            if (cpos >= 0) {
+              const uint8_t* rr = ar.rowrank + ce * nbr;
+              double* nz = ar.nzval + cpos;
+#pragma unroll
+              for (int m = 0; m < BTM; ++m) {
+                const int r = 8 * m + 2 * t;
+                if (r < nbr) {
+                  unsigned rk0, rk1 = 255u;
+                  if ((nbr & 1) == 0) { const unsigned v = __ldg(reinterpret_cast<const unsigned short*>(rr + r)); rk0 = v & 0xffu; rk1 = v >> 8; }
+                  else { rk0 = __ldg(rr + r); if (r + 1 < nbr) rk1 = __ldg(rr + r + 1); }
+                  // bit 7 of a rank marks the entries shared with the neighbour cell.  Storing the others instead of adding
+                  // them measured SLOWER (48.2 vs 46.6 ms at 128^3: divergent store / atomic paths), so everything is added
+                  const double v0 = failed ? qnan : acc[jj][m][0], v1 = failed ? qnan : acc[jj][m][1];
+                  if (rk0 != 255u) atomicAdd(nz + (rk0 & 0x7fu), v0);
+                  if (rk1 != 255u) atomicAdd(nz + (rk1 & 0x7fu), v1);
+                }
+              }
+            }
+          }
+      }
       // ---- store
 #pragma unroll
       for (int jj = 0; jj < NJ; ++jj)
-        if (col[jj] < NC) {
+        if (col[jj] < NC && (keepS || !cA[jj])) {
           double* dst = cA[jj] ? Sc + (int64_t)col[jj] * nbr : gc;
 #pragma unroll
           for (int m = 0; m < BTM; ++m) {
@@ -978,13 +1012,13 @@ int cw_prepare(ghb_ctx* ctx, Plan& p) {
   return GHB_OK;
 }
 
-template <int NI, int NB, bool KEEPX, bool SPARSE, bool PAD = false>
+template <int NI, int NB, bool KEEPX, bool SPARSE, bool PAD = false, bool SCAT = false>
 static int launch_cw(ghb_ctx* ctx, const Plan& p, CwArgs& ar) {
   constexpr int WPC = GHB_CW_WPC;
   // PAD classes: as many CTAs per SM as their shared memory allows (the register cap follows)
   constexpr int fit = (int)(233472u / (WPC * CwCfg<NI, NB>::WARP_BYTES + CwCfg<NI, NB>::SH_BYTES_PAD + 1024u));
   constexpr int MINB = PAD ? (fit < 1 ? 1 : (fit > 4 ? 4 : fit)) : GHB_CW_MINB;
-  auto kern = condense_cw_kernel<NI, NB, WPC, MINB, KEEPX, SPARSE, PAD>;
+  auto kern = condense_cw_kernel<NI, NB, WPC, MINB, KEEPX, SPARSE, PAD, SCAT>;
   const size_t smem = CwCfg<NI, NB>::smem_bytes(WPC, PAD);
   static KernelSetup ks;
   int per_sm = 0;
@@ -998,6 +1032,10 @@ static int launch_cw(ghb_ctx* ctx, const Plan& p, CwArgs& ar) {
 
 template <int NI, int NB>
 static int launch_cw_shape(ghb_ctx* ctx, const Plan& p, CwArgs& ar) {
+  if (ar.nzval) {
+    if (p.all_touched) return launch_cw<NI, NB, false, false, false, true>(ctx, p, ar);
+    return launch_cw<NI, NB, false, true, false, true>(ctx, p, ar);
+  }
   if (ar.X) {
     if (p.all_touched) return launch_cw<NI, NB, true, false>(ctx, p, ar);
     return launch_cw<NI, NB, true, true>(ctx, p, ar);
@@ -1008,14 +1046,19 @@ static int launch_cw_shape(ghb_ctx* ctx, const Plan& p, CwArgs& ar) {
 
 template <int NI>
 static int launch_cw_pad(ghb_ctx* ctx, const Plan& p, CwArgs& ar) {
+  if (ar.nzval) return launch_cw<NI, GHB_CW_PAD_NB, false, true, true, true>(ctx, p, ar);
   if (ar.X) return launch_cw<NI, GHB_CW_PAD_NB, true, true, true>(ctx, p, ar);
   return launch_cw<NI, GHB_CW_PAD_NB, false, true, true>(ctx, p, ar);
 }
 
-int launch_condense_cw(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
-                       double* g, int32_t* info, double* X) {
+static int launch_condense_cw_impl(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
+                                   double* g, int32_t* info, double* X, const ScatterArgs* sc) {
   const int nf = p.nfields, fb = p.boundary[0] - 1;
   CwArgs ar;
+  ar.nzval = sc ? sc->nzval : nullptr;
+  ar.colpos = sc ? sc->colpos : nullptr;
+  ar.rowrank = sc ? sc->rowrank : nullptr;
+  ar.keepS = sc ? sc->keepS : nullptr;
   ar.ldtab = reinterpret_cast<const uint2*>(p.d_cw);
   ar.rowA12 = reinterpret_cast<const uint32_t*>(p.d_cw + p.cw_off[0]);
   ar.colA21 = reinterpret_cast<const int32_t*>(p.d_cw + p.cw_off[1]);
@@ -1043,6 +1086,16 @@ int launch_condense_cw(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double
 #undef X
   }
   return fail(ctx, GHB_EUNSUPPORTED, "condense_cw: shape not instantiated");
+}
+
+int launch_condense_cw(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
+                       double* g, int32_t* info, double* X) {
+  return launch_condense_cw_impl(ctx, p, ncells, A, b, S, g, info, X, nullptr);
+}
+
+int launch_condense_cw_scatter(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
+                               double* g, int32_t* info, const ScatterArgs& sc) {
+  return launch_condense_cw_impl(ctx, p, ncells, A, b, S, g, info, nullptr, &sc);
 }
 
 }  // namespace ghb

@@ -200,6 +200,33 @@ class SlabAssembler:
                 exchange_cut_plane(self.send_buf, self.ghost, L.rank, L.world, self.group)
         self.ctx.assemble_numeric_slab(S, g, self.ghost, self.dirichlet_values, nzval, rhs)
 
+    def _exchange(self, exchange=None):
+        L = self.layout
+        if exchange is not None:
+            exchange(self.send_buf, self.ghost, L.rank, L.world, self.group)
+        elif getattr(self.ctx, "comm_size", 1) == L.world:
+            self.ctx.exchange_cut_plane(self.send_buf, self.ghost)          # NCCL behind the C ABI (ghb_comm_init)
+        else:
+            exchange_cut_plane(self.send_buf, self.ghost, L.rank, L.world, self.group)
+
+    def condense_assemble(self, plan, A, b, S, g, info, nzval, rhs, exchange=None, events=None):
+        """fused step of a slab: the condensation kernel scatters S_K into nzval itself (no second pass over S); S_K is
+        kept only for Dirichlet cells and for the bottom layer that feeds the cut-plane exchange"""
+        L = self.layout
+        self.ctx.use_torch_stream()
+        self.ctx.assemble_select(self._pid)
+        keep = L.layer if (L.world > 1 and L.rank > 0) else 0
+        nzval.zero_()
+        if events:
+            events[0].record()                               # brackets the fused kernel alone (bench roofline)
+        self.ctx.condense_scatter_slab(plan, L.ncells, A, b, S, g, info, nzval, keep, zero_nzval=False)
+        if events:
+            events[1].record()
+        if L.world > 1:
+            self.pack(S, g)
+            self._exchange(exchange)
+        self.ctx.assemble_finish_slab(S, g, self.ghost, self.dirichlet_values, nzval, rhs)
+
     def allgather_lambda(self, lam_owned):
         """collective 2 through the C ABI (grouped ncclBroadcast, no object gather): the global free-dof vector"""
         L = self.layout

@@ -189,12 +189,24 @@ int ghb_pack_cut_plane_f64(ghb_ctx* ctx, int64_t ncut, int n_b, int ncols, const
 int ghb_assemble_numeric_slab_f64(ghb_ctx* ctx, const double* S, const double* g, const double* ghost,
                                   const double* dirichlet_vals, double* nzval, double* rhs);
 
+/* Fused slab path (device pointers, plans with a cell-warp kernel): ghb_condense_scatter_slab_f64 condenses the local cells
+ * and adds S_K straight into the zeroed nzval (every entry has at most two contributions, so the floating-point atomics
+ * are order-independent and bit-equal to the gather); S_K is stored only for the cells with a Dirichlet dof and for
+ * the first keep_cut cells (the layer whose cut-plane columns go down), g_K for all; zero_nzval = 0 if the caller has
+ * zeroed nzval itself.  After ghb_pack_cut_plane_f64 and
+ * the exchange, ghb_assemble_finish_slab_f64 adds the ghost cells' contributions and gathers the rhs. */
+int ghb_condense_scatter_slab_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A, const double* b, double* S,
+                                  double* g, int32_t* info, double* nzval, int64_t keep_cut, int zero_nzval);
+int ghb_assemble_finish_slab_f64(ghb_ctx* ctx, const double* S, const double* g, const double* ghost,
+                                 const double* dirichlet_vals, double* nzval, double* rhs);
+
 /* Condensation + numeric assembly in one call (S_K, g_K never seen by the caller; they live in a device scratch
  * buffer between the two kernels).  Host records are streamed in chunks (option stream_chunk_bytes, 256 MB): the H2D
  * copy of chunk k+1 overlaps the condensation of chunk k, and the columns whose cells are all condensed are assembled
  * and copied back while later records are still arriving.  Pinned caller memory is copied from directly; PAGEABLE
  * caller memory (a Julia Array, a numpy array) is staged through two pinned buffers owned by the ctx, filled by host
- * threads, so that the copies stay asynchronous. */
+ * threads, so that the copies stay asynchronous.  With DEVICE records and a cell-warp plan the two kernels are one
+ * (option fused_assembly, default on): S_K goes from the accumulators into nzval, see the slab variant above. */
 int ghb_condense_assemble_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A, const double* b,
                               const double* dirichlet_vals, int64_t ndirichlet, double* nzval, double* rhs,
                               int32_t* info);

@@ -982,3 +982,82 @@ def test_ill_conditioned_cells_follow_kappa_eps(ctx, name):
     for kappa, eS, eg in rows:
         assert max(eS, eg) < 256 * kappa * eps, (kappa, eS, eg)
     assert max(rows[0][1], rows[0][2]) < TOL
+
+
+@pytest.mark.parametrize("name,dims,ndofs_f", [("C3_hdg_k2_3d", (6, 5, 4), 6), ("C2_rth_k2_2d", (9, 7), 3),
+                                               ("elasticity_k1_2d", (6, 5), 4), ("hdg_equal_order_3d", (3, 3, 3), 6)])
+def test_fused_scatter_assembly_bit_equal_to_gather(ctx, name, dims, ndofs_f):
+    """fused path of ghb_condense_assemble_f64 (device records, cell-warp plans): the condensation kernel adds S_K into
+    the zeroed nzval with floating-point atomics.  Every entry has at most two contributions, so the result must be
+    BIT-equal to the owner-computes gather (option fused_assembly = 0) -- with and without the Dirichlet lift, twice in a
+    row (no stale sums), and next to a singular cell (NaN lands on exactly the same entries)."""
+    plan = _dev_plan(ctx, name)
+    assert plan.kernel_name.startswith("cw_")
+    sk = gh.CartesianSkeleton(dims, ctx)
+    M = gh.FacetFESpace(sk, ndofs_f, sk.facet_is_boundary())
+    assem = gh.SparseMatrixAssembler(M)
+    colptr, rowval, nnz = assem.symbolic()
+    n = sk.ncells
+    assert assem.cell_ids.shape[1] == plan.n_b
+    A, b = _synth(ctx, plan, 11, n)
+    dv = torch.linspace(-1, 1, max(M.num_dirichlet_dofs, 1), dtype=torch.float64, device="cuda")
+    for singular in (False, True):
+        if singular:
+            A[n // 2].zero_()
+        for lift in (dv, None):
+            res = []
+            for fused in (1, 0, 1):
+                ctx.set_option("fused_assembly", fused)
+                nz = torch.full((nnz,), float("nan"), dtype=torch.float64, device="cuda")
+                rhs = torch.full((assem.nrows,), float("nan"), dtype=torch.float64, device="cuda")
+                info = torch.empty(n, dtype=torch.int32, device="cuda")
+                assem.select()
+                ctx.condense_assemble(plan, n, A, b, lift, nz, rhs, info)
+                res.append((nz.cpu().numpy(), rhs.cpu().numpy(), info.cpu().numpy()))
+            ctx.set_option("fused_assembly", 1)
+            for k in (0, 2):
+                assert np.array_equal(res[k][0], res[1][0], equal_nan=True)
+                assert np.array_equal(res[k][1], res[1][1], equal_nan=True)
+                assert np.array_equal(res[k][2], res[1][2])
+            assert bool(np.isnan(res[0][0]).any()) == singular
+
+
+@pytest.mark.parametrize("gdims,world", [((4, 3, 6), 3), ((5, 8), 2)])
+def test_fused_slab_step_matches_global(ctx, gdims, world):
+    """SlabAssembler.condense_assemble (fused scatter + cut-plane pack from the kept bottom layer + ghost scatter) on every
+    slab, exchange emulated by a copy: concatenated column segments bit-equal to the single-context gather."""
+    from gridaphybrid_b200.distributed import SlabAssembler, SlabLayout
+    D = len(gdims)
+    name, nf = ("C3_hdg_k2_3d", 6) if D == 3 else ("C2_rth_k2_2d", 3)
+    plan = _dev_plan(ctx, name)
+    L0 = SlabLayout(gdims, nf, 0, 1)
+    n = L0.ncells_global
+    A, b = _synth(ctx, plan, 0, n)
+    ids = L0.cell_dof_ids(torch.arange(n, device="cuda"))
+    ndir = int((-ids).max().item())
+    dv = torch.linspace(-2, 2, ndir, dtype=torch.float64, device="cuda")
+    S = torch.empty((n, plan.n_b ** 2), dtype=torch.float64, device="cuda"); g = torch.empty((n, plan.n_b), dtype=torch.float64, device="cuda")
+    ctx.condense(plan, n, A, b, S, g, None)
+    nnz = ctx.assemble_symbolic(n, plan.n_b, ids, L0.nrows_global)
+    nz0 = torch.empty(nnz, dtype=torch.float64, device="cuda"); rhs0 = torch.empty(L0.nrows_global, dtype=torch.float64, device="cuda")
+    ctx.assemble_numeric(S, g, dv, nz0, rhs0)
+    ctxs = [gh.Context(0) for _ in range(world)]
+    asms = [SlabAssembler(ctxs[r], gdims, nf, r, world, dirichlet_values=dv) for r in range(world)]
+    plans = [c.plan_blocks(CONFIGS[name]["ndofs"], CONFIGS[name]["touched"], CONFIGS[name]["interior"], CONFIGS[name]["boundary"]) for c in ctxs]
+    outs = []
+    # the sender side of every cut first (what the NCCL exchange overlaps in the real run): run ranks top-down
+    for r in range(world - 1, -1, -1):
+        a, L = asms[r], asms[r].layout
+        sl = slice(L.cell_start, L.cell_start + L.ncells)
+        Sr = torch.full((L.ncells, plan.n_b ** 2), float("nan"), dtype=torch.float64, device="cuda")
+        gr = torch.empty((L.ncells, plan.n_b), dtype=torch.float64, device="cuda")
+        z = torch.full((a.nnz,), float("nan"), dtype=torch.float64, device="cuda"); rr = torch.empty(a.nrows_local, dtype=torch.float64, device="cuda")
+        fake = lambda send, recv, rank, w, group: recv.copy_(asms[rank + 1].send_buf) if recv is not None else None
+        a.condense_assemble(plans[r], A[sl].contiguous(), b[sl].contiguous(), Sr, gr, None, z, rr, exchange=fake)
+        torch.cuda.synchronize()
+        outs.append((r, z.cpu().numpy(), rr.cpu().numpy()))
+    outs.sort()
+    assert np.array_equal(np.concatenate([o_[1] for o_ in outs]), nz0.cpu().numpy())
+    assert np.array_equal(np.concatenate([o_[2] for o_ in outs]), rhs0.cpu().numpy())
+    for c in ctxs:
+        c.close()
