@@ -64,7 +64,7 @@ FP64_PEAK_TFLOPS = 37.1      # measured DMMA peak of this pool's B200 (profiles/
 HBM_BUDGET = 165e9           # bytes of a GPU's 180 GB a step may keep resident
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full` capture, per cell
-NCU_DRAM_BYTES_PER_CELL = {"cw_34_36": 55765}
+NCU_DRAM_BYTES_PER_CELL = {"cw_34_36": 57108}
 NCU_TRAFFIC_SOURCE = "profiles/r02_cw_summary.md (ncu --set full, 131072-cell launch, scaled per cell)"
 
 
