@@ -109,10 +109,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
                              capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
-        keep = set(objs)                                   # drop objects of older versions of the same files
-        for o in glob.glob(os.path.join(objdir, "*.o")):
-            if o not in keep and os.path.getmtime(o) < __import__("time").time() - 86400:
-                os.remove(o)
+        if not os.environ.get("GHB_LIB_PATH"):             # the default library: drop the objects of older versions / variants
+            keep = set(objs)
+            for o in glob.glob(os.path.join(objdir, "*.o")):
+                if o not in keep:
+                    os.remove(o)
         with open(SO_PATH + ".srchash", "w") as f:
             f.write(_source_hash())
     return SO_PATH

@@ -28,9 +28,37 @@ static bool is_pinned_host_ptr(const void* p) {
   return at.type == cudaMemoryTypeHost;
 }
 
+// device temporaries / events of one call: released on every exit path (stream-ordered free; events after a sync of the
+// side streams so that no copy into a caller buffer is still in flight when an error is returned)
+struct CallTmp {
+  ghb_ctx* ctx;
+  std::vector<void*> dev;
+  std::vector<cudaEvent_t> ev;
+  bool side_streams = false;
+  explicit CallTmp(ghb_ctx* c) : ctx(c) {}
+  cudaError_t alloc(void** p, size_t bytes) {
+    cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+    if (e == cudaSuccess) dev.push_back(*p);
+    return e;
+  }
+  cudaError_t event(cudaEvent_t* e) {
+    cudaError_t r = cudaEventCreateWithFlags(e, cudaEventDisableTiming);
+    if (r == cudaSuccess) ev.push_back(*e);
+    return r;
+  }
+  ~CallTmp() {
+    if (side_streams) {
+      if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+      if (ctx->d2h_stream) cudaStreamSynchronize(ctx->d2h_stream);
+    }
+    for (void* p : dev) cudaFreeAsync(p, ctx->stream);
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  }
+};
+
 // pageable -> pinned staging copy on a few host threads (one memcpy stream does not reach the PCIe rate)
 static void host_copy_parallel(void* dst, const void* src, size_t bytes) {
-  unsigned nt = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+  unsigned nt = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));   // 16 threads measured no better (host copy bandwidth)
   if (bytes < ((size_t)8 << 20)) nt = 1;
   if (nt == 1) { memcpy(dst, src, bytes); return; }
   std::vector<std::thread> th;
@@ -629,8 +657,9 @@ int ghb_condense_assemble_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const d
   const bool hostA = !is_device_ptr(A), hostb = !is_device_ptr(b);
   if (hostA != hostb) return fail(ctx, GHB_EINVAL, "ghb_condense_assemble_f64: A and b must both be host or both device");
   double *dS = nullptr, *dg = nullptr;
-  GHB_CUDA(ctx, cudaMallocAsync((void**)&dS, (size_t)ncells * p->n_b * p->n_b * sizeof(double), ctx->stream));
-  GHB_CUDA(ctx, cudaMallocAsync((void**)&dg, (size_t)ncells * p->n_b * sizeof(double), ctx->stream));
+  CallTmp tmp(ctx);
+  GHB_CUDA(ctx, tmp.alloc((void**)&dS, (size_t)ncells * p->n_b * p->n_b * sizeof(double)));
+  GHB_CUDA(ctx, tmp.alloc((void**)&dg, (size_t)ncells * p->n_b * sizeof(double)));
   Arg<int32_t> di(ctx, info, info ? (size_t)ncells : 0, false, true); GHB_TRY(di.rc);
   int rc = GHB_OK;
   if (!hostA && p->use_cw && ctx->opt.fused_assembly) {
@@ -691,14 +720,15 @@ int ghb_condense_assemble_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const d
         }
       if (rc == GHB_OK) ctx->pinned_bytes = stage_bytes;
     }
+    tmp.side_streams = true;
     if (rc == GHB_OK) {
       for (int i = 0; i < 2; ++i) {
-        GHB_CUDA(ctx, cudaMallocAsync((void**)&dA[i], (size_t)chunk * p->lenA * 8, ctx->stream));
-        GHB_CUDA(ctx, cudaMallocAsync((void**)&db[i], (size_t)chunk * p->lenb * 8, ctx->stream));
-        GHB_CUDA(ctx, cudaEventCreateWithFlags(&h2d_done[i], cudaEventDisableTiming));
-        GHB_CUDA(ctx, cudaEventCreateWithFlags(&k_done[i], cudaEventDisableTiming));
+        GHB_CUDA(ctx, tmp.alloc((void**)&dA[i], (size_t)chunk * p->lenA * 8));
+        GHB_CUDA(ctx, tmp.alloc((void**)&db[i], (size_t)chunk * p->lenb * 8));
+        GHB_CUDA(ctx, tmp.event(&h2d_done[i]));
+        GHB_CUDA(ctx, tmp.event(&k_done[i]));
       }
-      GHB_CUDA(ctx, cudaEventCreateWithFlags(&g_done, cudaEventDisableTiming));
+      GHB_CUDA(ctx, tmp.event(&g_done));
       GHB_CUDA(ctx, cudaEventRecord(k_done[0], ctx->stream));
       GHB_CUDA(ctx, cudaEventRecord(k_done[1], ctx->stream));
     }
@@ -743,18 +773,9 @@ int ghb_condense_assemble_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const d
       cudaError_t e = cudaStreamSynchronize(ctx->d2h_stream);
       if (e != cudaSuccess && rc == GHB_OK) rc = fail(ctx, GHB_ECUDA, std::string("D2H: ") + cudaGetErrorString(e));
     }
-    for (int i = 0; i < 2; ++i) {
-      if (dA[i]) cudaFreeAsync(dA[i], ctx->stream);
-      if (db[i]) cudaFreeAsync(db[i], ctx->stream);
-      if (h2d_done[i]) cudaEventDestroy(h2d_done[i]);
-      if (k_done[i]) cudaEventDestroy(k_done[i]);
-    }
-    if (g_done) cudaEventDestroy(g_done);
   }
-  cudaFreeAsync(dS, ctx->stream);
-  cudaFreeAsync(dg, ctx->stream);
   if (rc == GHB_OK) rc = di.finish();
-  return rc;
+  return rc;   // ~CallTmp releases dS, dg, the chunk buffers and the events on this and on every early-return path
 }
 
 int ghb_backsub_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A, const double* b,
