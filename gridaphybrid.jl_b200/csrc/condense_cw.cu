@@ -5,7 +5,7 @@
 // Why: the 4-warps-per-cell kernels of condense_dmma.cu spend most of their time in named barriers between the panel
 // warp and the column-tile owners (profiles/r01_condense_dmma_summary.md: 7.7 barrier stalls per issue, 12.5 k
 // warp-instructions per cell).  Here every warp owns a whole cell: nothing to synchronise, 12-16 independent cells per SM.
-// The first version of this kernel (profiles/r02_cw_v1.md) executed 9.9 k warp-instructions per cell, two thirds of them
+// The first version of this kernel (profiles/r02_cw_summary.md) executed 9.9 k warp-instructions per cell, two thirds of them
 // integer address arithmetic; this version takes every address from tables built once per plan (loader), once per CTA
 // (A21 fragments) or once per cell (pivoted row addresses), ~5 k warp-instructions per cell.
 //

@@ -1061,3 +1061,54 @@ def test_fused_slab_step_matches_global(ctx, gdims, world):
     assert np.array_equal(np.concatenate([o_[2] for o_ in outs]), rhs0.cpu().numpy())
     for c in ctxs:
         c.close()
+
+
+def test_round2_entry_points_edge_cases(ctx):
+    """argument / state checks of the entry points added in round 2: options, pattern handles, device buffers, the NCCL
+    exchanges before ghb_comm_init, the fused slab pair before its symbolic phase."""
+    with pytest.raises(gh.GhbError) as e:
+        ctx.set_option("no_such_option", 1)
+    assert e.value.code == gh._lib.GHB_EINVAL
+    c2 = gh.Context(0)
+    try:
+        with pytest.raises(gh.GhbError) as e:
+            c2.exchange_cut_plane(torch.zeros(4, dtype=torch.float64, device="cuda"), None)
+        assert e.value.code == gh._lib.GHB_ESTATE
+        with pytest.raises(gh.GhbError) as e:
+            c2.allgather_lambda(torch.zeros(4, dtype=torch.float64, device="cuda"), [4], torch.zeros(4, dtype=torch.float64, device="cuda"))
+        assert e.value.code == gh._lib.GHB_ESTATE
+        assert c2.assemble_current() == -1 and c2.factors_generation == -1
+        with pytest.raises(gh.GhbError) as e:
+            c2.assemble_select(0)
+        assert e.value.code == gh._lib.GHB_EINVAL
+        plan = c2.plan_blocks([30, 4, 36], np.ones((3, 3), bool), [1, 2], [3])
+        z = torch.zeros(8, dtype=torch.float64, device="cuda")
+        with pytest.raises(gh.GhbError) as e:       # fused slab call without a symbolic phase
+            c2._asm_shape = (1, 1)
+            c2.condense_scatter_slab(plan, 1, torch.zeros(plan.lenA, dtype=torch.float64, device="cuda"),
+                                     torch.zeros(plan.lenb, dtype=torch.float64, device="cuda"),
+                                     torch.zeros(36 * 36, dtype=torch.float64, device="cuda"), torch.zeros(36, dtype=torch.float64, device="cuda"),
+                                     None, z, 0)
+        assert e.value.code == gh._lib.GHB_ESTATE
+        # two patterns on one context: handles 0 and 1, select / release
+        sk = gh.CartesianSkeleton((3, 2), c2)
+        a1 = gh.SparseMatrixAssembler(gh.FacetFESpace(sk, 2, sk.facet_is_boundary()), ctx=c2)
+        a2 = gh.SparseMatrixAssembler(gh.FacetFESpace(sk, 3, sk.facet_is_boundary()), ctx=c2)
+        _, _, n1 = a1.symbolic(); _, _, n2 = a2.symbolic()
+        assert (a1._pid, a2._pid) == (0, 1) and n1 != n2 and c2.assemble_current() == 1
+        a1.select(); assert c2.assemble_current() == 0
+        c2.assemble_release(1)
+        with pytest.raises(gh.GhbError) as e:
+            c2.assemble_select(1)
+        assert e.value.code == gh._lib.GHB_ESTATE
+        # factors generation advances with every keep_factors condensation
+        A = torch.empty((3, plan.lenA), dtype=torch.float64, device="cuda"); b = torch.empty((3, plan.lenb), dtype=torch.float64, device="cuda")
+        c2.synth_fill(plan, 0, 3, A, b)
+        S = torch.empty((3, 36 * 36), dtype=torch.float64, device="cuda"); g = torch.empty((3, 36), dtype=torch.float64, device="cuda")
+        c2.condense(plan, 3, A, b, S, g, None, keep_factors=True); g1 = c2.factors_generation
+        c2.condense(plan, 3, A, b, S, g, None, keep_factors=True)
+        assert c2.factors_generation == g1 + 1
+        c2.condense(plan, 3, A, b, S, g, None)
+        assert c2.factors_generation == -1          # a plain condensation invalidates the stored factors
+    finally:
+        c2.close()
