@@ -495,7 +495,7 @@ def run_ours(args):
         del lam_owned, u
 
     # ---- e2e: C-ABI with host buffers, bounded sample, copies inside the timed region ----
-    e2e, e2e_pageable, cpu_base = None, None, None
+    e2e, e2e_pageable, cpu_base, e2e_affine = None, None, None, None
     sdims = tuple(args.e2e_dims) if args.e2e_dims else ((64, 64, 32) if D == 3 and n_i < 64 else ((24, 24, 16) if D == 3 else (512, 256)))
     sn = min(int(np.prod(sdims)), ncells)
     if sn == int(np.prod(sdims)):
@@ -535,6 +535,36 @@ def run_ours(args):
         e2e_pageable = {"value": sn * world / dtp, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "h2d_gbs_aggregate": h2d * world / dtp / 1e9,
                         "sample": "same sample, pageable numpy arrays in and out (pinned staging inside the library)"}
+        # informational: past the PCIe ceiling of the record path -- for an affine family the host ships tables + per-cell
+        # coefficient vectors (ghb_expand_records_f64 generates the records on the device) and gets the CSC values back
+        e2e_affine = None
+        if args.config == "C3" and world == 1:
+            ntab = 7
+            rng = np.random.default_rng(5)
+            TAh = torch.as_tensor(np.concatenate([A[:1].cpu().numpy(), 1e-3 * rng.standard_normal((ntab - 1, plan.lenA))])).pin_memory()
+            Tbh = torch.as_tensor(np.concatenate([b[:1].cpu().numpy(), 1e-3 * rng.standard_normal((ntab - 1, plan.lenb))])).pin_memory()
+            coefh = gh.cartesian_coefficients(sdims, tuple(1.0 / d for d in sdims), dev).cpu().pin_memory()
+            dA2 = torch.empty((sn, plan.lenA), dtype=torch.float64, device=dev)
+            db2 = torch.empty((sn, plan.lenb), dtype=torch.float64, device=dev)
+
+            def affine_step():
+                ctx.expand_records(plan, sn, ntab, TAh, Tbh, coefh, dA2, db2)       # host tables + coefficients in
+                ctx.condense_assemble(plan, sn, dA2, db2, None, hz, hr, hinfo)       # CSC values + rhs out (host)
+
+            sass.select()
+            for _ in range(2):
+                affine_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                affine_step()
+            torch.cuda.synchronize()
+            dta = (time.perf_counter() - t0) / args.steps
+            e2e_affine = {"value": sn / dta, "unit": "cells/s",
+                          "h2d_bytes_per_step": int((TAh.numel() + Tbh.numel() + coefh.numel()) * 8), "d2h_bytes_per_step": d2h,
+                          "note": "affine record family (7 tables): tables + coefficient vectors from pinned host memory through "
+                                  "ghb_expand_records_f64, then ghb_condense_assemble_f64 with host nzval/rhs; D2H-bound"}
+            del dA2, db2
         del hA, hb, hz, hr, pA, pb, pz, pr
 
     # ---- informational: the same step with the records generated on the device from an affine family:
@@ -603,7 +633,8 @@ def run_ours(args):
                            if ncells * (lenA + lenb) * 8 > 256e6 else "inputs smaller than L2 (launch-bound configuration)",
                            "kernel": plan.kernel_name + (" + fused scatter into nzval" if fused else ", then gather_nzval"),
                            "nnz_per_gpu": int(slab.nnz) * nchunk},
-                "clocks": clk.summary(), "e2e": e2e, "e2e_pageable": e2e_pageable, "gpu_launches": int(launches),
+                "clocks": clk.summary(), "e2e": e2e, "e2e_pageable": e2e_pageable, "e2e_affine_family": e2e_affine,
+                "gpu_launches": int(launches),
                 "roofline": roof, "cpu_baseline": cpu_base, "backsub": backsub, "device_generated_records": devgen,
                 "multi_gpu_check": check, ("two_kernel_step" if fused else "fused_assembly"): other}
         print(json.dumps(line))

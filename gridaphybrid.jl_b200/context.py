@@ -157,6 +157,24 @@ class Context:
             _ptr(Tb, np.float64, ntab * plan.lenb, "Tb"), _ptr(coef, np.float64, ncells * ntab, "coef"),
             _ptr(A, np.float64, ncells * plan.lenA, "A"), _ptr(b, np.float64, ncells * plan.lenb, "b")))
 
+    def condense_affine(self, plan: BlockPlan, ncells, ntab, TA, Tb, coef, S, g, info=None):
+        """S_K, g_K of an affine family without materialising the records (generated in the loader of the condensation
+        kernel); bit-identical to expand_records + condense."""
+        self._check(self._L.ghb_condense_affine_f64(
+            self._h, plan.id, int(ncells), int(ntab), _ptr(TA, np.float64, ntab * plan.lenA, "TA"),
+            _ptr(Tb, np.float64, ntab * plan.lenb, "Tb"), _ptr(coef, np.float64, ncells * ntab, "coef"),
+            _ptr(S, np.float64, ncells * plan.n_b ** 2, "S"), _ptr(g, np.float64, ncells * plan.n_b, "g"),
+            _ptr(info, np.int32, ncells, "info")))
+
+    def condense_assemble_affine(self, plan: BlockPlan, ncells, ntab, TA, Tb, coef, dirichlet_vals, nzval, rhs, info=None):
+        """coefficients -> CSC values + rhs in one call (selected symbolic pattern)."""
+        nrows, nnz = self._asm_shape
+        self._check(self._L.ghb_condense_assemble_affine_f64(
+            self._h, plan.id, int(ncells), int(ntab), _ptr(TA, np.float64, ntab * plan.lenA, "TA"),
+            _ptr(Tb, np.float64, ntab * plan.lenb, "Tb"), _ptr(coef, np.float64, ncells * ntab, "coef"),
+            _ptr(dirichlet_vals, np.float64), _len(dirichlet_vals), _ptr(nzval, np.float64, nnz, "nzval"),
+            _ptr(rhs, np.float64, nrows, "rhs"), _ptr(info, np.int32, ncells, "info")))
+
     def assemble_symbolic(self, ncells, n_b, cell_ids, nrows) -> int:
         nnz = ctypes.c_int64(0)
         self._check(self._L.ghb_assemble_symbolic(self._h, int(ncells), int(n_b),

@@ -169,6 +169,7 @@ void ghb_destroy(ghb_ctx* ctx) {
   for (int i = 0; i < 2; ++i)
     if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
   if (ctx->comm) comm_free(ctx);
+  if (ctx->gen_scratch) cudaFree(ctx->gen_scratch);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
@@ -455,6 +456,90 @@ int ghb_expand_records_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, int ntab, 
   GHB_TRY(launch_expand_records(ctx, ncells, p->lenA, ntab, dTA.dev, dc.dev, dA.dev));
   GHB_TRY(launch_expand_records(ctx, ncells, p->lenb, ntab, dTb.dev, dc.dev, db.dev));
   GHB_TRY(dA.finish()); GHB_TRY(db.finish());
+  return GHB_OK;
+}
+
+// records of an affine family for plans without a GEN kernel: chunks of records expanded into a device temporary
+static int condense_affine_chunked(ghb_ctx* ctx, const Plan& p, int64_t ncells, int ntab, const double* TA, const double* Tb,
+                                   const double* coef, double* S, double* g, int32_t* info, CallTmp& tmp) {
+  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(ncells, ((int64_t)256 << 20) / ((p.lenA + p.lenb) * 8)));
+  double *tA = nullptr, *tb = nullptr;
+  GHB_CUDA(ctx, tmp.alloc((void**)&tA, (size_t)chunk * p.lenA * 8));
+  GHB_CUDA(ctx, tmp.alloc((void**)&tb, (size_t)chunk * p.lenb * 8));
+  for (int64_t c0 = 0; c0 < ncells; c0 += chunk) {
+    const int64_t nc = std::min(chunk, ncells - c0);
+    GHB_TRY(launch_expand_records(ctx, nc, p.lenA, ntab, TA, coef + c0 * ntab, tA));
+    GHB_TRY(launch_expand_records(ctx, nc, p.lenb, ntab, Tb, coef + c0 * ntab, tb));
+    GHB_TRY(launch_condense(ctx, p, nc, tA, tb, S + c0 * p.n_b * p.n_b, g + c0 * p.n_b, info ? info + c0 : nullptr, nullptr));
+  }
+  return GHB_OK;
+}
+
+int ghb_condense_affine_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, int ntab, const double* TA, const double* Tb,
+                            const double* coef, double* S, double* g, int32_t* info) {
+  Plan* p = get_plan(ctx, plan_id);
+  if (!p) return fail(ctx, GHB_EINVAL, "ghb_condense_affine_f64: bad plan id");
+  if (ncells < 0 || ntab < 1 || ntab > 16 || !TA || !Tb || !coef || !S || !g)
+    return fail(ctx, GHB_EINVAL, "ghb_condense_affine_f64: bad argument (need 1 <= ntab <= 16, non-null arrays)");
+  if (ncells == 0) return GHB_OK;
+  cudaSetDevice(ctx->device);
+  ctx->fac.plan_id = -1;
+  Arg<double> dTA(ctx, TA, (size_t)ntab * p->lenA, true, false); GHB_TRY(dTA.rc);
+  Arg<double> dTb(ctx, Tb, (size_t)ntab * p->lenb, true, false); GHB_TRY(dTb.rc);
+  Arg<double> dc(ctx, coef, (size_t)ncells * ntab, true, false); GHB_TRY(dc.rc);
+  Arg<double> dS(ctx, S, (size_t)ncells * p->n_b * p->n_b, false, true); GHB_TRY(dS.rc);
+  Arg<double> dg(ctx, g, (size_t)ncells * p->n_b, false, true); GHB_TRY(dg.rc);
+  Arg<int32_t> di(ctx, info, info ? (size_t)ncells : 0, false, true); GHB_TRY(di.rc);
+  CallTmp tmp(ctx);
+  const bool gen = cw_gen_supported(*p) && !(((uintptr_t)dTA.dev | (uintptr_t)dTb.dev) & 15);
+  if (gen)
+    GHB_TRY(launch_condense_cw_gen(ctx, *p, ncells, ntab, dTA.dev, dTb.dev, dc.dev, dS.dev, dg.dev, di.dev, nullptr));
+  else
+    GHB_TRY(condense_affine_chunked(ctx, *p, ncells, ntab, dTA.dev, dTb.dev, dc.dev, dS.dev, dg.dev, di.dev, tmp));
+  GHB_TRY(dS.finish()); GHB_TRY(dg.finish()); GHB_TRY(di.finish());
+  return GHB_OK;
+}
+
+int ghb_condense_assemble_affine_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, int ntab, const double* TA,
+                                     const double* Tb, const double* coef, const double* dirichlet_vals_in,
+                                     int64_t ndirichlet, double* nzval, double* rhs, int32_t* info) {
+  Plan* p = get_plan(ctx, plan_id);
+  if (!p) return fail(ctx, GHB_EINVAL, "ghb_condense_assemble_affine_f64: bad plan id");
+  if (!ctx->as.valid) return fail(ctx, GHB_ESTATE, "ghb_condense_assemble_affine_f64: call ghb_assemble_symbolic first");
+  const AsmState& as = ctx->as;
+  if (as.nghost) return fail(ctx, GHB_ESTATE, "ghb_condense_assemble_affine_f64: the cached pattern has ghost cells (slab mode)");
+  if (ncells != as.ncells || p->n_b != as.n_b)
+    return fail(ctx, GHB_EINVAL, "ghb_condense_assemble_affine_f64: ncells / n_b differ from the symbolic phase");
+  if (ntab < 1 || ntab > 16 || !TA || !Tb || !coef || !nzval || !rhs || ndirichlet < 0)
+    return fail(ctx, GHB_EINVAL, "ghb_condense_assemble_affine_f64: bad argument (need 1 <= ntab <= 16, non-null arrays)");
+  cudaSetDevice(ctx->device);
+  Arg<double> dd(ctx, dirichlet_vals_in, dirichlet_vals_in ? (size_t)ndirichlet : 0, true, false); GHB_TRY(dd.rc);
+  Arg<double> dTA(ctx, TA, (size_t)ntab * p->lenA, true, false); GHB_TRY(dTA.rc);
+  Arg<double> dTb(ctx, Tb, (size_t)ntab * p->lenb, true, false); GHB_TRY(dTb.rc);
+  Arg<double> dc(ctx, coef, (size_t)ncells * ntab, true, false); GHB_TRY(dc.rc);
+  Arg<double> dz(ctx, nzval, (size_t)as.nnz, false, true); GHB_TRY(dz.rc);
+  Arg<double> dr(ctx, rhs, (size_t)as.nrows, false, true); GHB_TRY(dr.rc);
+  Arg<int32_t> di(ctx, info, info ? (size_t)ncells : 0, false, true); GHB_TRY(di.rc);
+  CallTmp tmp(ctx);
+  double *dS = nullptr, *dg = nullptr;
+  GHB_CUDA(ctx, tmp.alloc((void**)&dS, (size_t)ncells * p->n_b * p->n_b * sizeof(double)));
+  GHB_CUDA(ctx, tmp.alloc((void**)&dg, (size_t)ncells * p->n_b * sizeof(double)));
+  const bool gen = cw_gen_supported(*p) && !(((uintptr_t)dTA.dev | (uintptr_t)dTb.dev) & 15);
+  if (gen && ctx->opt.fused_assembly) {
+    // one kernel from coefficients to CSC values: records generated in the loader, S_K scattered into the zeroed nzval
+    GHB_TRY(asm_scatter_prepare(ctx, 0));
+    GHB_CUDA(ctx, cudaMemsetAsync(dz.dev, 0, (size_t)as.nnz * sizeof(double), ctx->stream));
+    ScatterArgs sc{dz.dev, as.d_colpos, as.d_rowrank, dd.dev ? as.d_keepS : nullptr};
+    GHB_TRY(launch_condense_cw_gen(ctx, *p, ncells, ntab, dTA.dev, dTb.dev, dc.dev, dS, dg, di.dev, &sc));
+    GHB_TRY(asm_numeric_range(ctx, dS, dg, nullptr, dd.dev, dz.dev, dr.dev, 0, as.nrows, ASM_RHS));
+  } else {
+    if (gen)
+      GHB_TRY(launch_condense_cw_gen(ctx, *p, ncells, ntab, dTA.dev, dTb.dev, dc.dev, dS, dg, di.dev, nullptr));
+    else
+      GHB_TRY(condense_affine_chunked(ctx, *p, ncells, ntab, dTA.dev, dTb.dev, dc.dev, dS, dg, di.dev, tmp));
+    GHB_TRY(asm_numeric(ctx, dS, dg, nullptr, dd.dev, dz.dev, dr.dev));
+  }
+  GHB_TRY(dz.finish()); GHB_TRY(dr.finish()); GHB_TRY(di.finish());
   return GHB_OK;
 }
 

@@ -126,6 +126,9 @@ struct ghb_ctx {
   // NCCL communicator of the multi-GPU exchanges (comm.cu; ncclComm_t, loaded at run time)
   void* comm = nullptr;
   int comm_rank = 0, comm_size = 1;
+  // scratch records of the kernels that generate their element records themselves (condense_cw_gen.cu)
+  double* gen_scratch = nullptr;
+  size_t gen_scratch_bytes = 0;
 };
 
 namespace ghb {
@@ -247,6 +250,11 @@ int launch_condense_cw(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double
                        double* g, int32_t* info, double* X);
 int launch_condense_dmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
                          double* g, int32_t* info, double* X = nullptr);
+struct ScatterArgs;
+// records of an affine family generated inside the condensation kernel (sc != NULL: fused assembly as well)
+bool cw_gen_supported(const Plan& p);
+int launch_condense_cw_gen(ghb_ctx* ctx, const Plan& p, int64_t ncells, int ntab, const double* TA, const double* Tb,
+                           const double* coef, double* S, double* g, int32_t* info, const ScatterArgs* sc);
 // dispatch: tuned kernel when the plan has one and no factors are requested, else the generic kernel
 int launch_condense(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
                     double* g, int32_t* info, double* X);

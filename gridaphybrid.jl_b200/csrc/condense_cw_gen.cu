@@ -1,0 +1,72 @@
+// condense_cw_gen.cu -- the cell-warp kernel with the element records of an affine family generated in its loader
+// (/root/reference/src/GridapAPIExtensions.jl:442-451 and src/SumFacetsMap.jl:19-30 produce the cell
+// matrices the reference condenses; here A_K = sum_t coef[K][t] TA[t] is formed per batch of cells inside the
+// condensation kernel and never written to HBM).  Own translation unit: the GEN instantiations compile in parallel with
+// the resident-record ones of condense_cw.cu.
+#include "condense_cw_kernel.cuh"
+
+namespace ghb {
+
+bool cw_gen_supported(const Plan& p) {
+  // tuned instantiations only; 16-byte pairs of record elements
+  return p.use_cw && !p.cw_pad && p.lenA % 2 == 0 && p.lenb % 2 == 0;
+}
+
+template <int NI, int NB, bool SPARSE, bool SCAT>
+static int launch_cw_gen(ghb_ctx* ctx, const Plan& p, CwArgs& ar) {
+  constexpr int WPC = GHB_CW_WPC;
+  auto kern = condense_cw_kernel<NI, NB, WPC, GHB_CW_MINB, false, SPARSE, false, SCAT, true>;
+  const size_t smem = CwCfg<NI, NB>::smem_bytes(WPC, false, true);
+  static KernelSetup ks;
+  int per_sm = 0;
+  GHB_TRY(kernel_setup(ctx, p.opt, kern, 32 * WPC, smem, GHB_CW_CARVEOUT, ks, "condense_cw_kernel<GEN>", &per_sm));
+  const int64_t want = (ar.ncells + WPC - 1) / WPC;
+  const int64_t grid = std::min<int64_t>(want, (int64_t)ctx->sm_count * per_sm);
+  // one scratch record per resident warp, rewritten for every cell (L2-resident: 148 SMs x 16 warps x 39.8 kB = 94 MB on C3)
+  ar.slot = ((int64_t)p.lenA + p.lenb + 15) & ~(int64_t)15;
+  const size_t need = (size_t)grid * WPC * ar.slot * sizeof(double);
+  if (ctx->gen_scratch_bytes < need) {
+    if (ctx->gen_scratch) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->gen_scratch); }
+    ctx->gen_scratch = nullptr; ctx->gen_scratch_bytes = 0;
+    if (cudaMalloc((void**)&ctx->gen_scratch, need) != cudaSuccess) { cudaGetLastError(); return fail(ctx, GHB_ENOMEM, "condense_cw<GEN>: scratch records"); }
+    ctx->gen_scratch_bytes = need;
+  }
+  ar.scratch = ctx->gen_scratch;
+  // chunk of table elements staged per TMA round: two buffers of ntab x E doubles inside the WPC images
+  ar.gen_E = (int)std::min<size_t>(1024, ((size_t)WPC * CwCfg<NI, NB>::WARP_BYTES / (2 * (size_t)ar.ntab * 8)) & ~(size_t)1);
+  kern<<<(unsigned)grid, 32 * WPC, smem, ctx->stream>>>(ar);
+  GHB_LAUNCHED(ctx);
+  return GHB_OK;
+}
+
+template <int NI, int NB>
+static int launch_cw_gen_shape(ghb_ctx* ctx, const Plan& p, CwArgs& ar) {
+  if (ar.nzval) {
+    if (p.all_touched) return launch_cw_gen<NI, NB, false, true>(ctx, p, ar);
+    return launch_cw_gen<NI, NB, true, true>(ctx, p, ar);
+  }
+  if (p.all_touched) return launch_cw_gen<NI, NB, false, false>(ctx, p, ar);
+  return launch_cw_gen<NI, NB, true, false>(ctx, p, ar);
+}
+
+int launch_condense_cw_gen(ghb_ctx* ctx, const Plan& p, int64_t ncells, int ntab, const double* TA, const double* Tb,
+                           const double* coef, double* S, double* g, int32_t* info, const ScatterArgs* sc) {
+  if (!cw_gen_supported(p)) return fail(ctx, GHB_EUNSUPPORTED, "condense_cw<GEN>: plan without a tuned cell-warp kernel");
+  if (ntab < 1 || ntab > 16) return fail(ctx, GHB_EINVAL, "condense_cw<GEN>: need 1 <= ntab <= 16");
+  if (((uintptr_t)TA | (uintptr_t)Tb) & 15) return fail(ctx, GHB_EUNSUPPORTED, "condense_cw<GEN>: tables must be 16-byte aligned (TMA bulk copies)");
+  CwArgs ar;
+  cw_fill_args(p, ar);
+  ar.nzval = sc ? sc->nzval : nullptr;
+  ar.colpos = sc ? sc->colpos : nullptr;
+  ar.rowrank = sc ? sc->rowrank : nullptr;
+  ar.keepS = sc ? sc->keepS : nullptr;
+  ar.ncells = ncells;
+  ar.A = nullptr; ar.b = nullptr; ar.S = S; ar.g = g; ar.info = info; ar.X = nullptr;
+  ar.TA = TA; ar.Tb = Tb; ar.coef = coef; ar.ntab = ntab;
+#define X(a, b) if (p.n_i == a && p.n_b == b) return launch_cw_gen_shape<a, b>(ctx, p, ar);
+  GHB_CW_SHAPES(X)
+#undef X
+  return fail(ctx, GHB_EUNSUPPORTED, "condense_cw<GEN>: shape not instantiated");
+}
+
+}  // namespace ghb

@@ -48,6 +48,35 @@ class AffineRecordFamily:
         return PackedCells(A, b, plan.ndofs, plan.touched)
 
 
+    def _tables(self, dev):
+        if self._dev is None or self._dev[0].device != dev:
+            self._dev = (torch.as_tensor(self.TA, device=dev), torch.as_tensor(self.Tb, device=dev))
+        return self._dev
+
+    def condense(self, ctx: Context, plan: BlockPlan, coef: torch.Tensor, S=None, g=None, info=None):
+        """coef [ncells][ntab] (device) -> (S_K, g_K): the records are formed in the loader of the condensation kernel
+        and never written to HBM (`ghb_condense_affine_f64`)."""
+        ncells = int(coef.shape[0])
+        assert coef.shape[1] == self.ntab and self.TA.shape[1] == plan.lenA and self.Tb.shape[1] == plan.lenb
+        dev = coef.device
+        TA, Tb = self._tables(dev)
+        if S is None:
+            S = torch.empty((ncells, plan.n_b * plan.n_b), dtype=torch.float64, device=dev)
+        if g is None:
+            g = torch.empty((ncells, plan.n_b), dtype=torch.float64, device=dev)
+        ctx.use_torch_stream()
+        ctx.condense_affine(plan, ncells, self.ntab, TA, Tb, coef.contiguous(), S, g, info)
+        return S, g
+
+    def condense_assemble(self, ctx: Context, plan: BlockPlan, coef: torch.Tensor, dirichlet_vals, nzval, rhs, info=None):
+        """coefficients -> CSC values + rhs of the selected symbolic pattern (`ghb_condense_assemble_affine_f64`)."""
+        TA, Tb = self._tables(coef.device)
+        ctx.use_torch_stream()
+        ctx.condense_assemble_affine(plan, int(coef.shape[0]), self.ntab, TA, Tb, coef.contiguous(), dirichlet_vals,
+                                     nzval, rhs, info)
+        return nzval, rhs
+
+
 def cartesian_coefficients(dims, h, device, cell_start=0, ncells=None, extra=None) -> torch.Tensor:
     """Coefficient vectors of the cells of a Cartesian mesh (x fastest), [ncells][1 + 2 D (+ extras)]:
     1, [idx_a == 0] per axis (the low-side facet is a boundary facet: its owner-normal sign flips, e.g.

@@ -121,6 +121,21 @@ int ghb_restrict_facet_dofs_i64(ghb_ctx* ctx, int64_t ncells, int nlfacets, int 
 int ghb_expand_records_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, int ntab, const double* TA, const double* Tb,
                            const double* coef, double* A, double* b);
 
+/* The same family condensed WITHOUT materialising the records: the condensation kernel forms A_K, b_K in its loader (a
+ * batch of cells per CTA: every table element is fetched once per batch; the records live in per-warp scratch that stays
+ * in L2), so the 8(lenA+lenb) bytes per cell never reach HBM -- the element-matrix generation of the reference's
+ * lazy_map chain (src/GridapAPIExtensions.jl:442-451 -> src/HybridAffineFEOperators.jl:338) fused into the loader.
+ * Results are bit-identical to ghb_expand_records_f64 followed by ghb_condense_f64 / ghb_condense_assemble_f64 (same
+ * summation order).  Plans without a tuned cell-warp kernel (ghb_plan_kernel_name not "cw_<n_i>_<n_b>") or with odd
+ * record lengths expand chunks of records into a device temporary instead (same results).  TA, Tb, coef may be host
+ * pointers (staged).  ghb_condense_assemble_affine_f64 needs the selected symbolic pattern like
+ * ghb_condense_assemble_f64. */
+int ghb_condense_affine_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, int ntab, const double* TA, const double* Tb,
+                            const double* coef, double* S, double* g, int32_t* info);
+int ghb_condense_assemble_affine_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, int ntab, const double* TA,
+                                     const double* Tb, const double* coef, const double* dirichlet_vals,
+                                     int64_t ndirichlet, double* nzval, double* rhs, int32_t* info);
+
 /* ---- (f-3) bulk -> skeleton L2 projection dofs --------------------------------------------------
  * replaces compute_bulk_to_skeleton_l2_projection_dofs (src/GridapAPIExtensions.jl:453-500; called per (cell, local facet)
  * by the elasticity / Hencky forms through test/P_m.jl:4-23): X = A \ B with A [nbatch][n*n] the facet mass matrices of
