@@ -5,6 +5,13 @@
 // the resident-record ones of condense_cw.cu.
 #include "condense_cw_kernel.cuh"
 
+#ifndef GHB_CW_GEN_WPC
+#define GHB_CW_GEN_WPC 8      // cells per batch = warps per CTA of the GEN kernels (rows of the DMMA tile that forms the records)
+#endif
+#ifndef GHB_CW_GEN_MINB
+#define GHB_CW_GEN_MINB (16 / GHB_CW_GEN_WPC)
+#endif
+
 namespace ghb {
 
 bool cw_gen_supported(const Plan& p) {
@@ -14,8 +21,8 @@ bool cw_gen_supported(const Plan& p) {
 
 template <int NI, int NB, bool SPARSE, bool SCAT>
 static int launch_cw_gen(ghb_ctx* ctx, const Plan& p, CwArgs& ar) {
-  constexpr int WPC = GHB_CW_WPC;
-  auto kern = condense_cw_kernel<NI, NB, WPC, GHB_CW_MINB, false, SPARSE, false, SCAT, true>;
+  constexpr int WPC = GHB_CW_GEN_WPC;
+  auto kern = condense_cw_kernel<NI, NB, WPC, GHB_CW_GEN_MINB, false, SPARSE, false, SCAT, true>;
   const size_t smem = CwCfg<NI, NB>::smem_bytes(WPC, false, true);
   static KernelSetup ks;
   int per_sm = 0;
@@ -32,8 +39,10 @@ static int launch_cw_gen(ghb_ctx* ctx, const Plan& p, CwArgs& ar) {
     ctx->gen_scratch_bytes = need;
   }
   ar.scratch = ctx->gen_scratch;
-  // chunk of table elements staged per TMA round: two buffers of ntab x E doubles inside the WPC images
-  ar.gen_E = (int)std::min<size_t>(1024, ((size_t)WPC * CwCfg<NI, NB>::WARP_BYTES / (2 * (size_t)ar.ntab * 8)) & ~(size_t)1);
+  // chunk of table elements staged per TMA round: two buffers of ntab x E doubles inside the WPC images, E = 4 (mod 16)
+  const size_t cap = std::min<size_t>(2048, (size_t)WPC * CwCfg<NI, NB>::WARP_BYTES / (2 * (size_t)ar.ntab * 8));
+  if (cap < 20) return fail(ctx, GHB_EUNSUPPORTED, "condense_cw<GEN>: images too small to stage the tables");
+  ar.gen_E = (int)(((cap - 4) & ~(size_t)15) + 4);
   kern<<<(unsigned)grid, 32 * WPC, smem, ctx->stream>>>(ar);
   GHB_LAUNCHED(ctx);
   return GHB_OK;

@@ -173,7 +173,7 @@ struct CwArgs {
   double* scratch;          // [gridDim.x * WPC][slot] the record of the cell a warp is working on (stays in L2)
   int64_t slot;             // doubles per scratch record (lenA + lenb rounded up to 128 bytes)
   int ntab;
-  int gen_E;                // table elements per staged chunk (even; 2 buffers x ntab x gen_E doubles fit the WPC images)
+  int gen_E;                // table elements per staged chunk (= 4 mod 16; 2 buffers x ntab x gen_E doubles fit the WPC images)
 };
 
 // record loads: the records of a GEN kernel are rewritten in place by the CTA itself -- no non-coherent loads
@@ -206,11 +206,11 @@ struct CwCfg {
   static constexpr unsigned SH_COLBASE = SH_BYTES;
   static constexpr unsigned SH_ROWINFO = SH_COLBASE + 4 * (NI + NB + 1) * 8;
   static constexpr unsigned SH_BYTES_PAD = SH_ROWINFO + 2 * ((NI + NB + 7) & ~7);
-  // GEN kernels add: coef[16 tables][WPC cells of the batch] (f64)
-  static constexpr unsigned SH_COEF = (SH_BYTES + 15u) & ~15u;
+  // GEN kernels add: the two mbarriers of the table staging ring
+  static constexpr unsigned SH_BAR = (SH_BYTES + 15u) & ~15u;
   static constexpr int MAXTAB = 16;
   static size_t smem_bytes(int wpc, bool pad = false, bool gen = false) {
-    return (size_t)wpc * WARP_BYTES + (gen ? SH_COEF + 8u * MAXTAB * wpc + 16u : (pad ? SH_BYTES_PAD : SH_BYTES));
+    return (size_t)wpc * WARP_BYTES + (gen ? SH_BAR + 16u : (pad ? SH_BYTES_PAD : SH_BYTES));
   }
   // position-table entry of image row r: byte offset of the row | swizzle bits (4,5) | r << 16
   __host__ __device__ static constexpr unsigned enc(unsigned r) { return r * ROWB | ((r & 6u) << 3) | (r << 16); }
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
   constexpr int RT = C::RT, NPL = C::NPL, DUMMY = C::DUMMY;
   constexpr int BTM = C::BTM;
   static_assert(!PAD || (SPARSE && NI % 8 == 0), "PAD kernels are instantiated for padded shapes");
-  static_assert(!GEN || (!PAD && WPC % 2 == 0), "GEN kernels: tuned shapes, an even number of warps");
+  static_assert(!GEN || (!PAD && WPC <= 8), "GEN kernels: tuned shapes, at most 8 cells per batch (rows of a DMMA tile)");
   const int nir = PAD ? ar.n_i : NI, nbr = PAD ? ar.n_b : NB;       // real sizes
   const int NC = nbr + 1;                                           // right-hand-side columns: A12 | b1
   const int CTB = PAD ? (NC + 7) / 8 : C::CTB;
@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
   for (unsigned i = lane; i < C::WARP_BYTES / 8; i += 32) reinterpret_cast<double*>(wsp)[i] = 0.0;
   for (int i = threadIdx.x; i < 8; i += 32 * WPC) reinterpret_cast<double*>(shp)[i] = 1.0;
   if (GEN && threadIdx.x == 0) {
-    const unsigned bars = (unsigned)__cvta_generic_to_shared(shp) + C::SH_COEF + 8u * C::MAXTAB * WPC;
+    const unsigned bars = (unsigned)__cvta_generic_to_shared(shp) + C::SH_BAR;
     mbar_init(bars, 1u); mbar_init(bars + 8u, 1u);
     fence_mbar_init();
   }
@@ -418,28 +418,26 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
   const int64_t wstride = (int64_t)gridDim.x * WPC;
-  const unsigned a_coef = a_sh + C::SH_COEF;
   const int ntab = ar.ntab;
   double* const slot0 = GEN ? ar.scratch + (int64_t)blockIdx.x * WPC * ar.slot : nullptr;   // scratch records of this CTA
-  // coefficients of a batch -> shared memory, [table][cell of the batch]; cells past the end get zeros
-  auto stage_coef = [&](const int64_t base) {
-    if ((int)threadIdx.x < WPC * ntab) {
-      const int w = threadIdx.x % WPC, tq = threadIdx.x / WPC;
-      const double c = base + w < ar.ncells ? __ldg(ar.coef + (base + w) * ntab + tq) : 0.0;
-      sts64(a_coef + 8u * threadIdx.x, c);
-    }
-  };
-  // out[w][e] = sum_t coef[w][t] T[t][e] for the WPC cells of the batch.  The tables come in chunks of gen_E elements:
-  // one thread issues a TMA bulk copy per table into a two-deep staging ring that occupies the (dead) images of the WPC
-  // warps, the copies of chunk k+1 fly while chunk k is combined.  Per step a thread combines two 16-byte pairs of
-  // elements for the WPC cells; the sum runs in table order from 0.0 like expand_records_kernel (glue.cu): the records
-  // are bit-identical to its.
+  // Records of a batch: out[w][e] = sum_t coef[w][t] T[t][e] for the WPC cells of the batch is a small GEMM and runs on
+  // DMMA: rows = cells of the batch (8 rows; WPC of them used), k = tables (4 per step, zero-padded), columns = 8 record
+  // elements per tile.  The A operand (coefficients) is loaded once per batch, the B operand comes from table chunks of
+  // gen_E elements that one thread brings in with TMA bulk copies -- a two-deep staging ring laid over the (dead) images
+  // of the WPC warps, chunk k+1 flies while chunk k is combined -- and the D fragments (two consecutive elements of one
+  // cell per lane) go to the scratch records with 16-byte stores.  DMMA accumulates in ascending k from C: the sum runs in
+  // table order from 0.0 like expand_records_kernel (glue.cu), zero-padded steps add +0.
   const unsigned a_stage = (unsigned)__cvta_generic_to_shared(smem_raw);
-  const unsigned a_bar = a_coef + 8u * C::MAXTAB * WPC;
+  const unsigned a_bar = a_sh + C::SH_BAR;
   unsigned gphase = 0u;                                      // parity of the two staging barriers
-  auto gen_records = [&]() {
-    const int E = ar.gen_E;
+  auto gen_records = [&](const int64_t base) {
+    const int E = ar.gen_E;                                  // = 4 (mod 16): the B-fragment loads of a half-warp (4 tables x 4 elements) hit 16 distinct banks
     const int nchA = (lenA + E - 1) / E, nch = nchA + (lenb + E - 1) / E;
+    const int KS = (ntab + 3) >> 2;
+    double ca[4];                                            // A fragments: coef[cell g][4s + t]
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+      ca[s] = (g < WPC && base + g < ar.ncells && 4 * s + t < ntab) ? __ldg(ar.coef + (base + g) * ntab + 4 * s + t) : 0.0;
     auto issue = [&](const int k, const int buf) {
       const bool isA = k < nchA;
       const int len = isA ? lenA : lenb;
@@ -451,40 +449,43 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
       for (int tq = 0; tq < ntab; ++tq)
         bulk_g2s(a_stage + (unsigned)((buf * ntab + tq) * E) * 8u, T + (size_t)tq * len, (unsigned)cnt * 8u, bar);
     };
+    __syncthreads();          // every warp is done with its previous cell: images and scratch records are free
     if (threadIdx.x == 0) { issue(0, 0); if (nch > 1) issue(1, 1); }
+    double* const dlane = slot0 + (g < WPC ? g : 0) * ar.slot + 2 * t;   // this lane's D fragments: cell g, elements 2t, 2t+1
     for (int k = 0; k < nch; ++k) {
       const int buf = k & 1;
       const bool isA = k < nchA;
       const int e0 = (isA ? k : k - nchA) * E, cnt = min(E, (isA ? lenA : lenb) - e0);
-      double* dst0 = slot0 + (isA ? 0 : lenA) + e0;
-      const unsigned sb = a_stage + (unsigned)(buf * ntab * E) * 8u;
+      double* const dst = dlane + (isA ? 0 : lenA) + e0;
+      // B fragment of k-step s: T[4s + t][e0 + 8 tile + g]
+      const unsigned sb = a_stage + (unsigned)((buf * ntab + t) * E + g) * 8u;
       mbar_wait(a_bar + 8u * (unsigned)buf, (gphase >> buf) & 1u);
       gphase ^= 1u << buf;
-      for (int i = threadIdx.x; 2 * i < cnt; i += 64 * WPC) {
-        const int i1 = i + 32 * WPC;
-        const bool has1 = 2 * i1 < cnt;
-        double2 acc0[WPC], acc1[WPC];
+      const int ntile = (cnt + 7) >> 3;
+      constexpr int TU = 4;                                  // independent tiles in flight per warp
+      for (int tl0 = warp; tl0 < ntile; tl0 += TU * WPC) {
+        double d[TU][2];
 #pragma unroll
-        for (int w = 0; w < WPC; ++w) { acc0[w] = make_double2(0.0, 0.0); acc1[w] = make_double2(0.0, 0.0); }
-#pragma unroll 4
-        for (int tq = 0; tq < ntab; ++tq) {
-          double2 v0, v1 = make_double2(0.0, 0.0);
-          lds128(sb + (unsigned)(tq * E) * 8u + 16u * (unsigned)i, v0.x, v0.y);
-          if (has1) lds128(sb + (unsigned)(tq * E) * 8u + 16u * (unsigned)i1, v1.x, v1.y);
-          double c[WPC];
+        for (int u = 0; u < TU; ++u) { d[u][0] = 0.0; d[u][1] = 0.0; }
 #pragma unroll
-          for (int w = 0; w < WPC; w += 2) lds128(a_coef + 8u * (unsigned)(WPC * tq + w), c[w], c[w + 1]);
+        for (int s = 0; s < 4; ++s) {
+          if (s >= KS) break;
+          const bool tv = 4 * s + t < ntab;
+          double bv[TU];
 #pragma unroll
-          for (int w = 0; w < WPC; ++w) {
-            acc0[w].x = fma(c[w], v0.x, acc0[w].x); acc0[w].y = fma(c[w], v0.y, acc0[w].y);
-            acc1[w].x = fma(c[w], v1.x, acc1[w].x); acc1[w].y = fma(c[w], v1.y, acc1[w].y);
+          for (int u = 0; u < TU; ++u) {
+            const int tl = tl0 + u * WPC;
+            bv[u] = (tv && 8 * tl + g < cnt) ? lds64(sb + (unsigned)(4 * s * E + 8 * tl) * 8u) : 0.0;
           }
-        }
 #pragma unroll
-        for (int w = 0; w < WPC; ++w) {
-          double2* d = reinterpret_cast<double2*>(dst0 + w * ar.slot);
-          d[i] = acc0[w];
-          if (has1) d[i1] = acc1[w];
+          for (int u = 0; u < TU; ++u) dmma(d[u][0], d[u][1], ca[s], bv[u]);
+        }
+        if (g < WPC) {
+#pragma unroll
+          for (int u = 0; u < TU; ++u) {
+            const int tl = tl0 + u * WPC;
+            if (8 * tl + 2 * t < cnt) *reinterpret_cast<double2*>(dst + 8 * tl) = make_double2(d[u][0], d[u][1]);
+          }
         }
       }
       __syncthreads();                                       // chunk k is consumed (and, for the last one: the records are complete)
@@ -494,12 +495,9 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
     for (unsigned o = 16u * lane; o < C::WARP_BYTES; o += 512u) sts128(ws + o, 0.0, 0.0);
     __syncwarp();
   };
-  if (GEN) stage_coef((int64_t)blockIdx.x * WPC);
   for (int64_t cell = (int64_t)blockIdx.x * WPC + warp; GEN ? (cell - warp < ar.ncells) : (cell < ar.ncells); cell += wstride) {
     if (GEN) {
-      __syncthreads();        // every warp is done with the record of its previous cell; the coefficients are in place
-      gen_records();          // ends with a barrier: the WPC records of the batch are complete
-      stage_coef(cell - warp + wstride);   // next batch (read after the barrier at the top of the loop)
+      gen_records(cell - warp);   // starts and ends with a barrier: the WPC records of the batch are complete
       if (cell >= ar.ncells) continue;
     }
     const double* Arec = GEN ? slot0 + warp * ar.slot : ar.A + cell * lenA;
