@@ -170,6 +170,7 @@ void ghb_destroy(ghb_ctx* ctx) {
     if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
   if (ctx->comm) comm_free(ctx);
   if (ctx->gen_scratch) cudaFree(ctx->gen_scratch);
+  if (ctx->gen_tab) cudaFree(ctx->gen_tab);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
@@ -491,7 +492,7 @@ int ghb_condense_affine_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, int ntab,
   Arg<double> dg(ctx, g, (size_t)ncells * p->n_b, false, true); GHB_TRY(dg.rc);
   Arg<int32_t> di(ctx, info, info ? (size_t)ncells : 0, false, true); GHB_TRY(di.rc);
   CallTmp tmp(ctx);
-  const bool gen = cw_gen_supported(*p) && !(((uintptr_t)dTA.dev | (uintptr_t)dTb.dev) & 15);
+  const bool gen = cw_gen_supported(*p);
   if (gen)
     GHB_TRY(launch_condense_cw_gen(ctx, *p, ncells, ntab, dTA.dev, dTb.dev, dc.dev, dS.dev, dg.dev, di.dev, nullptr));
   else
@@ -524,7 +525,7 @@ int ghb_condense_assemble_affine_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, 
   double *dS = nullptr, *dg = nullptr;
   GHB_CUDA(ctx, tmp.alloc((void**)&dS, (size_t)ncells * p->n_b * p->n_b * sizeof(double)));
   GHB_CUDA(ctx, tmp.alloc((void**)&dg, (size_t)ncells * p->n_b * sizeof(double)));
-  const bool gen = cw_gen_supported(*p) && !(((uintptr_t)dTA.dev | (uintptr_t)dTb.dev) & 15);
+  const bool gen = cw_gen_supported(*p);
   if (gen && ctx->opt.fused_assembly) {
     // one kernel from coefficients to CSC values: records generated in the loader, S_K scattered into the zeroed nzval
     GHB_TRY(asm_scatter_prepare(ctx, 0));

@@ -15,8 +15,7 @@
 namespace ghb {
 
 bool cw_gen_supported(const Plan& p) {
-  // tuned instantiations only; 16-byte pairs of record elements
-  return p.use_cw && !p.cw_pad && p.lenA % 2 == 0 && p.lenb % 2 == 0;
+  return p.use_cw && !p.cw_pad;      // the tuned instantiations
 }
 
 template <int NI, int NB, bool SPARSE, bool SCAT>
@@ -30,7 +29,7 @@ static int launch_cw_gen(ghb_ctx* ctx, const Plan& p, CwArgs& ar) {
   const int64_t want = (ar.ncells + WPC - 1) / WPC;
   const int64_t grid = std::min<int64_t>(want, (int64_t)ctx->sm_count * per_sm);
   // one scratch record per resident warp, rewritten for every cell (L2-resident: 148 SMs x 16 warps x 39.8 kB = 94 MB on C3)
-  ar.slot = ((int64_t)p.lenA + p.lenb + 15) & ~(int64_t)15;
+  ar.slot = ((int64_t)ar.lenAp + ar.lenbp + 15) & ~(int64_t)15;
   const size_t need = (size_t)grid * WPC * ar.slot * sizeof(double);
   if (ctx->gen_scratch_bytes < need) {
     if (ctx->gen_scratch) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->gen_scratch); }
@@ -39,10 +38,10 @@ static int launch_cw_gen(ghb_ctx* ctx, const Plan& p, CwArgs& ar) {
     ctx->gen_scratch_bytes = need;
   }
   ar.scratch = ctx->gen_scratch;
-  // chunk of table elements staged per TMA round: two buffers of ntab x E doubles inside the WPC images, E = 4 (mod 16)
-  const size_t cap = std::min<size_t>(2048, (size_t)WPC * CwCfg<NI, NB>::WARP_BYTES / (2 * (size_t)ar.ntab * 8));
-  if (cap < 20) return fail(ctx, GHB_EUNSUPPORTED, "condense_cw<GEN>: images too small to stage the tables");
-  ar.gen_E = (int)(((cap - 4) & ~(size_t)15) + 4);
+  // chunk of table elements a warp stages per TMA round: two buffers of ntab rows of E + 4 doubles inside its image
+  const size_t cap = std::min<size_t>(1028, (size_t)CwCfg<NI, NB>::WARP_BYTES / (2 * (size_t)ar.ntab * 8));
+  if (cap < 20) return fail(ctx, GHB_EUNSUPPORTED, "condense_cw<GEN>: image too small to stage the tables");
+  ar.gen_E = (int)((cap - 4) & ~(size_t)15);
   kern<<<(unsigned)grid, 32 * WPC, smem, ctx->stream>>>(ar);
   GHB_LAUNCHED(ctx);
   return GHB_OK;
@@ -62,7 +61,6 @@ int launch_condense_cw_gen(ghb_ctx* ctx, const Plan& p, int64_t ncells, int ntab
                            const double* coef, double* S, double* g, int32_t* info, const ScatterArgs* sc) {
   if (!cw_gen_supported(p)) return fail(ctx, GHB_EUNSUPPORTED, "condense_cw<GEN>: plan without a tuned cell-warp kernel");
   if (ntab < 1 || ntab > 16) return fail(ctx, GHB_EINVAL, "condense_cw<GEN>: need 1 <= ntab <= 16");
-  if (((uintptr_t)TA | (uintptr_t)Tb) & 15) return fail(ctx, GHB_EUNSUPPORTED, "condense_cw<GEN>: tables must be 16-byte aligned (TMA bulk copies)");
   CwArgs ar;
   cw_fill_args(p, ar);
   ar.nzval = sc ? sc->nzval : nullptr;
@@ -71,7 +69,27 @@ int launch_condense_cw_gen(ghb_ctx* ctx, const Plan& p, int64_t ncells, int ntab
   ar.keepS = sc ? sc->keepS : nullptr;
   ar.ncells = ncells;
   ar.A = nullptr; ar.b = nullptr; ar.S = S; ar.g = g; ar.info = info; ar.X = nullptr;
-  ar.TA = TA; ar.Tb = Tb; ar.coef = coef; ar.ntab = ntab;
+  ar.coef = coef; ar.ntab = ntab;
+  // TMA bulk copies need 16-byte aligned table rows: odd record lengths (or unaligned caller tables) go through a padded
+  // copy owned by the context (ntab rows of lenAp = lenA + (lenA & 1) doubles, zero padding; 8 (lenA + lenb) ntab bytes)
+  ar.lenAp = p.lenA + (p.lenA & 1); ar.lenbp = p.lenb + (p.lenb & 1);
+  if (ar.lenAp != p.lenA || ar.lenbp != p.lenb || (((uintptr_t)TA | (uintptr_t)Tb) & 15)) {
+    const size_t need = (size_t)ntab * (ar.lenAp + ar.lenbp) * sizeof(double);
+    if (ctx->gen_tab_bytes < need) {
+      if (ctx->gen_tab) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->gen_tab); }
+      ctx->gen_tab = nullptr; ctx->gen_tab_bytes = 0;
+      if (cudaMalloc((void**)&ctx->gen_tab, need) != cudaSuccess) { cudaGetLastError(); return fail(ctx, GHB_ENOMEM, "condense_cw<GEN>: padded tables"); }
+      ctx->gen_tab_bytes = need;
+    }
+    double* pA = ctx->gen_tab;
+    double* pb = pA + (size_t)ntab * ar.lenAp;
+    GHB_CUDA(ctx, cudaMemsetAsync(ctx->gen_tab, 0, need, ctx->stream));
+    GHB_CUDA(ctx, cudaMemcpy2DAsync(pA, (size_t)ar.lenAp * 8, TA, (size_t)p.lenA * 8, (size_t)p.lenA * 8, ntab, cudaMemcpyDeviceToDevice, ctx->stream));
+    GHB_CUDA(ctx, cudaMemcpy2DAsync(pb, (size_t)ar.lenbp * 8, Tb, (size_t)p.lenb * 8, (size_t)p.lenb * 8, ntab, cudaMemcpyDeviceToDevice, ctx->stream));
+    ar.TA = pA; ar.Tb = pb;
+  } else {
+    ar.TA = TA; ar.Tb = Tb;
+  }
 #define X(a, b) if (p.n_i == a && p.n_b == b) return launch_cw_gen_shape<a, b>(ctx, p, ar);
   GHB_CW_SHAPES(X)
 #undef X

@@ -167,13 +167,14 @@ struct CwArgs {
   const uint8_t* rowrank;   // [ncells][n_b][n_b] rank of row li inside the column of lj, 255: not assembled
   const uint8_t* keepS;     // [ncells] 1: also store S_K (Dirichlet lift, cut-plane pack); NULL: never
   // records of an affine family generated in the loader (GEN kernels): A_K = sum_t coef[K][t] TA[t]
-  const double* TA;         // [ntab][lenA]
-  const double* Tb;         // [ntab][lenb]
+  const double* TA;         // [ntab][lenAp] rows padded to an even length (16-byte aligned rows for the TMA copies)
+  const double* Tb;         // [ntab][lenbp]
+  int lenAp, lenbp;
   const double* coef;       // [ncells][ntab]
   double* scratch;          // [gridDim.x * WPC][slot] the record of the cell a warp is working on (stays in L2)
-  int64_t slot;             // doubles per scratch record (lenA + lenb rounded up to 128 bytes)
+  int64_t slot;             // doubles per scratch record (lenAp + lenbp rounded up to 128 bytes); b_K sits at offset lenAp
   int ntab;
-  int gen_E;                // table elements per staged chunk (= 4 mod 16; 2 buffers x ntab x gen_E doubles fit the WPC images)
+  int gen_E;                // table elements per staged chunk (a multiple of 16; 2 buffers x ntab x (gen_E + 4) doubles fit an image)
 };
 
 // record loads: the records of a GEN kernel are rewritten in place by the CTA itself -- no non-coherent loads
@@ -206,11 +207,11 @@ struct CwCfg {
   static constexpr unsigned SH_COLBASE = SH_BYTES;
   static constexpr unsigned SH_ROWINFO = SH_COLBASE + 4 * (NI + NB + 1) * 8;
   static constexpr unsigned SH_BYTES_PAD = SH_ROWINFO + 2 * ((NI + NB + 7) & ~7);
-  // GEN kernels add: the two mbarriers of the table staging ring
+  // GEN kernels add: two mbarriers per warp (table staging rings) and 16 zero bytes
   static constexpr unsigned SH_BAR = (SH_BYTES + 15u) & ~15u;
   static constexpr int MAXTAB = 16;
   static size_t smem_bytes(int wpc, bool pad = false, bool gen = false) {
-    return (size_t)wpc * WARP_BYTES + (gen ? SH_BAR + 16u : (pad ? SH_BYTES_PAD : SH_BYTES));
+    return (size_t)wpc * WARP_BYTES + (gen ? SH_BAR + 16u * wpc + 16u : (pad ? SH_BYTES_PAD : SH_BYTES));
   }
   // position-table entry of image row r: byte offset of the row | swizzle bits (4,5) | r << 16
   __host__ __device__ static constexpr unsigned enc(unsigned r) { return r * ROWB | ((r & 6u) << 3) | (r << 16); }
@@ -367,7 +368,8 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
   for (int i = threadIdx.x; i < 8; i += 32 * WPC) reinterpret_cast<double*>(shp)[i] = 1.0;
   if (GEN && threadIdx.x == 0) {
     const unsigned bars = (unsigned)__cvta_generic_to_shared(shp) + C::SH_BAR;
-    mbar_init(bars, 1u); mbar_init(bars + 8u, 1u);
+    for (int w = 0; w < 2 * WPC; ++w) mbar_init(bars + 8u * w, 1u);
+    sts128(bars + 16u * WPC, 0.0, 0.0);
     fence_mbar_init();
   }
   for (int i = threadIdx.x; i <= NI; i += 32 * WPC) {
@@ -422,76 +424,94 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
   double* const slot0 = GEN ? ar.scratch + (int64_t)blockIdx.x * WPC * ar.slot : nullptr;   // scratch records of this CTA
   // Records of a batch: out[w][e] = sum_t coef[w][t] T[t][e] for the WPC cells of the batch is a small GEMM and runs on
   // DMMA: rows = cells of the batch (8 rows; WPC of them used), k = tables (4 per step, zero-padded), columns = 8 record
-  // elements per tile.  The A operand (coefficients) is loaded once per batch, the B operand comes from table chunks of
-  // gen_E elements that one thread brings in with TMA bulk copies -- a two-deep staging ring laid over the (dead) images
-  // of the WPC warps, chunk k+1 flies while chunk k is combined -- and the D fragments (two consecutive elements of one
-  // cell per lane) go to the scratch records with 16-byte stores.  DMMA accumulates in ascending k from C: the sum runs in
-  // table order from 0.0 like expand_records_kernel (glue.cu), zero-padded steps add +0.
-  const unsigned a_stage = (unsigned)__cvta_generic_to_shared(smem_raw);
-  const unsigned a_bar = a_sh + C::SH_BAR;
+  // elements per tile.  The element range is cut into chunks of gen_E elements that the warps take round-robin; a warp
+  // brings the ntab table rows of its chunk in with TMA bulk copies (lane 0 issues) -- a two-deep staging ring laid over
+  // its own (dead) image, the copies of its next chunk fly while it combines the current one, no CTA barrier inside the
+  // phase -- holds the A operand (coefficients) in registers for the whole batch, and sends the D fragments (two
+  // consecutive elements of one cell per lane) to the scratch records of all WPC cells with 16-byte stores.  DMMA
+  // accumulates in ascending k from C: the sum runs in table order from 0.0 like expand_records_kernel (glue.cu),
+  // zero-padded steps add +0 -- the records are bit-identical to its.
+  const unsigned a_bar = a_sh + C::SH_BAR + 16u * (unsigned)warp;   // the warp's two staging barriers
+  const unsigned a_zero = a_sh + C::SH_BAR + 16u * WPC;             // eight zero bytes (B fragments of zero-padded tables)
   unsigned gphase = 0u;                                      // parity of the two staging barriers
   auto gen_records = [&](const int64_t base) {
-    const int E = ar.gen_E;                                  // = 4 (mod 16): the B-fragment loads of a half-warp (4 tables x 4 elements) hit 16 distinct banks
-    const int nchA = (lenA + E - 1) / E, nch = nchA + (lenb + E - 1) / E;
+    const int E = ar.gen_E;                                  // elements per chunk, a multiple of 16
+    const int RS = E + 4;                                    // row stride of the ring = 4 (mod 16): the B-fragment loads of a half-warp (4 tables x 4 elements) hit 16 distinct banks
+    const int lenAp = ar.lenAp, lenbp = ar.lenbp;            // generated lengths: a padding element may follow the record
+    const int nchA = (lenAp + E - 1) / E, nch = nchA + (lenbp + E - 1) / E;
     const int KS = (ntab + 3) >> 2;
     double ca[4];                                            // A fragments: coef[cell g][4s + t]
 #pragma unroll
     for (int s = 0; s < 4; ++s)
       ca[s] = (g < WPC && base + g < ar.ncells && 4 * s + t < ntab) ? __ldg(ar.coef + (base + g) * ntab + 4 * s + t) : 0.0;
+    if (lane < WPC && base + wstride + lane < ar.ncells)     // the coefficients of the next batch: DRAM -> L2 now
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ar.coef + (base + wstride + lane) * ntab));
     auto issue = [&](const int k, const int buf) {
       const bool isA = k < nchA;
-      const int len = isA ? lenA : lenb;
+      const int len = isA ? lenAp : lenbp;
       const int e0 = (isA ? k : k - nchA) * E, cnt = min(E, len - e0);
       const double* T = (isA ? ar.TA : ar.Tb) + e0;
       const unsigned bar = a_bar + 8u * (unsigned)buf;
-      fence_proxy_async();                                   // the images were written through the generic proxy
+      fence_proxy_async();                                   // the image was written through the generic proxy
       mbar_expect_tx(bar, (unsigned)(ntab * cnt) * 8u);
       for (int tq = 0; tq < ntab; ++tq)
-        bulk_g2s(a_stage + (unsigned)((buf * ntab + tq) * E) * 8u, T + (size_t)tq * len, (unsigned)cnt * 8u, bar);
+        bulk_g2s(ws + (unsigned)((buf * ntab + tq) * RS) * 8u, T + (size_t)tq * len, (unsigned)cnt * 8u, bar);
     };
-    __syncthreads();          // every warp is done with its previous cell: images and scratch records are free
-    if (threadIdx.x == 0) { issue(0, 0); if (nch > 1) issue(1, 1); }
+    // the warp's own image is free as soon as its own cell is done: its first two chunks fly while it waits for the others
+    if (lane == 0) { if (warp < nch) issue(warp, 0); if (warp + WPC < nch) issue(warp + WPC, 1); }
+    __syncthreads();          // every warp is done with its previous cell: the scratch records are free
     double* const dlane = slot0 + (g < WPC ? g : 0) * ar.slot + 2 * t;   // this lane's D fragments: cell g, elements 2t, 2t+1
-    for (int k = 0; k < nch; ++k) {
-      const int buf = k & 1;
+    for (int k = warp, buf = 0; k < nch; k += WPC, buf ^= 1) {
       const bool isA = k < nchA;
-      const int e0 = (isA ? k : k - nchA) * E, cnt = min(E, (isA ? lenA : lenb) - e0);
-      double* const dst = dlane + (isA ? 0 : lenA) + e0;
-      // B fragment of k-step s: T[4s + t][e0 + 8 tile + g]
-      const unsigned sb = a_stage + (unsigned)((buf * ntab + t) * E + g) * 8u;
+      const int e0 = (isA ? k : k - nchA) * E, cnt = min(E, (isA ? lenAp : lenbp) - e0);
+      double* const dst = dlane + (isA ? 0 : lenAp) + e0;
+      // B fragment of k-step s: T[4s + t][e0 + 8 tile + g]; the lanes of a zero-padded table read a zero with stride 0
+      unsigned sbs[4], sst[4];
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const bool tv = 4 * s + t < ntab;
+        sbs[s] = tv ? ws + (unsigned)((buf * ntab + 4 * s + t) * RS + g) * 8u : a_zero;
+        sst[s] = tv ? 64u : 0u;
+      }
       mbar_wait(a_bar + 8u * (unsigned)buf, (gphase >> buf) & 1u);
       gphase ^= 1u << buf;
-      const int ntile = (cnt + 7) >> 3;
-      constexpr int TU = 4;                                  // independent tiles in flight per warp
-      for (int tl0 = warp; tl0 < ntile; tl0 += TU * WPC) {
+      const int nfull = cnt >> 3;                            // whole tiles; a last partial tile goes the predicated way
+      constexpr int TU = 4;                                  // independent tiles in flight
+      int tl0 = 0;
+      for (; tl0 + TU <= nfull; tl0 += TU) {
         double d[TU][2];
 #pragma unroll
         for (int u = 0; u < TU; ++u) { d[u][0] = 0.0; d[u][1] = 0.0; }
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
           if (s >= KS) break;
-          const bool tv = 4 * s + t < ntab;
           double bv[TU];
 #pragma unroll
-          for (int u = 0; u < TU; ++u) {
-            const int tl = tl0 + u * WPC;
-            bv[u] = (tv && 8 * tl + g < cnt) ? lds64(sb + (unsigned)(4 * s * E + 8 * tl) * 8u) : 0.0;
-          }
+          for (int u = 0; u < TU; ++u) bv[u] = lds64(sbs[s] + (unsigned)(tl0 + u) * sst[s]);
 #pragma unroll
           for (int u = 0; u < TU; ++u) dmma(d[u][0], d[u][1], ca[s], bv[u]);
         }
         if (g < WPC) {
+          double* dp = dst + 8 * tl0;
 #pragma unroll
-          for (int u = 0; u < TU; ++u) {
-            const int tl = tl0 + u * WPC;
-            if (8 * tl + 2 * t < cnt) *reinterpret_cast<double2*>(dst + 8 * tl) = make_double2(d[u][0], d[u][1]);
-          }
+          for (int u = 0; u < TU; ++u) *reinterpret_cast<double2*>(dp + 8 * u) = make_double2(d[u][0], d[u][1]);
         }
       }
-      __syncthreads();                                       // chunk k is consumed (and, for the last one: the records are complete)
-      if (threadIdx.x == 0 && k + 2 < nch) issue(k + 2, buf);
+      for (; 8 * tl0 < cnt; ++tl0) {                         // the last tiles of the chunk, one at a time
+        double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          if (s >= KS) break;
+          const double bv = 8 * tl0 + g < cnt ? lds64(sbs[s] + (unsigned)tl0 * sst[s]) : 0.0;
+          dmma(d0, d1, ca[s], bv);
+        }
+        if (g < WPC && 8 * tl0 + 2 * t < cnt) *reinterpret_cast<double2*>(dst + 8 * tl0) = make_double2(d0, d1);
+      }
+      __syncwarp();                                          // the warp is done with this buffer
+      if (lane == 0 && k + 2 * WPC < nch) issue(k + 2 * WPC, buf);
     }
-    // the staging ring overwrote the images: restore the zeros the cell code relies on (pad columns, dummy row, inverse tiles)
+    __syncthreads();          // the WPC records of the batch are complete
+    // the staging ring overwrote the image: restore the zeros the cell code relies on (pad columns, dummy row, inverse tiles)
     for (unsigned o = 16u * lane; o < C::WARP_BYTES; o += 512u) sts128(ws + o, 0.0, 0.0);
     __syncwarp();
   };
@@ -501,7 +521,7 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
       if (cell >= ar.ncells) continue;
     }
     const double* Arec = GEN ? slot0 + warp * ar.slot : ar.A + cell * lenA;
-    const double* brec = GEN ? Arec + lenA : ar.b + cell * lenb;
+    const double* brec = GEN ? Arec + ar.lenAp : ar.b + cell * lenb;
     // ------------------------------------------------------------------ load A11 (table-driven 8-byte cp.async)
     // the table entries of a batch are fetched before its copies are issued (the registers are free at this point)
     {
@@ -1018,6 +1038,7 @@ inline void cw_fill_args(const Plan& p, CwArgs& ar) {
   ar.pf22_off = p.cw_pf[4]; ar.pf22_len = p.cw_pf[5];
   ar.lenA = p.lenA; ar.lenb = p.lenb;
   ar.TA = nullptr; ar.Tb = nullptr; ar.coef = nullptr; ar.scratch = nullptr; ar.slot = 0; ar.ntab = 0;
+  ar.lenAp = 0; ar.lenbp = 0; ar.gen_E = 0;
 }
 
 }  // namespace

@@ -14,6 +14,7 @@ from tests.helpers import (CONFIGS, DarcyProblem, dense_to_record, oracle_plan, 
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-11
+CW_GEN_NAMES = ["C3_hdg_k2_3d", "C2_rth_k2_2d", "hdg_equal_order_3d", "elasticity_k1_2d"]   # tuned cell-warp shapes
 
 
 def _dev_plan(ctx, name, fresh=False):
@@ -670,6 +671,83 @@ def test_affine_family_records_on_device(ctx, dims, order):
     assert np.abs(x - x0).max() < 1e-10
     err, err0 = p.l2_error_u(x[:nc * nu].reshape(nc, nu)), p.l2_error_u(x0[:nc * nu].reshape(nc, nu))
     assert err < (1e-12 if nc <= 16 else 1e-11) and err < 10 * max(err0, 1e-13)
+
+
+def _random_family(ctx, plan, ntab, seed):
+    """tables of a synthetic affine family: a well-conditioned base record plus small perturbation tables"""
+    rng = np.random.default_rng(seed)
+    A0, b0 = _synth(ctx, plan, 77, 1)
+    TA = np.concatenate([A0.cpu().numpy(), 1e-2 * rng.standard_normal((ntab - 1, plan.lenA))])
+    Tb = np.concatenate([b0.cpu().numpy(), rng.standard_normal((ntab - 1, plan.lenb))])
+    return gh.AffineRecordFamily(TA, Tb), rng
+
+
+@pytest.mark.parametrize("name", CW_GEN_NAMES + ["C1_hdg_k1_2d", "hencky_k1_2d"])
+@pytest.mark.parametrize("ntab,ncells", [(1, 5), (7, 1003), (16, 300), (5, 4737)])
+def test_affine_family_condensed_in_the_loader(ctx, name, ntab, ncells):
+    """SURVEY 8f-1 / VERDICT item 2: ghb_condense_affine_f64 forms A_K = sum_t coef[K][t] TA[t] inside the condensation
+    kernel (TMA-staged table chunks, DMMA combination per batch of 8 cells, records in per-warp scratch) -- S_K, g_K and
+    info must be BIT-equal to ghb_expand_records_f64 followed by ghb_condense_f64, for every tuned cell-warp shape (even
+    and odd record lengths, untouched blocks), ragged cell counts around the batch size and the resident grid, 1..16
+    tables, next to singular cells (all-zero coefficients), and for the plans that fall back to chunked expansion."""
+    plan = _dev_plan(ctx, name)
+    fam, rng = _random_family(ctx, plan, ntab, ntab * 1000 + ncells)
+    coef = np.concatenate([np.ones((ncells, 1)), rng.uniform(-1, 1, (ncells, ntab - 1))], axis=1)
+    for c in {0, ncells // 2, ncells - 1}:
+        if ncells > 3:
+            coef[c] = 0.0                                      # A_K = 0: singular, info = 1, NaN outputs
+    coef_d = torch.as_tensor(coef, device="cuda")
+    cells = fam.expand(ctx, plan, coef_d)
+    S0 = torch.empty((ncells, plan.n_b ** 2), dtype=torch.float64, device="cuda")
+    g0 = torch.empty((ncells, plan.n_b), dtype=torch.float64, device="cuda")
+    i0 = torch.empty(ncells, dtype=torch.int32, device="cuda")
+    ctx.condense(plan, ncells, cells.A, cells.b, S0, g0, i0)
+    i1 = torch.full((ncells,), -7, dtype=torch.int32, device="cuda")
+    S1, g1 = fam.condense(ctx, plan, coef_d, info=i1)
+    assert torch.equal(i0, i1) and int((i1 != 0).sum()) == (3 if ncells > 3 else 0)
+    assert np.array_equal(S0.cpu().numpy(), S1.cpu().numpy(), equal_nan=True)
+    assert np.array_equal(g0.cpu().numpy(), g1.cpu().numpy(), equal_nan=True)
+    # a second batch through the same context (scratch records and staging barriers are reused), host pointers throughout
+    n2 = min(ncells, 77)
+    S2 = np.empty((n2, plan.n_b ** 2)); g2 = np.empty((n2, plan.n_b)); i2 = np.empty(n2, dtype=np.int32)
+    ctx.condense_affine(plan, n2, ntab, fam.TA, fam.Tb, coef[:n2].copy(), S2, g2, i2)
+    assert np.array_equal(S2, S0[:n2].cpu().numpy(), equal_nan=True) and np.array_equal(g2, g0[:n2].cpu().numpy(), equal_nan=True)
+    assert np.array_equal(i2, i0[:n2].cpu().numpy())
+
+
+@pytest.mark.parametrize("name,dims,ndofs_f", [("C3_hdg_k2_3d", (6, 5, 4), 6), ("C2_rth_k2_2d", (9, 7), 3),
+                                               ("elasticity_k1_2d", (6, 5), 4), ("C1_hdg_k1_2d", (7, 6), 2)])
+def test_affine_family_to_csc_in_one_call(ctx, name, dims, ndofs_f):
+    """ghb_condense_assemble_affine_f64 (coefficients -> CSC values + rhs; for cell-warp plans ONE kernel: records formed in
+    the loader, S_K scattered into nzval) is bit-equal to expand + ghb_condense_assemble_f64, with and without the Dirichlet
+    lift, with the fused assembly on and off, and for a plan without a cell-warp kernel."""
+    plan = _dev_plan(ctx, name)
+    sk = gh.CartesianSkeleton(dims, ctx)
+    M = gh.FacetFESpace(sk, ndofs_f, sk.facet_is_boundary())
+    assem = gh.SparseMatrixAssembler(M)
+    colptr, rowval, nnz = assem.symbolic()
+    n = sk.ncells
+    assert assem.cell_ids.shape[1] == plan.n_b
+    fam, rng = _random_family(ctx, plan, 7, 5)
+    coef = torch.as_tensor(np.concatenate([np.ones((n, 1)), rng.uniform(-1, 1, (n, 6))], axis=1), device="cuda")
+    cells = fam.expand(ctx, plan, coef)
+    dv = torch.linspace(-1, 1, max(M.num_dirichlet_dofs, 1), dtype=torch.float64, device="cuda")
+    for lift in (dv, None):
+        for fused in (1, 0):
+            ctx.set_option("fused_assembly", fused)
+            assem.select()
+            nz0 = torch.full((nnz,), float("nan"), dtype=torch.float64, device="cuda"); rhs0 = torch.full((assem.nrows,), float("nan"), dtype=torch.float64, device="cuda")
+            nz1 = nz0.clone(); rhs1 = rhs0.clone()
+            i0 = torch.empty(n, dtype=torch.int32, device="cuda"); i1 = torch.empty_like(i0)
+            ctx.condense_assemble(plan, n, cells.A, cells.b, lift, nz0, rhs0, i0)
+            fam.condense_assemble(ctx, plan, coef, lift, nz1, rhs1, i1)
+            assert torch.equal(nz0, nz1) and torch.equal(rhs0, rhs1) and torch.equal(i0, i1) and not bool(i1.any())
+    ctx.set_option("fused_assembly", 1)
+    # bad arguments
+    with pytest.raises(gh.GhbError):
+        ctx.condense_affine(plan, 1, 17, np.zeros((17, plan.lenA)), np.zeros((17, plan.lenb)), np.zeros((1, 17)),
+                            np.zeros((1, plan.n_b ** 2)), np.zeros((1, plan.n_b)))
+    ctx.condense_affine(plan, 0, 1, fam.TA[:1], fam.Tb[:1], np.zeros((0, 1)), np.zeros((0, plan.n_b ** 2)), np.zeros((0, plan.n_b)))
 
 
 @pytest.mark.parametrize("n,m", [(3, 1), (6, 30), (6, 1), (18, 60), (18, 7), (32, 9), (25, 16)])

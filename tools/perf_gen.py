@@ -10,6 +10,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import gridaphybrid_b200 as gh  # noqa: E402
 
 ctx = gh.Context(0)
+if os.environ.get("MAXCTAS"):
+    ctx.set_option("max_ctas_per_sm", int(os.environ["MAXCTAS"]))
 dims = tuple(int(x) for x in os.environ.get("DIMS", "96,96,96").split(","))
 n = int(np.prod(dims))
 shape = os.environ.get("SHAPE", "C3")
