@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
   // Records of a batch: out[w][e] = sum_t coef[w][t] T[t][e] for the WPC cells of the batch is a small GEMM and runs on
   // DMMA: rows = cells of the batch (8 rows; WPC of them used), k = tables (4 per step, zero-padded), columns = 8 record
   // elements per tile.  The element range is cut into chunks of gen_E elements that the warps take round-robin; a warp
-  // brings the ntab table rows of its chunk in with TMA bulk copies (lane 0 issues) -- a two-deep staging ring laid over
+  // brings the ntab table rows of its chunk in with TMA bulk copies (one lane per table issues) -- a two-deep staging ring laid over
   // its own (dead) image, the copies of its next chunk fly while it combines the current one, no CTA barrier inside the
   // phase -- holds the A operand (coefficients) in registers for the whole batch, and sends the D fragments (two
   // consecutive elements of one cell per lane) to the scratch records of all WPC cells with 16-byte stores.  DMMA
@@ -452,16 +452,34 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
       const int e0 = (isA ? k : k - nchA) * E, cnt = min(E, len - e0);
       const double* T = (isA ? ar.TA : ar.Tb) + e0;
       const unsigned bar = a_bar + 8u * (unsigned)buf;
-      fence_proxy_async();                                   // the image was written through the generic proxy
-      mbar_expect_tx(bar, (unsigned)(ntab * cnt) * 8u);
-      for (int tq = 0; tq < ntab; ++tq)
-        bulk_g2s(ws + (unsigned)((buf * ntab + tq) * RS) * 8u, T + (size_t)tq * len, (unsigned)cnt * 8u, bar);
+      if (lane == 0) mbar_expect_tx(bar, (unsigned)(ntab * cnt) * 8u);
+      __syncwarp();
+      if (lane < ntab) {                                     // lane tq brings in the row of table tq
+        fence_proxy_async();                                 // the image was written through the generic proxy
+        bulk_g2s(ws + (unsigned)((buf * ntab + lane) * RS) * 8u, T + (size_t)lane * len, (unsigned)cnt * 8u, bar);
+      }
     };
     // the warp's own image is free as soon as its own cell is done: its first two chunks fly while it waits for the others
-    if (lane == 0) { if (warp < nch) issue(warp, 0); if (warp + WPC < nch) issue(warp + WPC, 1); }
+#ifdef GHB_CW_GEN_KO
+    if (base == (int64_t)blockIdx.x * WPC || GHB_CW_GEN_KO == 2) {
+#else
+    {
+#endif
+      if (warp < nch) issue(warp, 0);
+      if (warp + WPC < nch) issue(warp + WPC, 1);
+    }
     __syncthreads();          // every warp is done with its previous cell: the scratch records are free
     double* const dlane = slot0 + (g < WPC ? g : 0) * ar.slot + 2 * t;   // this lane's D fragments: cell g, elements 2t, 2t+1
-    for (int k = warp, buf = 0; k < nch; k += WPC, buf ^= 1) {
+#ifdef GHB_CW_GEN_KO       // knock-out experiments (timing only, wrong results): 1: generate the first batch only,
+                           // 2: no scratch stores after the first batch, 3: no TMA / DMMA after the first batch, stores only
+    const bool ko_first = base == (int64_t)blockIdx.x * WPC;
+    const bool ko_skip = GHB_CW_GEN_KO == 1 && !ko_first;
+    const bool ko_nostore = GHB_CW_GEN_KO == 2 && !ko_first;
+    const bool ko_notma = GHB_CW_GEN_KO == 3 && !ko_first;
+#else
+    const bool ko_skip = false, ko_nostore = false, ko_notma = false;
+#endif
+    for (int k = warp, buf = 0; k < nch && !ko_skip; k += WPC, buf ^= 1) {
       const bool isA = k < nchA;
       const int e0 = (isA ? k : k - nchA) * E, cnt = min(E, (isA ? lenAp : lenbp) - e0);
       double* const dst = dlane + (isA ? 0 : lenAp) + e0;
@@ -473,8 +491,10 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
         sbs[s] = tv ? ws + (unsigned)((buf * ntab + 4 * s + t) * RS + g) * 8u : a_zero;
         sst[s] = tv ? 64u : 0u;
       }
-      mbar_wait(a_bar + 8u * (unsigned)buf, (gphase >> buf) & 1u);
-      gphase ^= 1u << buf;
+      if (!ko_notma) {
+        mbar_wait(a_bar + 8u * (unsigned)buf, (gphase >> buf) & 1u);
+        gphase ^= 1u << buf;
+      }
       const int nfull = cnt >> 3;                            // whole tiles; a last partial tile goes the predicated way
       constexpr int TU = 4;                                  // independent tiles in flight
       int tl0 = 0;
@@ -487,11 +507,16 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
           if (s >= KS) break;
           double bv[TU];
 #pragma unroll
-          for (int u = 0; u < TU; ++u) bv[u] = lds64(sbs[s] + (unsigned)(tl0 + u) * sst[s]);
+          for (int u = 0; u < TU; ++u) bv[u] = ko_notma ? 1.0 : lds64(sbs[s] + (unsigned)(tl0 + u) * sst[s]);
+          if (!ko_notma) {
 #pragma unroll
-          for (int u = 0; u < TU; ++u) dmma(d[u][0], d[u][1], ca[s], bv[u]);
+            for (int u = 0; u < TU; ++u) dmma(d[u][0], d[u][1], ca[s], bv[u]);
+          } else {
+#pragma unroll
+            for (int u = 0; u < TU; ++u) d[u][0] += bv[u] * ca[s];
+          }
         }
-        if (g < WPC) {
+        if (g < WPC && !ko_nostore) {
           double* dp = dst + 8 * tl0;
 #pragma unroll
           for (int u = 0; u < TU; ++u) *reinterpret_cast<double2*>(dp + 8 * u) = make_double2(d[u][0], d[u][1]);
@@ -508,7 +533,7 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
         if (g < WPC && 8 * tl0 + 2 * t < cnt) *reinterpret_cast<double2*>(dst + 8 * tl0) = make_double2(d0, d1);
       }
       __syncwarp();                                          // the warp is done with this buffer
-      if (lane == 0 && k + 2 * WPC < nch) issue(k + 2 * WPC, buf);
+      if (k + 2 * WPC < nch && !ko_notma) issue(k + 2 * WPC, buf);
     }
     __syncthreads();          // the WPC records of the batch are complete
     // the staging ring overwrote the image: restore the zeros the cell code relies on (pad columns, dummy row, inverse tiles)
