@@ -212,6 +212,24 @@ function expand_records(k::StaticCondensationMap, t::AbstractArray, rep::Vector{
   PackedCells(A, b, pr.ndofs, pr.touched)
 end
 
+# f-1 without materialising the records: the condensation kernel forms A_K = sum_t coef[t,K] TA[:,t] in its loader
+# (bit-identical to expand_records + the resident path); returns the assembled system like assemble_condensed
+function assemble_affine(k::StaticCondensationMap, t::AbstractArray, rep::Vector{Int}, coef_rep::Matrix{Float64},
+                         coef::Matrix{Float64}, cell_ids::Matrix{Int64}, nfree, dirichlet_values;
+                         pattern = symbolic(cell_ids, nfree))
+  pr = pack(t[rep]); id, q = plan(k, pr)
+  TA = Matrix((coef_rep' \ pr.A')'); Tb = Matrix((coef_rep' \ pr.b')')
+  ncells = size(coef, 2); ntab = size(coef, 1)
+  check(ccall((:ghb_assemble_select, lib), Cint, (Ptr{Cvoid}, Cint), ctx(), pattern.id))
+  nzval = Vector{Float64}(undef, length(pattern.rowval)); rhs = Vector{Float64}(undef, nfree); info = Vector{Int32}(undef, ncells)
+  check(ccall((:ghb_condense_assemble_affine_f64, lib), Cint,
+              (Ptr{Cvoid}, Cint, Int64, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64},
+               Ptr{Float64}, Ptr{Int32}),
+              ctx(), id, ncells, ntab, TA, Tb, coef, dirichlet_values, length(dirichlet_values), nzval, rhs, info))
+  Gridap.Helpers.@check all(==(0), info)
+  SparseMatrixCSC(nfree, nfree, pattern.colptr, pattern.rowval, nzval), rhs
+end
+
 # f-4: CSR hand-off.  The pattern is structurally symmetric: rowptr/colval are the colptr/rowval of
 # ghb_assemble_pattern; ghb_assemble_numeric_csr_f64(ctx, S, g, dv, ndv, nzval, rhs) fills the values in row-major order
 # (S must be a device array; it is transposed in place) -> SparseMatrixCSR{1}(m, n, rowptr, colval, nzval).
