@@ -429,7 +429,7 @@ int ghb_l2_projection_dofs_f64(ghb_ctx* ctx, int64_t nbatch, int n, int nrhs, co
                                int32_t* info) {
   if (!ctx) return GHB_EINVAL;
   if (nbatch < 0 || n < 1 || nrhs < 1 || !A || !B || !X) return fail(ctx, GHB_EINVAL, "ghb_l2_projection_dofs_f64: bad argument");
-  if (n > 32) return fail(ctx, GHB_EUNSUPPORTED, "ghb_l2_projection_dofs_f64: n > 32 (one row per lane)");
+  if (n > 128) return fail(ctx, GHB_EUNSUPPORTED, "ghb_l2_projection_dofs_f64: n > 128");
   if (nbatch == 0) return GHB_OK;
   cudaSetDevice(ctx->device);
   Arg<double> dA(ctx, A, (size_t)nbatch * n * n, true, false); GHB_TRY(dA.rc);

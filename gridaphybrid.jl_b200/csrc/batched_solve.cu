@@ -2,7 +2,8 @@
 // Replaces compute_bulk_to_skeleton_l2_projection_dofs (/root/reference/src/GridapAPIExtensions.jl:453-500: `A\B` per
 // (cell, local facet) with A the facet mass matrix of the skeleton space, n x n, and B the n x m moments of the bulk
 // basis -- or a vector -- used by the elasticity / Hencky forms through test/P_m.jl:4-23).  Julia's `\` on a square dense
-// matrix is an LU with partial pivoting (dgetrf + dgetrs); here, one warp per system (n <= 32):
+// matrix is an LU with partial pivoting (dgetrf + dgetrs); here, one warp per system for n <= 32 (one CTA per system in
+// shared memory for 32 < n <= 128, see batched_solve_big_kernel):
 //   * factorisation with one row per lane in registers: partial pivoting among the rows not chosen yet (exact
 //     first-maximum rule, like idamax), implicit pivoting (rows never move); the factors are written to the warp's
 //     shared-memory slot in pivoted order (row of step k -> row k), L below the diagonal, U above, 1/u_kk on it;
@@ -154,7 +155,103 @@ __global__ void __launch_bounds__(256) batched_solve_kernel(int64_t nbatch, int 
   }
 }
 
+// ---- 32 < n <= 128: one CTA (4 warps) per system, LU with partial pivoting in shared memory ------------------------
+// (facet spaces of vector-valued unknowns at high order, e.g. 3 x 15 = 45 dofs per facet for k = 4 in 3-D).  The matrix
+// lives in shared memory with leading dimension n + 1; per step: warp 0 finds the pivot (first maximum of |a| in the
+// current row order, like idamax), the rows are swapped physically (dlaswp) together with the row-index vector, every
+// thread owns one row of the trailing update.  The right-hand sides go through in chunks of 32 columns held in shared
+// memory: dgetrs's forward and backward substitution, one (row group, column) per thread.
+__global__ void __launch_bounds__(128) batched_solve_big_kernel(int64_t nbatch, int n, int m, const double* __restrict__ A,
+                                                                const double* __restrict__ B, double* __restrict__ X,
+                                                                int32_t* __restrict__ info) {
+  extern __shared__ double sm[];
+  const int ld = n + 1;
+  double* F = sm;                         // [n][ld] row-major: L below the diagonal (unit), U on and above
+  double* Xc = F + (size_t)n * ld;        // [n][33]  chunk of right-hand sides
+  int* perm = reinterpret_cast<int*>(Xc + (size_t)n * 33);   // [n] source row of every position
+  __shared__ int s_piv, s_bad;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  for (int64_t s = blockIdx.x; s < nbatch; s += gridDim.x) {
+    const double* As = A + s * (int64_t)n * n;
+    for (int e = tid; e < n * n; e += 128) { const int j = e / n, i = e - j * n; F[i * ld + j] = As[e]; }   // column-major in
+    for (int i = tid; i < n; i += 128) perm[i] = i;
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+    for (int k = 0; k < n; ++k) {
+      if (wid == 0) {
+        // idamax over positions k..n-1: largest |a|, lowest position on ties; NaN counts as 0 (after a zero pivot)
+        unsigned long long best = 0ull; int bi = n;
+        for (int i = k + lane; i < n; i += 32) {
+          const double v = F[i * ld + k];
+          const unsigned long long bits = v == v ? ((unsigned long long)__double_as_longlong(v) & 0x7fffffffffffffffull) : 0ull;
+          if (bits > best || (bits == best && i < bi)) { best = bits; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0) {
+          s_piv = bi;
+          if (best == 0ull && s_bad == 0) s_bad = k + 1;      // dgetrf's info: first exactly zero pivot
+        }
+      }
+      __syncthreads();
+      const int p = s_piv;
+      if (p != k) {                                           // dlaswp: whole rows trade places
+        for (int j = tid; j < n; j += 128) { const double t0 = F[k * ld + j]; F[k * ld + j] = F[p * ld + j]; F[p * ld + j] = t0; }
+        if (tid == 0) { const int t0 = perm[k]; perm[k] = perm[p]; perm[p] = t0; }
+        __syncthreads();
+      }
+      const double rinv = 1.0 / F[k * ld + k];                // dgetf2 scales the column by the reciprocal of the pivot
+      for (int i = k + 1 + tid; i < n; i += 128) {
+        const double l = F[i * ld + k] * rinv;
+        F[i * ld + k] = l;
+        for (int j = k + 1; j < n; ++j) F[i * ld + j] = fma(-l, F[k * ld + j], F[i * ld + j]);
+      }
+      __syncthreads();
+    }
+    const int bad = s_bad;
+    if (info && tid == 0) info[s] = bad;
+    const double* Bs = B + s * (int64_t)n * m;
+    double* Xs = X + s * (int64_t)n * m;
+    for (int c0 = 0; c0 < m; c0 += 32) {
+      const int c = c0 + lane, nc = min(32, m - c0);
+      for (int i = wid; i < n; i += 4) Xc[i * 33 + lane] = lane < nc ? Bs[perm[i] + (int64_t)n * c] : 0.0;   // P B
+      __syncthreads();
+      for (int k = 0; k < n; ++k) {                           // L y = P B (unit lower)
+        const double xk = Xc[k * 33 + lane];
+        for (int i = k + 1 + wid; i < n; i += 4) Xc[i * 33 + lane] = fma(-F[i * ld + k], xk, Xc[i * 33 + lane]);
+        __syncthreads();
+      }
+      for (int k = n - 1; k >= 0; --k) {                      // U x = y
+        if (wid == 0) Xc[k * 33 + lane] = Xc[k * 33 + lane] / F[k * ld + k];
+        __syncthreads();
+        const double xk = Xc[k * 33 + lane];
+        for (int i = wid; i < k; i += 4) Xc[i * 33 + lane] = fma(-F[i * ld + k], xk, Xc[i * 33 + lane]);
+        __syncthreads();
+      }
+      for (int i = wid; i < n; i += 4)
+        if (lane < nc) Xs[i + (int64_t)n * c] = bad ? qnan : Xc[i * 33 + lane];
+      __syncthreads();
+    }
+  }
+}
+
 }  // namespace
+
+static int launch_bs_big(ghb_ctx* ctx, int64_t nbatch, int n, int m, const double* A, const double* B, double* X, int32_t* info) {
+  const size_t smem = ((size_t)n * (n + 1) + (size_t)n * 33) * sizeof(double) + (size_t)n * sizeof(int);
+  auto kern = batched_solve_big_kernel;
+  GHB_SMEM_OPTIN(ctx, kern, smem);
+  const int per_sm = std::max(1, (int)(200000 / (smem + 1024)));
+  const int64_t blocks = std::min<int64_t>(nbatch, (int64_t)ctx->sm_count * std::min(per_sm, 8));
+  kern<<<(unsigned)blocks, 128, smem, ctx->stream>>>(nbatch, n, m, A, B, X, info);
+  GHB_LAUNCHED(ctx);
+  return GHB_OK;
+}
 
 template <int NMAX>
 static int launch_bs(ghb_ctx* ctx, int64_t nbatch, int n, int m, const double* A, const double* B, double* X, int32_t* info) {
@@ -174,7 +271,8 @@ int launch_batched_solve(ghb_ctx* ctx, int64_t nbatch, int n, int m, const doubl
   if (n <= 8) return launch_bs<8>(ctx, nbatch, n, m, A, B, X, info);
   if (n <= 16) return launch_bs<16>(ctx, nbatch, n, m, A, B, X, info);
   if (n <= 24) return launch_bs<24>(ctx, nbatch, n, m, A, B, X, info);
-  return launch_bs<32>(ctx, nbatch, n, m, A, B, X, info);
+  if (n <= 32) return launch_bs<32>(ctx, nbatch, n, m, A, B, X, info);
+  return launch_bs_big(ctx, nbatch, n, m, A, B, X, info);
 }
 
 }  // namespace ghb

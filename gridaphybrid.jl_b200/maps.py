@@ -234,10 +234,54 @@ def lazy_map(k, t, *args, ctx: Context | None = None, keep_factors: bool = False
     raise TypeError(f"lazy_map: unsupported map {type(k)}")
 
 
+def _touched_blocks(X: ArrayBlock):
+    """`findall(X.touched)` in Julia's (column-major) order, 0-based index tuples"""
+    t = X.touched
+    if t.ndim == 1:
+        return [(i,) for i in range(t.shape[0]) if t[i]]
+    return [(i, j) for j in range(t.shape[1]) for i in range(t.shape[0]) if t[i, j]]
+
+
+def _block(X: ArrayBlock, idx):
+    return X.array[idx[0]] if len(idx) == 1 else X.array[idx[0]][idx[1]]
+
+
 def compute_bulk_to_skeleton_l2_projection_dofs(A, B, ctx: Context | None = None, info=None):
     """`lazy_map(compute_bulk_to_skeleton_l2_projection_dofs, A_array, B_array)` of test/P_m.jl:4-23, evaluated on the
     batch (src/GridapAPIExtensions.jl:453-500: `A\\B` per (cell, local facet)).  A [nbatch, n, n] facet mass matrices,
-    B [nbatch, n, m] bulk-basis moments or [nbatch, n] (FE function) -> X like B (device tensors)."""
+    B [nbatch, n, m] bulk-basis moments or [nbatch, n] (FE function) -> X like B (device tensors).
+
+    Block arguments (`ArrayBlock`s whose entries carry the batch as their leading dimension) follow the reference's
+    overloads, src/GridapAPIExtensions.jl:547-760:
+      * (VectorBlock, VectorBlock), same touched mask: the map applied to every touched entry (`:551-590`; the entries
+        may be blocks themselves) -> VectorBlock;
+      * (MatrixBlock, MatrixBlock), one touched block each, in the same block row (`:617-663`): `A[.,b1] \\ B[.,b2]`
+        placed at `[1, b2]` of a `1 x nb` MatrixBlock;
+      * (MatrixBlock, VectorBlock of vectors), one touched block each (`:665-697`): the plain array `A_blk \\ B_blk`;
+      * (MatrixBlock, VectorBlock of matrices), one touched block each (`:699-742`): a VectorBlock of length 1."""
+    if isinstance(A, ArrayBlock) and isinstance(B, ArrayBlock):
+        f = compute_bulk_to_skeleton_l2_projection_dofs
+        if A.touched.ndim == 1 and B.touched.ndim == 1:
+            assert A.touched.shape == B.touched.shape and np.array_equal(A.touched, B.touched)
+            r = [f(A.array[i], B.array[i], ctx) if A.touched[i] else None for i in range(len(A.array))]
+            return ArrayBlock(r, A.touched.copy())
+        nA, nB = _touched_blocks(A), _touched_blocks(B)
+        assert len(nA) == len(nB) == 1, "exactly one touched block in A and in B"
+        ai, bi = _block(A, nA[0]), _block(B, nB[0])
+        if A.touched.ndim == 2 and B.touched.ndim == 2:
+            assert A.touched.shape == B.touched.shape and nA[0][0] == nB[0][0]
+            tb, nb = nB[0][1], A.touched.shape[0]
+            touched = np.zeros((1, nb), dtype=bool)
+            touched[0, tb] = True
+            row = [None] * nb
+            row[tb] = f(ai, bi, ctx)
+            return ArrayBlock([row], touched)
+        assert A.touched.ndim == 2 and B.touched.ndim == 1 and A.touched.shape[1] == B.touched.shape[0]
+        x = f(ai, bi, ctx)
+        if torch.as_tensor(bi).dim() == 2:          # blocks of B are vectors (one right-hand side): plain array
+            return x
+        assert nA[0][0] == nB[0][0] and nA[0][1] == nB[0][0] and A.touched.shape[0] == A.touched.shape[1]
+        return ArrayBlock([x], np.ones(1, dtype=bool))
     ctx = ctx or default_context()
     dev = torch.device("cuda", ctx.device)
     A = torch.as_tensor(A, dtype=torch.float64).to(dev)

@@ -141,7 +141,8 @@ int ghb_condense_assemble_affine_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, 
  * by the elasticity / Hencky forms through test/P_m.jl:4-23): X = A \ B with A [nbatch][n*n] the facet mass matrices of
  * the skeleton space (column-major) and B [nbatch][n*nrhs] the moments of the bulk basis (nrhs = 1: a FE function).
  * Like Julia's `\` on a square dense matrix: LU-type elimination with partial pivoting; info[s] = k+1 if the k-th pivot
- * column of system s is exactly zero (then X of that system is NaN); info may be NULL.  n <= 32. */
+ * column of system s is exactly zero (then X of that system is NaN); info may be NULL.  n <= 128 (one warp per system
+ * up to 32, one CTA per system above). */
 int ghb_l2_projection_dofs_f64(ghb_ctx* ctx, int64_t nbatch, int n, int nrhs, const double* A, const double* B, double* X,
                                int32_t* info);
 

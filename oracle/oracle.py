@@ -686,3 +686,42 @@ def l2_projection_dofs(A, B):
             continue
         X[s], _ = lapack.dgetrs(lu, piv, Bm[s])
     return (X[:, :, 0] if vec else X), info
+
+
+def l2_projection_dofs_blocks(A, B):
+    """Block overloads of compute_bulk_to_skeleton_l2_projection_dofs (/root/reference/src/GridapAPIExtensions.jl:547-742),
+    restated on batched blocks: `A`, `B` are (array, touched) pairs -- nested lists of [nbatch, ...] numpy arrays (or of
+    such pairs) and a boolean mask.  Returns the same kind of pair, or a plain array for the (MatrixBlock, VectorBlock of
+    vectors) overload (`:665-697`)."""
+    (Aa, At), (Ba, Bt) = A, B
+    At, Bt = np.asarray(At, dtype=bool), np.asarray(Bt, dtype=bool)
+
+    def findall(t):
+        if t.ndim == 1:
+            return [(i,) for i in range(t.shape[0]) if t[i]]
+        return [(i, j) for j in range(t.shape[1]) for i in range(t.shape[0]) if t[i, j]]
+
+    def ev(a, b):
+        if isinstance(a, tuple):
+            return l2_projection_dofs_blocks(a, b)
+        return l2_projection_dofs(a, b)[0]
+
+    if At.ndim == 1 and Bt.ndim == 1:                       # :547-590 VectorBlock x VectorBlock, entry by entry
+        assert At.shape == Bt.shape and np.array_equal(At, Bt)
+        return [ev(Aa[i], Ba[i]) if At[i] else None for i in range(len(Aa))], At.copy()
+    nA, nB = findall(At), findall(Bt)
+    assert len(nA) == len(nB) == 1
+    ai = Aa[nA[0][0]][nA[0][1]]
+    if Bt.ndim == 2:                                        # :617-663 MatrixBlock x MatrixBlock -> 1 x nb MatrixBlock
+        assert At.shape == Bt.shape and nA[0][0] == nB[0][0]
+        tb, nb = nB[0][1], At.shape[0]
+        touched = np.zeros((1, nb), dtype=bool)
+        touched[0, tb] = True
+        row = [None] * nb
+        row[tb] = ev(ai, Ba[nB[0][0]][nB[0][1]])
+        return [row], touched
+    bi = Ba[nB[0][0]]
+    if np.asarray(bi).ndim == 2:                            # :665-697 blocks of B are vectors: the plain array
+        return ev(ai, bi)
+    assert nA[0][0] == nB[0][0] and nA[0][1] == nB[0][0]    # :699-742 blocks of B are matrices: VectorBlock of length 1
+    return [ev(ai, bi)], np.ones(1, dtype=bool)

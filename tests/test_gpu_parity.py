@@ -776,6 +776,95 @@ def test_l2_projection_dofs(ctx, n, m):
         assert x.shape == (5, n) and np.array_equal(x, X[:5, :, 0])
 
 
+@pytest.mark.parametrize("n,m", [(33, 5), (45, 45), (64, 70), (96, 1), (128, 33)])
+def test_l2_projection_dofs_large_systems(ctx, n, m):
+    """n > 32 (facet spaces of vector-valued unknowns at high order): the one-CTA-per-system LU with partial pivoting
+    against dgetrf/dgetrs -- SPD mass-matrix-like systems at the 1e-11 bar, general matrices that need pivoting, exact
+    singularity -> dgetrf's info and NaN."""
+    rng = np.random.default_rng(n + m)
+    nb = 40
+    Q = rng.standard_normal((nb, n, n))
+    A = Q @ np.transpose(Q, (0, 2, 1)) / n + 0.5 * np.eye(n)
+    A[nb // 2:] = rng.standard_normal((nb - nb // 2, n, n)) + np.roll(3.0 * np.eye(n), 1, axis=0)   # pivoting needed
+    A[7] = 0.0
+    A[8, :, 40 if n > 40 else 3] = 0.0
+    B = rng.standard_normal((nb, n, m))
+    X0, info0 = o.l2_projection_dofs(A, B)
+    info = torch.empty(nb, dtype=torch.int32, device="cuda")
+    X = gh.compute_bulk_to_skeleton_l2_projection_dofs(A, B, ctx, info).cpu().numpy()
+    info = info.cpu().numpy()
+    assert info.tolist() == info0.tolist() and info[7] == 1 and info[8] != 0
+    ok = info0 == 0
+    assert np.isnan(X[~ok]).all()
+    assert rel_err_cells(X[ok], X0[ok]) < 1e-9           # general random matrices: conditioning, not the kernel
+    assert rel_err_cells(X[:7], X0[:7]) < TOL            # SPD mass-matrix-like systems: the 1e-11 bar
+    with pytest.raises(gh.GhbError) as e:
+        ctx.l2_projection_dofs(1, 129, 1, np.zeros(129 * 129), np.zeros(129), np.zeros(129))
+    assert e.value.code == gh._lib.GHB_EUNSUPPORTED
+
+
+def test_l2_projection_dofs_block_overloads(ctx):
+    """the ArrayBlock overloads of compute_bulk_to_skeleton_l2_projection_dofs (src/GridapAPIExtensions.jl:547-742) on the
+    batch: per-local-facet VectorBlocks (nested one level, untouched entries skipped), single-touched-block MatrixBlocks
+    with the result placed at [1, b2], the vector and the several-right-hand-sides forms -- block structure identical to
+    the oracle's restatement, values against dgetrf/dgetrs."""
+    rng = np.random.default_rng(11)
+    nb, n, m = 30, 6, 9
+
+    def spd(k):
+        Q = rng.standard_normal((nb, k, k))
+        return Q @ np.transpose(Q, (0, 2, 1)) / k + 0.5 * np.eye(k)
+
+    def same(x, y):
+        if isinstance(y, tuple):
+            assert isinstance(x, gh.ArrayBlock) and np.array_equal(x.touched, y[1])
+            flat_x = x.array if x.touched.ndim == 1 else x.array[0]
+            flat_y = y[0] if y[1].ndim == 1 else y[0][0]
+            assert len(flat_x) == len(flat_y)
+            for ex, ey in zip(flat_x, flat_y):
+                assert (ex is None) == (ey is None)
+                if ey is not None:
+                    same(ex, ey)
+        else:
+            assert rel_err_cells(x.cpu().numpy().reshape(nb, -1), np.asarray(y).reshape(nb, -1)) < TOL
+
+    f = gh.compute_bulk_to_skeleton_l2_projection_dofs
+    # MatrixBlock x MatrixBlock: A touched at [1,2], B at [1,3] of a 3 x 3 block layout -> 1 x 3 MatrixBlock, entry [1,3]
+    tA = np.zeros((3, 3), bool); tA[0, 1] = True
+    tB = np.zeros((3, 3), bool); tB[0, 2] = True
+    Ablk, Bblk = spd(n), rng.standard_normal((nb, n, m))
+    arrA = [[None, Ablk, None], [None] * 3, [None] * 3]
+    arrB = [[None, None, Bblk], [None] * 3, [None] * 3]
+    r = f(gh.ArrayBlock(arrA, tA), gh.ArrayBlock(arrB, tB), ctx)
+    same(r, o.l2_projection_dofs_blocks((arrA, tA), (arrB, tB)))
+    assert r.touched.shape == (1, 3) and r.touched.tolist() == [[False, False, True]]
+    # MatrixBlock x VectorBlock of vectors (one right-hand side) -> plain array; of matrices -> VectorBlock of length 1
+    tA2 = np.zeros((2, 2), bool); tA2[0, 0] = True
+    tb2 = np.array([True, False])
+    arrA2 = [[Ablk, None], [None, None]]
+    bvec, bmat = rng.standard_normal((nb, n)), rng.standard_normal((nb, n, m))
+    r = f(gh.ArrayBlock(arrA2, tA2), gh.ArrayBlock([bvec, None], tb2), ctx)
+    assert isinstance(r, torch.Tensor) and r.shape == (nb, n)
+    same(r, o.l2_projection_dofs_blocks((arrA2, tA2), ([bvec, None], tb2)))
+    r = f(gh.ArrayBlock(arrA2, tA2), gh.ArrayBlock([bmat, None], tb2), ctx)
+    assert isinstance(r, gh.ArrayBlock) and r.touched.tolist() == [True]
+    same(r, o.l2_projection_dofs_blocks((arrA2, tA2), ([bmat, None], tb2)))
+    # VectorBlock over the local facets (4 facets, the third untouched), entries are the MatrixBlock pairs above
+    tf = np.array([True, True, False, True])
+    facA, facB, facA0, facB0 = [], [], [], []
+    for lf in range(4):
+        if not tf[lf]:
+            facA.append(None); facB.append(None); facA0.append(None); facB0.append(None)
+            continue
+        a_, b_ = spd(n), rng.standard_normal((nb, n, m))
+        aa = [[None, a_, None], [None] * 3, [None] * 3]; bb = [[None, None, b_], [None] * 3, [None] * 3]
+        facA.append(gh.ArrayBlock(aa, tA)); facB.append(gh.ArrayBlock(bb, tB))
+        facA0.append((aa, tA)); facB0.append((bb, tB))
+    r = f(gh.ArrayBlock(facA, tf), gh.ArrayBlock(facB, tf), ctx)
+    same(r, o.l2_projection_dofs_blocks((facA0, tf), (facB0, tf)))
+    assert r.array[2] is None and r.array[3].touched.tolist() == [[False, False, True]]
+
+
 def test_next_row_entry_points_edge_cases(ctx):
     """empty batches and bad arguments of the SURVEY 8f entry points: expand, L2 projection, CSR hand-off."""
     plan = _dev_plan(ctx, "C1_hdg_k1_2d")
@@ -786,7 +875,7 @@ def test_next_row_entry_points_edge_cases(ctx):
                            np.zeros((1, plan.lenA)), np.zeros((1, plan.lenb)))                                      # ntab > 16
     ctx.l2_projection_dofs(0, 4, 3, np.zeros(0), np.zeros(0), np.zeros(0))                                          # empty
     with pytest.raises(gh.GhbError) as e:
-        ctx.l2_projection_dofs(1, 33, 1, np.zeros(33 * 33), np.zeros(33), np.zeros(33))                             # n > 32
+        ctx.l2_projection_dofs(1, 129, 1, np.zeros(129 * 129), np.zeros(129), np.zeros(129))                        # n > 128
     assert e.value.code == gh._lib.GHB_EUNSUPPORTED
     # identity systems through host pointers (staged by the library), ragged sizes
     for n, m in [(1, 1), (2, 5), (5, 33)]:

@@ -210,3 +210,26 @@ def test_left_looking_bottom_block_lane_emulation(shape):
     spec.loader.exec_module(mod)
     mod.run(*shape)            # asserts error < 1e-12 and no NaN; prints the worst bank-conflict degree
     assert mod.SIGMA == [0, 2, 1, 3, 6, 4, 7, 5]
+
+
+def test_l2_projection_block_overloads_restatement():
+    """block overloads of compute_bulk_to_skeleton_l2_projection_dofs (src/GridapAPIExtensions.jl:547-742): result placed
+    at [1, b2] of a 1 x nb MatrixBlock; plain array for one right-hand side; VectorBlock of length 1 for several;
+    VectorBlocks entry by entry with untouched entries skipped."""
+    rng = np.random.default_rng(0)
+    nb, n, m = 5, 4, 3
+    A = rng.standard_normal((nb, n, n)) + 3 * np.eye(n)
+    B = rng.standard_normal((nb, n, m))
+    tA = np.zeros((3, 3), bool); tA[0, 1] = True
+    tB = np.zeros((3, 3), bool); tB[0, 2] = True
+    aa = [[None, A, None], [None] * 3, [None] * 3]; bb = [[None, None, B], [None] * 3, [None] * 3]
+    r, t = o.l2_projection_dofs_blocks((aa, tA), (bb, tB))
+    assert t.tolist() == [[False, False, True]] and np.allclose(r[0][2], np.linalg.solve(A, B), rtol=1e-12, atol=0)
+    t2 = np.zeros((2, 2), bool); t2[0, 0] = True
+    x = o.l2_projection_dofs_blocks(([[A, None], [None, None]], t2), ([B[:, :, 0], None], np.array([True, False])))
+    assert isinstance(x, np.ndarray) and np.allclose(x, np.linalg.solve(A, B[:, :, :1])[:, :, 0], rtol=1e-12, atol=0)
+    r, t = o.l2_projection_dofs_blocks(([[A, None], [None, None]], t2), ([B, None], np.array([True, False])))
+    assert t.tolist() == [True] and np.allclose(r[0], np.linalg.solve(A, B), rtol=1e-12, atol=0)
+    tf = np.array([True, False])
+    r, t = o.l2_projection_dofs_blocks(([(aa, tA), None], tf), ([(bb, tB), None], tf))
+    assert t.tolist() == [True, False] and r[1] is None and r[0][1].tolist() == [[False, False, True]]
