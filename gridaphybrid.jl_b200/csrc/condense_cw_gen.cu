@@ -38,6 +38,10 @@ static int launch_cw_gen(ghb_ctx* ctx, const Plan& p, CwArgs& ar) {
     ctx->gen_scratch_bytes = need;
   }
   ar.scratch = ctx->gen_scratch;
+  // chunk of table elements a warp stages per TMA round: two buffers of ntab rows of E + 4 doubles inside its image
+  const size_t cap = std::min<size_t>(1028, (size_t)CwCfg<NI, NB>::WARP_BYTES / (2 * (size_t)ar.ntab * 8));
+  if (cap < 20) return fail(ctx, GHB_EUNSUPPORTED, "condense_cw<GEN>: image too small to stage the tables");
+  ar.gen_E = cap >= 36 ? (int)((cap - 4) & ~(size_t)31) : 16;   // whole groups of four 8-element tiles where the image allows
   kern<<<(unsigned)grid, 32 * WPC, smem, ctx->stream>>>(ar);
   GHB_LAUNCHED(ctx);
   return GHB_OK;
