@@ -97,6 +97,7 @@ static void options_from_env(Options& o) {
   o.warp_two_rows = (int)env_i64("GHB_WARP_TWO_ROWS", o.warp_two_rows);
   o.debug = (int)env_i64("GHB_DEBUG", o.debug);
   o.fused_assembly = (int)env_i64("GHB_FUSED_ASSEMBLY", o.fused_assembly);
+  o.cw_back = (int)env_i64("GHB_CW_BACK", o.cw_back);
   o.stream_chunk_bytes = std::max<int64_t>(1, env_i64("GHB_STREAM_CHUNK_BYTES", o.stream_chunk_bytes));
 }
 
@@ -193,6 +194,7 @@ int ghb_set_option(ghb_ctx* ctx, const char* name, int64_t value) {
   else if (n == "warp_two_rows") o.warp_two_rows = (int)value;
   else if (n == "debug") o.debug = (int)value;
   else if (n == "fused_assembly") o.fused_assembly = (int)value;
+  else if (n == "cw_back") o.cw_back = (int)value;
   else if (n == "stream_chunk_bytes") o.stream_chunk_bytes = std::max<int64_t>(1, value);
   else return fail(ctx, GHB_EINVAL, "ghb_set_option: unknown option " + n);
   for (Plan* p : ctx->plans)          // launch-time knobs follow; the kernel choice of existing plans does not change
@@ -891,7 +893,9 @@ int ghb_backsub_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A, 
     if (!A || !b) return fail(ctx, GHB_EINVAL, "ghb_backsub_f64: A and b must both be given or both NULL");
     Arg<double> dA(ctx, A, (size_t)ncells * p->lenA, true, false); GHB_TRY(dA.rc);
     Arg<double> db(ctx, b, (size_t)ncells * p->lenb, true, false); GHB_TRY(db.rc);
-    if (p->use_dmma)
+    if (p->use_cw && ctx->opt.cw_back)
+      GHB_TRY(launch_backsub_cw(ctx, *p, ncells, dA.dev, db.dev, lambda_free, lambda_dirichlet, dids.dev, du.dev, di.dev));
+    else if (p->use_dmma)
       GHB_TRY(launch_backsub_dmma(ctx, *p, ncells, dA.dev, db.dev, lambda_free, lambda_dirichlet, dids.dev, du.dev, di.dev));
     else if (p->use_large)
       GHB_TRY(launch_backsub_large(ctx, *p, ncells, dA.dev, db.dev, lambda_free, lambda_dirichlet, dids.dev, du.dev, di.dev));

@@ -33,6 +33,7 @@ struct Options {
   int warp_one_cell = 0;      // GHB_WARP_ONE_CELL   small-cell kernels: one cell per warp
   int warp_two_rows = 0;      // GHB_WARP_TWO_ROWS   (16,8): two rows per lane
   int debug = 0;              // GHB_DEBUG           print launch geometry
+  int cw_back = 1;            // GHB_CW_BACK         backward map of cell-warp plans on the cell-warp kernel (0: dmma / generic)
   int fused_assembly = 1;     // GHB_FUSED_ASSEMBLY  condensation kernels scatter S_K into nzval themselves (cell-warp plans)
   int64_t stream_chunk_bytes = (int64_t)256 << 20;   // GHB_STREAM_CHUNK_BYTES: chunk of the host-record streaming path
 };
@@ -252,6 +253,8 @@ int launch_condense_cw(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double
                        double* g, int32_t* info, double* X);
 int launch_condense_dmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
                          double* g, int32_t* info, double* X = nullptr);
+int launch_backsub_cw(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, const double* lam_free,
+                      const double* lam_dir, const int64_t* ids, double* u, int32_t* info);
 struct ScatterArgs;
 // records of an affine family generated inside the condensation kernel (sc != NULL: fused assembly as well)
 bool cw_gen_supported(const Plan& p);

@@ -14,9 +14,6 @@ static bool cw_shape(int ni, int nb) {
   return false;
 }
 
-// padded classes of the shape-generic (PAD) kernels: n_i <= NI, n_b <= 40
-#define GHB_CW_PAD_NB 40
-#define GHB_CW_PAD_CLASSES(X) X(16) X(24) X(32) X(40) X(48) X(56) X(64)
 
 static int cw_pad_class(int ni) {
 #define X(a) if (ni <= a) return a;

@@ -174,6 +174,11 @@ struct CwArgs {
   double* scratch;          // [gridDim.x * WPC][slot] the record of the cell a warp is working on (stays in L2)
   int64_t slot;             // doubles per scratch record (lenAp + lenbp rounded up to 128 bytes); b_K sits at offset lenAp
   int ntab;
+  // backward map (BACK kernels, BackwardStaticCondensationMap): u_K = A11^-1 (b1 - A12 lambda_K)
+  const double* lam_free;   // free skeleton dof values
+  const double* lam_dir;    // Dirichlet skeleton dof values (may be NULL: zeros)
+  const int64_t* ids;       // [ncells][n_b] 1-based skeleton dof ids, < 0: Dirichlet
+  double* u;                // [ncells][n_i] interior dof values, condensed order
   int gen_E;                // table elements per staged chunk (a multiple of 16; 2 buffers x ntab x (gen_E + 4) doubles fit an image)
 };
 
@@ -339,12 +344,13 @@ __device__ __forceinline__ void panel_factor(double (&a)[8], double (&a2)[8], co
 // generate the WPC records of an affine family together (every table element is fetched once per batch and combined with
 // the WPC coefficient vectors), each into the warp's private scratch record -- rewritten for every cell, so it lives in
 // L2 -- and after one barrier every warp condenses its own cell from its scratch record exactly as from a resident one.
-template <int NI, int NB, int WPC, int MINB, bool KEEPX, bool SPARSE, bool PAD, bool SCAT, bool GEN = false>
+template <int NI, int NB, int WPC, int MINB, bool KEEPX, bool SPARSE, bool PAD, bool SCAT, bool GEN = false, bool BACK = false>
 __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArgs ar) {
   using C = CwCfg<NI, NB>;
   constexpr int RT = C::RT, NPL = C::NPL, DUMMY = C::DUMMY;
   constexpr int BTM = C::BTM;
   static_assert(!PAD || (SPARSE && NI % 8 == 0), "PAD kernels are instantiated for padded shapes");
+  static_assert(!BACK || (!KEEPX && !SCAT && !GEN), "BACK kernels: the backward map on resident records");
   static_assert(!GEN || (!PAD && WPC <= 8), "GEN kernels: tuned shapes, at most 8 cells per batch (rows of a DMMA tile)");
   const int nir = PAD ? ar.n_i : NI, nbr = PAD ? ar.n_b : NB;       // real sizes
   const int NC = nbr + 1;                                           // right-hand-side columns: A12 | b1
@@ -744,7 +750,7 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
     }
 
     // ------------------------------------------------------------------ phase B: column tiles of [A12 b1]
-    if (!GEN && GHB_CW_PREFETCH == 2 && lane == 0) {
+    if (!GEN && !BACK && GHB_CW_PREFETCH == 2 && lane == 0) {
       l2_prefetch(Arec + ar.pf21_off, (unsigned)ar.pf21_len * 8u);
       if (ar.pf22_len > 0) l2_prefetch(Arec + ar.pf22_off, (unsigned)ar.pf22_len * 8u);
     }
@@ -1024,7 +1030,117 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
           }
         }
     };
-    {
+    if (BACK) {
+      // ---- backward map (/root/reference/src/BackwardStaticCondensationMap.jl:84-99): r = b1 - A12 lambda_K (gemv!),
+      //      u_K = A11^-1 r (getrs! on the factors just computed).  The lane holds column g of every A12 tile: it
+      //      accumulates A12(row, 8J + g) lambda(8J + g) over the tiles J for its rows, the eight lanes of equal t then
+      //      add up their columns; every column of the right-hand-side tile carries the same r (only column 0 is stored).
+      double racc[RT][2];
+#pragma unroll
+      for (int j = 0; j < RT; ++j) { racc[j][0] = 0.0; racc[j][1] = 0.0; }
+      const int ctba = (nbr + 7) >> 3;
+#pragma unroll 1
+      for (int J = 0; J < ctba; ++J) {
+        const int col = 8 * J + g;
+        const bool cAl = col < nbr;
+        double lamv = 0.0;
+        if (cAl) {
+          const int64_t id = __ldg(ar.ids + cell * nbr + col);
+          lamv = id > 0 ? __ldg(ar.lam_free + (id - 1)) : ((id < 0 && ar.lam_dir) ? __ldg(ar.lam_dir + (-id - 1)) : 0.0);
+        }
+#pragma unroll
+        for (int j = 0; j < RT; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            if (j == RT - 1 && 4 * e >= NPL) continue;
+            double v = 0.0;
+            if (PAD) {
+              if (o[j][e] >= 0 && cAl) {
+                const int base = (int)lds_u32(a_colbase + 4u * (unsigned)((nir + col) * nf + (o[j][e] >> 8)));
+                if (base >= 0) v = __ldg(Arec + base + (o[j][e] & 0xff));
+              }
+            } else {
+              if (o[j][e] >= 0 && cAl) v = __ldg(Arec + o[j][e]);
+              o[j][e] += st8[j][e];
+            }
+            racc[j][e] = fma(-v, lamv, racc[j][e]);
+          }
+      }
+      double T[RT][2];
+#pragma unroll
+      for (int j = 0; j < RT; ++j) {
+        unsigned w0, w1;
+        lds_2u32(a_prow + 32u * j + 8u * (unsigned)t, w0, w1);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          double r = racc[j][e];
+          r += __shfl_xor_sync(0xffffffffu, r, 4);
+          r += __shfl_xor_sync(0xffffffffu, r, 8);
+          r += __shfl_xor_sync(0xffffffffu, r, 16);
+          const unsigned row = (e ? w1 : w0) >> 16;
+          double bv = 0.0;
+          if (!(j == RT - 1 && 4 * e >= NPL) && row < (unsigned)nir && !(j == RT - 1 && !(e ? vl1 : vl0))) {
+            if (PAD) {
+              unsigned short si;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(si) : "r"(a_rowinfo + (row << 1)));
+              const int base = (int)lds_u32(a_colbase + 4u * (unsigned)(ntot * nf + (int)(si >> 8)));
+              bv = __ldg(brec + base + (int)(si & 0xffu));
+            } else {
+              unsigned short h;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(a_rowb + (row << 1)));
+              bv = __ldg(brec + (int)h);
+            }
+            T[j][e] = bv + r;
+          } else {
+            T[j][e] = 0.0;
+          }
+        }
+      }
+      // Z = L^-1 P r
+#pragma unroll
+      for (int q = 0; q < RT; ++q) {
+        double b0, b1;
+        lds128(a_invL + 512u * q + 64u * g + T16, b0, b1);
+        double z0 = 0.0, z1 = 0.0;
+        dmma(z0, z1, T[q][0], b0);
+        if (q < RT - 1 || NPL > 4) dmma(z0, z1, T[q][1], b1);
+        T[q][0] = z0; T[q][1] = z1;
+#pragma unroll
+        for (int i = q + 1; i < RT; ++i) {
+          double l0, l1;
+          lds128(rb[i] + 64u * q, l0, l1);
+          dmma(T[i][0], T[i][1], T[q][0], l0);
+          dmma(T[i][0], T[i][1], T[q][1], l1);
+        }
+      }
+      // u = U^-1 Z
+#pragma unroll
+      for (int q = RT - 1; q >= 0; --q) {
+        double b0, b1;
+        lds128(rb[q] + 64u * q, b0, b1);
+        double x0 = 0.0, x1 = 0.0;
+        dmma(x0, x1, T[q][0], b0);
+        if (q < RT - 1 || NPL > 4) dmma(x0, x1, T[q][1], b1);
+        T[q][0] = x0; T[q][1] = x1;
+#pragma unroll
+        for (int p = q - 1; p >= 0; --p) {
+          double u0, u1;
+          lds128(rb[p] + 64u * q, u0, u1);
+          dmma(T[p][0], T[p][1], T[q][0], u0);
+          if (q < RT - 1 || NPL > 4) dmma(T[p][0], T[p][1], T[q][1], u1);
+        }
+      }
+      if (g == 0) {
+        double* uc = ar.u + cell * (int64_t)nir;
+#pragma unroll
+        for (int p = 0; p < RT; ++p)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int k = 8 * p + 4 * e + t;
+            if (8 * p + 4 * e < NI && k < nir && (p < RT - 1 || (e ? vl1 : vl0))) uc[k] = failed ? qnan : T[p][e];
+          }
+      }
+    } else {
       int J = 0;
       if (GHB_CW_NJ == 2 && !PAD) {
 #pragma unroll 1
@@ -1064,6 +1180,7 @@ inline void cw_fill_args(const Plan& p, CwArgs& ar) {
   ar.lenA = p.lenA; ar.lenb = p.lenb;
   ar.TA = nullptr; ar.Tb = nullptr; ar.coef = nullptr; ar.scratch = nullptr; ar.slot = 0; ar.ntab = 0;
   ar.lenAp = 0; ar.lenbp = 0; ar.gen_E = 0;
+  ar.lam_free = nullptr; ar.lam_dir = nullptr; ar.ids = nullptr; ar.u = nullptr;
 }
 
 }  // namespace
@@ -1076,3 +1193,6 @@ inline void cw_fill_args(const Plan& p, CwArgs& ar) {
 #else
 #define GHB_CW_SHAPES(X) X(34, 36) X(33, 12) X(40, 36) X(21, 16)
 #endif
+// padded classes of the shape-generic (PAD) kernels: n_i <= NI, n_b <= 40
+#define GHB_CW_PAD_NB 40
+#define GHB_CW_PAD_CLASSES(X) X(16) X(24) X(32) X(40) X(48) X(56) X(64)

@@ -115,7 +115,8 @@ def test_persistent_grid_wraps(ctx, name):
 
 
 @pytest.mark.parametrize("name", ["C1_hdg_k1_2d", "C2_rth_k2_2d", "C2_rth_k3_2d", "C3_hdg_k2_3d", "multifield_2skel",
-                                  "odd_shapes", "C4_elasticity_k2_3d", "C5_hencky_k1_3d"])
+                                  "odd_shapes", "C4_elasticity_k2_3d", "C5_hencky_k1_3d", "hdg_equal_order_3d",
+                                  "elasticity_k1_2d", "hencky_k1_2d", "rth_k0_2d"])
 def test_backsub_parity_and_factor_reuse(ctx, name):
     plan, op = _dev_plan(ctx, name), oracle_plan(name)
     n = 33
@@ -934,6 +935,42 @@ def test_cellwarp_kernel(ctx, name):
         u = torch.empty((n, plan.n_i), dtype=torch.float64, device="cuda")
         ctx.backsub(plan, n, None, None, torch.as_tensor(lam, device="cuda"), None, torch.as_tensor(ids, device="cuda"), u, None)
         assert rel_err_cells(u.cpu().numpy()[ok], u0[ok]) < TOL
+
+
+@pytest.mark.parametrize("name", CW_NAMES + ["hencky_k1_2d", "multifield_2skel", "odd_shapes"])
+def test_cellwarp_backward_map(ctx, name):
+    """BackwardStaticCondensationMap on the cell-warp kernel (BACK instantiations: tuned shapes and the shape-generic
+    classes): u_K against the oracle on a batch that wraps the persistent grid, without Dirichlet values (NULL -> zeros),
+    dgetrf info + NaN for a singular cell and clean neighbours, and agreement with the other backward kernel of the plan
+    (option cw_back = 0: 4-warps-per-cell DMMA or generic)."""
+    plan, op = _dev_plan(ctx, name), oracle_plan(name)
+    assert plan.kernel_name.startswith("cw")
+    n = 2501
+    A, b = _synth(ctx, plan, 17, n)
+    A[1234].zero_()
+    rng = np.random.default_rng(4)
+    nfree, ndir = 300, 40
+    ids = rng.integers(1, nfree + 1, (n, plan.n_b))
+    neg = rng.random((n, plan.n_b)) < 0.15
+    ids[neg] = -rng.integers(1, ndir + 1, int(neg.sum()))
+    lam_f, lam_d = rng.standard_normal(nfree), rng.standard_normal(ndir)
+    ids_d, lf, ld = torch.as_tensor(ids, device="cuda"), torch.as_tensor(lam_f, device="cuda"), torch.as_tensor(lam_d, device="cuda")
+    ok = np.ones(n, bool); ok[1234] = False
+    for dvals, dref in ((ld, lam_d), (None, np.zeros(ndir))):
+        u0, info0 = oc.backsub(op, A.cpu().numpy(), b.cpu().numpy(), o.cell_dof_values(lam_f, dref, ids))
+        res = []
+        for cw_back in (1, 0):
+            ctx.set_option("cw_back", cw_back)
+            u = torch.full((n, plan.n_i), 7.0, dtype=torch.float64, device="cuda")
+            info = torch.full((n,), -3, dtype=torch.int32, device="cuda")
+            ctx.backsub(plan, n, A, b, lf, dvals, ids_d, u, info)
+            res.append((u.cpu().numpy(), info.cpu().numpy()))
+        ctx.set_option("cw_back", 1)
+        for u, info in res:
+            assert info.tolist() == info0.tolist() and info[1234] == 1 and not info[ok].any()
+            assert np.isnan(u[1234]).all() and np.isfinite(u[ok]).all()
+            assert rel_err_cells(u[ok], u0[ok]) < TOL
+        assert rel_err_cells(res[0][0][ok], res[1][0][ok]) < TOL
 
 
 def test_cellwarp_pivot_ties_follow_lapack(ctx):
