@@ -98,6 +98,7 @@ static void options_from_env(Options& o) {
   o.debug = (int)env_i64("GHB_DEBUG", o.debug);
   o.fused_assembly = (int)env_i64("GHB_FUSED_ASSEMBLY", o.fused_assembly);
   o.cw_back = (int)env_i64("GHB_CW_BACK", o.cw_back);
+  o.cw_q4 = (int)env_i64("GHB_CW_Q4", o.cw_q4);
   o.stream_chunk_bytes = std::max<int64_t>(1, env_i64("GHB_STREAM_CHUNK_BYTES", o.stream_chunk_bytes));
 }
 
@@ -195,10 +196,11 @@ int ghb_set_option(ghb_ctx* ctx, const char* name, int64_t value) {
   else if (n == "debug") o.debug = (int)value;
   else if (n == "fused_assembly") o.fused_assembly = (int)value;
   else if (n == "cw_back") o.cw_back = (int)value;
+  else if (n == "cw_q4") o.cw_q4 = (int)value;
   else if (n == "stream_chunk_bytes") o.stream_chunk_bytes = std::max<int64_t>(1, value);
   else return fail(ctx, GHB_EINVAL, "ghb_set_option: unknown option " + n);
   for (Plan* p : ctx->plans)          // launch-time knobs follow; the kernel choice of existing plans does not change
-    if (p) { p->opt.max_ctas_per_sm = o.max_ctas_per_sm; p->opt.debug = o.debug; p->opt.dmma_ll = o.dmma_ll; p->opt.ll_ctas = o.ll_ctas; }
+    if (p) { p->opt.max_ctas_per_sm = o.max_ctas_per_sm; p->opt.debug = o.debug; p->opt.dmma_ll = o.dmma_ll; p->opt.ll_ctas = o.ll_ctas; p->opt.cw_q4 = o.cw_q4; }
   return GHB_OK;
 }
 

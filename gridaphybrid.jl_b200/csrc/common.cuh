@@ -33,6 +33,7 @@ struct Options {
   int warp_one_cell = 0;      // GHB_WARP_ONE_CELL   small-cell kernels: one cell per warp
   int warp_two_rows = 0;      // GHB_WARP_TWO_ROWS   (16,8): two rows per lane
   int debug = 0;              // GHB_DEBUG           print launch geometry
+  int cw_q4 = 1;              // GHB_CW_Q4           interleaved row tiles / 256-bit accesses for the n_b = 36 shapes (A/B knob)
   int cw_back = 1;            // GHB_CW_BACK         backward map of cell-warp plans on the cell-warp kernel (0: dmma / generic)
   int fused_assembly = 1;     // GHB_FUSED_ASSEMBLY  condensation kernels scatter S_K into nzval themselves (cell-warp plans)
   int64_t stream_chunk_bytes = (int64_t)256 << 20;   // GHB_STREAM_CHUNK_BYTES: chunk of the host-record streaming path
@@ -61,6 +62,7 @@ struct Plan {
   unsigned char* d_cw = nullptr;  // its tables in one block: loader | rowA12 | colA21 | rowb (byte offsets cw_off)
   int cw_nld = 0;
   size_t cw_off[5] = {0, 0, 0, 0, 0};
+  bool cw_q4 = false;             // the plan's blocks allow the 256-bit (interleaved row tile) instantiation
   int cw_pad = 0;                 // 0: tuned instantiation of the exact shape; else the padded n_i class of the generic one
   bool use_warp = false;          // register-resident warp kernels for small cells (condense_warp.cu)
   bool use_large = false;         // streamed large-cell kernel, 64 < n_i <= 128 (condense_large.cu)

@@ -128,6 +128,16 @@ int cw_prepare(ghb_ctx* ctx, Plan& p) {
     p.cw_off[0] = b0; p.cw_off[1] = b0 + b1; p.cw_off[2] = b0 + b1 + b2; p.cw_off[3] = b0 + b1 + b2 + b3;
     p.cw_off[4] = b0 + b1 + b2 + b3 + b4;
   }
+  // Q4 kernels (256-bit accesses): every A21 / A22 block, the records and the outputs must be 32-byte aligned
+  {
+    const int nfq = p.nfields, fbq = p.boundary.empty() ? 0 : p.boundary[0] - 1;
+    bool ok = !p.cw_pad && p.boundary.size() == 1 && p.n_b % 4 == 0 && p.lenA % 4 == 0;
+    for (int f = 0; f < nfq && ok; ++f) {
+      const int64_t bo = p.block_offset[fbq + nfq * f];      // (lambda, f): A21 blocks and A22
+      if (bo >= 0 && bo % 4 != 0) ok = false;
+    }
+    p.cw_q4 = ok;
+  }
   // bounding record ranges of the A12 / A21 / A22 blocks (L2 prefetches)
   const int nf = p.nfields;
   auto range = [&](bool rows_int, bool cols_int, int& off, int& len) {
@@ -151,13 +161,13 @@ int cw_prepare(ghb_ctx* ctx, Plan& p) {
   return GHB_OK;
 }
 
-template <int NI, int NB, bool KEEPX, bool SPARSE, bool PAD = false, bool SCAT = false>
+template <int NI, int NB, bool KEEPX, bool SPARSE, bool PAD = false, bool SCAT = false, bool Q4 = false>
 static int launch_cw(ghb_ctx* ctx, const Plan& p, CwArgs& ar) {
   constexpr int WPC = GHB_CW_WPC;
   // PAD classes: as many CTAs per SM as their shared memory allows (the register cap follows)
   constexpr int fit = (int)(233472u / (WPC * CwCfg<NI, NB>::WARP_BYTES + CwCfg<NI, NB>::SH_BYTES_PAD + 1024u));
   constexpr int MINB = PAD ? (fit < 1 ? 1 : (fit > 4 ? 4 : fit)) : GHB_CW_MINB;
-  auto kern = condense_cw_kernel<NI, NB, WPC, MINB, KEEPX, SPARSE, PAD, SCAT>;
+  auto kern = condense_cw_kernel<NI, NB, WPC, MINB, KEEPX, SPARSE, PAD, SCAT, false, false, Q4>;
   const size_t smem = CwCfg<NI, NB>::smem_bytes(WPC, PAD);
   static KernelSetup ks;
   int per_sm = 0;
@@ -171,6 +181,22 @@ static int launch_cw(ghb_ctx* ctx, const Plan& p, CwArgs& ar) {
 
 template <int NI, int NB>
 static int launch_cw_shape(ghb_ctx* ctx, const Plan& p, CwArgs& ar) {
+#ifdef GHB_CW_Q4_BUILD   // measured slower (50.0 vs 51.6 M cells/s on C3, profiles/r02_cw_summary.md): not built by default
+  if constexpr (NB == 36) {        // interleaved row tiles with 256-bit accesses where the plan's blocks are 32-byte aligned
+    if (p.cw_q4 && p.opt.cw_q4) {
+      if (ar.nzval) {
+        if (p.all_touched) return launch_cw<NI, NB, false, false, false, true, true>(ctx, p, ar);
+        return launch_cw<NI, NB, false, true, false, true, true>(ctx, p, ar);
+      }
+      if (ar.X) {
+        if (p.all_touched) return launch_cw<NI, NB, true, false, false, false, true>(ctx, p, ar);
+        return launch_cw<NI, NB, true, true, false, false, true>(ctx, p, ar);
+      }
+      if (p.all_touched) return launch_cw<NI, NB, false, false, false, false, true>(ctx, p, ar);
+      return launch_cw<NI, NB, false, true, false, false, true>(ctx, p, ar);
+    }
+  }
+#endif
   if (ar.nzval) {
     if (p.all_touched) return launch_cw<NI, NB, false, false, false, true>(ctx, p, ar);
     return launch_cw<NI, NB, false, true, false, true>(ctx, p, ar);

@@ -18,10 +18,10 @@ bool cw_gen_supported(const Plan& p) {
   return p.use_cw && !p.cw_pad;      // the tuned instantiations
 }
 
-template <int NI, int NB, bool SPARSE, bool SCAT>
+template <int NI, int NB, bool SPARSE, bool SCAT, bool Q4 = false>
 static int launch_cw_gen(ghb_ctx* ctx, const Plan& p, CwArgs& ar) {
   constexpr int WPC = GHB_CW_GEN_WPC;
-  auto kern = condense_cw_kernel<NI, NB, WPC, GHB_CW_GEN_MINB, false, SPARSE, false, SCAT, true>;
+  auto kern = condense_cw_kernel<NI, NB, WPC, GHB_CW_GEN_MINB, false, SPARSE, false, SCAT, true, false, Q4>;
   const size_t smem = CwCfg<NI, NB>::smem_bytes(WPC, false, true);
   static KernelSetup ks;
   int per_sm = 0;
@@ -49,6 +49,19 @@ static int launch_cw_gen(ghb_ctx* ctx, const Plan& p, CwArgs& ar) {
 
 template <int NI, int NB>
 static int launch_cw_gen_shape(ghb_ctx* ctx, const Plan& p, CwArgs& ar) {
+#ifdef GHB_CW_Q4_BUILD   // measured slower (50.0 vs 51.6 M cells/s on C3, profiles/r02_cw_summary.md): not built by default
+  if constexpr (NB == 36) {
+    // 256-bit accesses: the scratch record keeps the block offsets of the plan and is 128-byte aligned
+    if (p.cw_q4 && p.opt.cw_q4 && ar.lenAp == p.lenA) {
+      if (ar.nzval) {
+        if (p.all_touched) return launch_cw_gen<NI, NB, false, true, true>(ctx, p, ar);
+        return launch_cw_gen<NI, NB, true, true, true>(ctx, p, ar);
+      }
+      if (p.all_touched) return launch_cw_gen<NI, NB, false, false, true>(ctx, p, ar);
+      return launch_cw_gen<NI, NB, true, false, true>(ctx, p, ar);
+    }
+  }
+#endif
   if (ar.nzval) {
     if (p.all_touched) return launch_cw_gen<NI, NB, false, true>(ctx, p, ar);
     return launch_cw_gen<NI, NB, true, true>(ctx, p, ar);

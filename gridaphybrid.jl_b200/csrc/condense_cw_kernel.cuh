@@ -187,6 +187,17 @@ template <bool GEN>
 __device__ __forceinline__ double ldrec(const double* p) { return GEN ? *p : __ldg(p); }
 template <bool GEN>
 __device__ __forceinline__ double2 ldrec2(const double2* p) { return GEN ? *p : __ldg(p); }
+// 256-bit accesses (sm_100: LDG.E.256 / STG.E.256), 32-byte aligned addresses
+template <bool GEN>
+__device__ __forceinline__ void ldrec4(const double* p, double& a, double& b, double& c, double& d) {
+  if (GEN) asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+  else asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+template <bool GEN>
+__device__ __forceinline__ void strec4(double* p, double a, double b, double c, double d) {
+  if (GEN) asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+  else asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
 
 template <int NI, int NB>
 struct CwCfg {
@@ -344,12 +355,19 @@ __device__ __forceinline__ void panel_factor(double (&a)[8], double (&a2)[8], co
 // generate the WPC records of an affine family together (every table element is fetched once per batch and combined with
 // the WPC coefficient vectors), each into the warp's private scratch record -- rewritten for every cell, so it lives in
 // L2 -- and after one barrier every warp condenses its own cell from its scratch record exactly as from a resident one.
-template <int NI, int NB, int WPC, int MINB, bool KEEPX, bool SPARSE, bool PAD, bool SCAT, bool GEN = false, bool BACK = false>
+// Q4 (NB = 36 shapes whose A21 / A22 blocks, records and outputs are 32-byte aligned): the boundary row tiles 0..3 are
+// INTERLEAVED -- tile m holds the rows 4n + m, n = 0..7 -- so that a lane's A21 fragments of the four tiles are four
+// consecutive rows of one column (one 256-bit load instead of four 64-bit ones: 100 instead of 250 A21 loads per cell),
+// and its D fragments of the four tiles are the eight consecutive rows 8t .. 8t+7 of a column of S (two 256-bit stores /
+// A22 loads instead of four 128-bit ones).  Tile 4 keeps the rows 32 + n.
+template <int NI, int NB, int WPC, int MINB, bool KEEPX, bool SPARSE, bool PAD, bool SCAT, bool GEN = false, bool BACK = false,
+          bool Q4 = false>
 __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArgs ar) {
   using C = CwCfg<NI, NB>;
   constexpr int RT = C::RT, NPL = C::NPL, DUMMY = C::DUMMY;
   constexpr int BTM = C::BTM;
   static_assert(!PAD || (SPARSE && NI % 8 == 0), "PAD kernels are instantiated for padded shapes");
+  static_assert(!Q4 || (!PAD && !BACK && C::BTM == 5 && NB % 4 == 0 && NB < 40), "Q4: four interleaved row tiles + a short fifth");
   static_assert(!BACK || (!KEEPX && !SCAT && !GEN), "BACK kernels: the backward map on resident records");
   static_assert(!GEN || (!PAD && WPC <= 8), "GEN kernels: tuned shapes, at most 8 cells per batch (rows of a DMMA tile)");
   const int nir = PAD ? ar.n_i : NI, nbr = PAD ? ar.n_b : NB;       // real sizes
@@ -925,12 +943,29 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
             }
             continue;
           }
+          if (Q4 && m < 4) continue;                         // tiles 0..3: interleaved rows, loaded below
           if (!SPARSE || ini != nullptr) {
             if (al16) {
               if (NB % 8 == 0 || r < NB) { const double2 v = ldrec2<GEN>(reinterpret_cast<const double2*>(ini + r)); acc[jj][m][0] = v.x; acc[jj][m][1] = v.y; }
             } else {
               if (NB % 8 == 0 || r < NB) acc[jj][m][0] = ldrec<GEN>(ini + r);
               if (NB % 8 == 0 || r + 1 < NB) acc[jj][m][1] = ldrec<GEN>(ini + r + 1);
+            }
+          }
+        }
+      }
+      if (Q4) {
+        // acc[m][e] = S[8t + 4e + m][col], m < 4: rows 8t .. 8t+7 of the column
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) {
+          const double* ini = cA[jj] ? ((SPARSE && ar.a22base < 0) ? nullptr : Arec + ar.a22base + col[jj] * NB) : brec + ar.b2base;
+          if (!SPARSE || ini != nullptr) {
+            if (cA[jj]) {                                    // A22 column: 32-byte aligned
+              ldrec4<GEN>(ini + 8 * t, acc[jj][0][0], acc[jj][1][0], acc[jj][2][0], acc[jj][3][0]);
+              ldrec4<GEN>(ini + 8 * t + 4, acc[jj][0][1], acc[jj][1][1], acc[jj][2][1], acc[jj][3][1]);
+            } else {                                         // b2 (the lanes of the right-hand-side column): 8-byte aligned
+#pragma unroll
+              for (int m = 0; m < 4; ++m) { acc[jj][m][0] = ldrec<GEN>(ini + 8 * t + m); acc[jj][m][1] = ldrec<GEN>(ini + 8 * t + 4 + m); }
             }
           }
         }
@@ -944,8 +979,14 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
             const bool okc = (!SPARSE || of >= 0) && (p < RT - 1 || (e ? vl1 : vl0));
             const double* src = Arec + (okc ? of : 0);
             double bf[BTM];
+            if (Q4) {                                        // rows 4g .. 4g+3 of the column in one load; tile 4: row 32 + g
+              bf[0] = 0.0; bf[1] = 0.0; bf[2] = 0.0; bf[3] = 0.0;
+              if (!(SPARSE || p == RT - 1) || okc) ldrec4<GEN>(src + 3 * g, bf[0], bf[1], bf[2], bf[3]);
+              bf[4] = (okc && vb) ? ldrec<GEN>(src + 32) : 0.0;
+            }
 #pragma unroll
             for (int m = 0; m < BTM; ++m) {
+              if (Q4) continue;
               if (PAD) {
                 bf[m] = 0.0;
                 if (of >= 0 && rinfo21[m] != 0xffffu) {
@@ -980,8 +1021,20 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
             if (cpos >= 0) {
               const uint8_t* rr = ar.rowrank + ce * nbr;
               double* nz = ar.nzval + cpos;
+              if (Q4) {                                      // rows 8t + 4e + m: four ranks per 32-bit load
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const unsigned rk4 = __ldg(reinterpret_cast<const unsigned*>(rr + 8 * t + 4 * e));
+#pragma unroll
+                  for (int m = 0; m < 4; ++m) {
+                    const unsigned rk = (rk4 >> (8 * m)) & 0xffu;
+                    if (rk != 255u) atomicAdd(nz + (rk & 0x7fu), failed ? qnan : acc[jj][m][e]);
+                  }
+                }
+              }
 #pragma unroll
               for (int m = 0; m < BTM; ++m) {
+                if (Q4 && m < 4) continue;
                 const int r = 8 * m + 2 * t;
                 if (r < nbr) {
                   unsigned rk0, rk1 = 255u;
@@ -1002,8 +1055,18 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
       for (int jj = 0; jj < NJ; ++jj)
         if (col[jj] < NC && (keepS || !cA[jj])) {
           double* dst = cA[jj] ? Sc + (int64_t)col[jj] * nbr : gc;
+          if (Q4) {                                          // rows 8t .. 8t+3 and 8t+4 .. 8t+7: 32-byte aligned in S and g
+            if (failed) {
+              strec4<GEN>(dst + 8 * t, qnan, qnan, qnan, qnan);
+              strec4<GEN>(dst + 8 * t + 4, qnan, qnan, qnan, qnan);
+            } else {
+              strec4<GEN>(dst + 8 * t, acc[jj][0][0], acc[jj][1][0], acc[jj][2][0], acc[jj][3][0]);
+              strec4<GEN>(dst + 8 * t + 4, acc[jj][0][1], acc[jj][1][1], acc[jj][2][1], acc[jj][3][1]);
+            }
+          }
 #pragma unroll
           for (int m = 0; m < BTM; ++m) {
+            if (Q4 && m < 4) continue;
             const int r = 8 * m + 2 * t;
             double v0 = acc[jj][m][0], v1 = acc[jj][m][1];
             if (failed) { v0 = qnan; v1 = qnan; }
