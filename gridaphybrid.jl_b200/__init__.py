@@ -14,6 +14,6 @@ from .maps import (BackwardStaticCondensationMap, RestrictArrayBlockMap, Scalar2
 from .skeleton import CartesianSkeleton, FacetFESpace, MultiFieldFacetFESpace  # noqa: F401
 from .assembly import (SparseMatrixAssembler, SparseMatrixCSC, SparseMatrixCSR, assemble_matrix_and_vector,  # noqa: F401
                        assemble_matrix_and_vector_csr, attach_dirichlet, condense_and_assemble)
-from .families import AffineRecordFamily, cartesian_coefficients  # noqa: F401
+from .families import AffineCells, AffineRecordFamily, cartesian_coefficients  # noqa: F401
 from .operators import (AffineFEOperator, HybridAffineFEOperator, HybridFEOperator,  # noqa: F401
                         hybrid_backslash_solve, solve_skeleton)

@@ -77,6 +77,43 @@ class AffineRecordFamily:
         return nzval, rhs
 
 
+class AffineCells:
+    """Lazy cell array of an affine family: what the reference's `lazy_map(::IntegrationMap, ...)` array is to its
+    assembler -- cell (A_K, b_K) exists only while it is being condensed.  `lazy_map(StaticCondensationMap(...), cells)`
+    condenses it through `ghb_condense_affine_f64` (records formed in the loader of the condensation kernel, never in
+    HBM); `.A`, `.b` materialise the packed records on first use (the backward map reads them), bit-identical to what the
+    kernel formed."""
+
+    def __init__(self, family: AffineRecordFamily, coef: torch.Tensor, ndofs, touched, ctx: Context | None = None):
+        self.family, self.coef = family, coef.contiguous()
+        self.ndofs = [int(x) for x in ndofs]
+        nf = len(self.ndofs)
+        self.touched = np.asarray(touched, dtype=bool).reshape(nf, nf)
+        self.ncells = int(coef.shape[0])
+        self.ctx = ctx
+        self._packed = None
+
+    def __len__(self):
+        return self.ncells
+
+    def materialise(self, ctx: Context, plan: BlockPlan) -> PackedCells:
+        if self._packed is None:
+            self._packed = self.family.expand(ctx, plan, self.coef)
+        return self._packed
+
+    def _need(self):
+        assert self._packed is not None, "AffineCells: records not materialised yet (materialise(ctx, plan))"
+        return self._packed
+
+    @property
+    def A(self):
+        return self._need().A
+
+    @property
+    def b(self):
+        return self._need().b
+
+
 def cartesian_coefficients(dims, h, device, cell_start=0, ncells=None, extra=None) -> torch.Tensor:
     """Coefficient vectors of the cells of a Cartesian mesh (x fastest), [ncells][1 + 2 D (+ extras)]:
     1, [idx_a == 0] per axis (the low-side facet is a boundary facet: its owner-normal sign flips, e.g.

@@ -52,7 +52,7 @@ class HybridAffineFEOperator:
         self.weakform, self.trial, self.test = weakform, trial, test
         self.bulk_fields, self.skeleton_fields = list(bulk_fields), list(skeleton_fields)
         matvec = weakform()                                                  # :18-28
-        assert isinstance(matvec, PackedCells)
+        assert isinstance(matvec, PackedCells) or hasattr(matvec, "family")       # packed records, or a lazy affine family
         condensed = lazy_map(StaticCondensationMap(self.bulk_fields, self.skeleton_fields), matvec)   # :31
         M = _setup_fe_spaces_skeleton_system(trial, self.skeleton_fields)    # :33
         L = _setup_fe_spaces_skeleton_system(test, self.skeleton_fields)
@@ -78,6 +78,8 @@ def _compute_hybridizable_from_skeleton_free_dof_values(lh_free, lh_dirichlet, a
     ctx = assem.ctx
     k = BackwardStaticCondensationMap(bulk_fields, skeleton_fields)
     plan = k.static_condensation.plan(matvec, ctx)
+    if hasattr(matvec, "family"):
+        matvec.materialise(ctx, plan)            # the backward map reads the records (bit-identical to the ones condensed)
     n = len(matvec)
     dev = assem.cell_ids.device
     u = torch.empty((n, plan.n_i), dtype=torch.float64, device=dev)

@@ -672,6 +672,14 @@ def test_affine_family_records_on_device(ctx, dims, order):
     assert np.abs(x - x0).max() < 1e-10
     err, err0 = p.l2_error_u(x[:nc * nu].reshape(nc, nu)), p.l2_error_u(x0[:nc * nu].reshape(nc, nu))
     assert err < (1e-12 if nc <= 16 else 1e-11) and err < 10 * max(err0, 1e-13)
+    # the same operator on the LAZY family (gh.AffineCells): the records are formed inside the condensation kernel
+    # (ghb_condense_affine_f64) and only materialised for the backward map -- bit-identical records, so the identical
+    # skeleton system, multipliers and full-space solution
+    lazy = lambda: gh.AffineCells(fam, coef, prob.prob.ndofs, prob.touched)
+    op_lazy = gh.HybridAffineFEOperator(lazy, trial, trial, [1, 2], [3])
+    assert np.array_equal(op_lazy.skeleton_op.matrix.nzval.cpu().numpy(), op.skeleton_op.matrix.nzval.cpu().numpy())
+    assert np.array_equal(op_lazy.skeleton_op.vector.cpu().numpy(), op.skeleton_op.vector.cpu().numpy())
+    assert np.array_equal(op_lazy.solve().cpu().numpy(), x)
 
 
 def _random_family(ctx, plan, ntab, seed):
