@@ -612,6 +612,16 @@ def run_ours(args):
                   "expand_then_condense": {"value": ncells / (gms2 * 1e-3), "ms": gms2,
                                            "note": "records written to HBM by ghb_expand_records_f64 first (round-2 path)"},
                   "checksums_equal": bool(same)}
+        # the backward map from the same coefficient vectors (ghb_backsub_affine_f64): with the step above the whole solve
+        # runs without the 83 GB of records ever existing
+        lam_b = torch.randn(slab.layout.nrows_local, dtype=torch.float64, device=dev)
+        u_b = torch.empty((ncells, plan.n_i), dtype=torch.float64, device=dev)
+        ids_b = slab.cell_ids[:ncells]
+        bms = timed3(lambda: fam.backsub(ctx, plan, coef, lam_b, None, ids_b, u_b, info))
+        assert int(info.abs().sum().item()) == 0
+        devgen["backsub"] = {"value": ncells / (bms * 1e-3), "unit": "cells/s", "ms": bms,
+                             "note": "BackwardStaticCondensationMap with the records formed in the loader (GEN + BACK kernel)"}
+        del lam_b, u_b
         del coef
 
     if rank == 0:

@@ -29,7 +29,7 @@ SYMBOLS = [
     "ghb_condense_scatter_slab_f64", "ghb_assemble_finish_slab_f64",
     "ghb_comm_unique_id", "ghb_comm_init", "ghb_comm_destroy", "ghb_exchange_cut_plane_f64", "ghb_allgather_lambda_f64",
     "ghb_plan_kernel_name", "ghb_plan_blocks", "ghb_plan_query", "ghb_condense_f64",
-    "ghb_restrict_facet_dofs_i64", "ghb_sum_facets_f64", "ghb_expand_records_f64", "ghb_condense_affine_f64", "ghb_condense_assemble_affine_f64", "ghb_l2_projection_dofs_f64", "ghb_assemble_symbolic", "ghb_assemble_pattern", "ghb_assemble_numeric_f64", "ghb_assemble_numeric_csr_f64",
+    "ghb_restrict_facet_dofs_i64", "ghb_sum_facets_f64", "ghb_expand_records_f64", "ghb_condense_affine_f64", "ghb_condense_assemble_affine_f64", "ghb_backsub_affine_f64", "ghb_l2_projection_dofs_f64", "ghb_assemble_symbolic", "ghb_assemble_pattern", "ghb_assemble_numeric_f64", "ghb_assemble_numeric_csr_f64",
     "ghb_assemble_symbolic_slab", "ghb_pack_cut_plane_f64", "ghb_assemble_numeric_slab_f64",
     "ghb_condense_assemble_f64", "ghb_backsub_f64", "ghb_scatter_free_dof_values", "ghb_synth_fill_f64",
     "ghb_cartesian_cell_wise_facets",
@@ -151,6 +151,7 @@ def lib():
     L.ghb_expand_records_f64.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp, vp]
     L.ghb_condense_affine_f64.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp, vp, vp]
     L.ghb_condense_assemble_affine_f64.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp, i64, vp, vp, vp]
+    L.ghb_backsub_affine_f64.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp, i64, vp, i64, vp, vp, vp]
     L.ghb_assemble_symbolic.argtypes = [vp, i64, i32, vp, i64, ctypes.POINTER(i64)]
     L.ghb_assemble_pattern.argtypes = [vp, vp, vp]
     L.ghb_assemble_numeric_f64.argtypes = [vp, vp, vp, vp, i64, vp, vp]

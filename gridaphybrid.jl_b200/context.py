@@ -175,6 +175,15 @@ class Context:
             _ptr(dirichlet_vals, np.float64), _len(dirichlet_vals), _ptr(nzval, np.float64, nnz, "nzval"),
             _ptr(rhs, np.float64, nrows, "rhs"), _ptr(info, np.int32, ncells, "info")))
 
+    def backsub_affine(self, plan: BlockPlan, ncells, ntab, TA, Tb, coef, lambda_free, lambda_dirichlet, cell_ids, u, info=None):
+        """backward map of an affine family with the records formed in the loader (ghb_backsub_affine_f64)"""
+        self._check(self._L.ghb_backsub_affine_f64(
+            self._h, plan.id, int(ncells), int(ntab), _ptr(TA, np.float64, ntab * plan.lenA, "TA"),
+            _ptr(Tb, np.float64, ntab * plan.lenb, "Tb"), _ptr(coef, np.float64, ncells * ntab, "coef"),
+            _ptr(lambda_free, np.float64), _len(lambda_free), _ptr(lambda_dirichlet, np.float64), _len(lambda_dirichlet),
+            _ptr(cell_ids, np.int64, ncells * plan.n_b, "cell_ids"), _ptr(u, np.float64, ncells * plan.n_i, "u"),
+            _ptr(info, np.int32, ncells, "info")))
+
     def assemble_symbolic(self, ncells, n_b, cell_ids, nrows) -> int:
         nnz = ctypes.c_int64(0)
         self._check(self._L.ghb_assemble_symbolic(self._h, int(ncells), int(n_b),

@@ -80,6 +80,16 @@ int launch_condense(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A
   return launch_condense_generic(ctx, p, ncells, A, b, S, g, info, X);
 }
 
+// backward map with the LU recomputed (as the reference does): kernel by plan
+int launch_backsub(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, const double* lam_free,
+                   const double* lam_dir, const int64_t* ids, double* u, int32_t* info) {
+  if (p.use_cw && ctx->opt.cw_back) return launch_backsub_cw(ctx, p, ncells, A, b, lam_free, lam_dir, ids, u, info);
+  if (p.use_dmma) return launch_backsub_dmma(ctx, p, ncells, A, b, lam_free, lam_dir, ids, u, info);
+  if (p.use_large) return launch_backsub_large(ctx, p, ncells, A, b, lam_free, lam_dir, ids, u, info);
+  if (p.use_warp) return launch_backsub_warp(ctx, p, ncells, A, b, lam_free, lam_dir, ids, u, info);
+  return launch_backsub_generic(ctx, p, ncells, A, b, lam_free, lam_dir, ids, u, info);
+}
+
 static int64_t env_i64(const char* name, int64_t dflt) {
   const char* e = getenv(name);
   return (e && *e) ? atoll(e) : dflt;
@@ -895,18 +905,49 @@ int ghb_backsub_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A, 
     if (!A || !b) return fail(ctx, GHB_EINVAL, "ghb_backsub_f64: A and b must both be given or both NULL");
     Arg<double> dA(ctx, A, (size_t)ncells * p->lenA, true, false); GHB_TRY(dA.rc);
     Arg<double> db(ctx, b, (size_t)ncells * p->lenb, true, false); GHB_TRY(db.rc);
-    if (p->use_cw && ctx->opt.cw_back)
-      GHB_TRY(launch_backsub_cw(ctx, *p, ncells, dA.dev, db.dev, lambda_free, lambda_dirichlet, dids.dev, du.dev, di.dev));
-    else if (p->use_dmma)
-      GHB_TRY(launch_backsub_dmma(ctx, *p, ncells, dA.dev, db.dev, lambda_free, lambda_dirichlet, dids.dev, du.dev, di.dev));
-    else if (p->use_large)
-      GHB_TRY(launch_backsub_large(ctx, *p, ncells, dA.dev, db.dev, lambda_free, lambda_dirichlet, dids.dev, du.dev, di.dev));
-    else if (p->use_warp)
-      GHB_TRY(launch_backsub_warp(ctx, *p, ncells, dA.dev, db.dev, lambda_free, lambda_dirichlet, dids.dev, du.dev, di.dev));
-    else
-      GHB_TRY(launch_backsub_generic(ctx, *p, ncells, dA.dev, db.dev, lambda_free, lambda_dirichlet, dids.dev, du.dev, di.dev));
+    GHB_TRY(launch_backsub(ctx, *p, ncells, dA.dev, db.dev, lambda_free, lambda_dirichlet, dids.dev, du.dev, di.dev));
     GHB_TRY(du.finish()); GHB_TRY(di.finish());
     return GHB_OK;
+  }
+  GHB_TRY(du.finish()); GHB_TRY(di.finish());
+  return GHB_OK;
+}
+
+int ghb_backsub_affine_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, int ntab, const double* TA, const double* Tb,
+                           const double* coef, const double* lambda_free_in, int64_t nlambda_free,
+                           const double* lambda_dirichlet_in, int64_t nlambda_dirichlet, const int64_t* cell_ids, double* u,
+                           int32_t* info) {
+  Plan* p = get_plan(ctx, plan_id);
+  if (!p) return fail(ctx, GHB_EINVAL, "ghb_backsub_affine_f64: bad plan id");
+  if (ncells < 0 || ntab < 1 || ntab > 16 || !TA || !Tb || !coef || !cell_ids || !u || !lambda_free_in ||
+      nlambda_free < 0 || nlambda_dirichlet < 0)
+    return fail(ctx, GHB_EINVAL, "ghb_backsub_affine_f64: bad argument (need 1 <= ntab <= 16, non-null arrays)");
+  if (ncells == 0) return GHB_OK;
+  cudaSetDevice(ctx->device);
+  Arg<double> dTA(ctx, TA, (size_t)ntab * p->lenA, true, false); GHB_TRY(dTA.rc);
+  Arg<double> dTb(ctx, Tb, (size_t)ntab * p->lenb, true, false); GHB_TRY(dTb.rc);
+  Arg<double> dc(ctx, coef, (size_t)ncells * ntab, true, false); GHB_TRY(dc.rc);
+  Arg<double> dlf(ctx, lambda_free_in, (size_t)nlambda_free, true, false); GHB_TRY(dlf.rc);
+  Arg<double> dld(ctx, lambda_dirichlet_in, lambda_dirichlet_in ? (size_t)nlambda_dirichlet : 0, true, false); GHB_TRY(dld.rc);
+  Arg<int64_t> dids(ctx, cell_ids, (size_t)ncells * p->n_b, true, false); GHB_TRY(dids.rc);
+  Arg<double> du(ctx, u, (size_t)ncells * p->n_i, false, true); GHB_TRY(du.rc);
+  Arg<int32_t> di(ctx, info, info ? (size_t)ncells : 0, false, true); GHB_TRY(di.rc);
+  if (cw_gen_supported(*p) && ctx->opt.cw_back) {
+    GHB_TRY(launch_backsub_cw_gen(ctx, *p, ncells, ntab, dTA.dev, dTb.dev, dc.dev, dlf.dev, dld.dev, dids.dev, du.dev, di.dev));
+  } else {
+    // plans without a GEN kernel: chunks of records expanded into a device temporary
+    CallTmp tmp(ctx);
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(ncells, ((int64_t)256 << 20) / ((p->lenA + p->lenb) * 8)));
+    double *tA = nullptr, *tb = nullptr;
+    GHB_CUDA(ctx, tmp.alloc((void**)&tA, (size_t)chunk * p->lenA * 8));
+    GHB_CUDA(ctx, tmp.alloc((void**)&tb, (size_t)chunk * p->lenb * 8));
+    for (int64_t c0 = 0; c0 < ncells; c0 += chunk) {
+      const int64_t nc = std::min(chunk, ncells - c0);
+      GHB_TRY(launch_expand_records(ctx, nc, p->lenA, ntab, dTA.dev, dc.dev + c0 * ntab, tA));
+      GHB_TRY(launch_expand_records(ctx, nc, p->lenb, ntab, dTb.dev, dc.dev + c0 * ntab, tb));
+      GHB_TRY(launch_backsub(ctx, *p, nc, tA, tb, dlf.dev, dld.dev, dids.dev + c0 * p->n_b, du.dev + c0 * p->n_i,
+                             di.dev ? di.dev + c0 : nullptr));
+    }
   }
   GHB_TRY(du.finish()); GHB_TRY(di.finish());
   return GHB_OK;

@@ -257,6 +257,11 @@ int launch_condense_dmma(ghb_ctx* ctx, const Plan& p, int64_t ncells, const doub
                          double* g, int32_t* info, double* X = nullptr);
 int launch_backsub_cw(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, const double* lam_free,
                       const double* lam_dir, const int64_t* ids, double* u, int32_t* info);
+int launch_backsub(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, const double* lam_free,
+                   const double* lam_dir, const int64_t* ids, double* u, int32_t* info);
+int launch_backsub_cw_gen(ghb_ctx* ctx, const Plan& p, int64_t ncells, int ntab, const double* TA, const double* Tb,
+                          const double* coef, const double* lam_free, const double* lam_dir, const int64_t* ids, double* u,
+                          int32_t* info);
 struct ScatterArgs;
 // records of an affine family generated inside the condensation kernel (sc != NULL: fused assembly as well)
 bool cw_gen_supported(const Plan& p);

@@ -18,10 +18,10 @@ bool cw_gen_supported(const Plan& p) {
   return p.use_cw && !p.cw_pad;      // the tuned instantiations
 }
 
-template <int NI, int NB, bool SPARSE, bool SCAT, bool Q4 = false>
+template <int NI, int NB, bool SPARSE, bool SCAT, bool Q4 = false, bool BACK = false>
 static int launch_cw_gen(ghb_ctx* ctx, const Plan& p, CwArgs& ar) {
   constexpr int WPC = GHB_CW_GEN_WPC;
-  auto kern = condense_cw_kernel<NI, NB, WPC, GHB_CW_GEN_MINB, false, SPARSE, false, SCAT, true, false, Q4>;
+  auto kern = condense_cw_kernel<NI, NB, WPC, GHB_CW_GEN_MINB, false, SPARSE, false, SCAT, true, BACK, Q4>;
   const size_t smem = CwCfg<NI, NB>::smem_bytes(WPC, false, true);
   static KernelSetup ks;
   int per_sm = 0;
@@ -70,21 +70,9 @@ static int launch_cw_gen_shape(ghb_ctx* ctx, const Plan& p, CwArgs& ar) {
   return launch_cw_gen<NI, NB, true, false>(ctx, p, ar);
 }
 
-int launch_condense_cw_gen(ghb_ctx* ctx, const Plan& p, int64_t ncells, int ntab, const double* TA, const double* Tb,
-                           const double* coef, double* S, double* g, int32_t* info, const ScatterArgs* sc) {
-  if (!cw_gen_supported(p)) return fail(ctx, GHB_EUNSUPPORTED, "condense_cw<GEN>: plan without a tuned cell-warp kernel");
-  if (ntab < 1 || ntab > 16) return fail(ctx, GHB_EINVAL, "condense_cw<GEN>: need 1 <= ntab <= 16");
-  CwArgs ar;
-  cw_fill_args(p, ar);
-  ar.nzval = sc ? sc->nzval : nullptr;
-  ar.colpos = sc ? sc->colpos : nullptr;
-  ar.rowrank = sc ? sc->rowrank : nullptr;
-  ar.keepS = sc ? sc->keepS : nullptr;
-  ar.ncells = ncells;
-  ar.A = nullptr; ar.b = nullptr; ar.S = S; ar.g = g; ar.info = info; ar.X = nullptr;
-  ar.coef = coef; ar.ntab = ntab;
-  // TMA bulk copies need 16-byte aligned table rows: odd record lengths (or unaligned caller tables) go through a padded
-  // copy owned by the context (ntab rows of lenAp = lenA + (lenA & 1) doubles, zero padding; 8 (lenA + lenb) ntab bytes)
+// tables for the TMA copies: 16-byte aligned rows (odd record lengths or unaligned caller tables go through a zero-padded
+// copy owned by the context: ntab rows of lenAp = lenA + (lenA & 1) doubles)
+static int gen_tables(ghb_ctx* ctx, const Plan& p, int ntab, const double* TA, const double* Tb, CwArgs& ar) {
   ar.lenAp = p.lenA + (p.lenA & 1); ar.lenbp = p.lenb + (p.lenb & 1);
   if (ar.lenAp != p.lenA || ar.lenbp != p.lenb || (((uintptr_t)TA | (uintptr_t)Tb) & 15)) {
     const size_t need = (size_t)ntab * (ar.lenAp + ar.lenbp) * sizeof(double);
@@ -103,10 +91,50 @@ int launch_condense_cw_gen(ghb_ctx* ctx, const Plan& p, int64_t ncells, int ntab
   } else {
     ar.TA = TA; ar.Tb = Tb;
   }
+  return GHB_OK;
+}
+
+int launch_condense_cw_gen(ghb_ctx* ctx, const Plan& p, int64_t ncells, int ntab, const double* TA, const double* Tb,
+                           const double* coef, double* S, double* g, int32_t* info, const ScatterArgs* sc) {
+  if (!cw_gen_supported(p)) return fail(ctx, GHB_EUNSUPPORTED, "condense_cw<GEN>: plan without a tuned cell-warp kernel");
+  if (ntab < 1 || ntab > 16) return fail(ctx, GHB_EINVAL, "condense_cw<GEN>: need 1 <= ntab <= 16");
+  CwArgs ar;
+  cw_fill_args(p, ar);
+  ar.nzval = sc ? sc->nzval : nullptr;
+  ar.colpos = sc ? sc->colpos : nullptr;
+  ar.rowrank = sc ? sc->rowrank : nullptr;
+  ar.keepS = sc ? sc->keepS : nullptr;
+  ar.ncells = ncells;
+  ar.A = nullptr; ar.b = nullptr; ar.S = S; ar.g = g; ar.info = info; ar.X = nullptr;
+  ar.coef = coef; ar.ntab = ntab;
+  GHB_TRY(gen_tables(ctx, p, ntab, TA, Tb, ar));
 #define X(a, b) if (p.n_i == a && p.n_b == b) return launch_cw_gen_shape<a, b>(ctx, p, ar);
   GHB_CW_SHAPES(X)
 #undef X
   return fail(ctx, GHB_EUNSUPPORTED, "condense_cw<GEN>: shape not instantiated");
+}
+
+// backward map with the records formed in the loader: u_K = A11^-1 (b1 - A12 lambda_K) straight from the coefficient
+// vectors -- with ghb_condense_assemble_affine_f64 the whole solve runs without the records ever existing in HBM
+int launch_backsub_cw_gen(ghb_ctx* ctx, const Plan& p, int64_t ncells, int ntab, const double* TA, const double* Tb,
+                          const double* coef, const double* lam_free, const double* lam_dir, const int64_t* ids, double* u,
+                          int32_t* info) {
+  if (!cw_gen_supported(p)) return fail(ctx, GHB_EUNSUPPORTED, "backsub_cw<GEN>: plan without a tuned cell-warp kernel");
+  if (ntab < 1 || ntab > 16) return fail(ctx, GHB_EINVAL, "backsub_cw<GEN>: need 1 <= ntab <= 16");
+  CwArgs ar;
+  cw_fill_args(p, ar);
+  ar.nzval = nullptr; ar.colpos = nullptr; ar.rowrank = nullptr; ar.keepS = nullptr;
+  ar.ncells = ncells;
+  ar.A = nullptr; ar.b = nullptr; ar.S = nullptr; ar.g = nullptr; ar.info = info; ar.X = nullptr;
+  ar.coef = coef; ar.ntab = ntab;
+  ar.lam_free = lam_free; ar.lam_dir = lam_dir; ar.ids = ids; ar.u = u;
+  GHB_TRY(gen_tables(ctx, p, ntab, TA, Tb, ar));
+#define X(a, b) \
+  if (p.n_i == a && p.n_b == b) \
+    return p.all_touched ? launch_cw_gen<a, b, false, false, false, true>(ctx, p, ar) : launch_cw_gen<a, b, true, false, false, true>(ctx, p, ar);
+  GHB_CW_SHAPES(X)
+#undef X
+  return fail(ctx, GHB_EUNSUPPORTED, "backsub_cw<GEN>: shape not instantiated");
 }
 
 }  // namespace ghb

@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
   constexpr int BTM = C::BTM;
   static_assert(!PAD || (SPARSE && NI % 8 == 0), "PAD kernels are instantiated for padded shapes");
   static_assert(!Q4 || (!PAD && !BACK && C::BTM == 5 && NB % 4 == 0 && NB < 40), "Q4: four interleaved row tiles + a short fifth");
-  static_assert(!BACK || (!KEEPX && !SCAT && !GEN), "BACK kernels: the backward map on resident records");
+  static_assert(!BACK || (!KEEPX && !SCAT), "BACK kernels: the backward map (resident records, or GEN: records formed in the loader)");
   static_assert(!GEN || (!PAD && WPC <= 8), "GEN kernels: tuned shapes, at most 8 cells per batch (rows of a DMMA tile)");
   const int nir = PAD ? ar.n_i : NI, nbr = PAD ? ar.n_b : NB;       // real sizes
   const int NC = nbr + 1;                                           // right-hand-side columns: A12 | b1
@@ -1120,10 +1120,10 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
             if (PAD) {
               if (o[j][e] >= 0 && cAl) {
                 const int base = (int)lds_u32(a_colbase + 4u * (unsigned)((nir + col) * nf + (o[j][e] >> 8)));
-                if (base >= 0) v = __ldg(Arec + base + (o[j][e] & 0xff));
+                if (base >= 0) v = ldrec<GEN>(Arec + base + (o[j][e] & 0xff));
               }
             } else {
-              if (o[j][e] >= 0 && cAl) v = __ldg(Arec + o[j][e]);
+              if (o[j][e] >= 0 && cAl) v = ldrec<GEN>(Arec + o[j][e]);
               o[j][e] += st8[j][e];
             }
             racc[j][e] = fma(-v, lamv, racc[j][e]);
@@ -1147,11 +1147,11 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
               unsigned short si;
               asm volatile("ld.shared.u16 %0, [%1];" : "=h"(si) : "r"(a_rowinfo + (row << 1)));
               const int base = (int)lds_u32(a_colbase + 4u * (unsigned)(ntot * nf + (int)(si >> 8)));
-              bv = __ldg(brec + base + (int)(si & 0xffu));
+              bv = ldrec<GEN>(brec + base + (int)(si & 0xffu));
             } else {
               unsigned short h;
               asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(a_rowb + (row << 1)));
-              bv = __ldg(brec + (int)h);
+              bv = ldrec<GEN>(brec + (int)h);
             }
             T[j][e] = bv + r;
           } else {

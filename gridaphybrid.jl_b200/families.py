@@ -68,6 +68,17 @@ class AffineRecordFamily:
         ctx.condense_affine(plan, ncells, self.ntab, TA, Tb, coef.contiguous(), S, g, info)
         return S, g
 
+    def backsub(self, ctx: Context, plan: BlockPlan, coef: torch.Tensor, lambda_free, lambda_dirichlet, cell_ids, u=None,
+                info=None):
+        """backward map u_K = A11^-1 (b1 - A12 lambda_K) from the coefficient vectors (`ghb_backsub_affine_f64`)."""
+        ncells = int(coef.shape[0])
+        TA, Tb = self._tables(coef.device)
+        if u is None:
+            u = torch.empty((ncells, plan.n_i), dtype=torch.float64, device=coef.device)
+        ctx.use_torch_stream()
+        ctx.backsub_affine(plan, ncells, self.ntab, TA, Tb, coef.contiguous(), lambda_free, lambda_dirichlet, cell_ids, u, info)
+        return u
+
     def condense_assemble(self, ctx: Context, plan: BlockPlan, coef: torch.Tensor, dirichlet_vals, nzval, rhs, info=None):
         """coefficients -> CSC values + rhs of the selected symbolic pattern (`ghb_condense_assemble_affine_f64`)."""
         TA, Tb = self._tables(coef.device)

@@ -78,14 +78,15 @@ def _compute_hybridizable_from_skeleton_free_dof_values(lh_free, lh_dirichlet, a
     ctx = assem.ctx
     k = BackwardStaticCondensationMap(bulk_fields, skeleton_fields)
     plan = k.static_condensation.plan(matvec, ctx)
-    if hasattr(matvec, "family"):
-        matvec.materialise(ctx, plan)            # the backward map reads the records (bit-identical to the ones condensed)
     n = len(matvec)
     dev = assem.cell_ids.device
     u = torch.empty((n, plan.n_i), dtype=torch.float64, device=dev)
     info = torch.empty((n,), dtype=torch.int32, device=dev)
     ctx.use_torch_stream()
-    ctx.backsub(plan, n, matvec.A, matvec.b, lh_free, lh_dirichlet, assem.cell_ids, u, info)
+    if hasattr(matvec, "family"):                # lazy affine family: the records are formed in the loader here as well
+        matvec.family.backsub(ctx, plan, matvec.coef, lh_free, lh_dirichlet, assem.cell_ids, u, info)
+    else:
+        ctx.backsub(plan, n, matvec.A, matvec.b, lh_free, lh_dirichlet, assem.cell_ids, u, info)
     x = torch.empty(n * plan.n_i + lh_free.numel(), dtype=torch.float64, device=dev)
     ctx.scatter_free_dof_values(plan, n, u, lh_free, x)
     return x

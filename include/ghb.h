@@ -135,6 +135,14 @@ int ghb_condense_affine_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, int ntab,
 int ghb_condense_assemble_affine_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, int ntab, const double* TA,
                                      const double* Tb, const double* coef, const double* dirichlet_vals,
                                      int64_t ndirichlet, double* nzval, double* rhs, int32_t* info);
+/* ... and the backward map (a11, src/BackwardStaticCondensationMap.jl:84-99) of the same family: u_K = A11^-1 (b1 -
+ * A12 lambda_K) with the records formed in the loader; arguments as ghb_backsub_f64.  With
+ * ghb_condense_assemble_affine_f64 the whole solve runs without the 8(lenA+lenb) bytes per cell ever existing in HBM.
+ * Bit-identical to ghb_expand_records_f64 + ghb_backsub_f64. */
+int ghb_backsub_affine_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, int ntab, const double* TA, const double* Tb,
+                           const double* coef, const double* lambda_free, int64_t nlambda_free,
+                           const double* lambda_dirichlet, int64_t nlambda_dirichlet, const int64_t* cell_ids, double* u,
+                           int32_t* info);
 
 /* ---- (f-3) bulk -> skeleton L2 projection dofs --------------------------------------------------
  * replaces compute_bulk_to_skeleton_l2_projection_dofs (src/GridapAPIExtensions.jl:453-500; called per (cell, local facet)

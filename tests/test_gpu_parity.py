@@ -724,6 +724,36 @@ def test_affine_family_condensed_in_the_loader(ctx, name, ntab, ncells):
     assert np.array_equal(i2, i0[:n2].cpu().numpy())
 
 
+@pytest.mark.parametrize("name", CW_GEN_NAMES + ["C1_hdg_k1_2d", "hencky_k1_2d"])
+@pytest.mark.parametrize("ntab,ncells", [(1, 9), (7, 2501), (16, 333)])
+def test_affine_family_backward_map_in_the_loader(ctx, name, ntab, ncells):
+    """ghb_backsub_affine_f64: the backward map with the records formed inside the kernel (GEN + BACK instantiations) is
+    BIT-equal to ghb_expand_records_f64 + ghb_backsub_f64 -- tuned cell-warp shapes, plans that fall back to chunked
+    expansion, singular cells (NaN + info), with and without Dirichlet values, host pointers."""
+    plan = _dev_plan(ctx, name)
+    fam, rng = _random_family(ctx, plan, ntab, ntab * 77 + ncells)
+    coef = np.concatenate([np.ones((ncells, 1)), rng.uniform(-1, 1, (ncells, ntab - 1))], axis=1)
+    coef[ncells // 2] = 0.0
+    coef_d = torch.as_tensor(coef, device="cuda")
+    cells = fam.expand(ctx, plan, coef_d)
+    nfree, ndir = 200, 30
+    ids = rng.integers(1, nfree + 1, (ncells, plan.n_b))
+    neg = rng.random((ncells, plan.n_b)) < 0.15
+    ids[neg] = -rng.integers(1, ndir + 1, int(neg.sum()))
+    lam_f, lam_d = rng.standard_normal(nfree), rng.standard_normal(ndir)
+    ids_d, lf, ld = torch.as_tensor(ids, device="cuda"), torch.as_tensor(lam_f, device="cuda"), torch.as_tensor(lam_d, device="cuda")
+    for dvals in (ld, None):
+        u0 = torch.empty((ncells, plan.n_i), dtype=torch.float64, device="cuda"); i0 = torch.empty(ncells, dtype=torch.int32, device="cuda")
+        ctx.backsub(plan, ncells, cells.A, cells.b, lf, dvals, ids_d, u0, i0)
+        i1 = torch.full((ncells,), -5, dtype=torch.int32, device="cuda")
+        u1 = fam.backsub(ctx, plan, coef_d, lf, dvals, ids_d, info=i1)
+        assert torch.equal(i0, i1) and int((i1 != 0).sum()) == 1 and int(i1[ncells // 2]) == 1
+        assert np.array_equal(u0.cpu().numpy(), u1.cpu().numpy(), equal_nan=True)
+    u2 = np.empty((ncells, plan.n_i)); i2 = np.empty(ncells, dtype=np.int32)
+    ctx.backsub_affine(plan, ncells, ntab, fam.TA, fam.Tb, coef, lam_f, None, ids, u2, i2)      # host pointers
+    assert np.array_equal(u2, u1.cpu().numpy(), equal_nan=True) and np.array_equal(i2, i1.cpu().numpy())
+
+
 @pytest.mark.parametrize("name,dims,ndofs_f", [("C3_hdg_k2_3d", (6, 5, 4), 6), ("C2_rth_k2_2d", (9, 7), 3),
                                                ("elasticity_k1_2d", (6, 5), 4), ("C1_hdg_k1_2d", (7, 6), 2)])
 def test_affine_family_to_csc_in_one_call(ctx, name, dims, ndofs_f):

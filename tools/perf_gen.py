@@ -72,6 +72,24 @@ if not eq:
     d = (S - S2).abs().max().item()
     print("max |dS|", d, "nan:", int(torch.isnan(S2).sum()))
     sys.exit(1)
+# backward map from coefficients
+nfree = 100000
+ids = torch.randint(1, nfree + 1, (n, plan.n_b), device="cuda", dtype=torch.int64)
+lam = torch.randn(nfree, dtype=torch.float64, device="cuda")
+u = torch.empty((n, plan.n_i), dtype=torch.float64, device="cuda"); u2 = torch.empty_like(u)
+tb0 = timed(lambda: ctx.backsub(plan, n, A, b, lam, None, ids, u, info))
+
+
+def back2():
+    fam.expand(ctx, plan, coef, A, b)
+    ctx.backsub(plan, n, A, b, lam, None, ids, u, info)
+
+
+tb2 = timed(back2)
+tbf = timed(lambda: fam.backsub(ctx, plan, coef, lam, None, ids, u2, info2))
+print(f"backsub (resident records):   {tb0:.2f} ms = {n / tb0 / 1e3:.1f} M cells/s")
+print(f"expand + backsub:             {tb2:.2f} ms = {n / tb2 / 1e3:.1f} M cells/s")
+print(f"backsub_affine (in the loader): {tbf:.2f} ms = {n / tbf / 1e3:.1f} M cells/s   bit-equal: {bool(torch.equal(u, u2))}")
 if os.environ.get("ASSEMBLE", "1") == "1" and shape == "C3":
     sk = gh.CartesianSkeleton(dims, ctx)
     M = gh.FacetFESpace(sk, 6, sk.facet_is_boundary())
