@@ -91,9 +91,9 @@ class AffineRecordFamily:
 class AffineCells:
     """Lazy cell array of an affine family: what the reference's `lazy_map(::IntegrationMap, ...)` array is to its
     assembler -- cell (A_K, b_K) exists only while it is being condensed.  `lazy_map(StaticCondensationMap(...), cells)`
-    condenses it through `ghb_condense_affine_f64` (records formed in the loader of the condensation kernel, never in
-    HBM); `.A`, `.b` materialise the packed records on first use (the backward map reads them), bit-identical to what the
-    kernel formed."""
+    condenses it through `ghb_condense_affine_f64` and the operators recover the bulk unknowns through
+    `ghb_backsub_affine_f64` (records formed in the loader of the kernels, never in HBM); `materialise` writes the packed
+    records out for callers that want them (bit-identical to what the kernels formed)."""
 
     def __init__(self, family: AffineRecordFamily, coef: torch.Tensor, ndofs, touched, ctx: Context | None = None):
         self.family, self.coef = family, coef.contiguous()
