@@ -447,6 +447,32 @@ def run_ours(args):
         if not fused:
             ctx.condense(plan, ncells, A, b, S, g, info)      # leave all of S_K behind for the legs below
 
+    # ---- launch-bound configurations (records smaller than L2, e.g. C1: 1 024 cells): the step captured in a CUDA graph
+    # (the C-ABI calls with device pointers are pure launch sequences on the context's stream) and replayed
+    graph_leg = None
+    if world == 1 and nchunk == 1 and ncells * (lenA + lenb) * 8 <= 256e6:
+        gph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(gph):
+            ctx.use_torch_stream()                              # the capture stream
+            ctx.condense(plan, ncells, A, b, S, g, info)
+            slab.assemble(S, g, nzval, rhs)
+        ctx.use_torch_stream()
+        nrep = max(20, args.steps)
+        for _ in range(3):
+            gph.replay()
+        barrier()
+        q0, q1 = ev(), ev()
+        q0.record()
+        for _ in range(nrep):
+            gph.replay()
+        q1.record()
+        barrier()
+        gms = q0.elapsed_time(q1) / nrep
+        graph_leg = {"value": total_cells / (gms * 1e-3), "unit": "cells/s", "ms_per_step": gms,
+                     "note": "the same two-kernel step captured once in a CUDA graph and replayed (launch-bound configuration)"}
+        del gph
+
     # ---- N > 1: the assembled system against a local property of the condensed cells (no second copy of the mesh needed):
     # sum(nzval) over all ranks == sum over all cells of the free-free entries of S_K (cut-plane contributions included)
     check = None
@@ -658,7 +684,7 @@ def run_ours(args):
                 "clocks": clk.summary(), "e2e": e2e, "e2e_pageable": e2e_pageable, "e2e_affine_family": e2e_affine,
                 "gpu_launches": int(launches),
                 "roofline": roof, "cpu_baseline": cpu_base, "backsub": backsub, "device_generated_records": devgen,
-                "multi_gpu_check": check, ("two_kernel_step" if fused else "fused_assembly"): other}
+                "multi_gpu_check": check, ("two_kernel_step" if fused else "fused_assembly"): other, "cuda_graph_step": graph_leg}
         print(json.dumps(line))
     if world > 1:
         ctx.comm_destroy()

@@ -1011,6 +1011,43 @@ def test_cellwarp_backward_map(ctx, name):
         assert rel_err_cells(res[0][0][ok], res[1][0][ok]) < TOL
 
 
+def test_step_captured_in_a_cuda_graph(ctx):
+    """launch-bound meshes (C1: 32 x 32 cells): the C-ABI calls with device pointers are pure launch sequences on the
+    context's stream, so condense -> assemble can be captured once in a CUDA graph and replayed; results bit-equal to the
+    eager step, also after the records changed in place."""
+    plan = _dev_plan(ctx, "C1_hdg_k1_2d")
+    sk = gh.CartesianSkeleton((32, 32), ctx)
+    M = gh.FacetFESpace(sk, 2, sk.facet_is_boundary())
+    assem = gh.SparseMatrixAssembler(M)
+    colptr, rowval, nnz = assem.symbolic()
+    n = sk.ncells
+    A, b = _synth(ctx, plan, 0, n)
+    S = torch.empty((n, plan.n_b ** 2), dtype=torch.float64, device="cuda"); g = torch.empty((n, plan.n_b), dtype=torch.float64, device="cuda")
+    info = torch.empty(n, dtype=torch.int32, device="cuda")
+    nz = torch.empty(nnz, dtype=torch.float64, device="cuda"); rhs = torch.empty(assem.nrows, dtype=torch.float64, device="cuda")
+
+    def step():
+        ctx.use_torch_stream()
+        assem.select()
+        ctx.condense(plan, n, A, b, S, g, info)
+        ctx.assemble_numeric(S, g, None, nz, rhs)
+
+    step()                                                   # warm-up: one-time kernel attributes outside the capture
+    torch.cuda.synchronize()
+    gph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gph):
+        step()
+    ctx.use_torch_stream()
+    for seed in (0, 5):
+        ctx.synth_fill(plan, seed * 1000, n, A, b)           # new records in the same buffers
+        step()
+        ref = (nz.clone(), rhs.clone())
+        nz.fill_(float("nan")); rhs.fill_(float("nan"))
+        gph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(nz, ref[0]) and torch.equal(rhs, ref[1]) and not bool(info.any())
+
+
 def test_cellwarp_pivot_ties_follow_lapack(ctx):
     """columns whose maxima tie exactly (or to within 2^-15) must pivot like dgetf2's idamax (first exact maximum): cells
     built from small integers make every elimination exact, so S agrees with the LAPACK oracle to rounding of the Schur
