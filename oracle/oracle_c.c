@@ -249,3 +249,109 @@ int ora_backsub(int nfields, const int32_t* ndofs, const int64_t* block_offset, 
   j.A = A; j.b = b; j.x = x; j.u = u; j.info = info;
   return ora_run(ora_backsub_worker, &j, ncells, nthreads);
 }
+
+/* ---- assembly of the condensed cells: Gridap's COO numeric loop + SparseArrays.sparse! -------------------------------
+ * `assemble_matrix_and_vector(SparseMatrixAssembler(M,L), data)` (/root/reference/src/HybridAffineFEOperators.jl:46) ends
+ * in Gridap's numeric loop (cells ascending, `for lj, for li`, push (i,j,v) when both ids are positive) followed
+ * by `sparse(I,J,V,m,n)`.  The latter lives in Julia's SparseArrays standard library (not in /root/reference; shipped with
+ * the pinned Julia 1.x): its published algorithm `sparse!` is restated here step by step --
+ *   (1) row counts -> shifted row pointers, (2) counting sort of (J,V) by row into an unsorted CSR with repeats,
+ *   (3) one sweep that combines the repeats of every row in COO order with the single auxiliary array klasttouch and
+ *       counts the entries per column, (4) column pointers, (5) counting sort of the CSR into the CSC (rows ascending
+ *       inside a column because the rows are visited in order).
+ * Serial, like the reference.  Outputs are Julia's: colptr [nfree+1] and rowval 1-based, duplicates summed in COO order,
+ * stored zeros kept.  Returns nnz, or -1 if `cap` (capacity of rowval / nzval) is too small, -2 if out of memory.
+ * Used by tests (against oracle.julia_sparse) and as the timed CPU baseline of bench.py. */
+int64_t ora_assemble_coo_csc(int64_t ncells, int n_b, const int64_t* ids, const double* S, const double* g, int64_t nfree,
+                             int64_t* colptr, int64_t* rowval, double* nzval, double* rhs, int64_t cap) {
+  const int64_t m = nfree, n = nfree;
+  /* Gridap's symbolic pass: count the triplets, then the numeric pass fills them */
+  int64_t coolen = 0;
+  for (int64_t c = 0; c < ncells; ++c) {
+    const int64_t* id = ids + c * n_b;
+    int np = 0;
+    for (int l = 0; l < n_b; ++l) np += id[l] > 0;
+    coolen += (int64_t)np * np;
+  }
+  int64_t* I = (int64_t*)malloc((size_t)(coolen > 0 ? coolen : 1) * sizeof(int64_t));
+  int64_t* J = (int64_t*)malloc((size_t)(coolen > 0 ? coolen : 1) * sizeof(int64_t));
+  double* V = (double*)malloc((size_t)(coolen > 0 ? coolen : 1) * sizeof(double));
+  int64_t* csrrowptr = (int64_t*)calloc((size_t)m + 2, sizeof(int64_t));
+  int64_t* csrcolval = (int64_t*)malloc((size_t)(coolen > 0 ? coolen : 1) * sizeof(int64_t));
+  double* csrnzval = (double*)malloc((size_t)(coolen > 0 ? coolen : 1) * sizeof(double));
+  int64_t* klasttouch = (int64_t*)calloc((size_t)n + 1, sizeof(int64_t));
+  if (!I || !J || !V || !csrrowptr || !csrcolval || !csrnzval || !klasttouch) {
+    free(I); free(J); free(V); free(csrrowptr); free(csrcolval); free(csrnzval); free(klasttouch);
+    return -2;
+  }
+  for (int64_t i = 0; i < m; ++i) rhs[i] = 0.0;
+  int64_t k = 0;
+  for (int64_t c = 0; c < ncells; ++c) {
+    const int64_t* id = ids + c * n_b;
+    const double* Sc = S + c * (int64_t)n_b * n_b;
+    for (int lj = 0; lj < n_b; ++lj) {
+      if (id[lj] <= 0) continue;
+      for (int li = 0; li < n_b; ++li)
+        if (id[li] > 0) { I[k] = id[li]; J[k] = id[lj]; V[k] = Sc[li + (int64_t)lj * n_b]; ++k; }
+    }
+    for (int li = 0; li < n_b; ++li)
+      if (id[li] > 0) rhs[id[li] - 1] += g[c * n_b + li];
+  }
+  /* sparse!: (1) row counts, shifted forward by one (1-based arithmetic kept: csrrowptr[i] is Julia's csrrowptr[i]) */
+  for (k = 0; k < coolen; ++k) csrrowptr[I[k] + 1] += 1;
+  int64_t countsum = 1;
+  csrrowptr[1] = 1;
+  for (int64_t i = 2; i <= m + 1; ++i) { const int64_t ov = csrrowptr[i]; csrrowptr[i] = countsum; countsum += ov; }
+  /* (2) counting sort of (J, V) into the CSR arrays; the write positions correct the row pointers */
+  for (k = 0; k < coolen; ++k) {
+    const int64_t Ik = I[k], csrk = csrrowptr[Ik + 1];
+    csrrowptr[Ik + 1] = csrk + 1;
+    csrcolval[csrk - 1] = J[k];
+    csrnzval[csrk - 1] = V[k];
+  }
+  /* (3) combine repeats row by row, count per column (colptr used as csccolptr, shifted forward by one) */
+  for (int64_t j = 0; j <= n; ++j) colptr[j] = 0;
+  int64_t writek = 1, newcsrrowptri = 1, origcsrrowptri = 1, origcsrrowptrip1 = m >= 1 ? csrrowptr[2] : 1;
+  for (int64_t i = 1; i <= m; ++i) {
+    for (int64_t readk = origcsrrowptri; readk < origcsrrowptrip1; ++readk) {
+      const int64_t j = csrcolval[readk - 1];
+      if (klasttouch[j] < newcsrrowptri) {
+        klasttouch[j] = writek;
+        if (writek != readk) { csrcolval[writek - 1] = j; csrnzval[writek - 1] = csrnzval[readk - 1]; }
+        ++writek;
+        colptr[j] += 1;                                   /* Julia: csccolptr[j+1] += 1 (array is 0-based here) */
+      } else {
+        const int64_t klt = klasttouch[j];
+        csrnzval[klt - 1] = csrnzval[klt - 1] + csrnzval[readk - 1];     /* combine = + , in COO order */
+      }
+    }
+    newcsrrowptri = writek;
+    origcsrrowptri = origcsrrowptrip1;
+    if (origcsrrowptrip1 != writek) csrrowptr[i + 1] = writek;
+    if (i < m) origcsrrowptrip1 = csrrowptr[i + 2];
+  }
+  /* (4) column pointers: slot j of colptr (0-based) plays Julia's csccolptr[j+1]; after the shift slot j holds the start
+   *     of column j (1-based columns), and step (5) advances it to the start of column j+1 -- i.e. slot j ends up as
+   *     Julia's final colptr[j+1], slot 0 stays colptr[1] = 1 */
+  countsum = 1;
+  colptr[0] = 1;
+  for (int64_t j = 1; j <= n; ++j) { const int64_t ov = colptr[j]; colptr[j] = countsum; countsum += ov; }
+  const int64_t nnz = countsum - 1;
+  int64_t rc = nnz;
+  if (nnz > cap) {
+    rc = -1;
+  } else {
+    /* (5) counting sort of the CSR into the CSC; the write positions correct the column pointers */
+    for (int64_t i = 1; i <= m; ++i) {
+      for (int64_t csrk = csrrowptr[i]; csrk < csrrowptr[i + 1]; ++csrk) {
+        const int64_t j = csrcolval[csrk - 1];
+        const int64_t csck = colptr[j];
+        colptr[j] = csck + 1;
+        rowval[csck - 1] = i;
+        nzval[csck - 1] = csrnzval[csrk - 1];
+      }
+    }
+  }
+  free(I); free(J); free(V); free(csrrowptr); free(csrcolval); free(csrnzval); free(klasttouch);
+  return rc;
+}

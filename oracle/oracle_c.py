@@ -74,3 +74,28 @@ def backsub(plan, A, b, x, nthreads=0):
                            _p(info, ctypes.c_int32), ctypes.c_int(nthreads))
     assert rc == 0
     return u, info
+
+
+def assemble_coo_csc(S, g, cell_ids, nfree):
+    """Gridap's COO numeric loop + SparseArrays.sparse! (serial C restatement, oracle_c.c): S [ncells, n_b*n_b] column-major
+    per cell, g [ncells, n_b], cell_ids [ncells, n_b] (1-based, <= 0 not assembled) -> (colptr, rowval, nzval, rhs),
+    Int64 1-based like SparseMatrixCSC{Float64,Int64}."""
+    S = np.ascontiguousarray(S, dtype=np.float64)
+    g = np.ascontiguousarray(g, dtype=np.float64)
+    ids = np.ascontiguousarray(cell_ids, dtype=np.int64)
+    ncells, n_b = ids.shape
+    cap = int(((ids > 0).sum(axis=1) ** 2).sum())
+    colptr = np.empty(nfree + 1, dtype=np.int64)
+    rowval = np.empty(max(cap, 1), dtype=np.int64)
+    nzval = np.empty(max(cap, 1), dtype=np.float64)
+    rhs = np.empty(nfree, dtype=np.float64)
+    L = lib()
+    L.ora_assemble_coo_csc.restype = ctypes.c_int64
+    L.ora_assemble_coo_csc.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_int64]
+    nnz = L.ora_assemble_coo_csc(ncells, n_b, ids.ctypes.data, S.ctypes.data, g.ctypes.data, nfree, colptr.ctypes.data,
+                                 rowval.ctypes.data, nzval.ctypes.data, rhs.ctypes.data, cap)
+    if nnz < 0:
+        raise RuntimeError(f"ora_assemble_coo_csc failed: {nnz}")
+    return colptr, rowval[:nnz].copy(), nzval[:nnz].copy(), rhs

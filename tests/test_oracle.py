@@ -233,3 +233,22 @@ def test_l2_projection_block_overloads_restatement():
     tf = np.array([True, False])
     r, t = o.l2_projection_dofs_blocks(([(aa, tA), None], tf), ([(bb, tB), None], tf))
     assert t.tolist() == [True, False] and r[1] is None and r[0][1].tolist() == [[False, False, True]]
+
+
+@pytest.mark.parametrize("seed,nb,shared", [(0, 6, True), (1, 4, False), (2, 9, True)])
+def test_c_assembly_equals_julia_sparse_restatement(seed, nb, shared):
+    """oracle_c.ora_assemble_coo_csc (Gridap's COO numeric loop + the step-by-step restatement of SparseArrays.sparse!,
+    the timed CPU baseline) against the oracle's literal `sparse(I,J,V)` semantics: colptr / rowval bit-equal, values
+    bit-equal (duplicates summed in COO order, also with more than two contributions per entry), rhs, Dirichlet ids
+    skipped, empty columns."""
+    rng = np.random.default_rng(seed)
+    nc, nfree = 37, 60 if shared else 37 * nb + 5
+    ids = np.stack([rng.choice(np.arange(1, nfree + 1), nb, replace=False) for _ in range(nc)])
+    ids[rng.random((nc, nb)) < 0.2] *= -1
+    S = rng.standard_normal((nc, nb * nb)); g = rng.standard_normal((nc, nb))
+    Sc = [S[c].reshape((nb, nb), order="F") for c in range(nc)]
+    c0, r0, z0, b0 = o.assemble_matrix_and_vector(Sc, list(g), ids, nfree)
+    c1, r1, z1, b1 = oc.assemble_coo_csc(S, g, ids, nfree)
+    assert np.array_equal(c0, c1) and np.array_equal(r0, r1) and np.array_equal(z0, z1) and np.array_equal(b0, b1)
+    M = sp.coo_matrix((np.concatenate([[0.0], z1]), (np.concatenate([[0], r1 - 1]), np.concatenate([[0], np.repeat(np.arange(nfree), np.diff(c1))]))), shape=(nfree, nfree))
+    assert M.nnz >= len(z1)
