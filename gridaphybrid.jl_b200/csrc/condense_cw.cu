@@ -66,10 +66,12 @@ static void cw_tables(const Plan& p, std::vector<uint2>& ld, std::vector<uint32_
       ld.push_back(make_uint2(src, dst));
     }
   std::stable_sort(ld.begin(), ld.end(), [](const uint2& x, const uint2& y) { return x.x < y.x; });
-  // padding of the last batch: zeros into the dummy row (plans with untouched blocks) or record element 0 into the scale
-  // array, which every panel rewrites before use (the copies of fully touched plans carry no zero-fill predicate)
-  while (ld.size() % 32)
-    ld.push_back(p.all_touched ? make_uint2(0u, C::OFF_SCALEU) : make_uint2(0xffffffffu, (uint32_t)C::DUMMY * C::ROWB));
+  // padding of the last batch (< 32 entries, each with a slot of its own so that no two copies of a batch write the same
+  // address): record element 0 (fully touched plans: their copies carry no zero-fill predicate) or zeros into the stage
+  // tile of panel 0, which the first panel rewrites completely before anything reads it
+  static_assert(NI >= 8, "a full first panel");
+  for (uint32_t i = 0; ld.size() % 32; ++i)
+    ld.push_back(make_uint2(p.all_touched ? 0u : 0xffffffffu, C::OFF_INVL + 8u * i));
   rowA12.assign(NI + 1, 0xffffffffu);
   rowb.assign(NI + 1, 0);
   for (int r = 0; r < NI && r < p.n_i; ++r) {
