@@ -89,3 +89,25 @@ elif which == "expand":
         ctx.expand_records(plan, n, ntab, TA, Tb, coef, A, b)
     torch.cuda.synchronize()
     print("expand", n)
+elif which in ("cw_back", "cw_gen", "cw_gen_back"):
+    plan = ctx.plan_blocks([30, 4, 36], ONES, [1, 2], [3])
+    n, ntab = 1 << 17, 7
+    A, b = records(plan, n)
+    rng = np.random.default_rng(0)
+    fam = gh.AffineRecordFamily(np.concatenate([A[:1].cpu().numpy(), 1e-3 * rng.standard_normal((ntab - 1, plan.lenA))]),
+                                np.concatenate([b[:1].cpu().numpy(), 1e-3 * rng.standard_normal((ntab - 1, plan.lenb))]))
+    coef = torch.cat([torch.ones((n, 1), dtype=torch.float64, device="cuda"), torch.rand((n, ntab - 1), dtype=torch.float64, device="cuda")], dim=1)
+    ids = torch.randint(1, 100001, (n, plan.n_b), device="cuda", dtype=torch.int64)
+    lam = torch.randn(100000, dtype=torch.float64, device="cuda")
+    u = torch.empty((n, plan.n_i), dtype=torch.float64, device="cuda")
+    S = torch.empty((n, plan.n_b ** 2), dtype=torch.float64, device="cuda"); g = torch.empty((n, plan.n_b), dtype=torch.float64, device="cuda")
+    info = torch.empty(n, dtype=torch.int32, device="cuda")
+    for _ in range(3):
+        if which == "cw_back":
+            ctx.backsub(plan, n, A, b, lam, None, ids, u, info)
+        elif which == "cw_gen":
+            fam.condense(ctx, plan, coef, S, g, info)
+        else:
+            fam.backsub(ctx, plan, coef, lam, None, ids, u, info)
+    torch.cuda.synchronize()
+    print(which, n, "info", int(info.abs().sum()))
