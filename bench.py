@@ -555,6 +555,18 @@ def run_ours(args):
         e2e_pageable = {"value": sn * world / dtp, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "h2d_gbs_aggregate": h2d * world / dtp / 1e9,
                         "sample": "same sample, pageable numpy arrays in and out (pinned staging inside the library)"}
+        # the same numpy arrays page-locked in place through the C ABI (ghb_host_register: what a Julia glue does once per
+        # array): copied from at the PCIe rate like torch's pinned tensors; the registration itself is timed separately
+        t0 = time.perf_counter()
+        for arr in (pA, pb, pz, pr):
+            ctx.host_register(arr)
+        reg_s = time.perf_counter() - t0
+        dtr = timed_e2e(pA, pb, pz, pr, pi, max(2, args.steps // 2))
+        for arr in (pA, pb, pz, pr):
+            ctx.host_unregister(arr)
+        assert np.array_equal(pz, hz.numpy()), "registered and pinned paths disagree"
+        e2e_pageable["registered_in_place"] = {"value": sn * world / dtr, "unit": "cells/s", "register_seconds_once": reg_s,
+                                               "note": "the same numpy arrays after ghb_host_register (cudaHostRegister)"}
         # informational: past the PCIe ceiling of the record path -- for an affine family the host ships tables + per-cell
         # coefficient vectors (ghb_expand_records_f64 generates the records on the device) and gets the CSC values back
         e2e_affine = None

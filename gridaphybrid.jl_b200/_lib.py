@@ -24,7 +24,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 # every symbol include/ghb.h declares (tests check the library exports each one)
 SYMBOLS = [
     "ghb_create", "ghb_destroy", "ghb_last_error", "ghb_set_stream", "ghb_synchronize", "ghb_launch_count",
-    "ghb_set_option", "ghb_device_alloc", "ghb_device_free", "ghb_copy", "ghb_factors_generation",
+    "ghb_set_option", "ghb_device_alloc", "ghb_device_free", "ghb_copy", "ghb_host_register", "ghb_host_unregister", "ghb_factors_generation",
     "ghb_assemble_current", "ghb_assemble_select", "ghb_assemble_release",
     "ghb_condense_scatter_slab_f64", "ghb_assemble_finish_slab_f64",
     "ghb_comm_unique_id", "ghb_comm_init", "ghb_comm_destroy", "ghb_exchange_cut_plane_f64", "ghb_allgather_lambda_f64",
@@ -162,6 +162,8 @@ def lib():
     L.ghb_device_alloc.argtypes = [vp, i64, ctypes.POINTER(vp)]
     L.ghb_device_free.argtypes = [vp, vp]
     L.ghb_copy.argtypes = [vp, vp, vp, i64]
+    L.ghb_host_register.argtypes = [vp, vp, i64]
+    L.ghb_host_unregister.argtypes = [vp, vp]
     L.ghb_factors_generation.argtypes = [vp]
     L.ghb_factors_generation.restype = i64
     L.ghb_assemble_current.argtypes = [vp]

@@ -104,6 +104,15 @@ class Context:
     def launch_count(self) -> int:
         return int(self._L.ghb_launch_count(self._h))
 
+    def host_register(self, arr):
+        """page-lock a host array in place (numpy array or CPU tensor); pair with host_unregister before it is freed"""
+        a = arr.numpy() if hasattr(arr, "numpy") and not isinstance(arr, np.ndarray) else arr
+        self._check(self._L.ghb_host_register(self._h, ctypes.c_void_p(a.ctypes.data), int(a.nbytes)))
+
+    def host_unregister(self, arr):
+        a = arr.numpy() if hasattr(arr, "numpy") and not isinstance(arr, np.ndarray) else arr
+        self._check(self._L.ghb_host_unregister(self._h, ctypes.c_void_p(a.ctypes.data)))
+
     def set_option(self, name: str, value: int):
         """debugging / A-B knobs (ghb_set_option): "cw", "dmma_ll", "force_generic", "factors_generic",
         "max_ctas_per_sm", "stream_chunk_bytes", ...; kernel-choice knobs act on plans created afterwards"""

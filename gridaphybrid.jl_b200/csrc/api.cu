@@ -183,6 +183,7 @@ void ghb_destroy(ghb_ctx* ctx) {
   if (ctx->comm) comm_free(ctx);
   if (ctx->gen_scratch) cudaFree(ctx->gen_scratch);
   if (ctx->gen_tab) cudaFree(ctx->gen_tab);
+  if (ctx->gen_need) cudaFree(ctx->gen_need);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
@@ -250,6 +251,31 @@ int ghb_copy(ghb_ctx* ctx, void* dst, const void* src, int64_t bytes) {
   cudaSetDevice(ctx->device);
   GHB_CUDA(ctx, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, ctx->stream));
   GHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return GHB_OK;
+}
+
+int ghb_host_register(ghb_ctx* ctx, void* ptr, int64_t bytes) {
+  if (!ctx || !ptr || bytes <= 0) return ctx ? fail(ctx, GHB_EINVAL, "ghb_host_register: bad argument") : GHB_EINVAL;
+  cudaSetDevice(ctx->device);
+  const cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault);
+  if (e != cudaSuccess) {
+    cudaGetLastError();                        // not sticky: do not let the next launch check trip over it
+    return fail(ctx, GHB_ECUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e));
+  }
+  return GHB_OK;
+}
+
+int ghb_host_unregister(ghb_ctx* ctx, void* ptr) {
+  if (!ctx || !ptr) return ctx ? fail(ctx, GHB_EINVAL, "ghb_host_unregister: bad argument") : GHB_EINVAL;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  if (ctx->d2h_stream) cudaStreamSynchronize(ctx->d2h_stream);
+  const cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ctx, GHB_ECUDA, std::string("cudaHostUnregister: ") + cudaGetErrorString(e));
+  }
   return GHB_OK;
 }
 

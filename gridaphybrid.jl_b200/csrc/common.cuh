@@ -132,6 +132,7 @@ struct ghb_ctx {
   // scratch records of the kernels that generate their element records themselves (condense_cw_gen.cu)
   double* gen_scratch = nullptr;
   size_t gen_scratch_bytes = 0;
+  uint16_t* gen_need = nullptr;         // chunk list of the GEN + BACK kernels
   double* gen_tab = nullptr;            // padded copy of the tables (odd record lengths / unaligned caller tables)
   size_t gen_tab_bytes = 0;
 };

@@ -3,6 +3,8 @@
 // matrices the reference condenses; here A_K = sum_t coef[K][t] TA[t] is formed per batch of cells inside the
 // condensation kernel and never written to HBM).  Own translation unit: the GEN instantiations compile in parallel with
 // the resident-record ones of condense_cw.cu.
+#include <vector>
+
 #include "condense_cw_kernel.cuh"
 
 #ifndef GHB_CW_GEN_WPC
@@ -42,6 +44,35 @@ static int launch_cw_gen(ghb_ctx* ctx, const Plan& p, CwArgs& ar) {
   const size_t cap = std::min<size_t>(1028, (size_t)CwCfg<NI, NB>::WARP_BYTES / (2 * (size_t)ar.ntab * 8));
   if (cap < 20) return fail(ctx, GHB_EUNSUPPORTED, "condense_cw<GEN>: image too small to stage the tables");
   ar.gen_E = cap >= 36 ? (int)((cap - 4) & ~(size_t)31) : 16;   // whole groups of four 8-element tiles where the image allows
+  if (BACK) {
+    // the backward map reads A11, A12 and b1 only: the chunks of the record that hold nothing else are not generated
+    const int E = ar.gen_E, nf = p.nfields;
+    const int nchA = (ar.lenAp + E - 1) / E, nchb = (ar.lenbp + E - 1) / E;
+    std::vector<uint16_t> need;
+    auto interior = [&](int f) { return std::find(p.interior.begin(), p.interior.end(), f + 1) != p.interior.end(); };
+    for (int k = 0; k < nchA; ++k) {
+      const int64_t lo = (int64_t)k * E, hi = std::min<int64_t>(lo + E, p.lenA);
+      bool hit = false;
+      for (int fj = 0; fj < nf && !hit; ++fj)
+        for (int fi = 0; fi < nf && !hit; ++fi) {
+          const int64_t bo = p.block_offset[fi + nf * fj];
+          if (bo < 0 || !interior(fi)) continue;                  // block rows of interior fields: A11 and A12
+          hit = bo < hi && bo + (int64_t)p.ndofs[fi] * p.ndofs[fj] > lo;
+        }
+      if (hit) need.push_back((uint16_t)k);
+    }
+    for (int k = 0; k < nchb; ++k) {
+      const int lo = k * E, hi = std::min(lo + E, p.lenb);
+      bool hit = false;
+      for (int f = 0; f < nf && !hit; ++f)
+        hit = interior(f) && p.field_offset_b[f] < hi && p.field_offset_b[f] + p.ndofs[f] > lo;
+      if (hit) need.push_back((uint16_t)(nchA + k));
+    }
+    if (!ctx->gen_need) GHB_CUDA(ctx, cudaMalloc((void**)&ctx->gen_need, 4096 * sizeof(uint16_t)));
+    if (need.size() > 4096) return fail(ctx, GHB_EUNSUPPORTED, "backsub_cw<GEN>: chunk list too long");
+    GHB_CUDA(ctx, cudaMemcpyAsync(ctx->gen_need, need.data(), need.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+    ar.gen_need = ctx->gen_need; ar.gen_nneed = (int)need.size();
+  }
   kern<<<(unsigned)grid, 32 * WPC, smem, ctx->stream>>>(ar);
   GHB_LAUNCHED(ctx);
   return GHB_OK;

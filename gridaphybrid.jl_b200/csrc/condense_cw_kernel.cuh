@@ -179,6 +179,8 @@ struct CwArgs {
   const double* lam_dir;    // Dirichlet skeleton dof values (may be NULL: zeros)
   const int64_t* ids;       // [ncells][n_b] 1-based skeleton dof ids, < 0: Dirichlet
   double* u;                // [ncells][n_i] interior dof values, condensed order
+  const uint16_t* gen_need; // chunks to generate (GEN + BACK: only those that hold A11, A12 or b1), NULL: all
+  int gen_nneed;
   int gen_E;                // table elements per staged chunk (a multiple of 16; 2 buffers x ntab x (gen_E + 4) doubles fit an image)
 };
 
@@ -462,7 +464,8 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
     const int E = ar.gen_E;                                  // elements per chunk, a multiple of 16
     const int RS = E + 4;                                    // row stride of the ring = 4 (mod 16): the B-fragment loads of a half-warp (4 tables x 4 elements) hit 16 distinct banks
     const int lenAp = ar.lenAp, lenbp = ar.lenbp;            // generated lengths: a padding element may follow the record
-    const int nchA = (lenAp + E - 1) / E, nch = nchA + (lenbp + E - 1) / E;
+    const int nchA = (lenAp + E - 1) / E;
+    const int nch = ar.gen_need ? ar.gen_nneed : nchA + (lenbp + E - 1) / E;   // entries of the chunk list
     const int KS = (ntab + 3) >> 2;
     double ca[4];                                            // A fragments: coef[cell g][4s + t]
 #pragma unroll
@@ -470,7 +473,8 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
       ca[s] = (g < WPC && base + g < ar.ncells && 4 * s + t < ntab) ? __ldg(ar.coef + (base + g) * ntab + 4 * s + t) : 0.0;
     if (lane < WPC && base + wstride + lane < ar.ncells)     // the coefficients of the next batch: DRAM -> L2 now
       asm volatile("prefetch.global.L2 [%0];" ::"l"(ar.coef + (base + wstride + lane) * ntab));
-    auto issue = [&](const int k, const int buf) {
+    auto issue = [&](const int kl, const int buf) {
+      const int k = ar.gen_need ? (int)__ldg(ar.gen_need + kl) : kl;      // chunk of the record behind list entry kl
       const bool isA = k < nchA;
       const int len = isA ? lenAp : lenbp;
       const int e0 = (isA ? k : k - nchA) * E, cnt = min(E, len - e0);
@@ -503,7 +507,8 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
 #else
     const bool ko_skip = false, ko_nostore = false, ko_notma = false;
 #endif
-    for (int k = warp, buf = 0; k < nch && !ko_skip; k += WPC, buf ^= 1) {
+    for (int kl = warp, buf = 0; kl < nch && !ko_skip; kl += WPC, buf ^= 1) {
+      const int k = ar.gen_need ? (int)__ldg(ar.gen_need + kl) : kl;
       const bool isA = k < nchA;
       const int e0 = (isA ? k : k - nchA) * E, cnt = min(E, (isA ? lenAp : lenbp) - e0);
       double* const dst = dlane + (isA ? 0 : lenAp) + e0;
@@ -557,7 +562,7 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
         if (g < WPC && 8 * tl0 + 2 * t < cnt) *reinterpret_cast<double2*>(dst + 8 * tl0) = make_double2(d0, d1);
       }
       __syncwarp();                                          // the warp is done with this buffer
-      if (k + 2 * WPC < nch && !ko_notma) issue(k + 2 * WPC, buf);
+      if (kl + 2 * WPC < nch && !ko_notma) issue(kl + 2 * WPC, buf);
     }
     __syncthreads();          // the WPC records of the batch are complete
     // the staging ring overwrote the image: restore the zeros the cell code relies on (pad columns, dummy row, inverse tiles)
@@ -1242,7 +1247,7 @@ inline void cw_fill_args(const Plan& p, CwArgs& ar) {
   ar.pf22_off = p.cw_pf[4]; ar.pf22_len = p.cw_pf[5];
   ar.lenA = p.lenA; ar.lenb = p.lenb;
   ar.TA = nullptr; ar.Tb = nullptr; ar.coef = nullptr; ar.scratch = nullptr; ar.slot = 0; ar.ntab = 0;
-  ar.lenAp = 0; ar.lenbp = 0; ar.gen_E = 0;
+  ar.lenAp = 0; ar.lenbp = 0; ar.gen_E = 0; ar.gen_need = nullptr; ar.gen_nneed = 0;
   ar.lam_free = nullptr; ar.lam_dir = nullptr; ar.ids = nullptr; ar.u = nullptr;
 }
 

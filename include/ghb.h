@@ -68,6 +68,12 @@ int ghb_set_option(ghb_ctx* ctx, const char* name, int64_t value);
 int ghb_device_alloc(ghb_ctx* ctx, int64_t bytes, void** out);
 int ghb_device_free(ghb_ctx* ctx, void* ptr);
 int ghb_copy(ghb_ctx* ctx, void* dst, const void* src, int64_t bytes);
+/* Page-lock caller memory in place (cudaHostRegister / cudaHostUnregister) for hosts without a CUDA library of their own:
+ * a Julia `Array` registered once is copied from at the PCIe rate by every later call (ghb_condense_assemble_f64 streams
+ * pinned records directly, pageable ones through a staging buffer at the host-memcpy rate).  The caller unregisters before
+ * the array is freed or moved. */
+int ghb_host_register(ghb_ctx* ctx, void* ptr, int64_t bytes);
+int ghb_host_unregister(ghb_ctx* ctx, void* ptr);
 /* Name of the condensation kernel variant chosen for a plan: "dmma_34_36", "dmma_33_12", "dmma_56_16" (FP64 DMMA,
    interior rows in shared memory, boundary rows in registers), "large_dmma" (64 < n_i <= 128, streamed), "warp_7_8", "warp_16_8" (register-resident),
    "cw_34_36", "cw_33_12", "cw_40_36", "cw_21_16" (one warp per cell, FP64 DMMA, csrc/condense_cw.cu), "generic" (any plan). */

@@ -1167,6 +1167,40 @@ def test_julia_glue_call_sequence():
         L.ghb_destroy(h)
 
 
+def test_host_register_in_place(ctx):
+    """ghb_host_register / ghb_host_unregister: a pageable numpy array page-locked in place is taken by the streaming path
+    as pinned memory (no staging copy) and gives the same CSC values; double registration and unknown pointers are errors."""
+    plan = _dev_plan(ctx, "C3_hdg_k2_3d")
+    sk = gh.CartesianSkeleton((5, 4, 3), ctx)
+    M = gh.FacetFESpace(sk, 6, sk.facet_is_boundary())
+    assem = gh.SparseMatrixAssembler(M)
+    colptr, rowval, nnz = assem.symbolic()
+    n = sk.ncells
+    A, b = _synth(ctx, plan, 3, n)
+    def own_pages(shape):
+        # an array that starts on a page boundary and shares no page with anything else (registration is per page)
+        cnt = int(np.prod(shape))
+        raw = np.empty(cnt + 2 * 512, dtype=np.float64)
+        off = (-raw.ctypes.data % 4096) // 8
+        return raw[off:off + cnt].reshape(shape), raw
+
+    (Ah, _k0), (bh, _k1) = own_pages(A.shape), own_pages(b.shape)
+    Ah[:] = A.cpu().numpy(); bh[:] = b.cpu().numpy()
+    z0, r0 = np.empty(nnz), np.empty(assem.nrows)
+    ctx.condense_assemble(plan, n, Ah, bh, None, z0, r0, None)                  # pageable
+    (z1, _k2), (r1, _k3) = own_pages((nnz,)), own_pages((assem.nrows,))
+    for arr in (Ah, bh, z1, r1):
+        ctx.host_register(arr)
+    with pytest.raises(gh.GhbError):
+        ctx.host_register(Ah)                                                     # already registered
+    ctx.condense_assemble(plan, n, Ah, bh, None, z1, r1, None)                  # pinned in place
+    for arr in (Ah, bh, z1, r1):
+        ctx.host_unregister(arr)
+    with pytest.raises(gh.GhbError):
+        ctx.host_unregister(Ah)                                                   # not registered any more
+    assert np.array_equal(z0, z1) and np.array_equal(r0, r1)
+
+
 def test_pageable_and_pinned_host_records_agree(ctx):
     """ghb_condense_assemble_f64 stages PAGEABLE records through its pinned double buffer (host threads) and copies
     pinned ones directly: identical results, several chunks."""
