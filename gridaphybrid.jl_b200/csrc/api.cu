@@ -532,7 +532,7 @@ int ghb_condense_affine_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, int ntab,
   Arg<double> dg(ctx, g, (size_t)ncells * p->n_b, false, true); GHB_TRY(dg.rc);
   Arg<int32_t> di(ctx, info, info ? (size_t)ncells : 0, false, true); GHB_TRY(di.rc);
   CallTmp tmp(ctx);
-  const bool gen = cw_gen_supported(*p);
+  const bool gen = cw_gen_supported(*p, ntab);
   if (gen)
     GHB_TRY(launch_condense_cw_gen(ctx, *p, ncells, ntab, dTA.dev, dTb.dev, dc.dev, dS.dev, dg.dev, di.dev, nullptr));
   else
@@ -565,7 +565,7 @@ int ghb_condense_assemble_affine_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, 
   double *dS = nullptr, *dg = nullptr;
   GHB_CUDA(ctx, tmp.alloc((void**)&dS, (size_t)ncells * p->n_b * p->n_b * sizeof(double)));
   GHB_CUDA(ctx, tmp.alloc((void**)&dg, (size_t)ncells * p->n_b * sizeof(double)));
-  const bool gen = cw_gen_supported(*p);
+  const bool gen = cw_gen_supported(*p, ntab);
   if (gen && ctx->opt.fused_assembly) {
     // one kernel from coefficients to CSC values: records generated in the loader, S_K scattered into the zeroed nzval
     GHB_TRY(asm_scatter_prepare(ctx, 0));
@@ -958,7 +958,7 @@ int ghb_backsub_affine_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, int ntab, 
   Arg<int64_t> dids(ctx, cell_ids, (size_t)ncells * p->n_b, true, false); GHB_TRY(dids.rc);
   Arg<double> du(ctx, u, (size_t)ncells * p->n_i, false, true); GHB_TRY(du.rc);
   Arg<int32_t> di(ctx, info, info ? (size_t)ncells : 0, false, true); GHB_TRY(di.rc);
-  if (cw_gen_supported(*p) && ctx->opt.cw_back) {
+  if (cw_gen_supported(*p, ntab) && ctx->opt.cw_back) {
     GHB_TRY(launch_backsub_cw_gen(ctx, *p, ncells, ntab, dTA.dev, dTb.dev, dc.dev, dlf.dev, dld.dev, dids.dev, du.dev, di.dev));
   } else {
     // plans without a GEN kernel: chunks of records expanded into a device temporary

@@ -16,15 +16,34 @@
 
 namespace ghb {
 
-bool cw_gen_supported(const Plan& p) {
-  return p.use_cw && !p.cw_pad;      // the tuned instantiations
+// a cell-warp plan whose image can stage two chunks of ntab table rows (E >= 16 elements)
+template <int NI, int NB>
+static bool gen_fits(int ntab) { return (size_t)CwCfg<NI, NB>::WARP_BYTES / (2 * (size_t)ntab * 8) >= 20; }
+
+bool cw_gen_supported(const Plan& p, int ntab) {
+  if (!p.use_cw || ntab < 1 || ntab > 16) return false;
+  if (p.cw_pad) {
+#define X(a) if (p.cw_pad == a) return gen_fits<a, GHB_CW_PAD_NB>(ntab);
+    GHB_CW_PAD_CLASSES(X)
+#undef X
+    return false;
+  }
+#define X(a, b) if (p.n_i == a && p.n_b == b) return gen_fits<a, b>(ntab);
+  GHB_CW_SHAPES(X)
+#undef X
+  return false;
 }
 
-template <int NI, int NB, bool SPARSE, bool SCAT, bool Q4 = false, bool BACK = false>
+template <int NI, int NB, bool SPARSE, bool SCAT, bool Q4 = false, bool BACK = false, bool PAD = false>
 static int launch_cw_gen(ghb_ctx* ctx, const Plan& p, CwArgs& ar) {
-  constexpr int WPC = GHB_CW_GEN_WPC;
-  auto kern = condense_cw_kernel<NI, NB, WPC, GHB_CW_GEN_MINB, false, SPARSE, false, SCAT, true, BACK, Q4>;
-  const size_t smem = CwCfg<NI, NB>::smem_bytes(WPC, false, true);
+  // tuned shapes: 2 CTAs of 8 warps; shape-generic classes: 8 warps per CTA where two images per ... fit, else 4
+  constexpr unsigned per8 = 8u * CwCfg<NI, NB>::WARP_BYTES + CwCfg<NI, NB>::SH_BAR_PAD + 16u * 8u + 16u + 1024u;
+  constexpr unsigned per4 = 4u * CwCfg<NI, NB>::WARP_BYTES + CwCfg<NI, NB>::SH_BAR_PAD + 16u * 4u + 16u + 1024u;
+  constexpr int WPC = !PAD ? GHB_CW_GEN_WPC : (per8 <= 233472u ? 8 : 4);
+  constexpr int fitp = (int)(233472u / (WPC == 8 ? per8 : per4));
+  constexpr int MINB = !PAD ? GHB_CW_GEN_MINB : (fitp < 1 ? 1 : (fitp > 16 / WPC ? 16 / WPC : fitp));
+  auto kern = condense_cw_kernel<NI, NB, WPC, MINB, false, SPARSE, PAD, SCAT, true, BACK, Q4>;
+  const size_t smem = CwCfg<NI, NB>::smem_bytes(WPC, PAD, true);
   static KernelSetup ks;
   int per_sm = 0;
   GHB_TRY(kernel_setup(ctx, p.opt, kern, 32 * WPC, smem, GHB_CW_CARVEOUT, ks, "condense_cw_kernel<GEN>", &per_sm));
@@ -127,8 +146,8 @@ static int gen_tables(ghb_ctx* ctx, const Plan& p, int ntab, const double* TA, c
 
 int launch_condense_cw_gen(ghb_ctx* ctx, const Plan& p, int64_t ncells, int ntab, const double* TA, const double* Tb,
                            const double* coef, double* S, double* g, int32_t* info, const ScatterArgs* sc) {
-  if (!cw_gen_supported(p)) return fail(ctx, GHB_EUNSUPPORTED, "condense_cw<GEN>: plan without a tuned cell-warp kernel");
   if (ntab < 1 || ntab > 16) return fail(ctx, GHB_EINVAL, "condense_cw<GEN>: need 1 <= ntab <= 16");
+  if (!cw_gen_supported(p, ntab)) return fail(ctx, GHB_EUNSUPPORTED, "condense_cw<GEN>: plan without a cell-warp kernel that can stage the tables");
   CwArgs ar;
   cw_fill_args(p, ar);
   ar.nzval = sc ? sc->nzval : nullptr;
@@ -139,6 +158,14 @@ int launch_condense_cw_gen(ghb_ctx* ctx, const Plan& p, int64_t ncells, int ntab
   ar.A = nullptr; ar.b = nullptr; ar.S = S; ar.g = g; ar.info = info; ar.X = nullptr;
   ar.coef = coef; ar.ntab = ntab;
   GHB_TRY(gen_tables(ctx, p, ntab, TA, Tb, ar));
+  if (p.cw_pad) {
+#define X(a)                                                                                                          \
+  if (p.cw_pad == a)                                                                                                  \
+    return ar.nzval ? launch_cw_gen<a, GHB_CW_PAD_NB, true, true, false, false, true>(ctx, p, ar)                     \
+                    : launch_cw_gen<a, GHB_CW_PAD_NB, true, false, false, false, true>(ctx, p, ar);
+    GHB_CW_PAD_CLASSES(X)
+#undef X
+  }
 #define X(a, b) if (p.n_i == a && p.n_b == b) return launch_cw_gen_shape<a, b>(ctx, p, ar);
   GHB_CW_SHAPES(X)
 #undef X
@@ -150,8 +177,8 @@ int launch_condense_cw_gen(ghb_ctx* ctx, const Plan& p, int64_t ncells, int ntab
 int launch_backsub_cw_gen(ghb_ctx* ctx, const Plan& p, int64_t ncells, int ntab, const double* TA, const double* Tb,
                           const double* coef, const double* lam_free, const double* lam_dir, const int64_t* ids, double* u,
                           int32_t* info) {
-  if (!cw_gen_supported(p)) return fail(ctx, GHB_EUNSUPPORTED, "backsub_cw<GEN>: plan without a tuned cell-warp kernel");
   if (ntab < 1 || ntab > 16) return fail(ctx, GHB_EINVAL, "backsub_cw<GEN>: need 1 <= ntab <= 16");
+  if (!cw_gen_supported(p, ntab)) return fail(ctx, GHB_EUNSUPPORTED, "backsub_cw<GEN>: plan without a cell-warp kernel that can stage the tables");
   CwArgs ar;
   cw_fill_args(p, ar);
   ar.nzval = nullptr; ar.colpos = nullptr; ar.rowrank = nullptr; ar.keepS = nullptr;
@@ -160,6 +187,11 @@ int launch_backsub_cw_gen(ghb_ctx* ctx, const Plan& p, int64_t ncells, int ntab,
   ar.coef = coef; ar.ntab = ntab;
   ar.lam_free = lam_free; ar.lam_dir = lam_dir; ar.ids = ids; ar.u = u;
   GHB_TRY(gen_tables(ctx, p, ntab, TA, Tb, ar));
+  if (p.cw_pad) {
+#define X(a) if (p.cw_pad == a) return launch_cw_gen<a, GHB_CW_PAD_NB, true, false, false, true, true>(ctx, p, ar);
+    GHB_CW_PAD_CLASSES(X)
+#undef X
+  }
 #define X(a, b) \
   if (p.n_i == a && p.n_b == b) \
     return p.all_touched ? launch_cw_gen<a, b, false, false, false, true>(ctx, p, ar) : launch_cw_gen<a, b, true, false, false, true>(ctx, p, ar);

@@ -227,9 +227,10 @@ struct CwCfg {
   static constexpr unsigned SH_BYTES_PAD = SH_ROWINFO + 2 * ((NI + NB + 7) & ~7);
   // GEN kernels add: two mbarriers per warp (table staging rings) and 16 zero bytes
   static constexpr unsigned SH_BAR = (SH_BYTES + 15u) & ~15u;
+  static constexpr unsigned SH_BAR_PAD = (SH_BYTES_PAD + 15u) & ~15u;
   static constexpr int MAXTAB = 16;
   static size_t smem_bytes(int wpc, bool pad = false, bool gen = false) {
-    return (size_t)wpc * WARP_BYTES + (gen ? SH_BAR + 16u * wpc + 16u : (pad ? SH_BYTES_PAD : SH_BYTES));
+    return (size_t)wpc * WARP_BYTES + (gen ? (pad ? SH_BAR_PAD : SH_BAR) + 16u * wpc + 16u : (pad ? SH_BYTES_PAD : SH_BYTES));
   }
   // position-table entry of image row r: byte offset of the row | swizzle bits (4,5) | r << 16
   __host__ __device__ static constexpr unsigned enc(unsigned r) { return r * ROWB | ((r & 6u) << 3) | (r << 16); }
@@ -371,7 +372,7 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
   static_assert(!PAD || (SPARSE && NI % 8 == 0), "PAD kernels are instantiated for padded shapes");
   static_assert(!Q4 || (!PAD && !BACK && C::BTM == 5 && NB % 4 == 0 && NB < 40), "Q4: four interleaved row tiles + a short fifth");
   static_assert(!BACK || (!KEEPX && !SCAT), "BACK kernels: the backward map (resident records, or GEN: records formed in the loader)");
-  static_assert(!GEN || (!PAD && WPC <= 8), "GEN kernels: tuned shapes, at most 8 cells per batch (rows of a DMMA tile)");
+  static_assert(!GEN || WPC <= 8, "GEN kernels: at most 8 cells per batch (rows of a DMMA tile)");
   const int nir = PAD ? ar.n_i : NI, nbr = PAD ? ar.n_b : NB;       // real sizes
   const int NC = nbr + 1;                                           // right-hand-side columns: A12 | b1
   const int CTB = PAD ? (NC + 7) / 8 : C::CTB;
@@ -393,7 +394,7 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
   for (unsigned i = lane; i < C::WARP_BYTES / 8; i += 32) reinterpret_cast<double*>(wsp)[i] = 0.0;
   for (int i = threadIdx.x; i < 8; i += 32 * WPC) reinterpret_cast<double*>(shp)[i] = 1.0;
   if (GEN && threadIdx.x == 0) {
-    const unsigned bars = (unsigned)__cvta_generic_to_shared(shp) + C::SH_BAR;
+    const unsigned bars = (unsigned)__cvta_generic_to_shared(shp) + (PAD ? C::SH_BAR_PAD : C::SH_BAR);
     for (int w = 0; w < 2 * WPC; ++w) mbar_init(bars + 8u * w, 1u);
     sts128(bars + 16u * WPC, 0.0, 0.0);
     fence_mbar_init();
@@ -457,8 +458,8 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
   // consecutive elements of one cell per lane) to the scratch records of all WPC cells with 16-byte stores.  DMMA
   // accumulates in ascending k from C: the sum runs in table order from 0.0 like expand_records_kernel (glue.cu),
   // zero-padded steps add +0 -- the records are bit-identical to its.
-  const unsigned a_bar = a_sh + C::SH_BAR + 16u * (unsigned)warp;   // the warp's two staging barriers
-  const unsigned a_zero = a_sh + C::SH_BAR + 16u * WPC;             // eight zero bytes (B fragments of zero-padded tables)
+  const unsigned a_bar = a_sh + (PAD ? C::SH_BAR_PAD : C::SH_BAR) + 16u * (unsigned)warp;   // the warp's two staging barriers
+  const unsigned a_zero = a_sh + (PAD ? C::SH_BAR_PAD : C::SH_BAR) + 16u * WPC;             // eight zero bytes (B fragments of zero-padded tables)
   unsigned gphase = 0u;                                      // parity of the two staging barriers
   auto gen_records = [&](const int64_t base) {
     const int E = ar.gen_E;                                  // elements per chunk, a multiple of 16

@@ -691,7 +691,7 @@ def _random_family(ctx, plan, ntab, seed):
     return gh.AffineRecordFamily(TA, Tb), rng
 
 
-@pytest.mark.parametrize("name", CW_GEN_NAMES + ["C1_hdg_k1_2d", "hencky_k1_2d"])
+@pytest.mark.parametrize("name", CW_GEN_NAMES + ["C1_hdg_k1_2d", "hencky_k1_2d", "rth_k0_2d", "multifield_2skel", "odd_shapes"])
 @pytest.mark.parametrize("ntab,ncells", [(1, 5), (7, 1003), (16, 300), (5, 4737)])
 def test_affine_family_condensed_in_the_loader(ctx, name, ntab, ncells):
     """SURVEY 8f-1 / VERDICT item 2: ghb_condense_affine_f64 forms A_K = sum_t coef[K][t] TA[t] inside the condensation
@@ -724,7 +724,7 @@ def test_affine_family_condensed_in_the_loader(ctx, name, ntab, ncells):
     assert np.array_equal(i2, i0[:n2].cpu().numpy())
 
 
-@pytest.mark.parametrize("name", CW_GEN_NAMES + ["C1_hdg_k1_2d", "hencky_k1_2d"])
+@pytest.mark.parametrize("name", CW_GEN_NAMES + ["C1_hdg_k1_2d", "hencky_k1_2d", "rth_k0_2d", "multifield_2skel"])
 @pytest.mark.parametrize("ntab,ncells", [(1, 9), (7, 2501), (16, 333)])
 def test_affine_family_backward_map_in_the_loader(ctx, name, ntab, ncells):
     """ghb_backsub_affine_f64: the backward map with the records formed inside the kernel (GEN + BACK instantiations) is

@@ -20,6 +20,13 @@ if shape == "C3":
 elif shape == "RTH2":     # (33,12): RT-H k=2 2-D, untouched (p,p) and (lambda, p)/(p, lambda) blocks
     t = np.ones((3, 3), bool); t[1, 1] = False; t[1, 2] = False; t[2, 1] = False
     ndofs, touched, I, B = [24, 9, 12], t, [1, 2], [3]
+if shape not in ("C3", "RTH2"):
+    if shape == "HDG3D_K1":       # Darcy HDG k=1 on hexes: u 3 x 8, p 8 | lambda 6 x 4 -> (32, 24), shape-generic class 32
+        ndofs, touched, I, B = [24, 8, 24], np.ones((3, 3), bool), [1, 2], [3]
+    else:
+        from tests.helpers import CONFIGS
+        c = CONFIGS[shape]
+        ndofs, touched, I, B = c["ndofs"], c["touched"], c["interior"], c["boundary"]
 plan = ctx.plan_blocks(ndofs, touched, I, B)
 ntab = int(os.environ.get("NTAB", "7"))
 rng = np.random.default_rng(0)
