@@ -132,9 +132,10 @@ int ghb_expand_records_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, int ntab, 
  * in L2), so the 8(lenA+lenb) bytes per cell never reach HBM -- the element-matrix generation of the reference's
  * lazy_map chain (src/GridapAPIExtensions.jl:442-451 -> src/HybridAffineFEOperators.jl:338) fused into the loader.
  * Results are bit-identical to ghb_expand_records_f64 followed by ghb_condense_f64 / ghb_condense_assemble_f64 (same
- * summation order).  Plans without a tuned cell-warp kernel (ghb_plan_kernel_name not "cw_<n_i>_<n_b>") or with odd
- * record lengths expand chunks of records into a device temporary instead (same results).  TA, Tb, coef may be host
- * pointers (staged).  ghb_condense_assemble_affine_f64 needs the selected symbolic pattern like
+ * summation order).  Every plan with a cell-warp kernel takes this path (ghb_plan_kernel_name "cw_<n_i>_<n_b>" or
+ * "cw_pad_<class>": n_i <= 64, n_b <= 40; odd record lengths go through zero-padded table rows); the other plans, and
+ * table counts whose staging does not fit the image of a small class, expand chunks of records into a device temporary
+ * instead (same results).  TA, Tb, coef may be host pointers (staged).  ghb_condense_assemble_affine_f64 needs the selected symbolic pattern like
  * ghb_condense_assemble_f64. */
 int ghb_condense_affine_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, int ntab, const double* TA, const double* Tb,
                             const double* coef, double* S, double* g, int32_t* info);
