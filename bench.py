@@ -600,13 +600,15 @@ def run_ours(args):
     # expand -> condense -> assemble from per-cell coefficient vectors; nothing of the size of the records crosses PCIe.
     # (Overwrites A, b: last leg.  The `e2e` key above stays the host-record path the contract asks for.)
     devgen = None
-    if world == 1 and args.config == "C3" and nchunk == 1:
+    if args.config == "C3" and nchunk == 1:
         ntab = 1 + 2 * 3
         rng = np.random.default_rng(3)
-        TA = np.concatenate([A[:1].cpu().numpy(), 1e-3 * rng.standard_normal((ntab - 1, plan.lenA))])
-        Tb = np.concatenate([b[:1].cpu().numpy(), 1e-3 * rng.standard_normal((ntab - 1, plan.lenb))])
+        A0r, b0r = torch.empty((1, plan.lenA), dtype=torch.float64, device=dev), torch.empty((1, plan.lenb), dtype=torch.float64, device=dev)
+        ctx.synth_fill(plan, 0, 1, A0r, b0r)                      # the same base record on every rank
+        TA = np.concatenate([A0r.cpu().numpy(), 1e-3 * rng.standard_normal((ntab - 1, plan.lenA))])
+        Tb = np.concatenate([b0r.cpu().numpy(), 1e-3 * rng.standard_normal((ntab - 1, plan.lenb))])
         fam = gh.AffineRecordFamily(TA, Tb)
-        coef = gh.cartesian_coefficients(cdims, tuple(1.0 / d for d in cdims), dev)
+        coef = gh.cartesian_coefficients(gdims, tuple(1.0 / d for d in gdims), dev, cell_start=cell_start, ncells=ncells)
 
         def gen_step():          # records written to HBM by ghb_expand_records_f64, then the resident-record step
             fam.expand(ctx, plan, coef, A, b)
@@ -617,8 +619,7 @@ def run_ours(args):
                 slab.assemble(S, g, nzval, rhs)
 
         def gen_fused_step():    # records formed in the loader of the condensation kernel: they never exist in HBM
-            ctx.assemble_select(slab._pid)
-            fam.condense_assemble(ctx, plan, coef, slab.dirichlet_values, nzval, rhs, info)
+            slab.condense_assemble_affine(plan, fam, coef, S, g, info, nzval, rhs)      # + cut-plane exchange at N > 1
 
         def timed3(f):
             f()
@@ -629,7 +630,7 @@ def run_ours(args):
                 f()
             g1.record()
             barrier()
-            return g0.elapsed_time(g1) / 3
+            return max_over_ranks(g0.elapsed_time(g1) / 3)
 
         gms2 = timed3(gen_step)
         assert int(info.abs().sum().item()) == 0
@@ -637,11 +638,11 @@ def run_ours(args):
         gms = timed3(gen_fused_step)
         assert int(info.abs().sum().item()) == 0
         same = ref_sum == (float(nzval.sum().item()), float(rhs.sum().item()))       # the two paths are bit-identical
-        devgen = {"value": ncells / (gms * 1e-3), "unit": "cells/s", "ms": gms, "h2d_bytes_per_step": int(coef.numel() * 8),
+        devgen = {"value": total_cells / (gms * 1e-3), "unit": "cells/s", "ms": gms, "h2d_bytes_per_step": int(coef.numel() * 8),
                   "note": "records of an affine family (7 tables) formed inside the condensation kernel "
-                          "(ghb_condense_assemble_affine_f64: TMA-staged table chunks, DMMA combination per batch of 8 cells, "
+                          "(ghb_condense_scatter_slab_affine_f64 + ghb_assemble_finish_slab_f64: TMA-staged table chunks, DMMA combination per batch of 8 cells, "
                           "scratch records in L2), condensed and assembled; coefficients counted as the host input",
-                  "expand_then_condense": {"value": ncells / (gms2 * 1e-3), "ms": gms2,
+                  "expand_then_condense": {"value": total_cells / (gms2 * 1e-3), "ms": gms2,
                                            "note": "records written to HBM by ghb_expand_records_f64 first (round-2 path)"},
                   "checksums_equal": bool(same)}
         # the backward map from the same coefficient vectors (ghb_backsub_affine_f64): with the step above the whole solve
@@ -649,9 +650,9 @@ def run_ours(args):
         lam_b = torch.randn(slab.layout.nrows_local, dtype=torch.float64, device=dev)
         u_b = torch.empty((ncells, plan.n_i), dtype=torch.float64, device=dev)
         ids_b = slab.cell_ids[:ncells]
-        bms = timed3(lambda: fam.backsub(ctx, plan, coef, lam_b, None, ids_b, u_b, info))
+        bms = timed3(lambda: fam.backsub(ctx, plan, coef, slab.allgather_lambda(lam_b), None, ids_b, u_b, info))
         assert int(info.abs().sum().item()) == 0
-        devgen["backsub"] = {"value": ncells / (bms * 1e-3), "unit": "cells/s", "ms": bms,
+        devgen["backsub"] = {"value": total_cells / (bms * 1e-3), "unit": "cells/s", "ms": bms,
                              "note": "BackwardStaticCondensationMap with the records formed in the loader (GEN + BACK kernel)"}
         del lam_b, u_b
         del coef

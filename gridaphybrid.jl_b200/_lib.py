@@ -26,7 +26,7 @@ SYMBOLS = [
     "ghb_create", "ghb_destroy", "ghb_last_error", "ghb_set_stream", "ghb_synchronize", "ghb_launch_count",
     "ghb_set_option", "ghb_device_alloc", "ghb_device_free", "ghb_copy", "ghb_host_register", "ghb_host_unregister", "ghb_factors_generation",
     "ghb_assemble_current", "ghb_assemble_select", "ghb_assemble_release",
-    "ghb_condense_scatter_slab_f64", "ghb_assemble_finish_slab_f64",
+    "ghb_condense_scatter_slab_f64", "ghb_condense_scatter_slab_affine_f64", "ghb_assemble_finish_slab_f64",
     "ghb_comm_unique_id", "ghb_comm_init", "ghb_comm_destroy", "ghb_exchange_cut_plane_f64", "ghb_allgather_lambda_f64",
     "ghb_plan_kernel_name", "ghb_plan_blocks", "ghb_plan_query", "ghb_condense_f64",
     "ghb_restrict_facet_dofs_i64", "ghb_sum_facets_f64", "ghb_expand_records_f64", "ghb_condense_affine_f64", "ghb_condense_assemble_affine_f64", "ghb_backsub_affine_f64", "ghb_l2_projection_dofs_f64", "ghb_assemble_symbolic", "ghb_assemble_pattern", "ghb_assemble_numeric_f64", "ghb_assemble_numeric_csr_f64",
@@ -159,6 +159,7 @@ def lib():
     L.ghb_set_option.argtypes = [vp, ctypes.c_char_p, i64]
     L.ghb_condense_scatter_slab_f64.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, vp, i64, i32]
     L.ghb_assemble_finish_slab_f64.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.ghb_condense_scatter_slab_affine_f64.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp, vp, vp, vp, i64, i32]
     L.ghb_device_alloc.argtypes = [vp, i64, ctypes.POINTER(vp)]
     L.ghb_device_free.argtypes = [vp, vp]
     L.ghb_copy.argtypes = [vp, vp, vp, i64]

@@ -267,6 +267,15 @@ class Context:
             _ptr(S, np.float64, ncells * plan.n_b ** 2, "S"), _ptr(g, np.float64, ncells * plan.n_b, "g"),
             _ptr(info, np.int32, ncells, "info"), _ptr(nzval, np.float64, nnz, "nzval"), int(keep_cut), int(bool(zero_nzval))))
 
+    def condense_scatter_slab_affine(self, plan, ncells, ntab, TA, Tb, coef, S, g, info, nzval, keep_cut, zero_nzval=True):
+        """the same with the records of an affine family formed in the loader (device arrays)"""
+        nrows, nnz = self._asm_shape
+        self._check(self._L.ghb_condense_scatter_slab_affine_f64(
+            self._h, plan.id, int(ncells), int(ntab), _ptr(TA, np.float64, ntab * plan.lenA, "TA"),
+            _ptr(Tb, np.float64, ntab * plan.lenb, "Tb"), _ptr(coef, np.float64, ncells * ntab, "coef"),
+            _ptr(S, np.float64, ncells * plan.n_b ** 2, "S"), _ptr(g, np.float64, ncells * plan.n_b, "g"),
+            _ptr(info, np.int32, ncells, "info"), _ptr(nzval, np.float64, nnz, "nzval"), int(keep_cut), int(bool(zero_nzval))))
+
     def assemble_finish_slab(self, S, g, ghost, dirichlet_vals, nzval, rhs):
         nrows, nnz = self._asm_shape
         self._check(self._L.ghb_assemble_finish_slab_f64(self._h, _ptr(S, np.float64), _ptr(g, np.float64),

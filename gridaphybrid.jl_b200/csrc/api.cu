@@ -698,6 +698,29 @@ int ghb_condense_scatter_slab_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, con
   return launch_condense_cw_scatter(ctx, *p, ncells, A, b, S, g, info, sc);
 }
 
+int ghb_condense_scatter_slab_affine_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, int ntab, const double* TA,
+                                         const double* Tb, const double* coef, double* S, double* g, int32_t* info,
+                                         double* nzval, int64_t keep_cut, int zero_nzval) {
+  Plan* p = get_plan(ctx, plan_id);
+  if (!p) return fail(ctx, GHB_EINVAL, "ghb_condense_scatter_slab_affine_f64: bad plan id");
+  if (!ctx->as.valid) return fail(ctx, GHB_ESTATE, "ghb_condense_scatter_slab_affine_f64: call ghb_assemble_symbolic_slab first");
+  const AsmState& as = ctx->as;
+  if (ncells != as.ncells_local || p->n_b != as.n_b || keep_cut < 0)
+    return fail(ctx, GHB_EINVAL, "ghb_condense_scatter_slab_affine_f64: ncells / n_b differ from the symbolic phase");
+  if (ntab < 1 || ntab > 16 || !TA || !Tb || !coef || !S || !g || !nzval)
+    return fail(ctx, GHB_EINVAL, "ghb_condense_scatter_slab_affine_f64: bad argument (need 1 <= ntab <= 16, non-null arrays)");
+  if (!cw_gen_supported(*p, ntab))
+    return fail(ctx, GHB_EUNSUPPORTED, "ghb_condense_scatter_slab_affine_f64: the plan has no cell-warp kernel that can stage the tables");
+  cudaSetDevice(ctx->device);
+  if (!is_device_ptr(TA) || !is_device_ptr(Tb) || !is_device_ptr(coef) || !is_device_ptr(S) || !is_device_ptr(g) ||
+      !is_device_ptr(nzval) || (info && !is_device_ptr(info)))
+    return fail(ctx, GHB_EUNSUPPORTED, "ghb_condense_scatter_slab_affine_f64: device pointers required");
+  GHB_TRY(asm_scatter_prepare(ctx, keep_cut));
+  if (zero_nzval) GHB_CUDA(ctx, cudaMemsetAsync(nzval, 0, (size_t)as.nnz * sizeof(double), ctx->stream));
+  ScatterArgs sc{nzval, as.d_colpos, as.d_rowrank, as.d_keepS};
+  return launch_condense_cw_gen(ctx, *p, ncells, ntab, TA, Tb, coef, S, g, info, &sc);
+}
+
 /* second half: contributions of the ghost cells (the packed buffer received from the slab above) and the rhs gather */
 int ghb_assemble_finish_slab_f64(ghb_ctx* ctx, const double* S, const double* g, const double* ghost,
                                  const double* dirichlet_vals, double* nzval, double* rhs) {

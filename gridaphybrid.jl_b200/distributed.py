@@ -227,6 +227,20 @@ class SlabAssembler:
             self._exchange(exchange)
         self.ctx.assemble_finish_slab(S, g, self.ghost, self.dirichlet_values, nzval, rhs)
 
+    def condense_assemble_affine(self, plan, family, coef, S, g, info, nzval, rhs, exchange=None):
+        """fused step of a slab from the coefficient vectors of an affine family (`ghb_condense_scatter_slab_affine_f64`): the
+        records of the slab's cells are formed in the loader of the condensation kernel and never exist in HBM"""
+        L = self.layout
+        self.ctx.use_torch_stream()
+        self.ctx.assemble_select(self._pid)
+        keep = L.layer if (L.world > 1 and L.rank > 0) else 0
+        TA, Tb = family._tables(coef.device)
+        self.ctx.condense_scatter_slab_affine(plan, L.ncells, family.ntab, TA, Tb, coef.contiguous(), S, g, info, nzval, keep)
+        if L.world > 1:
+            self.pack(S, g)
+            self._exchange(exchange)
+        self.ctx.assemble_finish_slab(S, g, self.ghost, self.dirichlet_values, nzval, rhs)
+
     def allgather_lambda(self, lam_owned):
         """collective 2 through the C ABI (grouped ncclBroadcast, no object gather): the global free-dof vector"""
         L = self.layout

@@ -228,6 +228,11 @@ int ghb_assemble_numeric_slab_f64(ghb_ctx* ctx, const double* S, const double* g
  * the exchange, ghb_assemble_finish_slab_f64 adds the ghost cells' contributions and gathers the rhs. */
 int ghb_condense_scatter_slab_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A, const double* b, double* S,
                                   double* g, int32_t* info, double* nzval, int64_t keep_cut, int zero_nzval);
+/* the same first half with the records of an affine family formed in the loader (see ghb_condense_affine_f64): a slab of
+ * a multi-GPU run goes from coefficient vectors to its share of nzval without the records existing; device pointers. */
+int ghb_condense_scatter_slab_affine_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, int ntab, const double* TA,
+                                         const double* Tb, const double* coef, double* S, double* g, int32_t* info,
+                                         double* nzval, int64_t keep_cut, int zero_nzval);
 int ghb_assemble_finish_slab_f64(ghb_ctx* ctx, const double* S, const double* g, const double* ghost,
                                  const double* dirichlet_vals, double* nzval, double* rhs);
 

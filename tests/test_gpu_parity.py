@@ -1372,6 +1372,28 @@ def test_fused_slab_step_matches_global(ctx, gdims, world):
     outs.sort()
     assert np.array_equal(np.concatenate([o_[1] for o_ in outs]), nz0.cpu().numpy())
     assert np.array_equal(np.concatenate([o_[2] for o_ in outs]), rhs0.cpu().numpy())
+    # the same slabs from the coefficient vectors of an affine family (ghb_condense_scatter_slab_affine_f64): bit-equal to
+    # the slab step on the expanded records
+    fam, rng = _random_family(ctx, plan, 5, 9)
+    coef = torch.as_tensor(np.concatenate([np.ones((n, 1)), rng.uniform(-1, 1, (n, 4))], axis=1), device="cuda")
+    cells = fam.expand(ctx, plan, coef)
+    for r in range(world - 1, -1, -1):
+        a, L = asms[r], asms[r].layout
+        sl = slice(L.cell_start, L.cell_start + L.ncells)
+        res = []
+        for affine in (False, True):
+            Sr = torch.full((L.ncells, plan.n_b ** 2), float("nan"), dtype=torch.float64, device="cuda")
+            gr = torch.empty((L.ncells, plan.n_b), dtype=torch.float64, device="cuda")
+            z = torch.full((a.nnz,), float("nan"), dtype=torch.float64, device="cuda"); rr = torch.empty(a.nrows_local, dtype=torch.float64, device="cuda")
+            fake = lambda send, recv, rank, w, group: recv.copy_(asms[rank + 1].send_buf) if recv is not None else None
+            if affine:
+                a.condense_assemble_affine(plans[r], fam, coef[sl].contiguous(), Sr, gr, None, z, rr, exchange=fake)
+            else:
+                a.condense_assemble(plans[r], cells.A[sl].contiguous(), cells.b[sl].contiguous(), Sr, gr, None, z, rr, exchange=fake)
+            torch.cuda.synchronize()
+            res.append((z.cpu().numpy(), rr.cpu().numpy(), a.send_buf.cpu().numpy().copy() if a.send_buf is not None else None))
+        assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+        assert (res[0][2] is None) or np.array_equal(res[0][2], res[1][2])
     for c in ctxs:
         c.close()
 
