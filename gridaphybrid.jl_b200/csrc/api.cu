@@ -563,9 +563,11 @@ int ghb_condense_assemble_affine_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, 
   Arg<int32_t> di(ctx, info, info ? (size_t)ncells : 0, false, true); GHB_TRY(di.rc);
   CallTmp tmp(ctx);
   double *dS = nullptr, *dg = nullptr;
-  GHB_CUDA(ctx, tmp.alloc((void**)&dS, (size_t)ncells * p->n_b * p->n_b * sizeof(double)));
-  GHB_CUDA(ctx, tmp.alloc((void**)&dg, (size_t)ncells * p->n_b * sizeof(double)));
   const bool gen = cw_gen_supported(*p, ntab);
+  // the fused kernel stores S_K only for the cells whose Dirichlet lift needs it: without Dirichlet values S is never touched
+  const bool needS = !(gen && ctx->opt.fused_assembly) || dd.dev != nullptr;
+  GHB_CUDA(ctx, tmp.alloc((void**)&dS, needS ? (size_t)ncells * p->n_b * p->n_b * sizeof(double) : 64));
+  GHB_CUDA(ctx, tmp.alloc((void**)&dg, (size_t)ncells * p->n_b * sizeof(double)));
   if (gen && ctx->opt.fused_assembly) {
     // one kernel from coefficients to CSC values: records generated in the loader, S_K scattered into the zeroed nzval
     GHB_TRY(asm_scatter_prepare(ctx, 0));
@@ -807,7 +809,9 @@ int ghb_condense_assemble_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const d
   if (hostA != hostb) return fail(ctx, GHB_EINVAL, "ghb_condense_assemble_f64: A and b must both be host or both device");
   double *dS = nullptr, *dg = nullptr;
   CallTmp tmp(ctx);
-  GHB_CUDA(ctx, tmp.alloc((void**)&dS, (size_t)ncells * p->n_b * p->n_b * sizeof(double)));
+  // the fused kernel stores S_K only for the cells whose Dirichlet lift needs it: without Dirichlet values S is never touched
+  const bool needS = !(!hostA && p->use_cw && ctx->opt.fused_assembly) || dirichlet_vals != nullptr;
+  GHB_CUDA(ctx, tmp.alloc((void**)&dS, needS ? (size_t)ncells * p->n_b * p->n_b * sizeof(double) : 64));
   GHB_CUDA(ctx, tmp.alloc((void**)&dg, (size_t)ncells * p->n_b * sizeof(double)));
   Arg<int32_t> di(ctx, info, info ? (size_t)ncells : 0, false, true); GHB_TRY(di.rc);
   int rc = GHB_OK;
