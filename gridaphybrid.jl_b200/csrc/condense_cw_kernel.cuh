@@ -526,7 +526,10 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
         gphase ^= 1u << buf;
       }
       const int nfull = cnt >> 3;                            // whole tiles; a last partial tile goes the predicated way
-      constexpr int TU = 4;                                  // independent tiles in flight
+#ifndef GHB_CW_GEN_TU
+#define GHB_CW_GEN_TU 4
+#endif
+      constexpr int TU = GHB_CW_GEN_TU;                      // independent tiles in flight
       int tl0 = 0;
       for (; tl0 + TU <= nfull; tl0 += TU) {
         double d[TU][2];
@@ -549,7 +552,15 @@ __global__ void __launch_bounds__(32 * WPC, MINB) condense_cw_kernel(const CwArg
         if (g < WPC && !ko_nostore) {
           double* dp = dst + 8 * tl0;
 #pragma unroll
-          for (int u = 0; u < TU; ++u) *reinterpret_cast<double2*>(dp + 8 * u) = make_double2(d[u][0], d[u][1]);
+          for (int u = 0; u < TU; ++u) {
+#if defined(GHB_CW_GEN_STORE) && GHB_CW_GEN_STORE == 1      // A/B: L2-only stores (no L1 write-through lookup)
+            __stcg(reinterpret_cast<double2*>(dp + 8 * u), make_double2(d[u][0], d[u][1]));
+#elif defined(GHB_CW_GEN_STORE) && GHB_CW_GEN_STORE == 2    // A/B: write-through hint
+            __stwt(reinterpret_cast<double2*>(dp + 8 * u), make_double2(d[u][0], d[u][1]));
+#else
+            *reinterpret_cast<double2*>(dp + 8 * u) = make_double2(d[u][0], d[u][1]);
+#endif
+          }
         }
       }
       for (; 8 * tl0 < cnt; ++tl0) {                         // the last tiles of the chunk, one at a time
