@@ -149,7 +149,7 @@ def lib():
     L.ghb_sum_facets_f64.argtypes = [vp, i64, i32, i64, vp, vp]
     L.ghb_l2_projection_dofs_f64.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp]
     L.ghb_expand_records_f64.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp, vp]
-    L.ghb_condense_affine_f64.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp, vp, vp]
+    L.ghb_condense_affine_f64.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp, vp, vp, i32]
     L.ghb_condense_assemble_affine_f64.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp, i64, vp, vp, vp]
     L.ghb_backsub_affine_f64.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp, i64, vp, i64, vp, vp, vp]
     L.ghb_assemble_symbolic.argtypes = [vp, i64, i32, vp, i64, ctypes.POINTER(i64)]

@@ -166,14 +166,14 @@ class Context:
             _ptr(Tb, np.float64, ntab * plan.lenb, "Tb"), _ptr(coef, np.float64, ncells * ntab, "coef"),
             _ptr(A, np.float64, ncells * plan.lenA, "A"), _ptr(b, np.float64, ncells * plan.lenb, "b")))
 
-    def condense_affine(self, plan: BlockPlan, ncells, ntab, TA, Tb, coef, S, g, info=None):
+    def condense_affine(self, plan: BlockPlan, ncells, ntab, TA, Tb, coef, S, g, info=None, keep_factors=False):
         """S_K, g_K of an affine family without materialising the records (generated in the loader of the condensation
         kernel); bit-identical to expand_records + condense."""
         self._check(self._L.ghb_condense_affine_f64(
             self._h, plan.id, int(ncells), int(ntab), _ptr(TA, np.float64, ntab * plan.lenA, "TA"),
             _ptr(Tb, np.float64, ntab * plan.lenb, "Tb"), _ptr(coef, np.float64, ncells * ntab, "coef"),
             _ptr(S, np.float64, ncells * plan.n_b ** 2, "S"), _ptr(g, np.float64, ncells * plan.n_b, "g"),
-            _ptr(info, np.int32, ncells, "info")))
+            _ptr(info, np.int32, ncells, "info"), int(bool(keep_factors))))
 
     def condense_assemble_affine(self, plan: BlockPlan, ncells, ntab, TA, Tb, coef, dirichlet_vals, nzval, rhs, info=None):
         """coefficients -> CSC values + rhs in one call (selected symbolic pattern)."""

@@ -90,6 +90,23 @@ int launch_backsub(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A,
   return launch_backsub_generic(ctx, p, ncells, A, b, lam_free, lam_dir, ids, u, info);
 }
 
+// factor storage of a keep_factors condensation: X = A11^-1 [A12 | b1] plus the info[] of that condensation (ghb_backsub_f64
+// with A = b = NULL reports it: a singular cell has NaN factors); `generation` lets a caller check the factors are its own
+static int factor_storage(ghb_ctx* ctx, const Plan& p, int plan_id, int64_t ncells, double** X, int32_t** finfo) {
+  const size_t need = (size_t)ncells * p.n_i * (p.n_b + 1) * sizeof(double) + (size_t)ncells * sizeof(int32_t);
+  if (ctx->fac.bytes < need) {
+    if (ctx->fac.d_X) cudaFree(ctx->fac.d_X);
+    ctx->fac.d_X = nullptr; ctx->fac.bytes = 0;
+    if (cudaMalloc((void**)&ctx->fac.d_X, need) != cudaSuccess) { cudaGetLastError(); return fail(ctx, GHB_ENOMEM, "factor storage"); }
+    ctx->fac.bytes = need;
+  }
+  ctx->fac.plan_id = plan_id; ctx->fac.ncells = ncells; ctx->fac.generation++;
+  ctx->fac.d_info = reinterpret_cast<int32_t*>(ctx->fac.d_X + (size_t)ncells * p.n_i * (p.n_b + 1));
+  *X = ctx->fac.d_X;
+  *finfo = ctx->fac.d_info;
+  return GHB_OK;
+}
+
 static int64_t env_i64(const char* name, int64_t dflt) {
   const char* e = getenv(name);
   return (e && *e) ? atoll(e) : dflt;
@@ -410,23 +427,8 @@ int ghb_condense_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, const double* A,
   cudaSetDevice(ctx->device);
   double* X = nullptr;
   int32_t* finfo = nullptr;
-  if (keep_factors) {
-    // factor storage X = A11^-1 [A12 | b1] plus the info[] of this condensation (ghb_backsub_f64 with A = b = NULL reports
-    // it: a singular cell has NaN factors); `generation` lets a caller check that the factors are still its own
-    size_t need = (size_t)ncells * p->n_i * (p->n_b + 1) * sizeof(double) + (size_t)ncells * sizeof(int32_t);
-    if (ctx->fac.bytes < need) {
-      if (ctx->fac.d_X) cudaFree(ctx->fac.d_X);
-      ctx->fac.d_X = nullptr; ctx->fac.bytes = 0;
-      if (cudaMalloc((void**)&ctx->fac.d_X, need) != cudaSuccess) { cudaGetLastError(); return fail(ctx, GHB_ENOMEM, "factor storage"); }
-      ctx->fac.bytes = need;
-    }
-    ctx->fac.plan_id = plan_id; ctx->fac.ncells = ncells; ctx->fac.generation++;
-    ctx->fac.d_info = reinterpret_cast<int32_t*>(ctx->fac.d_X + (size_t)ncells * p->n_i * (p->n_b + 1));
-    X = ctx->fac.d_X;
-    finfo = ctx->fac.d_info;
-  } else {
-    ctx->fac.plan_id = -1;
-  }
+  if (keep_factors) GHB_TRY(factor_storage(ctx, *p, plan_id, ncells, &X, &finfo));
+  else ctx->fac.plan_id = -1;
   Arg<double> dA(ctx, A, (size_t)ncells * p->lenA, true, false); GHB_TRY(dA.rc);
   Arg<double> db(ctx, b, (size_t)ncells * p->lenb, true, false); GHB_TRY(db.rc);
   Arg<double> dS(ctx, S, (size_t)ncells * p->n_b * p->n_b, false, true); GHB_TRY(dS.rc);
@@ -517,14 +519,17 @@ static int condense_affine_chunked(ghb_ctx* ctx, const Plan& p, int64_t ncells, 
 }
 
 int ghb_condense_affine_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, int ntab, const double* TA, const double* Tb,
-                            const double* coef, double* S, double* g, int32_t* info) {
+                            const double* coef, double* S, double* g, int32_t* info, int keep_factors) {
   Plan* p = get_plan(ctx, plan_id);
   if (!p) return fail(ctx, GHB_EINVAL, "ghb_condense_affine_f64: bad plan id");
   if (ncells < 0 || ntab < 1 || ntab > 16 || !TA || !Tb || !coef || !S || !g)
     return fail(ctx, GHB_EINVAL, "ghb_condense_affine_f64: bad argument (need 1 <= ntab <= 16, non-null arrays)");
   if (ncells == 0) return GHB_OK;
   cudaSetDevice(ctx->device);
-  ctx->fac.plan_id = -1;
+  double* X = nullptr;
+  int32_t* finfo = nullptr;
+  if (keep_factors) GHB_TRY(factor_storage(ctx, *p, plan_id, ncells, &X, &finfo));
+  else ctx->fac.plan_id = -1;
   Arg<double> dTA(ctx, TA, (size_t)ntab * p->lenA, true, false); GHB_TRY(dTA.rc);
   Arg<double> dTb(ctx, Tb, (size_t)ntab * p->lenb, true, false); GHB_TRY(dTb.rc);
   Arg<double> dc(ctx, coef, (size_t)ncells * ntab, true, false); GHB_TRY(dc.rc);
@@ -533,10 +538,25 @@ int ghb_condense_affine_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, int ntab,
   Arg<int32_t> di(ctx, info, info ? (size_t)ncells : 0, false, true); GHB_TRY(di.rc);
   CallTmp tmp(ctx);
   const bool gen = cw_gen_supported(*p, ntab);
-  if (gen)
-    GHB_TRY(launch_condense_cw_gen(ctx, *p, ncells, ntab, dTA.dev, dTb.dev, dc.dev, dS.dev, dg.dev, di.dev, nullptr));
-  else
-    GHB_TRY(condense_affine_chunked(ctx, *p, ncells, ntab, dTA.dev, dTb.dev, dc.dev, dS.dev, dg.dev, di.dev, tmp));
+  if (gen) {
+    GHB_TRY(launch_condense_cw_gen(ctx, *p, ncells, ntab, dTA.dev, dTb.dev, dc.dev, dS.dev, dg.dev, finfo ? finfo : di.dev, X, nullptr));
+  } else {
+    // plans without a GEN kernel: chunks of records expanded into a device temporary
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(ncells, ((int64_t)256 << 20) / ((p->lenA + p->lenb) * 8)));
+    double *tA = nullptr, *tb = nullptr;
+    GHB_CUDA(ctx, tmp.alloc((void**)&tA, (size_t)chunk * p->lenA * 8));
+    GHB_CUDA(ctx, tmp.alloc((void**)&tb, (size_t)chunk * p->lenb * 8));
+    int32_t* ip = finfo ? finfo : di.dev;
+    for (int64_t c0 = 0; c0 < ncells; c0 += chunk) {
+      const int64_t nc = std::min(chunk, ncells - c0);
+      GHB_TRY(launch_expand_records(ctx, nc, p->lenA, ntab, dTA.dev, dc.dev + c0 * ntab, tA));
+      GHB_TRY(launch_expand_records(ctx, nc, p->lenb, ntab, dTb.dev, dc.dev + c0 * ntab, tb));
+      GHB_TRY(launch_condense(ctx, *p, nc, tA, tb, dS.dev + c0 * p->n_b * p->n_b, dg.dev + c0 * p->n_b, ip ? ip + c0 : nullptr,
+                              X ? X + c0 * (int64_t)p->n_i * (p->n_b + 1) : nullptr));
+    }
+  }
+  if (finfo && di.dev)
+    GHB_CUDA(ctx, cudaMemcpyAsync(di.dev, finfo, (size_t)ncells * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
   GHB_TRY(dS.finish()); GHB_TRY(dg.finish()); GHB_TRY(di.finish());
   return GHB_OK;
 }
@@ -573,11 +593,11 @@ int ghb_condense_assemble_affine_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, 
     GHB_TRY(asm_scatter_prepare(ctx, 0));
     GHB_CUDA(ctx, cudaMemsetAsync(dz.dev, 0, (size_t)as.nnz * sizeof(double), ctx->stream));
     ScatterArgs sc{dz.dev, as.d_colpos, as.d_rowrank, dd.dev ? as.d_keepS : nullptr};
-    GHB_TRY(launch_condense_cw_gen(ctx, *p, ncells, ntab, dTA.dev, dTb.dev, dc.dev, dS, dg, di.dev, &sc));
+    GHB_TRY(launch_condense_cw_gen(ctx, *p, ncells, ntab, dTA.dev, dTb.dev, dc.dev, dS, dg, di.dev, nullptr, &sc));
     GHB_TRY(asm_numeric_range(ctx, dS, dg, nullptr, dd.dev, dz.dev, dr.dev, 0, as.nrows, ASM_RHS));
   } else {
     if (gen)
-      GHB_TRY(launch_condense_cw_gen(ctx, *p, ncells, ntab, dTA.dev, dTb.dev, dc.dev, dS, dg, di.dev, nullptr));
+      GHB_TRY(launch_condense_cw_gen(ctx, *p, ncells, ntab, dTA.dev, dTb.dev, dc.dev, dS, dg, di.dev, nullptr, nullptr));
     else
       GHB_TRY(condense_affine_chunked(ctx, *p, ncells, ntab, dTA.dev, dTb.dev, dc.dev, dS, dg, di.dev, tmp));
     GHB_TRY(asm_numeric(ctx, dS, dg, nullptr, dd.dev, dz.dev, dr.dev));
@@ -720,7 +740,7 @@ int ghb_condense_scatter_slab_affine_f64(ghb_ctx* ctx, int plan_id, int64_t ncel
   GHB_TRY(asm_scatter_prepare(ctx, keep_cut));
   if (zero_nzval) GHB_CUDA(ctx, cudaMemsetAsync(nzval, 0, (size_t)as.nnz * sizeof(double), ctx->stream));
   ScatterArgs sc{nzval, as.d_colpos, as.d_rowrank, as.d_keepS};
-  return launch_condense_cw_gen(ctx, *p, ncells, ntab, TA, Tb, coef, S, g, info, &sc);
+  return launch_condense_cw_gen(ctx, *p, ncells, ntab, TA, Tb, coef, S, g, info, nullptr, &sc);
 }
 
 /* second half: contributions of the ghost cells (the packed buffer received from the slab above) and the rhs gather */

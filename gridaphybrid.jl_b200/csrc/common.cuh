@@ -267,7 +267,7 @@ struct ScatterArgs;
 // records of an affine family generated inside the condensation kernel (sc != NULL: fused assembly as well)
 bool cw_gen_supported(const Plan& p, int ntab);
 int launch_condense_cw_gen(ghb_ctx* ctx, const Plan& p, int64_t ncells, int ntab, const double* TA, const double* Tb,
-                           const double* coef, double* S, double* g, int32_t* info, const ScatterArgs* sc);
+                           const double* coef, double* S, double* g, int32_t* info, double* X, const ScatterArgs* sc);
 // dispatch: tuned kernel when the plan has one and no factors are requested, else the generic kernel
 int launch_condense(ghb_ctx* ctx, const Plan& p, int64_t ncells, const double* A, const double* b, double* S,
                     double* g, int32_t* info, double* X);

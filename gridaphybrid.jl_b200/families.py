@@ -53,7 +53,7 @@ class AffineRecordFamily:
             self._dev = (torch.as_tensor(self.TA, device=dev), torch.as_tensor(self.Tb, device=dev))
         return self._dev
 
-    def condense(self, ctx: Context, plan: BlockPlan, coef: torch.Tensor, S=None, g=None, info=None):
+    def condense(self, ctx: Context, plan: BlockPlan, coef: torch.Tensor, S=None, g=None, info=None, keep_factors=False):
         """coef [ncells][ntab] (device) -> (S_K, g_K): the records are formed in the loader of the condensation kernel
         and never written to HBM (`ghb_condense_affine_f64`)."""
         ncells = int(coef.shape[0])
@@ -65,7 +65,7 @@ class AffineRecordFamily:
         if g is None:
             g = torch.empty((ncells, plan.n_b), dtype=torch.float64, device=dev)
         ctx.use_torch_stream()
-        ctx.condense_affine(plan, ncells, self.ntab, TA, Tb, coef.contiguous(), S, g, info)
+        ctx.condense_affine(plan, ncells, self.ntab, TA, Tb, coef.contiguous(), S, g, info, keep_factors=keep_factors)
         return S, g
 
     def backsub(self, ctx: Context, plan: BlockPlan, coef: torch.Tensor, lambda_free, lambda_dirichlet, cell_ids, u=None,

@@ -196,8 +196,7 @@ def lazy_map(k, t, *args, ctx: Context | None = None, keep_factors: bool = False
         info = torch.empty((n,), dtype=torch.int32, device=dev)
         ctx.use_torch_stream()
         if hasattr(t, "family"):                 # AffineCells: records formed in the loader of the condensation kernel
-            assert not keep_factors, "keep_factors needs resident records"
-            t.family.condense(ctx, plan, t.coef, S, g, info)
+            t.family.condense(ctx, plan, t.coef, S, g, info, keep_factors=keep_factors)
             return CondensedCells(S, g, info, plan.n_b, plan)
         ctx.condense(plan, n, t.A, t.b, S, g, info, keep_factors=keep_factors)
         return CondensedCells(S, g, info, plan.n_b, plan)

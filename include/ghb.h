@@ -135,10 +135,12 @@ int ghb_expand_records_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, int ntab, 
  * summation order).  Every plan with a cell-warp kernel takes this path (ghb_plan_kernel_name "cw_<n_i>_<n_b>" or
  * "cw_pad_<class>": n_i <= 64, n_b <= 40; odd record lengths go through zero-padded table rows); the other plans, and
  * table counts whose staging does not fit the image of a small class, expand chunks of records into a device temporary
- * instead (same results).  TA, Tb, coef may be host pointers (staged).  ghb_condense_assemble_affine_f64 needs the selected symbolic pattern like
+ * instead (same results).  TA, Tb, coef may be host pointers (staged).  keep_factors as in ghb_condense_f64:
+ * X = A11^-1 [A12 | b1] stays in the ctx and ghb_backsub_f64 with A = b = NULL recovers the bulk unknowns from it.
+ * ghb_condense_assemble_affine_f64 needs the selected symbolic pattern like
  * ghb_condense_assemble_f64. */
 int ghb_condense_affine_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, int ntab, const double* TA, const double* Tb,
-                            const double* coef, double* S, double* g, int32_t* info);
+                            const double* coef, double* S, double* g, int32_t* info, int keep_factors);
 int ghb_condense_assemble_affine_f64(ghb_ctx* ctx, int plan_id, int64_t ncells, int ntab, const double* TA,
                                      const double* Tb, const double* coef, const double* dirichlet_vals,
                                      int64_t ndirichlet, double* nzval, double* rhs, int32_t* info);

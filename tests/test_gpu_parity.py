@@ -754,6 +754,42 @@ def test_affine_family_backward_map_in_the_loader(ctx, name, ntab, ncells):
     assert np.array_equal(u2, u1.cpu().numpy(), equal_nan=True) and np.array_equal(i2, i1.cpu().numpy())
 
 
+@pytest.mark.parametrize("name", ["C3_hdg_k2_3d", "C2_rth_k2_2d", "hencky_k1_2d", "C1_hdg_k1_2d"])
+def test_affine_family_keep_factors(ctx, name):
+    """factor reuse on the affine path: ghb_condense_affine_f64(keep_factors) stores X = A11^-1 [A12 | b1] of the
+    records it formed in the loader; the backward map from those factors (A = b = NULL) is bit-equal to the one from the
+    factors of the expanded records and agrees with the recomputing backward map to the 1e-11 bar; a singular cell is
+    reported with NaN; the lazy AffineCells take keep_factors through lazy_map."""
+    plan = _dev_plan(ctx, name)
+    ncells, ntab = 1500, 7
+    fam, rng = _random_family(ctx, plan, ntab, 21)
+    coef = np.concatenate([np.ones((ncells, 1)), rng.uniform(-1, 1, (ncells, ntab - 1))], axis=1)
+    coef[700] = 0.0
+    coef_d = torch.as_tensor(coef, device="cuda")
+    nfree = 150
+    ids = torch.as_tensor(rng.integers(1, nfree + 1, (ncells, plan.n_b)), device="cuda")
+    lam = torch.as_tensor(rng.standard_normal(nfree), device="cuda")
+    cells = fam.expand(ctx, plan, coef_d)
+    S = torch.empty((ncells, plan.n_b ** 2), dtype=torch.float64, device="cuda"); g = torch.empty((ncells, plan.n_b), dtype=torch.float64, device="cuda")
+    u0 = torch.empty((ncells, plan.n_i), dtype=torch.float64, device="cuda"); i0 = torch.empty(ncells, dtype=torch.int32, device="cuda")
+    ctx.condense(plan, ncells, cells.A, cells.b, S, g, None, keep_factors=True)
+    ctx.backsub(plan, ncells, None, None, lam, None, ids, u0, i0)
+    gen0 = ctx.factors_generation
+    S1, g1 = fam.condense(ctx, plan, coef_d, keep_factors=True)
+    assert ctx.factors_generation == gen0 + 1
+    u1 = torch.empty_like(u0); i1 = torch.empty_like(i0)
+    ctx.backsub(plan, ncells, None, None, lam, None, ids, u1, i1)
+    assert torch.equal(i0, i1) and int(i1[700]) == 1 and int((i1 != 0).sum()) == 1
+    assert np.array_equal(S.cpu().numpy(), S1.cpu().numpy(), equal_nan=True)
+    assert np.array_equal(u0.cpu().numpy(), u1.cpu().numpy(), equal_nan=True)
+    ok = np.ones(ncells, bool); ok[700] = False
+    u2 = fam.backsub(ctx, plan, coef_d, lam, None, ids).cpu().numpy()
+    assert np.isnan(u1.cpu().numpy()[700]).all() and rel_err_cells(u1.cpu().numpy()[ok], u2[ok]) < TOL
+    lazy = gh.AffineCells(fam, coef_d, CONFIGS[name]["ndofs"], CONFIGS[name]["touched"])
+    cond = gh.lazy_map(gh.StaticCondensationMap(CONFIGS[name]["interior"], CONFIGS[name]["boundary"]), lazy, ctx=ctx, keep_factors=True)
+    assert ctx.factors_generation == gen0 + 2 and np.array_equal(cond.S.cpu().numpy(), S.cpu().numpy(), equal_nan=True)
+
+
 @pytest.mark.parametrize("name,dims,ndofs_f", [("C3_hdg_k2_3d", (6, 5, 4), 6), ("C2_rth_k2_2d", (9, 7), 3),
                                                ("elasticity_k1_2d", (6, 5), 4), ("C1_hdg_k1_2d", (7, 6), 2)])
 def test_affine_family_to_csc_in_one_call(ctx, name, dims, ndofs_f):
