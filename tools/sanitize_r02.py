@@ -34,6 +34,8 @@ for name in names:
     fam = gh.AffineRecordFamily(TA, Tb)
     coef = torch.cat([torch.ones((n, 1), dtype=torch.float64, device="cuda"), 0.1 * torch.rand((n, ntab - 1), dtype=torch.float64, device="cuda")], dim=1)
     fam.condense(ctx, plan, coef, S, g, info)                                # GEN (or the chunked fallback)
+    fam.condense(ctx, plan, coef, S, g, info, keep_factors=True)             # GEN + KEEPX
+    ctx.backsub(plan, n, None, None, lam, None, ids, u, None)                # backward map from those factors
     fam.backsub(ctx, plan, coef, lam, None, ids, u, info)                    # GEN + BACK
     print(name, plan.kernel_name, "info", int(info.abs().sum()))
 # fused scatter, resident records and GEN, on a small mesh
