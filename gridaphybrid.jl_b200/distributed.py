@@ -21,6 +21,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from ._lib import GHB_EUNSUPPORTED, GhbError
+
 
 class SlabLayout:
     """Closed-form global numbering for a z-slab partition of a Cartesian mesh `gdims` (x fastest)."""
@@ -235,7 +237,14 @@ class SlabAssembler:
         self.ctx.assemble_select(self._pid)
         keep = L.layer if (L.world > 1 and L.rank > 0) else 0
         TA, Tb = family._tables(coef.device)
-        self.ctx.condense_scatter_slab_affine(plan, L.ncells, family.ntab, TA, Tb, coef.contiguous(), S, g, info, nzval, keep)
+        try:
+            self.ctx.condense_scatter_slab_affine(plan, L.ncells, family.ntab, TA, Tb, coef.contiguous(), S, g, info, nzval, keep)
+        except GhbError as e:
+            if e.code != GHB_EUNSUPPORTED:
+                raise
+            # plans without a cell-warp kernel that can stage the tables: records written out first (same results)
+            cells = family.expand(self.ctx, plan, coef)
+            return self.condense_assemble(plan, cells.A, cells.b, S, g, info, nzval, rhs, exchange=exchange)
         if L.world > 1:
             self.pack(S, g)
             self._exchange(exchange)
